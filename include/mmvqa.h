@@ -1,0 +1,225 @@
+/* mmvqa.h -- C ABI of libmmvqa_sm100.so: the B200 (sm_100a) kernels behind the MMBERT
+ * fusion-encoder hot path of DannielSilva/MM-VQA.
+ *
+ * The reference has no FFI: its boundary is the Python nn.Module surface of models/
+ * (SURVEY.md section 8b).  Each entry point below names the reference code whose forward or
+ * backward arithmetic it replaces (file:line relative to the reference root).  The host
+ * side (mmvqa_b200/*.py) mirrors the reference classes and calls these through ctypes
+ * from torch.autograd.Function.forward/backward.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / pybind types.
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; buffers (including
+ *     workspaces) are owned and allocated by the caller; nothing here allocates.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it and the call
+ *     returns without synchronising (CUDA-graph capturable).
+ *   - return 0 on success, a negative MMVQA_ERR_* otherwise; mmvqa_last_error() returns a
+ *     thread-local message.  Nothing throws.
+ *   - `dtype` selects the activation storage type: MMVQA_F32 (fp32-accurate validation
+ *     path, SIMT FFMA GEMMs) or MMVQA_BF16 (production path: tcgen05/TMEM GEMMs fed by
+ *     TMA, fp32 accumulate).  Parameter vectors (bias, gamma, beta), LayerNorm statistics,
+ *     RealFormer scores and all gradients of parameters are fp32 in both modes.
+ *   - masks are float 1.0 / 0.0 of shape [B, T].
+ */
+#ifndef MMVQA_H_
+#define MMVQA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMVQA_ABI_VERSION 1
+
+enum { MMVQA_F32 = 0, MMVQA_BF16 = 1 };
+enum { MMVQA_ACT_NONE = 0, MMVQA_ACT_SERF = 1, MMVQA_ACT_GELU = 2, MMVQA_ACT_RELU = 3 };
+enum {
+  MMVQA_OK = 0,
+  MMVQA_ERR_ARG = -1,      /* bad shape / alignment / enum */
+  MMVQA_ERR_CUDA = -2,     /* a CUDA runtime or driver call failed */
+  MMVQA_ERR_ARCH = -3,     /* device is not sm_100 */
+  MMVQA_ERR_SMEM = -4      /* problem does not fit the kernel's shared-memory budget */
+};
+
+typedef void* mmvqa_stream_t;
+
+int mmvqa_abi_version(void);
+const char* mmvqa_last_error(void);
+/* compute capability major*10+minor of the current device, or a negative error */
+int mmvqa_device_sm(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t mmvqa_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * GEMM:  C[M,N] = epilogue( sum_k opA(A)[m,k] * opB(B)[n,k] )
+ *   a_trans = 0: A stored [M,K] row-major (K contiguous);  1: stored [K,M] (M contiguous)
+ *   b_trans = 0: B stored [N,K] row-major (nn.Linear weight layout); 1: stored [K,N]
+ *   replaces: every nn.Linear / einsum contraction on the path -- models/transformer.py:20,48,78
+ *   models/realformer.py:33,45,22-26, models/mmbert.py:133-148,164-166, image_encoding.py:74-113
+ *   (1x1 conv), SupConLoss/loss.py:69-71, and their autograd backward (dgrad / wgrad).
+ * Epilogues (acc = fp32 accumulator, bias fp32 [N] optional everywhere):
+ *   EPI_STORE      C = acc + bias
+ *   EPI_ACT        aux_out = acc + bias (pre-activation, optional) ; C = act(acc + bias)
+ *   EPI_RESIDUAL   C = dropout(acc + bias) + aux_in[m,n]   (nn.Dropout on the branch output,
+ *                  realformer.py:45,26 / transformer.py:79,86; dropout_p = 0 -> identity.  The keep
+ *                  decision is a counter hash of (dropout_seed, m*N+n), reproduced by mmvqa_dropout)
+ *   EPI_DACT       C = acc * act'(aux_in[m,n])          (dgrad through an activation)
+ *   EPI_ACT_ROWSUM rowsum_out[batch*M + m] += scale * sum_n act(acc)   (visual-token pooling;
+ *                  C unused; columns n >= N contribute act(0) = 0)
+ *   EPI_DACT_SCALE C = act'(acc) * rowscale[batch*M + m] * scale  (projector backward recompute)
+ * c_dtype may differ from dtype (fp32 output for weight gradients / logits).
+ * accumulate != 0: C += result with fp32 atomics (C must be fp32; used with split_k > 1
+ * or batch-reduction); the caller zero-fills C first.
+ * batch > 1: operands advance by a_batch_rows / b_batch_rows rows of their stored matrix
+ * per batch, C by c_batch_stride elements (0 with accumulate = sum over the batch).
+ * ---------------------------------------------------------------------------------- */
+enum { MMVQA_EPI_STORE = 0, MMVQA_EPI_ACT = 1, MMVQA_EPI_RESIDUAL = 2, MMVQA_EPI_DACT = 3,
+       MMVQA_EPI_ACT_ROWSUM = 4, MMVQA_EPI_DACT_SCALE = 5 };
+
+typedef struct mmvqa_gemm_args {
+  int dtype;                 /* operand dtype: MMVQA_F32 -> SIMT FFMA, MMVQA_BF16 -> tcgen05 */
+  int M, N, K;
+  const void* A; int64_t lda; int a_trans;
+  const void* B; int64_t ldb; int b_trans;
+  void* C; int64_t ldc; int c_dtype;
+  const float* bias;         /* [N] or NULL */
+  int epilogue; int act;
+  const void* aux_in; int64_t ld_aux_in;     /* dtype = `dtype` */
+  void* aux_out; int64_t ld_aux_out;         /* dtype = `dtype` */
+  float* rowsum_out;         /* EPI_ACT_ROWSUM */
+  const float* rowscale;     /* EPI_DACT_SCALE */
+  float scale;
+  int accumulate;
+  int split_k;               /* >= 1 */
+  int batch; int64_t a_batch_rows, b_batch_rows, c_batch_stride;
+  float dropout_p; uint64_t dropout_seed;    /* EPI_RESIDUAL only: C = dropout(acc + bias) + aux_in */
+} mmvqa_gemm_args;
+
+int mmvqa_gemm(const mmvqa_gemm_args* args, mmvqa_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Elementwise / reductions
+ * ---------------------------------------------------------------------------------- */
+/* y = act(x + bias).  replaces models/serf.py:23-24 (5 ATen kernels), transformer.py:7-8 */
+int mmvqa_bias_act_fwd(const void* x, const float* bias, void* y, int64_t rows, int cols, int act, int dtype,
+                       mmvqa_stream_t stream);
+/* dx = dy * act'(x + bias) */
+int mmvqa_bias_act_bwd(const void* x, const float* bias, const void* dy, void* dx, int64_t rows, int cols, int act,
+                       int dtype, mmvqa_stream_t stream);
+/* out[c] = sum_r x[r,c]  (bias gradients); out is overwritten */
+int mmvqa_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int cols, int dtype, mmvqa_stream_t stream);
+/* dst = (dst_dtype) src, n elements; fp32 <-> bf16 casts of weights and feature maps.
+ * rows/cols/ld form: copies [rows, cols] from src (ld_src) to dst (ld_dst), zero-filling cols..ld_dst */
+int mmvqa_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, mmvqa_stream_t stream);
+int mmvqa_cast_pad(const void* src, int src_dtype, int64_t ld_src, void* dst, int dst_dtype, int64_t ld_dst,
+                   int64_t rows, int cols, mmvqa_stream_t stream);
+/* x *= *scalar (device scalar); used to apply the incoming loss gradient without a host sync */
+int mmvqa_scale_by_device_scalar(void* x, int dtype, const float* scalar, float host_factor, int64_t n,
+                                 mmvqa_stream_t stream);
+
+/* y = x * keep / (1-p) with keep = hash(seed, element index) >= p: the same mask the EPI_RESIDUAL
+ * epilogue applied in forward, used on the incoming gradient in backward. */
+int mmvqa_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, int dtype, mmvqa_stream_t stream);
+
+/* fused residual + LayerNorm.  replaces transformer.py:78,83 (norm1), realformer.py:49-50 (ln1/ln2),
+ * mmbert.py:136 (classifier[1]).  y = LN(x + res) * gamma + beta; sum_out (optional) = x + res;
+ * mean/rstd [rows] fp32 are saved for backward. */
+int mmvqa_add_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y,
+                            void* sum_out, float* mean, float* rstd, int64_t rows, int cols, float eps, int dtype,
+                            mmvqa_stream_t stream);
+/* dx = d(LN)/d(xsum) . dy (+ dres_extra if non-NULL: an extra gradient of the same shape added into dx,
+ * i.e. the residual branch); dgamma/dbeta [cols] are ACCUMULATED with atomics (caller zero-fills). */
+int mmvqa_layernorm_bwd(const void* dy, const void* xsum, const float* gamma, const float* mean, const float* rstd,
+                        const void* dx_extra, void* dx, float* dgamma, float* dbeta, int64_t rows, int cols,
+                        int dtype, mmvqa_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Attention (short sequence: T <= 128, head dim <= 128; one CTA per (batch, head))
+ * ---------------------------------------------------------------------------------- */
+/* Transformer MHSA core, models/transformer.py:21-27.  qkv [B*T, 3*heads*d] packed q|k|v
+ * (output of the fused QKV GEMM), key-side mask, probs [B,heads,T,T] (dtype `dtype`) is the
+ * post-softmax matrix the reference keeps in self.scores and is reused by backward.
+ * dropout_p > 0 applies nn.Dropout to the probabilities before P.v (transformer.py:26) with the
+ * counter-hash mask of (dropout_seed, element index); probs holds the pre-dropout values. */
+int mmvqa_mhsa_fwd(const void* qkv, const float* mask, void* out, void* probs, int B, int T, int heads, int d,
+                   float dropout_p, uint64_t dropout_seed, int dtype, mmvqa_stream_t stream);
+int mmvqa_mhsa_bwd(const void* qkv, const void* probs, const void* dout, void* dqkv, int B, int T, int heads, int d,
+                   float dropout_p, uint64_t dropout_seed, int dtype, mmvqa_stream_t stream);
+/* RealFormer residual attention core, models/realformer.py:33-44.  kqv [B*T*heads, 3*d] packed
+ * k|q|v per (token, head) (output of the shared-weight kqv GEMM).  prev / scores / dscores are
+ * fp32 in the kernel-native layout [B, heads, T, T] (the Python side exposes the reference's
+ * [B,T,T,heads] as a permuted view).  scores = q.k/sqrt(d) + prev - 10000*(1-mask[b,i]) is both
+ * the softmax input and the tensor handed to the next layer.  Backward adds dscores_in (gradient
+ * arriving from the next layer through prev) and writes the total as dprev. */
+int mmvqa_rf_attn_fwd(const void* kqv, const float* prev, const float* mask, void* out, float* scores, int B, int T,
+                      int heads, int d, int dtype, mmvqa_stream_t stream);
+int mmvqa_rf_attn_bwd(const void* kqv, const float* scores, const void* dout, const float* dscores_in, void* dkqv,
+                      float* dprev, int B, int T, int heads, int d, int dtype, mmvqa_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Input fusion and pooling
+ * ---------------------------------------------------------------------------------- */
+/* BertEmbeddings (word+pos+type -> LN eps) fused with the visual-token overwrite of positions
+ * 0..nvis-1.  replaces models/mmbert.py:60-67 (B*nvis Python-level copies) + HF BertEmbeddings.
+ * vis is [nvis, B, H] fp32.  dropout_p is BertEmbeddings' dropout (text positions only). */
+int mmvqa_embed_ln_scatter_fwd(const int64_t* ids, const int64_t* seg, const float* word, const float* pos,
+                               const float* typ, const float* gamma, const float* beta, const float* vis, void* h,
+                               float* mean, float* rstd, int B, int T, int H, int nvis, int vocab, float eps,
+                               float dropout_p, uint64_t dropout_seed, int dtype, mmvqa_stream_t stream);
+/* dword/dpos/dtyp/dgamma/dbeta are accumulated with atomics (caller zero-fills); word row
+ * `padding_idx` receives no gradient (nn.Embedding(padding_idx=0)); dvis [nvis,B,H] is overwritten. */
+int mmvqa_embed_ln_scatter_bwd(const void* dh, const int64_t* ids, const int64_t* seg, const float* word,
+                               const float* pos, const float* typ, const float* gamma, const float* mean,
+                               const float* rstd, float* dword, float* dpos, float* dtyp, float* dgamma,
+                               float* dbeta, float* dvis, int B, int T, int H, int nvis, int padding_idx,
+                               float dropout_p, uint64_t dropout_seed, int dtype, mmvqa_stream_t stream);
+/* mask-weighted mean over tokens, models/mmbert.py:169-172 */
+int mmvqa_masked_mean_fwd(const void* h, const float* mask, void* out, int B, int T, int H, int dtype,
+                          mmvqa_stream_t stream);
+int mmvqa_masked_mean_bwd(const void* dout, const float* mask, void* dh, int B, int T, int H, int dtype,
+                          mmvqa_stream_t stream);
+/* row-wise L2 normalise (F.normalize(dim=1), mmbert.py:157), fp32 in/out */
+int mmvqa_l2norm_fwd(const float* x, float* y, float* inv_norm, int rows, int cols, mmvqa_stream_t stream);
+int mmvqa_l2norm_bwd(const float* y, const float* inv_norm, const float* dy, float* dx, int rows, int cols,
+                     mmvqa_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Losses
+ * ---------------------------------------------------------------------------------- */
+/* ASLSingleLabel, models/asl_singlelabel.py:23-52.  One pass: per-row loss, d(loss_row)/d(logits)
+ * (unscaled) and the smoothed one-hot the reference leaves in self.targets_classes (optional). */
+int mmvqa_asl_fwd_bwd(const void* logits, int64_t ld, const int64_t* target, float* loss_rows, float* dlogits,
+                      float* targets_classes, int B, int C, float gamma_pos, float gamma_neg, float eps, int dtype,
+                      mmvqa_stream_t stream);
+/* MLM loss: NLL(log_softmax(logits)) per row, pretrain/roco_utils.py:235-236; dlogits (dtype `dtype`)
+ * = (softmax - onehot) * scale, written in place of / next to the logits */
+int mmvqa_ce_fwd_bwd(const void* logits, int64_t ld, const int64_t* target, float* loss_rows, void* dlogits,
+                     int64_t ld_d, int64_t rows, int C, float scale, int dtype, mmvqa_stream_t stream);
+/* SupCon row pass, models/SupConLoss/loss.py:72-96, over logits = anchor.contrast^T (NOT yet divided
+ * by temperature) [R, N] fp32 for anchors row_offset..row_offset+R of the global N.  mask is the
+ * un-tiled [bsz, bsz] float mask (NULL = SimCLR identity).  Writes per-anchor loss terms
+ * -(T/Tb) * mean_log_prob_pos and G = d(sum of those)/d(logits) [R, N] fp32. */
+int mmvqa_supcon_rows(const float* logits, const float* mask, float* loss_rows, float* G, int R, int N, int bsz,
+                      int row_offset, float temperature, float base_temperature, mmvqa_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Optimiser: multi-tensor Adam, torch.optim.Adam semantics
+ * (vqamed2019/train.py:160, no amsgrad, L2 weight decay).  `table` is a DEVICE array of n_chunks
+ * descriptors, each a contiguous chunk (<= 32768 elements is a good size) of one parameter
+ * tensor; one CTA per chunk.  If bf16_out != NULL the updated parameter is also written as
+ * bf16 (refreshes the tensor-core weight cache in the same pass).
+ * ---------------------------------------------------------------------------------- */
+typedef struct mmvqa_adam_desc {
+  float* p; float* m; float* v; const float* g; void* bf16_out; int64_t n;
+} mmvqa_adam_desc;
+/* `step` (1-based) sets the bias corrections; if step_dev != NULL the kernel reads the step from
+ * that device int instead, so a captured CUDA graph can be replayed while the host bumps it. */
+int mmvqa_adam_step(const mmvqa_adam_desc* table, int n_chunks, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int step, const int* step_dev, float grad_scale, mmvqa_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMVQA_H_ */

@@ -1,0 +1,333 @@
+// attention.cu -- fused short-sequence attention (T <= 128), one CTA per (batch, head).
+//   RF = true : RealFormer residual attention, models/realformer.py:33-44
+//               S = q.k/sqrt(d) + prev - 10000*(1 - mask[b,i])   (QUERY-row offset, carried in S)
+//               writes S (fp32, the tensor the next layer receives), P = softmax_j S, out = P v
+//   RF = false: Transformer MHSA, models/transformer.py:21-27
+//               S = q.k/sqrt(d) - 10000*(1 - mask[b,j])          (KEY mask)
+//               writes P (the module's self.scores), optional dropout on P, out = P v
+// K/Q/V of the (batch, head) are staged once in shared memory as fp32; the T x T score tile never
+// leaves the SM except for the tensors the reference itself materialises; softmax is a
+// warp-shuffle reduction with the mask applied in registers.
+#include "common.cuh"
+
+namespace mmvqa {
+
+struct AttnLayout {
+  int64_t row_stride;   // elements between consecutive tokens of the same head
+  int64_t head_stride;  // elements between heads of the same token
+  int64_t tok_batch;    // elements between batches (= T * row_stride)
+  int q_off, k_off, v_off;
+};
+
+template <typename T>
+__device__ __forceinline__ void load_tile(float* dst, int dst_ld, const T* src, int64_t row_stride, int Tn, int d) {
+  for (int idx = threadIdx.x; idx < Tn * d; idx += blockDim.x) {
+    int t = idx / d, s = idx - t * d;
+    dst[t * dst_ld + s] = to_f(src[t * row_stride + s]);
+  }
+}
+
+template <typename T, bool RF>
+__global__ void __launch_bounds__(256) attn_fwd_kernel(const T* __restrict__ qkv, AttnLayout L,
+                                                       const float* __restrict__ prev, const float* __restrict__ mask,
+                                                       T* __restrict__ out, float* __restrict__ scores,
+                                                       T* __restrict__ probs, int Tn, int heads, int d, float drop_p,
+                                                       unsigned long long seed) {
+  extern __shared__ float sm[];
+  const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* Ks = sm;                       // [Tn][d+1]
+  float* Qs = Ks + Tn * (d + 1);        // [Tn][d]
+  float* Vs = Qs + Tn * d;              // [Tn][d]
+  float* Ps = Vs + Tn * d;              // [nwarp][Tn]
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const T* base = qkv + (int64_t)b * L.tok_batch + (int64_t)h * L.head_stride;
+  load_tile(Ks, d + 1, base + L.k_off, L.row_stride, Tn, d);
+  load_tile(Qs, d, base + L.q_off, L.row_stride, Tn, d);
+  load_tile(Vs, d, base + L.v_off, L.row_stride, Tn, d);
+  __syncthreads();
+  const float sqrt_d = sqrtf((float)d);
+  const int64_t sbase = ((int64_t)b * heads + h) * Tn * Tn;
+  const int H = heads * d;
+  const uint32_t thr = (uint32_t)(drop_p * 4294967296.0);
+  const float inv_keep = drop_p > 0.0f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  for (int i = warp; i < Tn; i += nwarp) {
+    float sc[4];
+    const float qoff = (RF && mask) ? -10000.0f * (1.0f - mask[b * Tn + i]) : 0.0f;
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = lane + 32 * jj;
+      sc[jj] = -INFINITY;
+      if (j < Tn) {
+        float dot = 0.0f;
+        const float* qr = Qs + i * d;
+        const float* kr = Ks + j * (d + 1);
+        for (int s = 0; s < d; ++s) dot = fmaf(qr[s], kr[s], dot);
+        float v = dot / sqrt_d;
+        if (RF) {
+          if (prev) v += prev[sbase + (int64_t)i * Tn + j];
+          v += qoff;
+          scores[sbase + (int64_t)i * Tn + j] = v;
+        } else if (mask) {
+          v -= 10000.0f * (1.0f - mask[b * Tn + j]);
+        }
+        sc[jj] = v;
+        mx = fmaxf(mx, v);
+      }
+    }
+    mx = warp_max(mx);
+    float sum = 0.0f;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = lane + 32 * jj;
+      if (j < Tn) {
+        sc[jj] = expf(sc[jj] - mx);
+        sum += sc[jj];
+      }
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = lane + 32 * jj;
+      if (j < Tn) {
+        float pr = sc[jj] * inv;
+        if (!RF) {
+          probs[sbase + (int64_t)i * Tn + j] = from_f<T>(pr);
+          if (drop_p > 0.0f) pr = hash32(seed, (uint64_t)(sbase + (int64_t)i * Tn + j)) >= thr ? pr * inv_keep : 0.0f;
+        }
+        Ps[warp * Tn + j] = pr;
+      }
+    }
+    __syncwarp();
+    for (int s = lane; s < d; s += 32) {
+      float acc = 0.0f;
+      const float* pw = Ps + warp * Tn;
+      for (int j = 0; j < Tn; ++j) acc = fmaf(pw[j], Vs[j * d + s], acc);
+      out[((int64_t)b * Tn + i) * H + h * d + s] = from_f<T>(acc);
+    }
+    __syncwarp();
+  }
+}
+
+template <typename T, bool RF>
+__global__ void __launch_bounds__(256) attn_bwd_kernel(const T* __restrict__ qkv, AttnLayout L,
+                                                       const float* __restrict__ scores, const T* __restrict__ probs,
+                                                       const T* __restrict__ dout, const float* __restrict__ dscores_in,
+                                                       T* __restrict__ dqkv, float* __restrict__ dprev, int Tn, int heads,
+                                                       int d, float drop_p, unsigned long long seed) {
+  extern __shared__ float sm[];
+  const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* X = sm;                        // [Tn][d+1]  V, then K, then Q
+  float* dO = X + Tn * (d + 1);         // [Tn][d]
+  float* P = dO + Tn * d;               // [Tn][Tn]   probabilities used by dV (post-dropout for MHSA)
+  float* dS = P + Tn * Tn;              // [Tn][Tn]   gradient of the pre-softmax scores
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int H = heads * d;
+  const T* base = qkv + (int64_t)b * L.tok_batch + (int64_t)h * L.head_stride;
+  T* dbase = dqkv + (int64_t)b * L.tok_batch + (int64_t)h * L.head_stride;
+  const int64_t sbase = ((int64_t)b * heads + h) * Tn * Tn;
+  load_tile(X, d + 1, base + L.v_off, L.row_stride, Tn, d);
+  load_tile(dO, d, dout + (int64_t)b * Tn * H + h * d, (int64_t)H, Tn, d);
+  __syncthreads();
+  const uint32_t thr = (uint32_t)(drop_p * 4294967296.0);
+  const float inv_keep = drop_p > 0.0f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  for (int i = warp; i < Tn; i += nwarp) {
+    float pr[4], dp[4];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = lane + 32 * jj;
+      pr[jj] = RF ? -INFINITY : 0.0f;
+      if (j < Tn) {
+        if (RF) {
+          pr[jj] = scores[sbase + (int64_t)i * Tn + j];
+          mx = fmaxf(mx, pr[jj]);
+        } else {
+          pr[jj] = to_f(probs[sbase + (int64_t)i * Tn + j]);
+        }
+      }
+    }
+    if (RF) {
+      mx = warp_max(mx);
+      float sum = 0.0f;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj)
+        if (lane + 32 * jj < Tn) {
+          pr[jj] = expf(pr[jj] - mx);
+          sum += pr[jj];
+        }
+      sum = warp_sum(sum);
+      const float inv = 1.0f / sum;
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) pr[jj] = (lane + 32 * jj < Tn) ? pr[jj] * inv : 0.0f;
+    }
+    float rowdot = 0.0f;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = lane + 32 * jj;
+      dp[jj] = 0.0f;
+      if (j < Tn) {
+        float acc = 0.0f;
+        const float* dr = dO + i * d;
+        const float* vr = X + j * (d + 1);
+        for (int s = 0; s < d; ++s) acc = fmaf(dr[s], vr[s], acc);
+        float pd = pr[jj];
+        if (!RF && drop_p > 0.0f) {
+          const bool keep = hash32(seed, (uint64_t)(sbase + (int64_t)i * Tn + j)) >= thr;
+          acc = keep ? acc * inv_keep : 0.0f;
+          pd = keep ? pd * inv_keep : 0.0f;
+        }
+        P[i * Tn + j] = pd;
+        dp[jj] = acc;
+        rowdot += pr[jj] * acc;
+      }
+    }
+    rowdot = warp_sum(rowdot);
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      const int j = lane + 32 * jj;
+      if (j < Tn) {
+        float g = pr[jj] * (dp[jj] - rowdot);
+        if (RF) {
+          if (dscores_in) g += dscores_in[sbase + (int64_t)i * Tn + j];
+          if (dprev) dprev[sbase + (int64_t)i * Tn + j] = g;
+        }
+        dS[i * Tn + j] = g;
+      }
+    }
+  }
+  __syncthreads();
+  const float inv_sqrt_d = 1.0f / sqrtf((float)d);
+  // dV[j][s] = sum_i P[i][j] dO[i][s]
+  for (int idx = threadIdx.x; idx < Tn * d; idx += blockDim.x) {
+    const int j = idx / d, s = idx - j * d;
+    float acc = 0.0f;
+    for (int i = 0; i < Tn; ++i) acc = fmaf(P[i * Tn + j], dO[i * d + s], acc);
+    dbase[L.v_off + (int64_t)j * L.row_stride + s] = from_f<T>(acc);
+  }
+  __syncthreads();
+  load_tile(X, d + 1, base + L.k_off, L.row_stride, Tn, d);
+  __syncthreads();
+  // dQ[i][s] = sum_j dS[i][j] K[j][s] / sqrt(d)
+  for (int idx = threadIdx.x; idx < Tn * d; idx += blockDim.x) {
+    const int i = idx / d, s = idx - i * d;
+    float acc = 0.0f;
+    for (int j = 0; j < Tn; ++j) acc = fmaf(dS[i * Tn + j], X[j * (d + 1) + s], acc);
+    dbase[L.q_off + (int64_t)i * L.row_stride + s] = from_f<T>(acc * inv_sqrt_d);
+  }
+  __syncthreads();
+  load_tile(X, d + 1, base + L.q_off, L.row_stride, Tn, d);
+  __syncthreads();
+  // dK[j][s] = sum_i dS[i][j] Q[i][s] / sqrt(d)
+  for (int idx = threadIdx.x; idx < Tn * d; idx += blockDim.x) {
+    const int j = idx / d, s = idx - j * d;
+    float acc = 0.0f;
+    for (int i = 0; i < Tn; ++i) acc = fmaf(dS[i * Tn + j], X[i * (d + 1) + s], acc);
+    dbase[L.k_off + (int64_t)j * L.row_stride + s] = from_f<T>(acc * inv_sqrt_d);
+  }
+}
+
+static int check_shape(const char* name, int B, int T, int heads, int d) {
+  MMVQA_REQUIRE(B > 0 && T > 0 && heads > 0 && d > 0, "%s: bad shape", name);
+  MMVQA_REQUIRE(T <= 128, "%s: sequence length %d > 128 (short-sequence kernel)", name, T);
+  MMVQA_REQUIRE(d <= 128, "%s: head dim %d > 128", name, d);
+  return MMVQA_OK;
+}
+
+template <typename T, bool RF>
+static int launch_fwd(const void* qkv, const AttnLayout& L, const float* prev, const float* mask, void* out, float* scores,
+                      void* probs, int B, int Tn, int heads, int d, float p, uint64_t seed, cudaStream_t st) {
+  size_t smem = sizeof(float) * ((size_t)Tn * (d + 1) + 2 * (size_t)Tn * d + 8 * (size_t)Tn);
+  if (smem > 227 * 1024) return set_err(MMVQA_ERR_SMEM, "attention fwd: T=%d d=%d needs %zu bytes of shared memory", Tn, d, smem);
+  auto kern = attn_fwd_kernel<T, RF>;
+  if (smem > 48 * 1024) MMVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<B * heads, 256, smem, st>>>((const T*)qkv, L, prev, mask, (T*)out, scores, (T*)probs, Tn, heads, d, p, seed);
+  MMVQA_LAUNCHED("attn_fwd");
+  return MMVQA_OK;
+}
+
+template <typename T, bool RF>
+static int launch_bwd(const void* qkv, const AttnLayout& L, const float* scores, const void* probs, const void* dout,
+                      const float* dscores_in, void* dqkv, float* dprev, int B, int Tn, int heads, int d, float p,
+                      uint64_t seed, cudaStream_t st) {
+  size_t smem = sizeof(float) * ((size_t)Tn * (d + 1) + (size_t)Tn * d + 2 * (size_t)Tn * Tn);
+  if (smem > 227 * 1024) return set_err(MMVQA_ERR_SMEM, "attention bwd: T=%d d=%d needs %zu bytes of shared memory", Tn, d, smem);
+  auto kern = attn_bwd_kernel<T, RF>;
+  if (smem > 48 * 1024) MMVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<B * heads, 256, smem, st>>>((const T*)qkv, L, scores, (const T*)probs, (const T*)dout, dscores_in, (T*)dqkv, dprev,
+                                     Tn, heads, d, p, seed);
+  MMVQA_LAUNCHED("attn_bwd");
+  return MMVQA_OK;
+}
+
+static AttnLayout rf_layout(int T, int heads, int d) {
+  AttnLayout L;
+  L.row_stride = (int64_t)heads * 3 * d;
+  L.head_stride = 3 * d;
+  L.tok_batch = (int64_t)T * L.row_stride;
+  L.k_off = 0; L.q_off = d; L.v_off = 2 * d;     // split order k, q, v (realformer.py:33)
+  return L;
+}
+static AttnLayout mhsa_layout(int T, int heads, int d) {
+  AttnLayout L;
+  const int H = heads * d;
+  L.row_stride = 3 * (int64_t)H;
+  L.head_stride = d;
+  L.tok_batch = (int64_t)T * L.row_stride;
+  L.q_off = 0; L.k_off = H; L.v_off = 2 * H;     // fused [q | k | v] projection
+  return L;
+}
+
+}  // namespace mmvqa
+
+using namespace mmvqa;
+
+extern "C" {
+
+int mmvqa_rf_attn_fwd(const void* kqv, const float* prev, const float* mask, void* out, float* scores, int B, int T,
+                      int heads, int d, int dtype, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(kqv && out && scores, "rf_attn_fwd: null pointer");
+  int rc = check_shape("rf_attn_fwd", B, T, heads, d);
+  if (rc) return rc;
+  AttnLayout L = rf_layout(T, heads, d);
+  if (dtype == MMVQA_F32) return launch_fwd<float, true>(kqv, L, prev, mask, out, scores, nullptr, B, T, heads, d, 0.f, 0, as_stream(stream));
+  if (dtype == MMVQA_BF16) return launch_fwd<__nv_bfloat16, true>(kqv, L, prev, mask, out, scores, nullptr, B, T, heads, d, 0.f, 0, as_stream(stream));
+  return set_err(MMVQA_ERR_ARG, "rf_attn_fwd: bad dtype %d", dtype);
+}
+
+int mmvqa_rf_attn_bwd(const void* kqv, const float* scores, const void* dout, const float* dscores_in, void* dkqv,
+                      float* dprev, int B, int T, int heads, int d, int dtype, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(kqv && scores && dout && dkqv, "rf_attn_bwd: null pointer");
+  int rc = check_shape("rf_attn_bwd", B, T, heads, d);
+  if (rc) return rc;
+  AttnLayout L = rf_layout(T, heads, d);
+  if (dtype == MMVQA_F32) return launch_bwd<float, true>(kqv, L, scores, nullptr, dout, dscores_in, dkqv, dprev, B, T, heads, d, 0.f, 0, as_stream(stream));
+  if (dtype == MMVQA_BF16) return launch_bwd<__nv_bfloat16, true>(kqv, L, scores, nullptr, dout, dscores_in, dkqv, dprev, B, T, heads, d, 0.f, 0, as_stream(stream));
+  return set_err(MMVQA_ERR_ARG, "rf_attn_bwd: bad dtype %d", dtype);
+}
+
+int mmvqa_mhsa_fwd(const void* qkv, const float* mask, void* out, void* probs, int B, int T, int heads, int d,
+                   float dropout_p, uint64_t dropout_seed, int dtype, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(qkv && out && probs, "mhsa_fwd: null pointer");
+  MMVQA_REQUIRE(dropout_p >= 0.0f && dropout_p < 1.0f, "mhsa_fwd: dropout_p must be in [0,1)");
+  int rc = check_shape("mhsa_fwd", B, T, heads, d);
+  if (rc) return rc;
+  AttnLayout L = mhsa_layout(T, heads, d);
+  if (dtype == MMVQA_F32) return launch_fwd<float, false>(qkv, L, nullptr, mask, out, nullptr, probs, B, T, heads, d, dropout_p, dropout_seed, as_stream(stream));
+  if (dtype == MMVQA_BF16) return launch_fwd<__nv_bfloat16, false>(qkv, L, nullptr, mask, out, nullptr, probs, B, T, heads, d, dropout_p, dropout_seed, as_stream(stream));
+  return set_err(MMVQA_ERR_ARG, "mhsa_fwd: bad dtype %d", dtype);
+}
+
+int mmvqa_mhsa_bwd(const void* qkv, const void* probs, const void* dout, void* dqkv, int B, int T, int heads, int d,
+                   float dropout_p, uint64_t dropout_seed, int dtype, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(qkv && probs && dout && dqkv, "mhsa_bwd: null pointer");
+  int rc = check_shape("mhsa_bwd", B, T, heads, d);
+  if (rc) return rc;
+  AttnLayout L = mhsa_layout(T, heads, d);
+  if (dtype == MMVQA_F32) return launch_bwd<float, false>(qkv, L, nullptr, probs, dout, nullptr, dqkv, nullptr, B, T, heads, d, dropout_p, dropout_seed, as_stream(stream));
+  if (dtype == MMVQA_BF16) return launch_bwd<__nv_bfloat16, false>(qkv, L, nullptr, probs, dout, nullptr, dqkv, nullptr, B, T, heads, d, dropout_p, dropout_seed, as_stream(stream));
+  return set_err(MMVQA_ERR_ARG, "mhsa_bwd: bad dtype %d", dtype);
+}
+
+}  // extern "C"

@@ -1,0 +1,173 @@
+// common.cuh -- shared helpers for libmmvqa_sm100.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include "../../include/mmvqa.h"
+
+namespace mmvqa {
+
+extern thread_local char g_err[512];
+extern std::atomic<int64_t> g_launches;
+
+int set_err(int code, const char* fmt, ...);
+
+#define MMVQA_REQUIRE(cond, ...)                                   \
+  do {                                                             \
+    if (!(cond)) return ::mmvqa::set_err(MMVQA_ERR_ARG, __VA_ARGS__); \
+  } while (0)
+
+// call after every kernel launch: counts it and converts launch errors
+#define MMVQA_LAUNCHED(name)                                                            \
+  do {                                                                                  \
+    ::mmvqa::g_launches.fetch_add(1, std::memory_order_relaxed);                        \
+    cudaError_t e__ = cudaPeekAtLastError();                                            \
+    if (e__ != cudaSuccess) {                                                           \
+      cudaGetLastError();                                                               \
+      return ::mmvqa::set_err(MMVQA_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e__)); \
+    }                                                                                   \
+  } while (0)
+
+#define MMVQA_CUDA(call)                                                                     \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess) return ::mmvqa::set_err(MMVQA_ERR_CUDA, #call ": %s", cudaGetErrorString(e__)); \
+  } while (0)
+
+static inline cudaStream_t as_stream(mmvqa_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+int num_sms();
+
+// ---------------------------------------------------------------------------------
+// element access templated on storage type
+// ---------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// 128-bit vector of T: 4 floats or 8 bf16
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 4;
+  float4 raw;
+  __device__ __forceinline__ void load(const float* p) { raw = *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ void store(float* p) const { *reinterpret_cast<float4*>(p) = raw; }
+  __device__ __forceinline__ float get(int i) const { return (&raw.x)[i]; }
+  __device__ __forceinline__ void set(int i, float v) { (&raw.x)[i] = v; }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  uint4 raw;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { raw = *reinterpret_cast<const uint4*>(p); }
+  __device__ __forceinline__ void store(__nv_bfloat16* p) const { *reinterpret_cast<uint4*>(p) = raw; }
+  __device__ __forceinline__ float get(int i) const {
+    uint32_t w = (&raw.x)[i >> 1];
+    return __uint_as_float((i & 1) ? (w & 0xffff0000u) : (w << 16));
+  }
+  __device__ __forceinline__ void set(int i, float v) {
+    uint32_t b = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
+    uint32_t& w = (&raw.x)[i >> 1];
+    w = (i & 1) ? ((w & 0x0000ffffu) | (b << 16)) : ((w & 0xffff0000u) | b);
+  }
+};
+
+// ---------------------------------------------------------------------------------
+// activations.  act codes: MMVQA_ACT_*
+//   SERF  models/serf.py:23-24   x * erf(log1p(exp(min(x, 50))))
+//   GELU  models/transformer.py:7-8   exact erf form
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float serf_f(float x) {
+  float sp = log1pf(expf(fminf(x, 50.0f)));
+  return x * erff(sp);
+}
+// d/dx serf = erf(sp) + x * 2/sqrt(pi) * exp(-sp^2) * sigmoid(x)   (x <= 50);  erf(sp(50)) beyond the clamp
+__device__ __forceinline__ float dserf_f(float x) {
+  float xc = fminf(x, 50.0f);
+  float sp = log1pf(expf(xc));
+  float e = erff(sp);
+  if (x > 50.0f) return e;
+  float sig = 1.0f / (1.0f + expf(-x));
+  return e + x * 1.1283791670955126f * expf(-sp * sp) * sig;
+}
+__device__ __forceinline__ float gelu_f(float x) { return x * 0.5f * (1.0f + erff(x * 0.7071067811865476f)); }
+__device__ __forceinline__ float dgelu_f(float x) {
+  return 0.5f * (1.0f + erff(x * 0.7071067811865476f)) + x * 0.3989422804014327f * expf(-0.5f * x * x);
+}
+template <int ACT> __device__ __forceinline__ float act_f(float x) {
+  if (ACT == MMVQA_ACT_SERF) return serf_f(x);
+  if (ACT == MMVQA_ACT_GELU) return gelu_f(x);
+  if (ACT == MMVQA_ACT_RELU) return fmaxf(x, 0.0f);
+  return x;
+}
+template <int ACT> __device__ __forceinline__ float dact_f(float x) {
+  if (ACT == MMVQA_ACT_SERF) return dserf_f(x);
+  if (ACT == MMVQA_ACT_GELU) return dgelu_f(x);
+  if (ACT == MMVQA_ACT_RELU) return x > 0.0f ? 1.0f : 0.0f;
+  return 1.0f;
+}
+__device__ __forceinline__ float act_rt(int act, float x) {
+  switch (act) {
+    case MMVQA_ACT_SERF: return serf_f(x);
+    case MMVQA_ACT_GELU: return gelu_f(x);
+    case MMVQA_ACT_RELU: return fmaxf(x, 0.0f);
+    default: return x;
+  }
+}
+__device__ __forceinline__ float dact_rt(int act, float x) {
+  switch (act) {
+    case MMVQA_ACT_SERF: return dserf_f(x);
+    case MMVQA_ACT_GELU: return dgelu_f(x);
+    case MMVQA_ACT_RELU: return x > 0.0f ? 1.0f : 0.0f;
+    default: return 1.0f;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// block-wide sum; `red` is >= 32 floats of shared memory; every thread gets the result
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : 0.0f;
+  t = warp_sum(t);
+  return t;
+}
+__device__ __forceinline__ float block_max(float v, float* red) {
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float t = (lane < nw) ? red[lane] : -INFINITY;
+  t = warp_max(t);
+  return t;
+}
+
+// counter-based dropout keep decision (one 32-bit hash per element); identical in fwd and bwd
+__device__ __forceinline__ uint32_t hash32(uint64_t seed, uint64_t idx) {
+  uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (uint32_t)(z >> 16);
+}
+
+}  // namespace mmvqa

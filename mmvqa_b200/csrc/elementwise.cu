@@ -1,0 +1,616 @@
+// elementwise.cu -- HBM-bound kernels of the fusion-encoder path: bias+activation, column sums,
+// casts, residual+LayerNorm (fwd/bwd), dropout.  All use 128-bit vectorised global accesses when
+// the row length and pointers allow it and fall back to scalar accesses otherwise.
+#include "common.cuh"
+#include <stdarg.h>
+
+namespace mmvqa {
+
+thread_local char g_err[512] = {0};
+std::atomic<int64_t> g_launches{0};
+
+int set_err(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// ---------------------------------------------------------------------------------
+// bias + activation
+// ---------------------------------------------------------------------------------
+template <typename T, bool BWD, bool VEC>
+__global__ void __launch_bounds__(256) bias_act_kernel(const T* __restrict__ x, const float* __restrict__ bias,
+                                                       const T* __restrict__ dy, T* __restrict__ out, int64_t rows,
+                                                       int cols, int act) {
+  if (VEC) {
+    constexpr int N = Vec16<T>::N;
+    const int vcols = cols / N;
+    const int64_t total = rows * (int64_t)vcols;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      int c0 = (int)(i % vcols) * N;
+      Vec16<T> v, g, o;
+      v.load(x + i * N);
+      if (BWD) g.load(dy + i * N);
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        float z = v.get(j) + (bias ? __ldg(bias + c0 + j) : 0.0f);
+        o.set(j, BWD ? g.get(j) * dact_rt(act, z) : act_rt(act, z));
+      }
+      o.store(out + i * N);
+    }
+  } else {
+    const int64_t total = rows * (int64_t)cols;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      int c = (int)(i % cols);
+      float z = to_f(x[i]) + (bias ? __ldg(bias + c) : 0.0f);
+      out[i] = from_f<T>(BWD ? to_f(dy[i]) * dact_rt(act, z) : act_rt(act, z));
+    }
+  }
+}
+
+template <typename T, bool BWD>
+static int bias_act_launch(const void* x, const float* bias, const void* dy, void* out, int64_t rows, int cols, int act,
+                           cudaStream_t st) {
+  if (rows <= 0 || cols <= 0) return MMVQA_OK;
+  bool vec = (cols % Vec16<T>::N == 0) && aligned16(x) && aligned16(out) && (!BWD || aligned16(dy));
+  int64_t work = rows * (int64_t)cols / (vec ? Vec16<T>::N : 1);
+  int grid = (int)((work + 255) / 256 < (int64_t)num_sms() * 16 ? (work + 255) / 256 : (int64_t)num_sms() * 16);
+  if (vec)
+    bias_act_kernel<T, BWD, true><<<grid, 256, 0, st>>>((const T*)x, bias, (const T*)dy, (T*)out, rows, cols, act);
+  else
+    bias_act_kernel<T, BWD, false><<<grid, 256, 0, st>>>((const T*)x, bias, (const T*)dy, (T*)out, rows, cols, act);
+  MMVQA_LAUNCHED("bias_act");
+  return MMVQA_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// column sums (bias gradients):  out[c] = sum_r x[r, c]
+// block = 32 columns x 8 row lanes; grid.y splits the rows; partial sums land with one atomic per
+// (block, column) into the zero-filled output.
+// ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int64_t ldx, float* __restrict__ out,
+                                                     int64_t rows, int cols, int64_t rows_per_block) {
+  __shared__ float red[8][33];
+  int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  int c = blockIdx.x * 32 + tx;
+  int64_t r0 = blockIdx.y * rows_per_block, r1 = r0 + rows_per_block;
+  if (r1 > rows) r1 = rows;
+  float s = 0.0f;
+  if (c < cols)
+    for (int64_t r = r0 + ty; r < r1; r += 8) s += to_f(x[r * ldx + c]);
+  red[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && c < cols) {
+    float t = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += red[j][tx];
+    atomicAdd(out + c, t);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// casts
+// ---------------------------------------------------------------------------------
+template <typename S, typename D>
+__global__ void __launch_bounds__(256) cast_kernel(const S* __restrict__ src, D* __restrict__ dst, int64_t n) {
+  int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) * 4;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (; i < n; i += stride) {
+    if (i + 3 < n) {
+      float a = to_f(src[i]), b = to_f(src[i + 1]), c = to_f(src[i + 2]), d = to_f(src[i + 3]);
+      dst[i] = from_f<D>(a); dst[i + 1] = from_f<D>(b); dst[i + 2] = from_f<D>(c); dst[i + 3] = from_f<D>(d);
+    } else {
+      for (int64_t j = i; j < n; ++j) dst[j] = from_f<D>(to_f(src[j]));
+    }
+  }
+}
+// specialised hot case: contiguous fp32 -> bf16 with 128-bit loads, 64-bit stores
+__global__ void __launch_bounds__(256) cast_f32_bf16_vec(const float4* __restrict__ src, uint2* __restrict__ dst,
+                                                         int64_t n4) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = src[i];
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    dst[i] = o;
+  }
+}
+
+template <typename S, typename D>
+__global__ void __launch_bounds__(256) cast_pad_kernel(const S* __restrict__ src, int64_t ld_src, D* __restrict__ dst,
+                                                       int64_t ld_dst, int64_t rows, int cols) {
+  int64_t total = rows * ld_dst;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / ld_dst;
+    int c = (int)(i - r * ld_dst);
+    dst[i] = from_f<D>(c < cols ? to_f(src[r * ld_src + c]) : 0.0f);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) scale_kernel(T* __restrict__ x, const float* __restrict__ scalar, float host_factor,
+                                                    int64_t n) {
+  float s = (scalar ? *scalar : 1.0f) * host_factor;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = from_f<T>(to_f(x[i]) * s);
+}
+
+// y = x * keep / (1-p), keep from the counter hash of (seed, element index)
+template <typename T>
+__global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, float p,
+                                                      uint64_t seed) {
+  uint32_t thr = (uint32_t)(p * 4294967296.0);
+  float inv = 1.0f / (1.0f - p);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = from_f<T>(hash32(seed, (uint64_t)i) >= thr ? to_f(x[i]) * inv : 0.0f);
+}
+
+// ---------------------------------------------------------------------------------
+// residual + LayerNorm.  One warp per row.  Fast path (cols <= 1024): the row lives in registers,
+// every global access is a 128-bit vector (VEC) or a scalar (unaligned / odd row length).
+// Generic path (cols > 1024): re-reads the row.  Two-pass mean / variance like ATen.
+// ---------------------------------------------------------------------------------
+constexpr int LN_CACHE = 32;  // values per lane -> rows up to 1024 columns stay in registers
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(128) add_ln_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         T* __restrict__ y, T* __restrict__ sum_out,
+                                                         float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                         int64_t rows, int cols, float eps) {
+  constexpr int N = VEC ? Vec16<T>::N : 1;
+  constexpr int ITER = LN_CACHE / N;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* xr = x + row * cols;
+  const T* rr = res ? res + row * cols : nullptr;
+  T* so = sum_out ? sum_out + row * cols : nullptr;
+  float v[LN_CACHE];
+  float s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < ITER; ++k) {
+    const int c = (k * 32 + lane) * N;
+    if (c < cols) {
+      if (VEC) {
+        Vec16<T> a, b;
+        a.load(xr + c);
+        if (rr) b.load(rr + c);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          float t = a.get(j) + (rr ? b.get(j) : 0.0f);
+          if (so) {  // normalise the value that is stored (bf16-rounded) so backward sees the same row
+            a.set(j, t);
+            t = a.get(j);
+          }
+          v[k * N + j] = t;
+          s += t;
+        }
+        if (so) a.store(so + c);
+      } else {
+        float t = to_f(xr[c]) + (rr ? to_f(rr[c]) : 0.0f);
+        if (so) {
+          T q = from_f<T>(t);
+          so[c] = q;
+          t = to_f(q);
+        }
+        v[k] = t;
+        s += t;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[k * N + j] = 0.0f;
+    }
+  }
+  const float mean = warp_sum(s) / (float)cols;
+  float q = 0.0f;
+#pragma unroll
+  for (int k = 0; k < ITER; ++k) {
+    const int c = (k * 32 + lane) * N;
+    if (c < cols) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        float d = v[k * N + j] - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)cols + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  T* yr = y + row * cols;
+#pragma unroll
+  for (int k = 0; k < ITER; ++k) {
+    const int c = (k * 32 + lane) * N;
+    if (c < cols) {
+      if (VEC) {
+        Vec16<T> o;
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+          o.set(j, (v[k * N + j] - mean) * rstd * __ldg(gamma + c + j) + __ldg(beta + c + j));
+        o.store(yr + c);
+      } else {
+        yr[c] = from_f<T>((v[k] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c));
+      }
+    }
+  }
+}
+
+// generic (any cols): re-reads the row from global memory
+template <typename T>
+__global__ void __launch_bounds__(128) add_ln_fwd_generic(const T* __restrict__ x, const T* __restrict__ res,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          T* __restrict__ y, T* __restrict__ sum_out,
+                                                          float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                          int64_t rows, int cols, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* xr = x + row * cols;
+  const T* rr = res ? res + row * cols : nullptr;
+  T* so = sum_out ? sum_out + row * cols : nullptr;
+  float s = 0.0f;
+  for (int c = lane; c < cols; c += 32) {
+    float t = to_f(xr[c]) + (rr ? to_f(rr[c]) : 0.0f);
+    if (so) {
+      T q = from_f<T>(t);
+      so[c] = q;
+      t = to_f(q);
+    }
+    s += t;
+  }
+  const float mean = warp_sum(s) / (float)cols;
+  float q = 0.0f;
+  for (int c = lane; c < cols; c += 32) {
+    float t = so ? to_f(so[c]) : to_f(xr[c]) + (rr ? to_f(rr[c]) : 0.0f);
+    q += (t - mean) * (t - mean);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)cols + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  for (int c = lane; c < cols; c += 32) {
+    float t = so ? to_f(so[c]) : to_f(xr[c]) + (rr ? to_f(rr[c]) : 0.0f);
+    y[row * cols + c] = from_f<T>((t - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c));
+  }
+}
+
+// backward.  Each warp walks rows (grid-stride); lanes own fixed columns, so dgamma/dbeta partials
+// accumulate in registers and are flushed through shared memory with one global atomic per
+// (block, column).  CACHED = cols <= 1024.
+template <typename T, bool VEC, bool CACHED>
+__global__ void __launch_bounds__(128) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ xsum,
+                                                     const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                     const float* __restrict__ rstd, const T* __restrict__ dx_extra,
+                                                     T* __restrict__ dx, float* __restrict__ dgamma,
+                                                     float* __restrict__ dbeta, int64_t rows, int cols) {
+  extern __shared__ float sm[];  // [2][cols] block partials
+  constexpr int N = VEC ? Vec16<T>::N : 1;
+  constexpr int ITER = LN_CACHE / N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  float dg[CACHED ? LN_CACHE : 1], db[CACHED ? LN_CACHE : 1];
+  if (CACHED) {
+#pragma unroll
+    for (int k = 0; k < LN_CACHE; ++k) dg[k] = db[k] = 0.0f;
+  }
+  for (int c = threadIdx.x; c < 2 * cols; c += blockDim.x) sm[c] = 0.0f;
+  __syncthreads();
+  for (int64_t row = blockIdx.x * (int64_t)nwarp + warp; row < rows; row += (int64_t)gridDim.x * nwarp) {
+    const float mu = mean[row], rs = rstd[row];
+    const T* dyr = dy + row * cols;
+    const T* xr = xsum + row * cols;
+    const T* er = dx_extra ? dx_extra + row * cols : nullptr;
+    T* dxr = dx + row * cols;
+    float s1 = 0.0f, s2 = 0.0f;
+    if (CACHED) {
+      float g_[LN_CACHE], xh_[LN_CACHE];
+#pragma unroll
+      for (int k = 0; k < ITER; ++k) {
+        const int c = (k * 32 + lane) * N;
+        if (c < cols) {
+          if (VEC) {
+            Vec16<T> a, b;
+            a.load(dyr + c);
+            b.load(xr + c);
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+              float g = a.get(j), xh = (b.get(j) - mu) * rs;
+              dg[k * N + j] += g * xh;
+              db[k * N + j] += g;
+              g *= __ldg(gamma + c + j);
+              g_[k * N + j] = g;
+              xh_[k * N + j] = xh;
+              s1 += g;
+              s2 += g * xh;
+            }
+          } else {
+            float g = to_f(dyr[c]), xh = (to_f(xr[c]) - mu) * rs;
+            dg[k] += g * xh;
+            db[k] += g;
+            g *= __ldg(gamma + c);
+            g_[k] = g;
+            xh_[k] = xh;
+            s1 += g;
+            s2 += g * xh;
+          }
+        }
+      }
+      s1 = warp_sum(s1) / (float)cols;
+      s2 = warp_sum(s2) / (float)cols;
+#pragma unroll
+      for (int k = 0; k < ITER; ++k) {
+        const int c = (k * 32 + lane) * N;
+        if (c < cols) {
+          if (VEC) {
+            Vec16<T> e, o;
+            if (er) e.load(er + c);
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+              o.set(j, rs * (g_[k * N + j] - s1 - xh_[k * N + j] * s2) + (er ? e.get(j) : 0.0f));
+            o.store(dxr + c);
+          } else {
+            dxr[c] = from_f<T>(rs * (g_[k] - s1 - xh_[k] * s2) + (er ? to_f(er[c]) : 0.0f));
+          }
+        }
+      }
+    } else {
+      for (int c = lane; c < cols; c += 32) {
+        float g = to_f(dyr[c]), xh = (to_f(xr[c]) - mu) * rs;
+        atomicAdd(&sm[c], g * xh);
+        atomicAdd(&sm[cols + c], g);
+        g *= __ldg(gamma + c);
+        s1 += g;
+        s2 += g * xh;
+      }
+      s1 = warp_sum(s1) / (float)cols;
+      s2 = warp_sum(s2) / (float)cols;
+      for (int c = lane; c < cols; c += 32) {
+        float g = to_f(dyr[c]) * __ldg(gamma + c), xh = (to_f(xr[c]) - mu) * rs;
+        dxr[c] = from_f<T>(rs * (g - s1 - xh * s2) + (er ? to_f(er[c]) : 0.0f));
+      }
+    }
+  }
+  if (dgamma == nullptr && dbeta == nullptr) return;
+  if (CACHED) {
+#pragma unroll
+    for (int k = 0; k < ITER; ++k) {
+      const int c = (k * 32 + lane) * N;
+      if (c < cols) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          atomicAdd(&sm[c + j], dg[k * N + j]);
+          atomicAdd(&sm[cols + c + j], db[k * N + j]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
+    if (dgamma) atomicAdd(dgamma + c, sm[c]);
+    if (dbeta) atomicAdd(dbeta + c, sm[cols + c]);
+  }
+}
+
+}  // namespace mmvqa
+
+using namespace mmvqa;
+
+extern "C" {
+
+int mmvqa_abi_version(void) { return MMVQA_ABI_VERSION; }
+const char* mmvqa_last_error(void) { return g_err; }
+int64_t mmvqa_launch_count(void) { return g_launches.load(); }
+
+int mmvqa_device_sm(void) {
+  int dev = 0, major = 0, minor = 0;
+  MMVQA_CUDA(cudaGetDevice(&dev));
+  MMVQA_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  MMVQA_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  return major * 10 + minor;
+}
+
+int mmvqa_bias_act_fwd(const void* x, const float* bias, void* y, int64_t rows, int cols, int act, int dtype,
+                       mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(x && y, "bias_act_fwd: null pointer");
+  MMVQA_REQUIRE(act >= MMVQA_ACT_NONE && act <= MMVQA_ACT_RELU, "bias_act_fwd: bad act %d", act);
+  if (dtype == MMVQA_F32) return bias_act_launch<float, false>(x, bias, nullptr, y, rows, cols, act, as_stream(stream));
+  if (dtype == MMVQA_BF16)
+    return bias_act_launch<__nv_bfloat16, false>(x, bias, nullptr, y, rows, cols, act, as_stream(stream));
+  return set_err(MMVQA_ERR_ARG, "bias_act_fwd: bad dtype %d", dtype);
+}
+
+int mmvqa_bias_act_bwd(const void* x, const float* bias, const void* dy, void* dx, int64_t rows, int cols, int act,
+                       int dtype, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(x && dy && dx, "bias_act_bwd: null pointer");
+  MMVQA_REQUIRE(act >= MMVQA_ACT_NONE && act <= MMVQA_ACT_RELU, "bias_act_bwd: bad act %d", act);
+  if (dtype == MMVQA_F32) return bias_act_launch<float, true>(x, bias, dy, dx, rows, cols, act, as_stream(stream));
+  if (dtype == MMVQA_BF16) return bias_act_launch<__nv_bfloat16, true>(x, bias, dy, dx, rows, cols, act, as_stream(stream));
+  return set_err(MMVQA_ERR_ARG, "bias_act_bwd: bad dtype %d", dtype);
+}
+
+int mmvqa_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int cols, int dtype, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(out && (x || rows == 0), "colsum: null pointer");
+  MMVQA_REQUIRE(cols > 0 && ldx >= cols, "colsum: bad cols/ld");
+  cudaStream_t st = as_stream(stream);
+  MMVQA_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)cols, st));
+  if (rows <= 0) return MMVQA_OK;
+  int gx = (cols + 31) / 32;
+  int64_t want = ((int64_t)num_sms() * 4 + gx - 1) / gx;  // row splits to fill the chip
+  int64_t rpb = (rows + want - 1) / want;
+  if (rpb < 64) rpb = 64;
+  int gy = (int)((rows + rpb - 1) / rpb);
+  dim3 grid(gx, gy);
+  if (dtype == MMVQA_F32)
+    colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ldx, out, rows, cols, rpb);
+  else if (dtype == MMVQA_BF16)
+    colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, out, rows, cols, rpb);
+  else
+    return set_err(MMVQA_ERR_ARG, "colsum: bad dtype %d", dtype);
+  MMVQA_LAUNCHED("colsum");
+  return MMVQA_OK;
+}
+
+int mmvqa_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(n >= 0 && (n == 0 || (src && dst)), "cast: null pointer");
+  if (n == 0) return MMVQA_OK;
+  cudaStream_t st = as_stream(stream);
+  int64_t maxg = (int64_t)num_sms() * 16;
+  if (src_dtype == MMVQA_F32 && dst_dtype == MMVQA_BF16 && n % 4 == 0 && aligned16(src) &&
+      (reinterpret_cast<uintptr_t>(dst) & 7) == 0) {
+    int64_t n4 = n / 4;
+    int grid = (int)((n4 + 255) / 256 < maxg ? (n4 + 255) / 256 : maxg);
+    cast_f32_bf16_vec<<<grid, 256, 0, st>>>((const float4*)src, (uint2*)dst, n4);
+    MMVQA_LAUNCHED("cast_f32_bf16");
+    return MMVQA_OK;
+  }
+  int64_t work = (n + 3) / 4;
+  int grid = (int)((work + 255) / 256 < maxg ? (work + 255) / 256 : maxg);
+  if (src_dtype == MMVQA_F32 && dst_dtype == MMVQA_BF16)
+    cast_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)src, (__nv_bfloat16*)dst, n);
+  else if (src_dtype == MMVQA_BF16 && dst_dtype == MMVQA_F32)
+    cast_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (float*)dst, n);
+  else if (src_dtype == MMVQA_F32 && dst_dtype == MMVQA_F32)
+    cast_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, n);
+  else if (src_dtype == MMVQA_BF16 && dst_dtype == MMVQA_BF16)
+    cast_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n);
+  else
+    return set_err(MMVQA_ERR_ARG, "cast: bad dtypes %d -> %d", src_dtype, dst_dtype);
+  MMVQA_LAUNCHED("cast");
+  return MMVQA_OK;
+}
+
+int mmvqa_cast_pad(const void* src, int src_dtype, int64_t ld_src, void* dst, int dst_dtype, int64_t ld_dst,
+                   int64_t rows, int cols, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(src && dst, "cast_pad: null pointer");
+  MMVQA_REQUIRE(ld_src >= cols && ld_dst >= cols && rows >= 0, "cast_pad: bad shape");
+  if (rows == 0) return MMVQA_OK;
+  cudaStream_t st = as_stream(stream);
+  int64_t total = rows * ld_dst, maxg = (int64_t)num_sms() * 16;
+  int grid = (int)((total + 255) / 256 < maxg ? (total + 255) / 256 : maxg);
+  if (src_dtype == MMVQA_F32 && dst_dtype == MMVQA_BF16)
+    cast_pad_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)src, ld_src, (__nv_bfloat16*)dst, ld_dst, rows, cols);
+  else if (src_dtype == MMVQA_BF16 && dst_dtype == MMVQA_F32)
+    cast_pad_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, ld_src, (float*)dst, ld_dst, rows, cols);
+  else if (src_dtype == MMVQA_F32 && dst_dtype == MMVQA_F32)
+    cast_pad_kernel<float, float><<<grid, 256, 0, st>>>((const float*)src, ld_src, (float*)dst, ld_dst, rows, cols);
+  else if (src_dtype == MMVQA_BF16 && dst_dtype == MMVQA_BF16)
+    cast_pad_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, ld_src, (__nv_bfloat16*)dst, ld_dst, rows, cols);
+  else
+    return set_err(MMVQA_ERR_ARG, "cast_pad: bad dtypes %d -> %d", src_dtype, dst_dtype);
+  MMVQA_LAUNCHED("cast_pad");
+  return MMVQA_OK;
+}
+
+int mmvqa_scale_by_device_scalar(void* x, int dtype, const float* scalar, float host_factor, int64_t n,
+                                 mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(n >= 0 && (n == 0 || x), "scale: null pointer");
+  if (n == 0) return MMVQA_OK;
+  int64_t maxg = (int64_t)num_sms() * 16;
+  int grid = (int)((n + 255) / 256 < maxg ? (n + 255) / 256 : maxg);
+  if (dtype == MMVQA_F32)
+    scale_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((float*)x, scalar, host_factor, n);
+  else if (dtype == MMVQA_BF16)
+    scale_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((__nv_bfloat16*)x, scalar, host_factor, n);
+  else
+    return set_err(MMVQA_ERR_ARG, "scale: bad dtype %d", dtype);
+  MMVQA_LAUNCHED("scale");
+  return MMVQA_OK;
+}
+
+int mmvqa_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, int dtype, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(n >= 0 && (n == 0 || (x && y)), "dropout: null pointer");
+  MMVQA_REQUIRE(p >= 0.0f && p < 1.0f, "dropout: p must be in [0,1)");
+  if (n == 0) return MMVQA_OK;
+  int64_t maxg = (int64_t)num_sms() * 16;
+  int grid = (int)((n + 255) / 256 < maxg ? (n + 255) / 256 : maxg);
+  if (dtype == MMVQA_F32)
+    dropout_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)x, (float*)y, n, p, seed);
+  else if (dtype == MMVQA_BF16)
+    dropout_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, p, seed);
+  else
+    return set_err(MMVQA_ERR_ARG, "dropout: bad dtype %d", dtype);
+  MMVQA_LAUNCHED("dropout");
+  return MMVQA_OK;
+}
+
+int mmvqa_add_layernorm_fwd(const void* x, const void* res, const float* gamma, const float* beta, void* y,
+                            void* sum_out, float* mean, float* rstd, int64_t rows, int cols, float eps, int dtype,
+                            mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(x && gamma && beta && y, "add_layernorm_fwd: null pointer");
+  MMVQA_REQUIRE(cols > 0 && rows >= 0, "add_layernorm_fwd: bad shape");
+  MMVQA_REQUIRE(dtype == MMVQA_F32 || dtype == MMVQA_BF16, "add_layernorm_fwd: bad dtype %d", dtype);
+  if (rows == 0) return MMVQA_OK;
+  cudaStream_t st = as_stream(stream);
+  int grid = (int)((rows + 3) / 4);
+  const int vn = dtype == MMVQA_F32 ? 4 : 8;
+  const bool cached = cols <= 32 * LN_CACHE;
+  const bool vec = cached && cols % vn == 0 && aligned16(x) && aligned16(y) && (!res || aligned16(res)) &&
+                   (!sum_out || aligned16(sum_out));
+#define LN_FWD(T, K) K<<<grid, 128, 0, st>>>((const T*)x, (const T*)res, gamma, beta, (T*)y, (T*)sum_out, mean, rstd, rows, cols, eps)
+  if (dtype == MMVQA_F32) {
+    if (vec) LN_FWD(float, (add_ln_fwd_kernel<float, true>));
+    else if (cached) LN_FWD(float, (add_ln_fwd_kernel<float, false>));
+    else LN_FWD(float, add_ln_fwd_generic<float>);
+  } else {
+    using B = __nv_bfloat16;
+    if (vec) LN_FWD(B, (add_ln_fwd_kernel<B, true>));
+    else if (cached) LN_FWD(B, (add_ln_fwd_kernel<B, false>));
+    else LN_FWD(B, add_ln_fwd_generic<B>);
+  }
+#undef LN_FWD
+  MMVQA_LAUNCHED("add_layernorm_fwd");
+  return MMVQA_OK;
+}
+
+int mmvqa_layernorm_bwd(const void* dy, const void* xsum, const float* gamma, const float* mean, const float* rstd,
+                        const void* dx_extra, void* dx, float* dgamma, float* dbeta, int64_t rows, int cols,
+                        int dtype, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(dy && xsum && gamma && mean && rstd && dx, "layernorm_bwd: null pointer");
+  MMVQA_REQUIRE(cols > 0 && rows >= 0, "layernorm_bwd: bad shape");
+  MMVQA_REQUIRE(dtype == MMVQA_F32 || dtype == MMVQA_BF16, "layernorm_bwd: bad dtype %d", dtype);
+  if (rows == 0) return MMVQA_OK;
+  cudaStream_t st = as_stream(stream);
+  int64_t want = (rows + 3) / 4, cap = (int64_t)num_sms() * 4;
+  int grid = (int)(want < cap ? want : cap);
+  size_t smem = sizeof(float) * 2 * (size_t)cols;
+  MMVQA_REQUIRE(smem <= 48 * 1024, "layernorm_bwd: cols %d too large", cols);
+  const int vn = dtype == MMVQA_F32 ? 4 : 8;
+  const bool cached = cols <= 32 * LN_CACHE;
+  const bool vec = cached && cols % vn == 0 && aligned16(dy) && aligned16(xsum) && aligned16(dx) &&
+                   (!dx_extra || aligned16(dx_extra));
+#define LN_BWD(T, V, C) ln_bwd_kernel<T, V, C><<<grid, 128, smem, st>>>((const T*)dy, (const T*)xsum, gamma, mean, rstd, (const T*)dx_extra, (T*)dx, dgamma, dbeta, rows, cols)
+  if (dtype == MMVQA_F32) {
+    if (vec) LN_BWD(float, true, true);
+    else if (cached) LN_BWD(float, false, true);
+    else LN_BWD(float, false, false);
+  } else {
+    using B = __nv_bfloat16;
+    if (vec) LN_BWD(B, true, true);
+    else if (cached) LN_BWD(B, false, true);
+    else LN_BWD(B, false, false);
+  }
+#undef LN_BWD
+  MMVQA_LAUNCHED("layernorm_bwd");
+  return MMVQA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,56 @@
+// gemm.cu -- mmvqa_gemm: argument validation and dispatch to the fp32 SIMT kernel (dtype F32) or the
+// tcgen05 / TMEM / TMA kernel (dtype BF16).  There is no fallback between the two: a bf16 problem
+// that violates the TMA alignment rules is an error, not a silent SIMT run.
+#include "gemm_common.cuh"
+
+using namespace mmvqa;
+
+extern "C" int mmvqa_gemm(const mmvqa_gemm_args* a, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(a != nullptr, "gemm: null args");
+  MMVQA_REQUIRE(a->dtype == MMVQA_F32 || a->dtype == MMVQA_BF16, "gemm: bad dtype %d", a->dtype);
+  MMVQA_REQUIRE(a->c_dtype == MMVQA_F32 || a->c_dtype == MMVQA_BF16, "gemm: bad c_dtype %d", a->c_dtype);
+  MMVQA_REQUIRE(a->M >= 0 && a->N >= 0 && a->K >= 0, "gemm: negative shape");
+  MMVQA_REQUIRE(a->epilogue >= MMVQA_EPI_STORE && a->epilogue <= MMVQA_EPI_DACT_SCALE, "gemm: bad epilogue %d", a->epilogue);
+  MMVQA_REQUIRE(a->act >= MMVQA_ACT_NONE && a->act <= MMVQA_ACT_RELU, "gemm: bad act %d", a->act);
+  const int batch = a->batch < 1 ? 1 : a->batch;
+  const int split_k = a->split_k < 1 ? 1 : a->split_k;
+  if (a->M == 0 || a->N == 0) return MMVQA_OK;
+  MMVQA_REQUIRE(a->A && a->B, "gemm: null operand");
+  MMVQA_REQUIRE(a->lda >= (a->a_trans ? a->M : a->K), "gemm: lda %lld too small", (long long)a->lda);
+  MMVQA_REQUIRE(a->ldb >= (a->b_trans ? a->N : a->K), "gemm: ldb %lld too small", (long long)a->ldb);
+  if (a->epilogue != MMVQA_EPI_ACT_ROWSUM) {
+    MMVQA_REQUIRE(a->C != nullptr && a->ldc >= a->N, "gemm: bad C / ldc");
+  } else {
+    MMVQA_REQUIRE(a->rowsum_out != nullptr, "gemm: EPI_ACT_ROWSUM needs rowsum_out");
+  }
+  if (a->epilogue == MMVQA_EPI_RESIDUAL || a->epilogue == MMVQA_EPI_DACT)
+    MMVQA_REQUIRE(a->aux_in != nullptr && a->ld_aux_in >= a->N, "gemm: epilogue %d needs aux_in", a->epilogue);
+  if (a->epilogue == MMVQA_EPI_DACT_SCALE) MMVQA_REQUIRE(a->rowscale != nullptr, "gemm: EPI_DACT_SCALE needs rowscale");
+  if (a->aux_out) MMVQA_REQUIRE(a->ld_aux_out >= a->N, "gemm: bad ld_aux_out");
+  if (a->accumulate || split_k > 1) {
+    MMVQA_REQUIRE(a->c_dtype == MMVQA_F32 && a->epilogue == MMVQA_EPI_STORE && (a->accumulate || split_k == 1),
+                  "gemm: split_k / accumulate need an fp32 C, EPI_STORE and accumulate != 0");
+  }
+  MMVQA_REQUIRE(a->dropout_p >= 0.0f && a->dropout_p < 1.0f, "gemm: dropout_p must be in [0,1)");
+  if (batch > 1 && !a->accumulate && a->epilogue != MMVQA_EPI_ACT_ROWSUM)
+    MMVQA_REQUIRE(a->c_batch_stride > 0, "gemm: batched store needs c_batch_stride");
+
+  mmvqa_gemm_args v = *a;
+  v.batch = batch;
+  v.split_k = split_k;
+  EpiParams ep;
+  ep.M = a->M; ep.N = a->N; ep.K = a->K;
+  ep.C = a->C; ep.ldc = a->ldc; ep.c_bf16 = (a->c_dtype == MMVQA_BF16);
+  ep.bias = a->bias; ep.epilogue = a->epilogue; ep.act = a->act;
+  ep.aux_in = a->aux_in; ep.ld_aux_in = a->ld_aux_in;
+  ep.aux_out = a->aux_out; ep.ld_aux_out = a->ld_aux_out;
+  ep.rowsum_out = a->rowsum_out; ep.rowscale = a->rowscale; ep.scale = a->scale;
+  ep.accumulate = a->accumulate; ep.split_k = split_k; ep.batch = batch;
+  ep.c_batch_stride = a->c_batch_stride;
+  ep.dropout_p = a->dropout_p; ep.dropout_seed = a->dropout_seed;
+  if (a->dtype == MMVQA_F32) return gemm_simt_f32(&v, ep, as_stream(stream));
+  int sm = mmvqa_device_sm();
+  if (sm < 0) return sm;
+  if (sm / 10 != 10) return set_err(MMVQA_ERR_ARCH, "gemm(bf16): tcgen05 path needs sm_100, device is sm_%d", sm);
+  return gemm_tc_bf16(&v, ep, as_stream(stream));
+}

@@ -1,0 +1,400 @@
+// gemm_tc.cu -- bf16 GEMM on the 5th-generation tensor cores of sm_100a:
+//   TMA (cp.async.bulk.tensor, 128-byte swizzle) -> shared-memory ring -> tcgen05.mma (one issuing
+//   thread, cta_group::1, 128 x BN x 16 per instruction) -> fp32 accumulator in TMEM -> tcgen05.ld ->
+//   fused epilogue (bias / SERF / GELU / ReLU / residual(+dropout) / act' / pooled row-sum) -> global.
+// Warp roles (192 threads): warp 0 = TMEM allocator + TMA producer, warp 1 = barrier init + MMA
+// issuer, warps 2..5 = epilogue (each owns the 32 TMEM lanes  (warp_idx & 3) * 32 ...).
+// Both operands may be K-major (contraction dim contiguous: activations x nn.Linear weights) or
+// MN-major (the transposed reads that dgrad / wgrad need) -- the latter use the MN-major UMMA
+// shared-memory descriptors, so no transposed copies of weights or activations are ever made.
+#include "gemm_common.cuh"
+#include <cuda.h>
+
+namespace mmvqa {
+
+constexpr int TC_BM = 128;      // UMMA M (cta_group::1)
+constexpr int TC_BK = 64;       // 64 bf16 = one 128-byte swizzle row
+constexpr int TC_UK = 16;       // UMMA K for 16-bit inputs
+constexpr int TC_THREADS = 192;
+
+// ---------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug traps (launch error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, version 1):
+//  [0,14) start >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 |
+//  [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+template <int BN>
+struct TcCfg {
+  static constexpr int STAGES = 4;
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
+  static constexpr int B_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+// ---------------------------------------------------------------------------------
+// kernel: one 128 x BN output tile (of one batch entry / one K split) per CTA
+// ---------------------------------------------------------------------------------
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                             const __grid_constant__ CUtensorMap tmB, EpiParams p,
+                                                             int a_batched, int b_batched) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
+  // barriers: full[s] at +8*s, empty[s] at +8*(STAGES+s), tmem_full at +8*2*STAGES, tmem ptr after
+  const uint32_t tmem_full_bar = bar_base + 8 * 2 * Cfg::STAGES;
+  const uint32_t tmem_ptr_addr = tmem_full_bar + 8;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * 2 * Cfg::STAGES + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
+  const int bz = blockIdx.z / p.split_k, ks = blockIdx.z % p.split_k;
+  const int kblocks = (p.K + TC_BK - 1) / TC_BK;
+  const int kb_per = (kblocks + p.split_k - 1) / p.split_k;
+  const int kb0 = ks * kb_per;
+  const int kb1 = min(kblocks, kb0 + kb_per);
+  const int nkb = max(0, kb1 - kb0);
+
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
+  } else if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      mbar_init(bar_base + 8 * s, 1);
+      mbar_init(bar_base + 8 * (Cfg::STAGES + s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = *tmem_ptr_gen;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % Cfg::STAGES;
+        const uint32_t ph = (uint32_t)(i / Cfg::STAGES) & 1u;
+        mbar_wait(bar_base + 8 * (Cfg::STAGES + s), ph ^ 1u);
+        const uint32_t full = bar_base + 8 * s;
+        mbar_expect_tx(full, Cfg::STAGE_BYTES);
+        const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+        const int k0 = (kb0 + i) * TC_BK;
+        if (A_MN) {  // stored [K, M]: two boxes of 64 (m) x 64 (k)
+          tma_load_3d(sa, &tmA, full, m0, k0, a_batched ? bz : 0);
+          tma_load_3d(sa + 8192, &tmA, full, m0 + 64, k0, a_batched ? bz : 0);
+        } else {     // stored [M, K]: one box of 64 (k) x 128 (m)
+          tma_load_3d(sa, &tmA, full, k0, m0, a_batched ? bz : 0);
+        }
+        if (B_MN) {  // stored [K, N]: BN/64 boxes of 64 (n) x 64 (k)
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_3d(sb + j * 8192, &tmB, full, n0 + j * 64, k0, b_batched ? bz : 0);
+        } else {     // stored [N, K]: one box of 64 (k) x BN (n)
+          tma_load_3d(sb, &tmB, full, k0, n0, b_batched ? bz : 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, majors, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int i = 0; i < nkb; ++i) {
+        const int s = i % Cfg::STAGES;
+        const uint32_t ph = (uint32_t)(i / Cfg::STAGES) & 1u;
+        mbar_wait(bar_base + 8 * s, ph);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+#pragma unroll
+        for (int j = 0; j < TC_BK / TC_UK; ++j) {
+          // K-major: 16 bf16 = 32 bytes inside the swizzled 128-byte row; SBO = 8 rows * 128 B.
+          // MN-major: 16 k-rows = 2 groups of 8 rows (1024 B each); LBO = next 64-wide MN group.
+          const uint64_t ad = A_MN ? make_sdesc(sa + j * 2048, 8192, 1024) : make_sdesc(sa + j * 32, 16, 1024);
+          const uint64_t bd = B_MN ? make_sdesc(sb + j * 2048, 8192, 1024) : make_sdesc(sb + j * 32, 16, 1024);
+          umma_bf16(tmem_acc, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
+        }
+        umma_commit(bar_base + 8 * (Cfg::STAGES + s));  // frees the smem slot when these MMAs retire
+      }
+      umma_commit(tmem_full_bar);                       // accumulator complete
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int g = warp & 3;                 // TMEM lane group this warp may read
+    const int m = m0 + g * 32 + lane;
+    const bool first = (ks == 0);
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    float rowsum = 0.0f;
+    const bool row_ok = m < p.M;
+    const bool skip = (nkb == 0 && ks != 0);
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 16) {
+      uint32_t r[16];
+      __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
+      tmem_ld16(tmem_acc + ((uint32_t)(g * 32) << 16) + (uint32_t)c, r);
+      tmem_ld_wait();
+      const int nb = n0 + c;
+      if (row_ok && !skip && nb < p.N) {
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = (nkb > 0) ? __uint_as_float(r[j]) : 0.0f;
+      const bool full16 = (nb + 16 <= p.N);
+      // fast path: plain / activation / residual stores of 16 contiguous, 16-byte aligned outputs
+      const int64_t off = (int64_t)bz * p.c_batch_stride + (int64_t)m * p.ldc + nb;
+      const bool c_al = full16 && !p.accumulate &&
+                        (p.c_bf16 ? ((off & 7) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0)
+                                  : ((off & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0));
+      bool done = false;
+      if (c_al && (p.epilogue == MMVQA_EPI_STORE || p.epilogue == MMVQA_EPI_ACT || p.epilogue == MMVQA_EPI_RESIDUAL ||
+                   p.epilogue == MMVQA_EPI_DACT)) {
+        const int64_t aoff_in = (int64_t)m * p.ld_aux_in + nb, aoff_out = (int64_t)m * p.ld_aux_out + nb;
+        const bool need_in = (p.epilogue == MMVQA_EPI_RESIDUAL || p.epilogue == MMVQA_EPI_DACT);
+        const bool in_al = !need_in || ((aoff_in & 7) == 0 && (reinterpret_cast<uintptr_t>(p.aux_in) & 15) == 0);
+        const bool has_out = (p.epilogue == MMVQA_EPI_ACT && p.aux_out != nullptr);
+        const bool out_al = !has_out || ((aoff_out & 7) == 0 && (reinterpret_cast<uintptr_t>(p.aux_out) & 15) == 0);
+        if (in_al && out_al) {
+          if (p.bias && first) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + nb + j);
+          }
+          if (has_out) {
+            Vec16<__nv_bfloat16> o0, o1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { o0.set(j, v[j]); o1.set(j, v[8 + j]); }
+            __nv_bfloat16* ao = reinterpret_cast<__nv_bfloat16*>(p.aux_out) + aoff_out;
+            o0.store(ao);
+            o1.store(ao + 8);
+          }
+          if (need_in) {
+            Vec16<__nv_bfloat16> i0, i1;
+            const __nv_bfloat16* ai = reinterpret_cast<const __nv_bfloat16*>(p.aux_in) + aoff_in;
+            i0.load(ai);
+            i1.load(ai + 8);
+            if (p.epilogue == MMVQA_EPI_RESIDUAL) {
+              if (p.dropout_p > 0.0f) {
+                const uint32_t thr = (uint32_t)(p.dropout_p * 4294967296.0);
+                const float inv = 1.0f / (1.0f - p.dropout_p);
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  v[j] = hash32(p.dropout_seed, (uint64_t)m * (uint64_t)p.N + (uint64_t)(nb + j)) >= thr ? v[j] * inv : 0.0f;
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { v[j] += i0.get(j); v[8 + j] += i1.get(j); }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { v[j] *= dact_rt(p.act, i0.get(j)); v[8 + j] *= dact_rt(p.act, i1.get(j)); }
+            }
+          } else if (p.epilogue == MMVQA_EPI_ACT) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = act_rt(p.act, v[j]);
+          }
+          if (p.c_bf16) {
+            Vec16<__nv_bfloat16> o0, o1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { o0.set(j, v[j]); o1.set(j, v[8 + j]); }
+            __nv_bfloat16* co = reinterpret_cast<__nv_bfloat16*>(p.C) + off;
+            o0.store(co);
+            o1.store(co + 8);
+          } else {
+            float4* co = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) co[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          done = true;
+        }
+      }
+      if (!done) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (nb + j < p.N) rowsum += epi_element<__nv_bfloat16>(p, bz, m, nb + j, v[j], first);
+      }
+      }
+    }
+    if (p.epilogue == MMVQA_EPI_ACT_ROWSUM && row_ok && !skip)
+      atomicAdd(p.rowsum_out + (int64_t)bz * p.M + m, rowsum * p.scale);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem_acc, Cfg::TMEM_COLS);
+}
+
+// ---------------------------------------------------------------------------------
+// host: tensor maps + dispatch
+// ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// 3-D map over a stored [rows, inner] bf16 matrix with `nbatch` slabs `batch_rows` rows apart.
+static int make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t rows, int64_t ld, int nbatch,
+                    int64_t batch_rows, int box_inner, int box_rows, const char* what) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_err(MMVQA_ERR_CUDA, "gemm(bf16): cuTensorMapEncodeTiled unavailable");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0)
+    return set_err(MMVQA_ERR_ARG, "gemm(bf16): operand %s needs a 16-byte aligned base and a leading dimension that is a multiple of 8 (ld=%lld)", what, (long long)ld);
+  const bool batched = nbatch > 1 && batch_rows > 0;
+  cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)rows, (cuuint64_t)(batched ? nbatch : 1)};
+  cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)(batched ? batch_rows * ld * 2 : rows * ld * 2)};
+  if (strides[1] % 16 != 0) strides[1] = (strides[1] + 15) / 16 * 16;
+  cuuint32_t box[3] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(MMVQA_ERR_CUDA, "gemm(bf16): cuTensorMapEncodeTiled(%s) failed with %d (inner=%lld rows=%lld ld=%lld)", what, (int)r, (long long)inner, (long long)rows, (long long)ld);
+  return MMVQA_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch_tc(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  CUtensorMap tmA, tmB;
+  int rc;
+  // A: K-major stored [M, K] -> inner K, box 64 x 128;  MN-major stored [K, M] -> inner M, box 64 x 64
+  if (A_MN) rc = make_map(&tmA, a->A, a->M, a->K, a->lda, a->batch, a->a_batch_rows, 64, 64, "A");
+  else rc = make_map(&tmA, a->A, a->K, a->M, a->lda, a->batch, a->a_batch_rows, 64, TC_BM, "A");
+  if (rc) return rc;
+  if (B_MN) rc = make_map(&tmB, a->B, a->N, a->K, a->ldb, a->batch, a->b_batch_rows, 64, 64, "B");
+  else rc = make_map(&tmB, a->B, a->K, a->N, a->ldb, a->batch, a->b_batch_rows, 64, BN, "B");
+  if (rc) return rc;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    MMVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    attr_set = true;
+  }
+  dim3 grid((a->N + BN - 1) / BN, (a->M + TC_BM - 1) / TC_BM, a->batch * a->split_k);
+  MMVQA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm(bf16): grid too large");
+  kern<<<grid, TC_THREADS, Cfg::SMEM, st>>>(tmA, tmB, ep, (a->batch > 1 && a->a_batch_rows > 0) ? 1 : 0,
+                                            (a->batch > 1 && a->b_batch_rows > 0) ? 1 : 0);
+  MMVQA_LAUNCHED("gemm_tc_bf16");
+  return MMVQA_OK;
+}
+
+template <int BN>
+static int launch_tc_major(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st) {
+  if (a->a_trans && a->b_trans) return launch_tc<BN, true, true>(a, ep, st);
+  if (a->a_trans) return launch_tc<BN, true, false>(a, ep, st);
+  if (a->b_trans) return launch_tc<BN, false, true>(a, ep, st);
+  return launch_tc<BN, false, false>(a, ep, st);
+}
+
+int gemm_tc_bf16(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st) {
+  // tile width: the widest BN that still gives the chip a full wave of CTAs (two for BN = 256);
+  // MN-major B needs BN % 64 == 0.
+  const int sms = num_sms();
+  const int64_t mt = (a->M + TC_BM - 1) / TC_BM;
+  const int64_t z = (int64_t)a->batch * a->split_k;
+  const int cand[4] = {256, 128, 64, 32};
+  const int ncand = a->b_trans ? 3 : 4;
+  int bn = cand[ncand - 1];
+  for (int i = 0; i < ncand; ++i) {
+    const int b = cand[i];
+    if (b > 32 && b / 2 >= a->N) continue;  // tile wider than twice the problem
+    const int64_t ctas = mt * ((a->N + b - 1) / b) * z;
+    if (ctas >= (int64_t)sms * (b == 256 ? 2 : 1)) { bn = b; break; }
+  }
+  switch (bn) {
+    case 256: return launch_tc_major<256>(a, ep, st);
+    case 128: return launch_tc_major<128>(a, ep, st);
+    case 64: return launch_tc_major<64>(a, ep, st);
+    default:
+      if (a->a_trans) return launch_tc<32, true, false>(a, ep, st);
+      return launch_tc<32, false, false>(a, ep, st);
+  }
+}
+
+}  // namespace mmvqa

@@ -1,0 +1,263 @@
+// losses.cu -- fused loss kernels (forward value and gradient in one launch):
+//   * ASLSingleLabel           models/asl_singlelabel.py:23-52
+//   * MLM cross entropy        pretrain/roco_utils.py:235-236  (log_softmax + NLL, every position)
+//   * SupCon row pass          models/SupConLoss/loss.py:72-96
+//   * multi-tensor Adam        vqamed2019/train.py:160 (torch.optim.Adam semantics)
+#include "common.cuh"
+
+namespace mmvqa {
+
+// ---------------------------------------------------------------------------------
+// ASL.  One block per sample.  With lp = log_softmax(x), p = exp(lp), y the target:
+//   w_y = (1-p_y)^gp, w_c = p_c^gn (c != y);  ts_c = onehot*(1-eps) + eps/C
+//   loss = -sum_c ts_c lp_c w_c
+//   dloss/dx_k = -a_k + p_k * sum_c a_c,   a_c = ts_c w_c (1 + gn lp_c)            (c != y)
+//                                           a_y = ts_y (w_y - gp lp_y p_y (1-p_y)^(gp-1))
+// ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) asl_kernel(const T* __restrict__ logits, int64_t ld,
+                                                  const int64_t* __restrict__ target, float* __restrict__ loss_rows,
+                                                  float* __restrict__ dlogits, float* __restrict__ targets_classes, int C,
+                                                  float gp, float gn, float eps) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const T* x = logits + (int64_t)b * ld;
+  const int y = (int)target[b];
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, to_f(x[c]));
+  mx = block_max(mx, red);
+  float se = 0.0f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) se += expf(to_f(x[c]) - mx);
+  se = block_sum(se, red);
+  const float lse = mx + logf(se);
+  const float smooth = eps > 0.0f ? eps / (float)C : 0.0f;
+  const float keep = eps > 0.0f ? 1.0f - eps : 1.0f;
+  float lsum = 0.0f, asum = 0.0f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const float lp = to_f(x[c]) - lse, p = expf(lp);
+    const float ts = (c == y ? keep : 0.0f) + smooth;
+    float w, a;
+    if (c == y) {
+      w = powf(1.0f - p, gp);
+      a = ts * (gp == 0.0f ? w : w - gp * lp * p * powf(1.0f - p, gp - 1.0f));
+    } else {
+      w = gn == 0.0f ? 1.0f : expf(gn * lp);
+      a = ts * w * (1.0f + gn * lp);
+    }
+    lsum += ts * lp * w;
+    asum += a;
+    if (targets_classes) targets_classes[(int64_t)b * C + c] = ts;
+  }
+  lsum = block_sum(lsum, red);
+  asum = block_sum(asum, red);
+  if (threadIdx.x == 0) loss_rows[b] = -lsum;
+  if (dlogits) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const float lp = to_f(x[c]) - lse, p = expf(lp);
+      const float ts = (c == y ? keep : 0.0f) + smooth;
+      float a;
+      if (c == y) {
+        const float w = powf(1.0f - p, gp);
+        a = ts * (gp == 0.0f ? w : w - gp * lp * p * powf(1.0f - p, gp - 1.0f));
+      } else {
+        const float w = gn == 0.0f ? 1.0f : expf(gn * lp);
+        a = ts * w * (1.0f + gn * lp);
+      }
+      dlogits[(int64_t)b * C + c] = -a + p * asum;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// cross entropy per row: loss = lse - x_y;  dlogits = (softmax - onehot) * scale
+// ---------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) ce_kernel(const T* __restrict__ logits, int64_t ld,
+                                                 const int64_t* __restrict__ target, float* __restrict__ loss_rows,
+                                                 T* __restrict__ dlogits, int64_t ld_d, int C, float scale) {
+  __shared__ float red[32];
+  const int64_t r = blockIdx.x;
+  const T* x = logits + r * ld;
+  const int y = (int)target[r];
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) mx = fmaxf(mx, to_f(x[c]));
+  mx = block_max(mx, red);
+  float se = 0.0f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) se += expf(to_f(x[c]) - mx);
+  se = block_sum(se, red);
+  const float lse = mx + logf(se);
+  if (threadIdx.x == 0 && loss_rows) loss_rows[r] = lse - to_f(x[y]);
+  if (dlogits) {
+    T* d = dlogits + r * ld_d;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float p = expf(to_f(x[c]) - lse);
+      d[c] = from_f<T>((p - (c == y ? 1.0f : 0.0f)) * scale);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// SupCon: one block per anchor row of raw = anchor . contrast^T (not yet divided by temperature)
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) supcon_rows_kernel(const float* __restrict__ raw, const float* __restrict__ mask,
+                                                          float* __restrict__ loss_rows, float* __restrict__ G, int N,
+                                                          int bsz, int row_offset, float temperature,
+                                                          float base_temperature) {
+  __shared__ float red[32];
+  const int r = blockIdx.x;
+  const int gi = row_offset + r;                 // global anchor index = its own column in the contrast set
+  const float* x = raw + (int64_t)r * N;
+  const float* mrow = mask ? mask + (int64_t)(gi % bsz) * bsz : nullptr;
+  const float inv_t = 1.0f / temperature;
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) mx = fmaxf(mx, x[j] * inv_t);   // max includes the self column
+  mx = block_max(mx, red);
+  float den = 0.0f, msum = 0.0f, mlog = 0.0f;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    if (j == gi) continue;
+    const float l = x[j] * inv_t - mx;
+    den += expf(l);
+    const float m = mrow ? mrow[j % bsz] : ((j % bsz) == (gi % bsz) ? 1.0f : 0.0f);
+    msum += m;
+    mlog += m * l;
+  }
+  den = block_sum(den, red);
+  msum = block_sum(msum, red);
+  mlog = block_sum(mlog, red);
+  const float logden = logf(den);
+  const float coef = -(temperature / base_temperature);
+  if (threadIdx.x == 0) loss_rows[r] = coef * ((mlog - msum * logden) / msum);
+  if (G) {
+    float* g = G + (int64_t)r * N;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+      float v = 0.0f;
+      if (j != gi) {
+        const float l = x[j] * inv_t - mx;
+        const float m = mrow ? mrow[j % bsz] : ((j % bsz) == (gi % bsz) ? 1.0f : 0.0f);
+        v = coef * (m / msum - expf(l) / den) * inv_t;
+      }
+      g[j] = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// multi-tensor Adam
+// ---------------------------------------------------------------------------------
+// one block per table entry (a chunk of one parameter tensor, built once on the host)
+__device__ __forceinline__ void adam_one(float& p, float& m, float& v, float g, float beta1, float beta2, float eps,
+                                         float wd, float step, float bc2_sqrt, float grad_scale) {
+  g *= grad_scale;
+  if (wd != 0.0f) g = fmaf(wd, p, g);
+  m = beta1 * m + (1.0f - beta1) * g;
+  v = beta2 * v + (1.0f - beta2) * g * g;
+  p -= step * m / (sqrtf(v) / bc2_sqrt + eps);
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(const mmvqa_adam_desc* __restrict__ table, float lr, float beta1,
+                                                   float beta2, float eps, float wd, float bc1, float bc2_sqrt,
+                                                   float grad_scale, const int* __restrict__ step_dev) {
+  const mmvqa_adam_desc d = table[blockIdx.x];
+  if (step_dev) {  // step counter lives on the device (CUDA-graph replay safe)
+    const float t = (float)(*step_dev);
+    bc1 = 1.0f - powf(beta1, t);
+    bc2_sqrt = sqrtf(1.0f - powf(beta2, t));
+  }
+  const float step = lr / bc1;
+  const bool vec = ((reinterpret_cast<uintptr_t>(d.p) | reinterpret_cast<uintptr_t>(d.m) | reinterpret_cast<uintptr_t>(d.v) |
+                     reinterpret_cast<uintptr_t>(d.g)) & 15) == 0 &&
+                   (d.bf16_out == nullptr || (reinterpret_cast<uintptr_t>(d.bf16_out) & 7) == 0);
+  int64_t done = 0;
+  if (vec) {
+    const int64_t n4 = d.n / 4;
+    for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+      float4 p = reinterpret_cast<float4*>(d.p)[i], m = reinterpret_cast<float4*>(d.m)[i];
+      float4 v = reinterpret_cast<float4*>(d.v)[i];
+      const float4 g = reinterpret_cast<const float4*>(d.g)[i];
+      adam_one(p.x, m.x, v.x, g.x, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
+      adam_one(p.y, m.y, v.y, g.y, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
+      adam_one(p.z, m.z, v.z, g.z, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
+      adam_one(p.w, m.w, v.w, g.w, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
+      reinterpret_cast<float4*>(d.p)[i] = p;
+      reinterpret_cast<float4*>(d.m)[i] = m;
+      reinterpret_cast<float4*>(d.v)[i] = v;
+      if (d.bf16_out) {
+        __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
+        uint2 o;
+        o.x = *reinterpret_cast<uint32_t*>(&lo);
+        o.y = *reinterpret_cast<uint32_t*>(&hi);
+        reinterpret_cast<uint2*>(d.bf16_out)[i] = o;
+      }
+    }
+    done = n4 * 4;
+  }
+  for (int64_t i = done + threadIdx.x; i < d.n; i += blockDim.x) {
+    float p = d.p[i], m = d.m[i], v = d.v[i];
+    adam_one(p, m, v, d.g[i], beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
+    d.p[i] = p;
+    d.m[i] = m;
+    d.v[i] = v;
+    if (d.bf16_out) reinterpret_cast<__nv_bfloat16*>(d.bf16_out)[i] = __float2bfloat16_rn(p);
+  }
+}
+
+}  // namespace mmvqa
+
+using namespace mmvqa;
+
+extern "C" {
+
+int mmvqa_asl_fwd_bwd(const void* logits, int64_t ld, const int64_t* target, float* loss_rows, float* dlogits,
+                      float* targets_classes, int B, int C, float gamma_pos, float gamma_neg, float eps, int dtype,
+                      mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(logits && target && loss_rows && B >= 0 && C > 0 && ld >= C, "asl: bad args");
+  if (B == 0) return MMVQA_OK;
+  if (dtype == MMVQA_F32)
+    asl_kernel<float><<<B, 256, 0, as_stream(stream)>>>((const float*)logits, ld, target, loss_rows, dlogits, targets_classes, C, gamma_pos, gamma_neg, eps);
+  else if (dtype == MMVQA_BF16)
+    asl_kernel<__nv_bfloat16><<<B, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)logits, ld, target, loss_rows, dlogits, targets_classes, C, gamma_pos, gamma_neg, eps);
+  else
+    return set_err(MMVQA_ERR_ARG, "asl: bad dtype %d", dtype);
+  MMVQA_LAUNCHED("asl_fwd_bwd");
+  return MMVQA_OK;
+}
+
+int mmvqa_ce_fwd_bwd(const void* logits, int64_t ld, const int64_t* target, float* loss_rows, void* dlogits,
+                     int64_t ld_d, int64_t rows, int C, float scale, int dtype, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(logits && target && rows >= 0 && C > 0 && ld >= C, "ce: bad args");
+  MMVQA_REQUIRE(!dlogits || ld_d >= C, "ce: bad ld_d");
+  MMVQA_REQUIRE(rows <= 2147483647LL, "ce: too many rows");
+  if (rows == 0) return MMVQA_OK;
+  if (dtype == MMVQA_F32)
+    ce_kernel<float><<<(int)rows, 256, 0, as_stream(stream)>>>((const float*)logits, ld, target, loss_rows, (float*)dlogits, ld_d, C, scale);
+  else if (dtype == MMVQA_BF16)
+    ce_kernel<__nv_bfloat16><<<(int)rows, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)logits, ld, target, loss_rows, (__nv_bfloat16*)dlogits, ld_d, C, scale);
+  else
+    return set_err(MMVQA_ERR_ARG, "ce: bad dtype %d", dtype);
+  MMVQA_LAUNCHED("ce_fwd_bwd");
+  return MMVQA_OK;
+}
+
+int mmvqa_supcon_rows(const float* logits, const float* mask, float* loss_rows, float* G, int R, int N, int bsz,
+                      int row_offset, float temperature, float base_temperature, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(logits && loss_rows && R >= 0 && N > 0 && bsz > 0 && N % bsz == 0, "supcon_rows: bad args");
+  MMVQA_REQUIRE(row_offset >= 0 && row_offset + R <= N, "supcon_rows: anchor rows out of range");
+  if (R == 0) return MMVQA_OK;
+  supcon_rows_kernel<<<R, 256, 0, as_stream(stream)>>>(logits, mask, loss_rows, G, N, bsz, row_offset, temperature, base_temperature);
+  MMVQA_LAUNCHED("supcon_rows");
+  return MMVQA_OK;
+}
+
+int mmvqa_adam_step(const mmvqa_adam_desc* table, int n_chunks, float lr, float beta1, float beta2, float eps,
+                    float weight_decay, int step, const int* step_dev, float grad_scale, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(table && n_chunks >= 0 && (step >= 1 || step_dev), "adam: bad args");
+  if (step < 1) step = 1;
+  if (n_chunks == 0) return MMVQA_OK;
+  const float bc1 = 1.0f - powf(beta1, (float)step);
+  const float bc2 = 1.0f - powf(beta2, (float)step);
+  adam_kernel<<<n_chunks, 256, 0, as_stream(stream)>>>(table, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, step_dev);
+  MMVQA_LAUNCHED("adam_step");
+  return MMVQA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,677 @@
+"""torch.autograd.Function wrappers: each forward/backward is a short sequence of C-ABI launches.
+
+These are the only place where autograd meets the CUDA library.  The nn.Module mirrors in
+``mmvqa_b200/models`` hold the parameters (reference names/shapes) and call these functions.
+All parameter gradients are produced in fp32; activations travel in the compute dtype.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_SERF, EPI_ACT, EPI_ACT_ROWSUM, EPI_DACT, EPI_DACT_SCALE,
+                   EPI_RESIDUAL, EPI_STORE, MMVQAError)
+from .config import compute_dtype
+
+Tensor = torch.Tensor
+_SM_COUNT = {}
+
+
+def _sms(device) -> int:
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _SM_COUNT:
+        _SM_COUNT[idx] = torch.cuda.get_device_properties(idx).multi_processor_count
+    return _SM_COUNT[idx]
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+# --------------------------------------------------------------------------------------
+# weight cache: fp32 master parameters -> compute-dtype GEMM operands (optionally concatenated)
+# --------------------------------------------------------------------------------------
+class WeightCache:
+    """Casts parameters to the compute dtype once per parameter version.
+
+    The key is the parameter identity; an entry is valid while every source parameter keeps its
+    ``_version`` and storage.  ``torch.optim`` steps and ``load_state_dict`` bump the version, the
+    fused Adam (mmvqa_b200.optim) refreshes the bf16 copy itself and re-validates the entry."""
+
+    def __init__(self):
+        self._entries = {}
+
+    def get(self, params: Sequence[Tensor], dtype: torch.dtype) -> Tensor:
+        key = (tuple(id(p) for p in params), dtype)
+        sig = tuple((p._version, p.data_ptr()) for p in params)
+        ent = self._entries.get(key)
+        if ent is not None and ent[0] == sig:
+            return ent[1]
+        with torch.no_grad():
+            flat = [p.detach().reshape(p.shape[0], -1) for p in params]
+            if dtype == torch.float32 and len(flat) == 1:
+                out = flat[0]
+            else:
+                rows = sum(f.shape[0] for f in flat)
+                out = ent[1] if ent is not None and ent[1].shape == (rows, flat[0].shape[1]) else torch.empty(
+                    rows, flat[0].shape[1], device=flat[0].device, dtype=dtype)
+                r = 0
+                for f in flat:
+                    ops.cast(f.contiguous(), dtype, out=out[r:r + f.shape[0]])
+                    r += f.shape[0]
+        self._entries[key] = (sig, out, [p for p in params])
+        return out
+
+    def bf16_target(self, p: Tensor) -> Optional[Tensor]:
+        """bf16 copy of a single parameter if one is cached (for the fused Adam to overwrite)."""
+        ent = self._entries.get(((id(p),), torch.bfloat16))
+        return None if ent is None else ent[1]
+
+    def revalidate(self, p: Tensor) -> None:
+        key = ((id(p),), torch.bfloat16)
+        ent = self._entries.get(key)
+        if ent is not None:
+            self._entries[key] = (((p._version, p.data_ptr()),), ent[1], ent[2])
+
+    def clear(self) -> None:
+        self._entries.clear()
+
+
+weight_cache = WeightCache()
+
+
+def invalidate_weight_cache() -> None:
+    weight_cache.clear()
+
+
+# --------------------------------------------------------------------------------------
+# GEMM helpers (all row-major 2-D views)
+# --------------------------------------------------------------------------------------
+def _pad_ld(t2d: Tensor, dtype: torch.dtype) -> Tuple[Tensor, int]:
+    """Return (tensor, ld) with the compute dtype and, for bf16, a leading dimension that is a
+    multiple of 8 elements (TMA needs 16-byte row strides)."""
+    rows, cols = t2d.shape
+    need = 8 if dtype == torch.bfloat16 else 1
+    if t2d.dtype == dtype and t2d.is_contiguous() and cols % need == 0 and t2d.data_ptr() % 16 == 0:
+        return t2d, cols
+    t2d = t2d.contiguous()
+    ld = _round_up(cols, need)
+    return ops.cast_pad(t2d, rows, cols, cols, dtype, ld), ld
+
+
+def _split_k_for(tiles: int, k: int, device, kblock: int = 64) -> int:
+    sms = _sms(device)
+    if tiles >= sms:
+        return 1
+    kblocks = max(1, (k + kblock - 1) // kblock)
+    return max(1, min(sms // max(tiles, 1), kblocks // 4 if kblocks >= 8 else 1))
+
+
+def gemm_dgrad(dy: Tensor, ld_dy: int, M: int, N: int, w: Tensor, K: int, *, epilogue=EPI_STORE, act=ACT_NONE,
+               aux_in: Optional[Tensor] = None, out_dtype: Optional[torch.dtype] = None) -> Tensor:
+    """dx[M,K] = dy[M,N] . w[N,K]   (w read MN-major: no transposed weight copy)."""
+    dx = torch.empty(M, K, device=dy.device, dtype=out_dtype or dy.dtype)
+    ops.gemm(M, K, N, dy, ld_dy, False, w, K, True, dx, K, epilogue=epilogue, act=act, aux_in=aux_in, ld_aux_in=K)
+    return dx
+
+
+def gemm_wgrad(dy: Tensor, ld_dy: int, M: int, N: int, x: Tensor, ld_x: int, K: int) -> Tensor:
+    """dW[N,K] (fp32) = dy[M,N]^T . x[M,K]   (both operands read MN-major); split-K when the output has
+    too few tiles to fill the chip."""
+    tile = 128 if dy.dtype == torch.bfloat16 else 64
+    tiles = ((N + tile - 1) // tile) * ((K + tile - 1) // tile)
+    sk = _split_k_for(tiles, M, dy.device, 64 if dy.dtype == torch.bfloat16 else 16)
+    if sk > 1:
+        dw = torch.zeros(N, K, device=dy.device, dtype=torch.float32)
+        ops.gemm(N, K, M, dy, ld_dy, True, x, ld_x, True, dw, K, accumulate=True, split_k=sk)
+    else:
+        dw = torch.empty(N, K, device=dy.device, dtype=torch.float32)
+        ops.gemm(N, K, M, dy, ld_dy, True, x, ld_x, True, dw, K)
+    return dw
+
+
+# --------------------------------------------------------------------------------------
+# casts
+# --------------------------------------------------------------------------------------
+class CastFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, dtype: torch.dtype):
+        ctx.src_dtype = x.dtype
+        return ops.cast(x.contiguous(), dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ops.cast(dy.contiguous(), ctx.src_dtype), None
+
+
+def to_compute(x: Tensor) -> Tensor:
+    dt = compute_dtype()
+    if x.dtype == dt:
+        return x if x.is_contiguous() else x.contiguous()
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    return CastFn.apply(x, dt)
+
+
+def to_float32(x: Tensor) -> Tensor:
+    if x.dtype == torch.float32:
+        return x
+    return CastFn.apply(x, torch.float32)
+
+
+# --------------------------------------------------------------------------------------
+# Linear (+ activation | + residual with dropout)
+# --------------------------------------------------------------------------------------
+class LinearFn(torch.autograd.Function):
+    """y = epilogue(x W^T + b).  act != NONE -> y = act(.) ; residual != None -> y = dropout(.) + residual."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, weight: Tensor, bias: Optional[Tensor], act: int, out_fp32: bool,
+                residual: Optional[Tensor], dropout_p: float, seed: int):
+        dt = x.dtype
+        w = weight_cache.get((weight,), dt)
+        N, K = w.shape
+        x2 = x.reshape(-1, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        out_dt = torch.float32 if out_fp32 else dt
+        y = torch.empty(M, N, device=x.device, dtype=out_dt)
+        pre = None
+        b = None if bias is None else bias.detach()
+        if act != ACT_NONE:
+            if residual is not None:
+                raise MMVQAError("LinearFn: activation and residual are exclusive")
+            pre = torch.empty(M, N, device=x.device, dtype=dt)
+            ops.gemm(M, N, K, x2, K, False, w, K, False, y, N, bias=b, epilogue=EPI_ACT, act=act, aux_out=pre, ld_aux_out=N)
+        elif residual is not None:
+            r2 = residual.reshape(M, N)
+            if not r2.is_contiguous():
+                r2 = r2.contiguous()
+            ops.gemm(M, N, K, x2, K, False, w, K, False, y, N, bias=b, epilogue=EPI_RESIDUAL, aux_in=r2, ld_aux_in=N,
+                     dropout_p=dropout_p, dropout_seed=seed)
+        else:
+            ops.gemm(M, N, K, x2, K, False, w, K, False, y, N, bias=b)
+        ctx.save_for_backward(x2, weight, pre)
+        ctx.meta = (act, dropout_p, seed, bias is not None, residual is not None, x.shape, weight.shape, dt)
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy: Tensor):
+        x2, weight, pre = ctx.saved_tensors
+        act, p, seed, has_bias, has_res, xshape, wshape, dt = ctx.meta
+        w = weight_cache.get((weight,), dt)
+        N, K = w.shape
+        M = x2.shape[0]
+        dy2 = dy.reshape(M, N)
+        dres = None
+        if has_res and ctx.needs_input_grad[5]:
+            dres = dy2.to(dt).view(*xshape[:-1], N) if dy2.dtype != dt else dy2.view(*xshape[:-1], N)
+        g, ld = _pad_ld(dy2, dt)
+        if has_res and p > 0.0:
+            if ld != N:
+                raise MMVQAError("dropout backward needs an 8-aligned width")
+            g = ops.dropout(g, p, seed)
+        if act != ACT_NONE:
+            if ld != N:
+                g = g[:, :N].contiguous()
+                ld = N
+            g = ops.bias_act_bwd(pre, None, g, act)
+            g, ld = _pad_ld(g, dt)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm_dgrad(g, ld, M, N, w, K).view(xshape)
+        if ctx.needs_input_grad[1]:
+            dw = gemm_wgrad(g, ld, M, N, x2, K, K).view(wshape)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = ops.colsum(g, M, N, ld)
+        return dx, dw, db, None, None, dres, None, None
+
+
+def linear(x: Tensor, weight: Tensor, bias: Optional[Tensor] = None, *, act: int = ACT_NONE, out_fp32: bool = False,
+           residual: Optional[Tensor] = None, dropout_p: float = 0.0, seed: int = 0) -> Tensor:
+    return LinearFn.apply(x, weight, bias, act, out_fp32, residual, dropout_p, seed)
+
+
+# --------------------------------------------------------------------------------------
+# standalone bias + activation (SERF module, gelu())
+# --------------------------------------------------------------------------------------
+class ActFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor, act: int):
+        x = x.contiguous()
+        ctx.save_for_backward(x)
+        ctx.act = act
+        return ops.bias_act_fwd(x, None, act)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.bias_act_bwd(x, None, dy.contiguous().to(x.dtype), ctx.act), None
+
+
+# --------------------------------------------------------------------------------------
+# residual + LayerNorm
+# --------------------------------------------------------------------------------------
+class AddLayerNormFn(torch.autograd.Function):
+    """y = LN(x + res) * gamma + beta   (res may be None)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, res: Optional[Tensor], gamma: Tensor, beta: Tensor, eps: float):
+        x = x.contiguous()
+        r = None if res is None else res.contiguous()
+        y, xsum, mean, rstd = ops.add_layernorm_fwd(x, r, gamma.detach(), beta.detach(), eps, want_sum=r is not None)
+        ctx.save_for_backward(x if xsum is None else xsum, gamma, mean, rstd)
+        ctx.has_res = res is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xsum, gamma, mean, rstd = ctx.saved_tensors
+        dg = torch.zeros_like(gamma, dtype=torch.float32)
+        db = torch.zeros_like(gamma, dtype=torch.float32)
+        dx = ops.layernorm_bwd(dy.contiguous().to(xsum.dtype), xsum, gamma.detach(), mean, rstd, None, dg, db)
+        return dx, (dx if ctx.has_res else None), dg, db, None
+
+
+def add_layer_norm(x: Tensor, res: Optional[Tensor], gamma: Tensor, beta: Tensor, eps: float) -> Tensor:
+    return AddLayerNormFn.apply(x, res, gamma, beta, eps)
+
+
+# --------------------------------------------------------------------------------------
+# pooling / normalisation
+# --------------------------------------------------------------------------------------
+class MaskedMeanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h: Tensor, maskf: Tensor):
+        ctx.save_for_backward(maskf)
+        ctx.T = h.shape[1]
+        return ops.masked_mean_fwd(h.contiguous(), maskf)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (maskf,) = ctx.saved_tensors
+        return ops.masked_mean_bwd(dout.contiguous(), maskf, ctx.T), None
+
+
+class L2NormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x: Tensor):
+        y, inv = ops.l2norm_fwd(x.contiguous())
+        ctx.save_for_backward(y, inv)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        y, inv = ctx.saved_tensors
+        return ops.l2norm_bwd(y, inv, dy.contiguous())
+
+
+# --------------------------------------------------------------------------------------
+# visual-token projector: v[b,:] = mean_hw act(W . f[b,:,hw])     (image_encoding.py:74,103)
+# --------------------------------------------------------------------------------------
+class VisTokFn(torch.autograd.Function):
+    """One pyramid level.  The [B, hidden, H, W] activation map is never materialised in forward;
+    backward recomputes the projection and materialises only G = act'(.) * dv / HW."""
+
+    @staticmethod
+    def forward(ctx, feat: Tensor, conv_w: Tensor, act: int, dtype: torch.dtype):
+        B, Cc, Hh, Ww = feat.shape
+        HW = Hh * Ww
+        w = weight_cache.get((conv_w,), dtype)            # [hidden, C]
+        hidden = w.shape[0]
+        f2 = feat.detach().reshape(B * Cc, HW)
+        fb, ld = _pad_ld(f2, dtype)                         # compute dtype, ld % 8 == 0 for bf16
+        v = torch.zeros(B, hidden, device=feat.device, dtype=torch.float32)
+        ops.gemm(hidden, HW, Cc, w, Cc, False, fb, ld, True, None, 0, epilogue=EPI_ACT_ROWSUM, act=act, rowsum_out=v,
+                 scale=1.0 / HW, batch=B, a_batch_rows=0, b_batch_rows=Cc)
+        ctx.save_for_backward(fb, conv_w)
+        ctx.meta = (act, dtype, B, Cc, Hh, Ww, ld, hidden, feat.dtype)
+        return v
+
+    @staticmethod
+    def backward(ctx, dv: Tensor):
+        fb, conv_w = ctx.saved_tensors
+        act, dtype, B, Cc, Hh, Ww, ld, hidden, fdt = ctx.meta
+        HW = Hh * Ww
+        w = weight_cache.get((conv_w,), dtype)
+        dv = dv.contiguous().float()
+        G = torch.empty(B, hidden, ld, device=fb.device, dtype=dtype)
+        ops.gemm(hidden, HW, Cc, w, Cc, False, fb, ld, True, G, ld, epilogue=EPI_DACT_SCALE, act=act, rowscale=dv,
+                 scale=1.0 / HW, batch=B, a_batch_rows=0, b_batch_rows=Cc, c_batch_stride=hidden * ld)
+        dw = dfeat = None
+        if ctx.needs_input_grad[1]:
+            dw = torch.zeros(hidden, Cc, device=fb.device, dtype=torch.float32)
+            ops.gemm(hidden, Cc, HW, G, ld, False, fb, ld, False, dw, Cc, accumulate=True, batch=B, a_batch_rows=hidden,
+                     b_batch_rows=Cc, c_batch_stride=0)
+            dw = dw.view(conv_w.shape)
+        if ctx.needs_input_grad[0]:
+            dfeat = torch.empty(B, Cc, HW, device=fb.device, dtype=torch.float32)
+            ops.gemm(Cc, HW, hidden, w, Cc, True, G, ld, True, dfeat, HW, batch=B, a_batch_rows=0, b_batch_rows=hidden,
+                     c_batch_stride=Cc * HW)
+            dfeat = dfeat.view(B, Cc, Hh, Ww).to(fdt)
+        return dfeat, dw, None, None
+
+
+def vistok_project(feat: Tensor, conv_w: Tensor, act: int) -> Tensor:
+    if feat.dtype not in (torch.float32, torch.bfloat16):
+        feat = feat.float()
+    return VisTokFn.apply(feat, conv_w, act, compute_dtype())
+
+
+# --------------------------------------------------------------------------------------
+# BertEmbeddings + visual-token scatter  (mmbert.py:60-67)
+# --------------------------------------------------------------------------------------
+class EmbedFuseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, seg, word, pos, typ, gamma, beta, vis, eps, p, seed, out_dtype, padding_idx):
+        ids = ids.contiguous().long()
+        seg = seg.contiguous().long()
+        visc = None if vis is None else vis.contiguous().float()
+        h, mean, rstd = ops.embed_ln_scatter_fwd(ids, seg, word.detach(), pos.detach(), typ.detach(), gamma.detach(),
+                                                 beta.detach(), visc, out_dtype, eps, p, seed)
+        ctx.save_for_backward(ids, seg, word, pos, typ, gamma, mean, rstd)
+        ctx.meta = (0 if vis is None else vis.shape[0], p, seed, padding_idx)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        ids, seg, word, pos, typ, gamma, mean, rstd = ctx.saved_tensors
+        nvis, p, seed, padding_idx = ctx.meta
+        B, T = ids.shape
+        H = word.shape[1]
+        need = ctx.needs_input_grad
+        dword = torch.zeros_like(word, dtype=torch.float32) if need[2] else None
+        dpos = torch.zeros_like(pos, dtype=torch.float32) if need[3] else None
+        dtyp = torch.zeros_like(typ, dtype=torch.float32) if need[4] else None
+        dgamma = torch.zeros_like(gamma, dtype=torch.float32) if need[5] else None
+        dbeta = torch.zeros_like(gamma, dtype=torch.float32) if need[6] else None
+        dvis = torch.empty(nvis, B, H, device=dh.device, dtype=torch.float32) if (nvis > 0 and need[7]) else None
+        ops.embed_ln_scatter_bwd(dh.contiguous(), ids, seg, word.detach(), pos.detach(), typ.detach(), gamma.detach(), mean,
+                                 rstd, dword, dpos, dtyp, dgamma, dbeta, dvis, nvis, padding_idx, p, seed)
+        return None, None, dword, dpos, dtyp, dgamma, dbeta, dvis, None, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------
+# Transformer multi-head self-attention core (fused QKV projection + attention)
+# --------------------------------------------------------------------------------------
+class MHSAFn(torch.autograd.Function):
+    """h = merge_heads(softmax(q k^T / sqrt(d) - 10000 (1 - mask_j)) v) with q,k,v = x W^T + b from ONE
+    [M,H] x [H,3H] GEMM.  Returns (h, probs)."""
+
+    @staticmethod
+    def forward(ctx, x, maskf, wq, bq, wk, bk, wv, bv, heads, p, seed):
+        dt = x.dtype
+        B, T, H = x.shape
+        d = H // heads
+        w = weight_cache.get((wq, wk, wv), dt)                       # [3H, H]
+        bias = torch.cat([bq.detach(), bk.detach(), bv.detach()]).float()
+        x2 = x.reshape(B * T, H)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        qkv = torch.empty(B * T, 3 * H, device=x.device, dtype=dt)
+        ops.gemm(B * T, 3 * H, H, x2, H, False, w, H, False, qkv, 3 * H, bias=bias)
+        out, probs = ops.mhsa_fwd(qkv, maskf, B, T, heads, d, p, seed)
+        ctx.save_for_backward(x2, qkv, probs, wq, wk, wv)
+        ctx.meta = (B, T, H, heads, d, p, seed, dt)
+        ctx.mark_non_differentiable(probs)
+        return out.view(B, T, H), probs
+
+    @staticmethod
+    def backward(ctx, dout, _dprobs):
+        x2, qkv, probs, wq, wk, wv = ctx.saved_tensors
+        B, T, H, heads, d, p, seed, dt = ctx.meta
+        w = weight_cache.get((wq, wk, wv), dt)
+        M = B * T
+        do2 = dout.reshape(M, H).contiguous().to(dt)
+        dqkv = ops.mhsa_bwd(qkv, probs, do2, B, T, heads, d, p, seed)
+        dx = gemm_dgrad(dqkv, 3 * H, M, 3 * H, w, H).view(B, T, H) if ctx.needs_input_grad[0] else None
+        dw = gemm_wgrad(dqkv, 3 * H, M, 3 * H, x2, H, H)
+        db = ops.colsum(dqkv, M, 3 * H)
+        return (dx, None, dw[:H], db[:H], dw[H:2 * H], db[H:2 * H], dw[2 * H:], db[2 * H:], None, None, None)
+
+
+class DropoutFn(torch.autograd.Function):
+    """nn.Dropout with the library's counter-hash mask (same mask regenerated in backward)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, p: float, seed: int):
+        ctx.meta = (p, seed)
+        return ops.dropout(x.contiguous(), p, seed)
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, seed = ctx.meta
+        return ops.dropout(dy.contiguous(), p, seed), None, None
+
+
+class RFAttentionFn(torch.autograd.Function):
+    """RealFormer attention sub-block without the out-projection (realformer.py:30-44):
+    shared-weight kqv GEMM + fused residual attention.  Returns (merged heads [B,T,H], scores [B,h,T,T])."""
+
+    @staticmethod
+    def forward(ctx, x, maskf, prev, kqv_w, heads):
+        ctx.set_materialize_grads(False)
+        dt = x.dtype
+        B, T, H = x.shape
+        d = H // heads
+        M = B * T
+        wk = weight_cache.get((kqv_w,), dt)
+        xin = x.reshape(M, H)
+        if not xin.is_contiguous():
+            xin = xin.contiguous()
+        kqv = torch.empty(M * heads, 3 * d, device=x.device, dtype=dt)
+        ops.gemm(M * heads, 3 * d, d, xin, d, False, wk, d, False, kqv, 3 * d)
+        prevc = None if prev is None else prev.contiguous().float()
+        attn, scores = ops.rf_attn_fwd(kqv, prevc, maskf, B, T, heads, d)
+        ctx.save_for_backward(xin, kqv, scores, kqv_w)
+        ctx.meta = (B, T, H, heads, d, dt, prev is not None)
+        return attn.view(B, T, H), scores
+
+    @staticmethod
+    def backward(ctx, dattn, dscores):
+        xin, kqv, scores, kqv_w = ctx.saved_tensors
+        B, T, H, heads, d, dt, has_prev = ctx.meta
+        M = B * T
+        wk = weight_cache.get((kqv_w,), dt)
+        if dattn is None:
+            da = torch.zeros(M, H, device=xin.device, dtype=dt)
+        else:
+            da = dattn.reshape(M, H).contiguous().to(dt)
+        ds = None if dscores is None else dscores.contiguous().float()
+        want_dprev = has_prev and ctx.needs_input_grad[2]
+        dkqv, dprev = ops.rf_attn_bwd(kqv, scores, da, ds, want_dprev, B, T, heads, d)
+        dwk = gemm_wgrad(dkqv, 3 * d, M * heads, 3 * d, xin, d, d).view(kqv_w.shape)
+        dx = torch.empty(M, H, device=xin.device, dtype=dt)
+        ops.gemm(M * heads, d, 3 * d, dkqv, 3 * d, False, wk, d, True, dx, d)
+        return dx.view(B, T, H), None, dprev, dwk, None
+
+
+# --------------------------------------------------------------------------------------
+# RealFormer encoder: L post-LN residual-attention blocks in one autograd node
+# --------------------------------------------------------------------------------------
+RF_PARAMS_PER_LAYER = 10  # kqv.w proj.w ln1.w ln1.b ff.0.w ff.0.b ff.2.w ff.2.b ln2.w ln2.b
+
+
+class RealFormerEncoderFn(torch.autograd.Function):
+    """models/realformer.py:30-51 x n_layers (mmbert.py:103-108), 7 launches per layer forward:
+    kqv GEMM | fused residual attention (prev in, scores out) | proj GEMM + dropout + residual |
+    LN1 | FF1 GEMM + bias + SERF | FF2 GEMM + bias + dropout + residual | LN2."""
+
+    @staticmethod
+    def forward(ctx, x, maskf, prev, heads, p1, p2, seed, *params):
+        ctx.set_materialize_grads(False)
+        dt = x.dtype
+        B, T, H = x.shape
+        d = H // heads
+        M = B * T
+        n_layers = len(params) // RF_PARAMS_PER_LAYER
+        xin = x.reshape(M, H)
+        if not xin.is_contiguous():
+            xin = xin.contiguous()
+        if prev is not None:
+            prev = prev.contiguous().float()
+        saved: List[Tensor] = []
+        scores = prev
+        for l in range(n_layers):
+            kqv_w, proj_w, g1, b1, w0, bb0, w2, bb2, g2, b2 = params[l * RF_PARAMS_PER_LAYER:(l + 1) * RF_PARAMS_PER_LAYER]
+            wk = weight_cache.get((kqv_w,), dt)
+            wp = weight_cache.get((proj_w,), dt)
+            wf0 = weight_cache.get((w0,), dt)
+            wf2 = weight_cache.get((w2,), dt)
+            kqv = torch.empty(M * heads, 3 * d, device=x.device, dtype=dt)
+            ops.gemm(M * heads, 3 * d, d, xin, d, False, wk, d, False, kqv, 3 * d)
+            attn, scores = ops.rf_attn_fwd(kqv, scores, maskf, B, T, heads, d)
+            y1 = torch.empty(M, H, device=x.device, dtype=dt)
+            ops.gemm(M, H, H, attn, H, False, wp, H, False, y1, H, epilogue=EPI_RESIDUAL, aux_in=xin, ld_aux_in=H,
+                     dropout_p=p1, dropout_seed=seed + 2 * l)
+            x1, _, mean1, rstd1 = ops.add_layernorm_fwd(y1, None, g1.detach(), b1.detach(), 1e-5, want_sum=False)
+            F4 = wf0.shape[0]
+            hpre = torch.empty(M, F4, device=x.device, dtype=dt)
+            hact = torch.empty(M, F4, device=x.device, dtype=dt)
+            ops.gemm(M, F4, H, x1, H, False, wf0, H, False, hact, F4, bias=bb0.detach(), epilogue=EPI_ACT, act=ACT_SERF,
+                     aux_out=hpre, ld_aux_out=F4)
+            y2 = torch.empty(M, H, device=x.device, dtype=dt)
+            ops.gemm(M, H, F4, hact, F4, False, wf2, F4, False, y2, H, bias=bb2.detach(), epilogue=EPI_RESIDUAL, aux_in=x1,
+                     ld_aux_in=H, dropout_p=p2, dropout_seed=seed + 2 * l + 1)
+            x2, _, mean2, rstd2 = ops.add_layernorm_fwd(y2, None, g2.detach(), b2.detach(), 1e-5, want_sum=False)
+            saved += [xin, kqv, scores, attn, y1, mean1, rstd1, x1, hpre, hact, y2, mean2, rstd2]
+            xin = x2
+        ctx.save_for_backward(*saved, *params)
+        ctx.meta = (B, T, H, heads, d, n_layers, p1, p2, seed, dt, prev is not None)
+        return xin.view(B, T, H), scores
+
+    @staticmethod
+    def backward(ctx, dy, dscores):
+        B, T, H, heads, d, n_layers, p1, p2, seed, dt, has_prev = ctx.meta
+        M = B * T
+        nsave = 13
+        saved = ctx.saved_tensors[:nsave * n_layers]
+        params = ctx.saved_tensors[nsave * n_layers:]
+        if dy is None:
+            dx = torch.zeros(M, H, device=saved[0].device, dtype=dt)
+        else:
+            dx = dy.reshape(M, H).contiguous()
+            if dx.dtype != dt:
+                dx = dx.to(dt)
+        ds = None if dscores is None else dscores.contiguous().float()
+        grads: List[Optional[Tensor]] = [None] * len(params)
+        for l in reversed(range(n_layers)):
+            xin, kqv, scores, attn, y1, mean1, rstd1, x1, hpre, hact, y2, mean2, rstd2 = saved[l * nsave:(l + 1) * nsave]
+            kqv_w, proj_w, g1, b1, w0, bb0, w2, bb2, g2, b2 = params[l * RF_PARAMS_PER_LAYER:(l + 1) * RF_PARAMS_PER_LAYER]
+            wk = weight_cache.get((kqv_w,), dt)
+            wp = weight_cache.get((proj_w,), dt)
+            wf0 = weight_cache.get((w0,), dt)
+            wf2 = weight_cache.get((w2,), dt)
+            F4 = wf0.shape[0]
+            dg2 = torch.zeros(H, device=dx.device, dtype=torch.float32)
+            db2 = torch.zeros(H, device=dx.device, dtype=torch.float32)
+            dy2 = ops.layernorm_bwd(dx, y2, g2.detach(), mean2, rstd2, None, dg2, db2)
+            dff = ops.dropout(dy2, p2, seed + 2 * l + 1) if p2 > 0.0 else dy2
+            dbb2 = ops.colsum(dff, M, H)
+            dw2 = gemm_wgrad(dff, H, M, H, hact, F4, F4)
+            dhpre = gemm_dgrad(dff, H, M, H, wf2, F4, epilogue=EPI_DACT, act=ACT_SERF, aux_in=hpre)
+            dbb0 = ops.colsum(dhpre, M, F4)
+            dw0 = gemm_wgrad(dhpre, F4, M, F4, x1, H, H)
+            dx1 = gemm_dgrad(dhpre, F4, M, F4, wf0, H, epilogue=EPI_RESIDUAL, aux_in=dy2)
+            dg1 = torch.zeros(H, device=dx.device, dtype=torch.float32)
+            db1 = torch.zeros(H, device=dx.device, dtype=torch.float32)
+            dy1 = ops.layernorm_bwd(dx1, y1, g1.detach(), mean1, rstd1, None, dg1, db1)
+            dpr = ops.dropout(dy1, p1, seed + 2 * l) if p1 > 0.0 else dy1
+            dwp = gemm_wgrad(dpr, H, M, H, attn, H, H)
+            dattn = gemm_dgrad(dpr, H, M, H, wp, H)
+            want_dprev = (l > 0) or (has_prev and ctx.needs_input_grad[2])
+            dkqv, dprev = ops.rf_attn_bwd(kqv, scores, dattn, ds, want_dprev, B, T, heads, d)
+            dwk = gemm_wgrad(dkqv, 3 * d, M * heads, 3 * d, xin, d, d)
+            # dx_in = dkqv . Wkqv (per head) + dy1 (residual around the attention block)
+            dxin = torch.empty(M, H, device=dx.device, dtype=dt)
+            ops.gemm(M * heads, d, 3 * d, dkqv, 3 * d, False, wk, d, True, dxin, d, epilogue=EPI_RESIDUAL, aux_in=dy1,
+                     ld_aux_in=d)
+            base = l * RF_PARAMS_PER_LAYER
+            grads[base:base + RF_PARAMS_PER_LAYER] = [dwk.view(kqv_w.shape), dwp, dg1, db1, dw0, dbb0, dw2, dbb2, dg2, db2]
+            dx = dxin
+            ds = dprev
+        dprev_out = ds if (has_prev and ctx.needs_input_grad[2]) else None
+        return (dx.view(B, T, H), None, dprev_out, None, None, None, None, *grads)
+
+
+# --------------------------------------------------------------------------------------
+# losses
+# --------------------------------------------------------------------------------------
+class ASLFn(torch.autograd.Function):
+    """ASLSingleLabel (models/asl_singlelabel.py:23-52): per-row loss + its gradient in one launch."""
+
+    @staticmethod
+    def forward(ctx, logits: Tensor, target: Tensor, gp: float, gn: float, eps: float, want_tc: bool):
+        lg = logits if logits.is_contiguous() else logits.contiguous()
+        Bn, Cn = lg.shape
+        loss_rows, dl, tc = ops.asl_fwd_bwd(lg, Cn, target.contiguous().long(), Cn, gp, gn, eps, True, want_tc)
+        ctx.save_for_backward(dl)
+        ctx.in_dtype = logits.dtype
+        if tc is None:
+            tc = torch.empty(0, device=lg.device)
+        ctx.mark_non_differentiable(tc)
+        return loss_rows, tc
+
+    @staticmethod
+    def backward(ctx, dloss_rows, _dtc):
+        (dl,) = ctx.saved_tensors
+        g = dl * dloss_rows.reshape(-1, 1).float()
+        return g.to(ctx.in_dtype), None, None, None, None, None
+
+
+class CrossEntropyRowsFn(torch.autograd.Function):
+    """NLL(log_softmax(logits)) per row (pretrain/roco_utils.py:235-236) with the gradient produced in
+    the same pass; `ld` lets the logits live in a padded buffer."""
+
+    @staticmethod
+    def forward(ctx, logits2d: Tensor, target: Tensor):
+        rows, Cn = logits2d.shape
+        ld = logits2d.stride(0)
+        if logits2d.stride(1) != 1:
+            logits2d = logits2d.contiguous()
+            ld = Cn
+        dl = torch.empty(rows, ld, device=logits2d.device, dtype=logits2d.dtype)
+        loss_rows = ops.ce_fwd_bwd(logits2d, ld, target.contiguous().long(), rows, Cn, 1.0, dl, ld)
+        ctx.save_for_backward(dl)
+        ctx.Cn = Cn
+        return loss_rows
+
+    @staticmethod
+    def backward(ctx, dloss_rows):
+        (dl,) = ctx.saved_tensors
+        g = dl[:, :ctx.Cn] * dloss_rows.reshape(-1, 1).to(dl.dtype)
+        return g, None
+
+
+class SupConFn(torch.autograd.Function):
+    """SupConLoss core (models/SupConLoss/loss.py:58-96) on the view-major contrast matrix F [N, D]:
+    raw = anchors . F^T on the tensor cores, then one fused row pass (max, masked exp-sum, positives
+    mean, gradient).  Returns the per-anchor losses."""
+
+    @staticmethod
+    def forward(ctx, Fm: Tensor, mask: Optional[Tensor], bsz: int, n_anchor_rows: int, temperature: float,
+                base_temperature: float, dtype: torch.dtype):
+        N, D = Fm.shape
+        Fc, ld = _pad_ld(Fm.detach(), dtype)
+        raw = torch.empty(n_anchor_rows, N, device=Fm.device, dtype=torch.float32)
+        ops.gemm(n_anchor_rows, N, D, Fc, ld, False, Fc, ld, False, raw, N)
+        loss_rows, G = ops.supcon_rows(raw, None if mask is None else mask.contiguous().float(), bsz, 0, temperature,
+                                       base_temperature, True)
+        ctx.save_for_backward(Fc, G)
+        ctx.meta = (N, D, ld, n_anchor_rows, dtype, Fm.dtype)
+        return loss_rows
+
+    @staticmethod
+    def backward(ctx, dloss_rows):
+        Fc, G = ctx.saved_tensors
+        N, D, ld, R, dtype, in_dtype = ctx.meta
+        Gs = G * dloss_rows.reshape(-1, 1).float()
+        Gc, ldg = _pad_ld(Gs, dtype)
+        dF = torch.zeros(N, D, device=Fc.device, dtype=torch.float32)
+        # anchor role: dF[:R] += G . F ;  contrast role: dF += G^T . F[:R]
+        ops.gemm(R, D, N, Gc, ldg, False, Fc, ld, True, dF, D, accumulate=True)
+        ops.gemm(N, D, R, Gc, ldg, True, Fc, ld, True, dF, D, accumulate=True)
+        return dF.to(in_dtype), None, None, None, None, None, None

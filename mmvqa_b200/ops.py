@@ -1,0 +1,281 @@
+"""Thin tensor-level wrappers over the C ABI (one Python function per entry point of include/mmvqa.h).
+
+Every function takes CUDA tensors, passes raw device pointers + the current CUDA stream, and raises
+``MMVQAError`` on a non-zero return code.  Nothing here allocates behind the caller's back except
+where the docstring says so, and nothing falls back to torch math.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_SERF, BF16, EPI_ACT, EPI_ACT_ROWSUM, EPI_DACT, EPI_DACT_SCALE,
+                   EPI_RESIDUAL, EPI_STORE, F32)
+
+Tensor = torch.Tensor
+ACT_CODES = {"none": ACT_NONE, "serf": ACT_SERF, "gelu": ACT_GELU, "relu": ACT_RELU}
+
+
+def dtype_code(t) -> int:
+    dt = t.dtype if isinstance(t, torch.Tensor) else t
+    if dt == torch.float32:
+        return F32
+    if dt == torch.bfloat16:
+        return BF16
+    raise L.MMVQAError(f"unsupported dtype {dt} (float32 or bfloat16 only)")
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[Tensor]) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise L.MMVQAError("mmvqa_b200 kernels need CUDA tensors: there is no CPU fallback for this path")
+    return t.data_ptr()
+
+
+def _cont(t: Tensor, name: str) -> Tensor:
+    if not t.is_contiguous():
+        raise L.MMVQAError(f"{name} must be contiguous")
+    return t
+
+
+# ------------------------------------------------------------------------------- GEMM
+def gemm(M: int, N: int, K: int, A: Tensor, lda: int, a_trans: bool, B: Tensor, ldb: int, b_trans: bool,
+         Cout: Optional[Tensor], ldc: int, *, bias: Optional[Tensor] = None, epilogue: int = EPI_STORE,
+         act: int = ACT_NONE, aux_in: Optional[Tensor] = None, ld_aux_in: int = 0, aux_out: Optional[Tensor] = None,
+         ld_aux_out: int = 0, rowsum_out: Optional[Tensor] = None, rowscale: Optional[Tensor] = None,
+         scale: float = 1.0, accumulate: bool = False, split_k: int = 1, batch: int = 1, a_batch_rows: int = 0,
+         b_batch_rows: int = 0, c_batch_stride: int = 0, dropout_p: float = 0.0, dropout_seed: int = 0) -> None:
+    """C[M,N] = epilogue(sum_k opA(A)[m,k] opB(B)[n,k]); see include/mmvqa.h for the epilogues."""
+    if A.dtype != B.dtype:
+        raise L.MMVQAError(f"gemm operands differ in dtype: {A.dtype} vs {B.dtype}")
+    if bias is not None and bias.dtype != torch.float32:
+        raise L.MMVQAError("gemm bias must be float32")
+    a = L.GemmArgs()
+    a.dtype = dtype_code(A)
+    a.M, a.N, a.K = M, N, K
+    a.A, a.lda, a.a_trans = _p(A), lda, int(a_trans)
+    a.B, a.ldb, a.b_trans = _p(B), ldb, int(b_trans)
+    a.C, a.ldc = _p(Cout), ldc
+    a.c_dtype = dtype_code(Cout) if Cout is not None else a.dtype
+    a.bias = _p(bias)
+    a.epilogue, a.act = epilogue, act
+    a.aux_in, a.ld_aux_in = _p(aux_in), ld_aux_in
+    a.aux_out, a.ld_aux_out = _p(aux_out), ld_aux_out
+    a.rowsum_out, a.rowscale, a.scale = _p(rowsum_out), _p(rowscale), scale
+    a.accumulate, a.split_k = int(accumulate), split_k
+    a.batch, a.a_batch_rows, a.b_batch_rows, a.c_batch_stride = batch, a_batch_rows, b_batch_rows, c_batch_stride
+    a.dropout_p, a.dropout_seed = dropout_p, dropout_seed
+    for t in (aux_in, aux_out):
+        if t is not None and t.dtype != A.dtype:
+            raise L.MMVQAError("gemm aux tensors must have the operand dtype")
+    L.check(L.lib().mmvqa_gemm(C.byref(a), _stream()), "mmvqa_gemm")
+
+
+# ------------------------------------------------------------------------------- elementwise
+def bias_act_fwd(x: Tensor, bias: Optional[Tensor], act: int, out: Optional[Tensor] = None) -> Tensor:
+    _cont(x, "x")
+    cols = x.shape[-1]
+    rows = x.numel() // cols if cols else 0
+    y = torch.empty_like(x) if out is None else out
+    L.check(L.lib().mmvqa_bias_act_fwd(_p(x), _p(bias), _p(y), rows, cols, act, dtype_code(x), _stream()), "bias_act_fwd")
+    return y
+
+
+def bias_act_bwd(x: Tensor, bias: Optional[Tensor], dy: Tensor, act: int) -> Tensor:
+    _cont(x, "x"), _cont(dy, "dy")
+    cols = x.shape[-1]
+    rows = x.numel() // cols if cols else 0
+    dx = torch.empty_like(x)
+    L.check(L.lib().mmvqa_bias_act_bwd(_p(x), _p(bias), _p(dy), _p(dx), rows, cols, act, dtype_code(x), _stream()),
+            "bias_act_bwd")
+    return dx
+
+
+def colsum(x: Tensor, rows: int, cols: int, ldx: Optional[int] = None) -> Tensor:
+    out = torch.empty(cols, device=x.device, dtype=torch.float32)
+    L.check(L.lib().mmvqa_colsum(_p(x), cols if ldx is None else ldx, _p(out), rows, cols, dtype_code(x), _stream()), "colsum")
+    return out
+
+
+def cast(src: Tensor, dst_dtype: torch.dtype, out: Optional[Tensor] = None) -> Tensor:
+    _cont(src, "src")
+    dst = torch.empty(src.shape, device=src.device, dtype=dst_dtype) if out is None else out
+    L.check(L.lib().mmvqa_cast(_p(src), dtype_code(src), _p(dst), dtype_code(dst), src.numel(), _stream()), "cast")
+    return dst
+
+
+def cast_pad(src: Tensor, rows: int, cols: int, ld_src: int, dst_dtype: torch.dtype, ld_dst: int) -> Tensor:
+    dst = torch.empty(rows, ld_dst, device=src.device, dtype=dst_dtype)
+    L.check(L.lib().mmvqa_cast_pad(_p(src), dtype_code(src), ld_src, _p(dst), dtype_code(dst), ld_dst, rows, cols, _stream()),
+            "cast_pad")
+    return dst
+
+
+def scale_(x: Tensor, scalar: Optional[Tensor], host_factor: float = 1.0) -> Tensor:
+    _cont(x, "x")
+    if scalar is not None and (scalar.dtype != torch.float32 or scalar.numel() != 1):
+        raise L.MMVQAError("scale_: scalar must be a 1-element float32 tensor")
+    L.check(L.lib().mmvqa_scale_by_device_scalar(_p(x), dtype_code(x), _p(scalar), host_factor, x.numel(), _stream()), "scale")
+    return x
+
+
+def dropout(x: Tensor, p: float, seed: int) -> Tensor:
+    _cont(x, "x")
+    y = torch.empty_like(x)
+    L.check(L.lib().mmvqa_dropout(_p(x), _p(y), x.numel(), p, seed, dtype_code(x), _stream()), "dropout")
+    return y
+
+
+def add_layernorm_fwd(x: Tensor, res: Optional[Tensor], gamma: Tensor, beta: Tensor, eps: float, want_sum: bool):
+    """returns (y, xsum or None, mean, rstd)."""
+    _cont(x, "x")
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    y = torch.empty_like(x)
+    xsum = torch.empty_like(x) if want_sum else None
+    mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+    rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    L.check(L.lib().mmvqa_add_layernorm_fwd(_p(x), _p(res), _p(gamma), _p(beta), _p(y), _p(xsum), _p(mean), _p(rstd), rows,
+                                           cols, eps, dtype_code(x), _stream()), "add_layernorm_fwd")
+    return y, xsum, mean, rstd
+
+
+def layernorm_bwd(dy: Tensor, xsum: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, dx_extra: Optional[Tensor],
+                  dgamma: Tensor, dbeta: Tensor) -> Tensor:
+    """dgamma / dbeta are ACCUMULATED into (caller zero-fills)."""
+    _cont(dy, "dy"), _cont(xsum, "xsum")
+    cols = dy.shape[-1]
+    rows = dy.numel() // cols
+    dx = torch.empty_like(dy)
+    L.check(L.lib().mmvqa_layernorm_bwd(_p(dy), _p(xsum), _p(gamma), _p(mean), _p(rstd), _p(dx_extra), _p(dx), _p(dgamma),
+                                       _p(dbeta), rows, cols, dtype_code(dy), _stream()), "layernorm_bwd")
+    return dx
+
+
+# ------------------------------------------------------------------------------- attention
+def rf_attn_fwd(kqv: Tensor, prev: Optional[Tensor], mask: Optional[Tensor], B: int, T: int, heads: int, d: int):
+    out = torch.empty(B * T, heads * d, device=kqv.device, dtype=kqv.dtype)
+    scores = torch.empty(B, heads, T, T, device=kqv.device, dtype=torch.float32)
+    L.check(L.lib().mmvqa_rf_attn_fwd(_p(kqv), _p(prev), _p(mask), _p(out), _p(scores), B, T, heads, d, dtype_code(kqv),
+                                     _stream()), "rf_attn_fwd")
+    return out, scores
+
+
+def rf_attn_bwd(kqv: Tensor, scores: Tensor, dout: Tensor, dscores_in: Optional[Tensor], want_dprev: bool, B: int, T: int,
+                heads: int, d: int):
+    dkqv = torch.empty_like(kqv)
+    dprev = torch.empty_like(scores) if want_dprev else None
+    L.check(L.lib().mmvqa_rf_attn_bwd(_p(kqv), _p(scores), _p(dout), _p(dscores_in), _p(dkqv), _p(dprev), B, T, heads, d,
+                                     dtype_code(kqv), _stream()), "rf_attn_bwd")
+    return dkqv, dprev
+
+
+def mhsa_fwd(qkv: Tensor, mask: Optional[Tensor], B: int, T: int, heads: int, d: int, p: float, seed: int):
+    out = torch.empty(B * T, heads * d, device=qkv.device, dtype=qkv.dtype)
+    probs = torch.empty(B, heads, T, T, device=qkv.device, dtype=qkv.dtype)
+    L.check(L.lib().mmvqa_mhsa_fwd(_p(qkv), _p(mask), _p(out), _p(probs), B, T, heads, d, p, seed, dtype_code(qkv), _stream()),
+            "mhsa_fwd")
+    return out, probs
+
+
+def mhsa_bwd(qkv: Tensor, probs: Tensor, dout: Tensor, B: int, T: int, heads: int, d: int, p: float, seed: int) -> Tensor:
+    dqkv = torch.empty_like(qkv)
+    L.check(L.lib().mmvqa_mhsa_bwd(_p(qkv), _p(probs), _p(dout), _p(dqkv), B, T, heads, d, p, seed, dtype_code(qkv), _stream()),
+            "mhsa_bwd")
+    return dqkv
+
+
+# ------------------------------------------------------------------------------- fusion / pooling
+def embed_ln_scatter_fwd(ids, seg, word, pos, typ, gamma, beta, vis, out_dtype, eps, p, seed):
+    B, T = ids.shape
+    H = word.shape[1]
+    nvis = 0 if vis is None else vis.shape[0]
+    h = torch.empty(B, T, H, device=word.device, dtype=out_dtype)
+    mean = torch.empty(B * T, device=word.device, dtype=torch.float32)
+    rstd = torch.empty(B * T, device=word.device, dtype=torch.float32)
+    L.check(L.lib().mmvqa_embed_ln_scatter_fwd(_p(ids), _p(seg), _p(word), _p(pos), _p(typ), _p(gamma), _p(beta), _p(vis), _p(h),
+                                              _p(mean), _p(rstd), B, T, H, nvis, word.shape[0], eps, p, seed, dtype_code(h),
+                                              _stream()), "embed_ln_scatter_fwd")
+    return h, mean, rstd
+
+
+def embed_ln_scatter_bwd(dh, ids, seg, word, pos, typ, gamma, mean, rstd, dword, dpos, dtyp, dgamma, dbeta, dvis, nvis,
+                         padding_idx, p, seed):
+    B, T = ids.shape
+    H = word.shape[1]
+    L.check(L.lib().mmvqa_embed_ln_scatter_bwd(_p(dh), _p(ids), _p(seg), _p(word), _p(pos), _p(typ), _p(gamma), _p(mean),
+                                              _p(rstd), _p(dword), _p(dpos), _p(dtyp), _p(dgamma), _p(dbeta), _p(dvis), B, T, H,
+                                              nvis, padding_idx, p, seed, dtype_code(dh), _stream()), "embed_ln_scatter_bwd")
+
+
+def masked_mean_fwd(h: Tensor, mask: Tensor) -> Tensor:
+    B, T, H = h.shape
+    out = torch.empty(B, H, device=h.device, dtype=h.dtype)
+    L.check(L.lib().mmvqa_masked_mean_fwd(_p(_cont(h, "h")), _p(mask), _p(out), B, T, H, dtype_code(h), _stream()), "masked_mean_fwd")
+    return out
+
+
+def masked_mean_bwd(dout: Tensor, mask: Tensor, T: int) -> Tensor:
+    B, H = dout.shape
+    dh = torch.empty(B, T, H, device=dout.device, dtype=dout.dtype)
+    L.check(L.lib().mmvqa_masked_mean_bwd(_p(_cont(dout, "dout")), _p(mask), _p(dh), B, T, H, dtype_code(dout), _stream()),
+            "masked_mean_bwd")
+    return dh
+
+
+def l2norm_fwd(x: Tensor):
+    rows, cols = x.shape
+    y = torch.empty_like(x)
+    inv = torch.empty(rows, device=x.device, dtype=torch.float32)
+    L.check(L.lib().mmvqa_l2norm_fwd(_p(_cont(x, "x")), _p(y), _p(inv), rows, cols, _stream()), "l2norm_fwd")
+    return y, inv
+
+
+def l2norm_bwd(y: Tensor, inv: Tensor, dy: Tensor) -> Tensor:
+    rows, cols = y.shape
+    dx = torch.empty_like(y)
+    L.check(L.lib().mmvqa_l2norm_bwd(_p(y), _p(inv), _p(_cont(dy, "dy")), _p(dx), rows, cols, _stream()), "l2norm_bwd")
+    return dx
+
+
+# ------------------------------------------------------------------------------- losses
+def asl_fwd_bwd(logits: Tensor, ld: int, target: Tensor, C_: int, gp: float, gn: float, eps: float, want_grad: bool,
+                want_tc: bool):
+    B = target.shape[0]
+    loss_rows = torch.empty(B, device=logits.device, dtype=torch.float32)
+    dl = torch.empty(B, C_, device=logits.device, dtype=torch.float32) if want_grad else None
+    tc = torch.empty(B, C_, device=logits.device, dtype=torch.float32) if want_tc else None
+    L.check(L.lib().mmvqa_asl_fwd_bwd(_p(logits), ld, _p(target), _p(loss_rows), _p(dl), _p(tc), B, C_, gp, gn, eps,
+                                     dtype_code(logits), _stream()), "asl_fwd_bwd")
+    return loss_rows, dl, tc
+
+
+def ce_fwd_bwd(logits: Tensor, ld: int, target: Tensor, rows: int, C_: int, scale: float, dlogits: Optional[Tensor], ld_d: int):
+    loss_rows = torch.empty(rows, device=logits.device, dtype=torch.float32)
+    L.check(L.lib().mmvqa_ce_fwd_bwd(_p(logits), ld, _p(target), _p(loss_rows), _p(dlogits), ld_d, rows, C_, scale,
+                                    dtype_code(logits), _stream()), "ce_fwd_bwd")
+    return loss_rows
+
+
+def supcon_rows(raw: Tensor, mask: Optional[Tensor], bsz: int, row_offset: int, temperature: float, base_temperature: float,
+                want_grad: bool):
+    R, N = raw.shape
+    loss_rows = torch.empty(R, device=raw.device, dtype=torch.float32)
+    G = torch.empty_like(raw) if want_grad else None
+    L.check(L.lib().mmvqa_supcon_rows(_p(_cont(raw, "raw")), _p(mask), _p(loss_rows), _p(G), R, N, bsz, row_offset, temperature,
+                                     base_temperature, _stream()), "supcon_rows")
+    return loss_rows, G
+
+
+def adam_step(table: Tensor, n_chunks: int, lr: float, beta1: float, beta2: float, eps: float, weight_decay: float,
+              step: int, step_dev: Optional[Tensor], grad_scale: float = 1.0) -> None:
+    L.check(L.lib().mmvqa_adam_step(C.cast(table.data_ptr(), C.POINTER(L.AdamDesc)), n_chunks, lr, beta1, beta2, eps,
+                                   weight_decay, step, _p(step_dev), grad_scale, _stream()), "adam_step")

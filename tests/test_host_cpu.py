@@ -1,0 +1,134 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/mmvqa.h declares, the module
+mirrors keep the reference's constructor surface / state-dict keys, and the product path fails loudly
+(no CPU fallback).  No compute calls: there is no GPU here."""
+import os
+import re
+import types
+
+import pytest
+import torch
+import torch.nn as nn
+
+import mmvqa_b200
+from mmvqa_b200 import _lib
+from mmvqa_b200.models import image_encoding as IE
+from mmvqa_b200.models import mmbert as MM
+from mmvqa_b200.models.asl_singlelabel import ASLSingleLabel
+from mmvqa_b200.models.realformer import ResEncoderBlock
+from mmvqa_b200.models.serf import SERF
+from mmvqa_b200.models.SupConLoss.loss import SupConLoss
+from mmvqa_b200.models.transformer import BertLayer, MultiHeadedSelfAttention, PositionWiseFeedForward
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    hdr = open(os.path.join(ROOT, "include", "mmvqa.h")).read()
+    declared = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(mmvqa_\w+)\s*\(", hdr, flags=re.M))
+    assert len(declared) >= 28
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = mmvqa_b200.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.mmvqa_abi_version() == _lib.ABI_VERSION
+    assert lib.mmvqa_launch_count() == 0
+
+
+def test_gemm_args_struct_matches_header_order():
+    hdr = open(os.path.join(ROOT, "include", "mmvqa.h")).read()
+    body = hdr[hdr.index("typedef struct mmvqa_gemm_args {"):hdr.index("} mmvqa_gemm_args;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split("{", 1)[1].split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        for part in decl.split(","):
+            names.append(re.findall(r"(\w+)\s*$", part.strip())[0])
+    assert names == [f[0] for f in _lib.GemmArgs._fields_]
+
+
+def test_no_cpu_fallback():
+    with pytest.raises(mmvqa_b200.MMVQAError):
+        SERF()(torch.randn(4, 8))                      # CPU tensor -> loud failure, never torch math
+    with pytest.raises(mmvqa_b200.MMVQAError):
+        ASLSingleLabel()(torch.randn(2, 5), torch.tensor([0, 1]))
+
+
+def _args(**over):
+    base = dict(task="MLM", clinicalbert="", num_vis=5, hidden_size=64, use_relu=False, heads=4, hidden_dropout_prob=0.1,
+                n_layers=2, vocab_size=120, transformer_model="realformer", cnn_encoder="tf_efficientnetv2_m",
+                dataset="VQA-Med")
+    base.update(over)
+    return types.SimpleNamespace(**base)
+
+
+def _model(**over):
+    from transformers import BertConfig, BertModel
+    old = MM.AutoModel.from_pretrained
+    MM.AutoModel.from_pretrained = staticmethod(lambda name, *a, **k: BertModel(BertConfig(
+        hidden_size=64, vocab_size=120, num_hidden_layers=1, num_attention_heads=4, intermediate_size=128,
+        max_position_embeddings=32)))
+    IE.models_dict[5]["tf_efficientnetv2_m"][0] = lambda *a, **k: nn.Identity()
+    IE.models_dict[5]["resnet152"][0] = lambda *a, **k: nn.Identity()
+    try:
+        return MM.Model(_args(**over), feat_dim=16)
+    finally:
+        MM.AutoModel.from_pretrained = old
+
+
+def test_state_dict_keys_match_the_reference(golden):
+    g = golden("models")
+    for name in ("vqa_realformer_effnet", "vqa_transformer_resnet_relu", "mlm_realformer_supcon", "mlm_transformer"):
+        c = g[name]
+        m = _model(**{k: v for k, v in c["args"].items()})
+        ours = {k: tuple(v.shape) for k, v in m.state_dict().items() if not k.startswith("transformer.trans.model.")}
+        ref = {k: tuple(v.shape) for k, v in c["state"].items()}
+        assert ours == ref, (set(ours) ^ set(ref))
+
+
+def test_module_surface():
+    a = _args()
+    m = _model()
+    assert isinstance(m.classifier, nn.Sequential) and isinstance(m.classifier[2], nn.Linear)
+    m.classifier[2] = nn.Linear(64, 7)                 # vqamed2019/train.py:137 swaps the head
+    assert hasattr(m.transformer, "bert_embedding") and hasattr(m.transformer, "trans") and hasattr(m.transformer, "mains")
+    t = _model(transformer_model="transformer")
+    assert isinstance(t.transformer.blocks, BertLayer) and t.transformer.n_layers == 2
+    with pytest.raises(NotImplementedError):
+        MM.get_transformer_model(_args(transformer_model="lstm"))
+    with pytest.raises(NotImplementedError):
+        IE.get_transfer(_args(cnn_encoder="vgg"))
+    b = ResEncoderBlock(emb_s=8, head_cnt=8)
+    assert tuple(b.kqv.weight.shape) == (24, 8) and b.kqv.bias is None and b.proj.bias is None
+    assert [type(x).__name__ for x in b.ff] == ["Linear", "SERF", "Linear", "Dropout"]
+    att = MultiHeadedSelfAttention(a)
+    x = torch.zeros(2, 3, 64)
+    assert att.split_last(x, (4, -1)).shape == (2, 3, 4, 16)
+    assert att.merge_last(att.split_last(x, (4, -1)), 2).shape == (2, 3, 64)
+    assert isinstance(PositionWiseFeedForward(a).fc1, nn.Linear)
+    for share in ("all", "att", "ffn", "none"):
+        BertLayer(a, share=share, norm="post")
+    crit = ASLSingleLabel()
+    assert (crit.gamma_pos, crit.gamma_neg, crit.eps, crit.reduction) == (0, 4, 0.1, "mean")
+    s = SupConLoss()
+    assert (s.temperature, s.contrast_mode, s.base_temperature) == (0.07, "all", 0.07)
+    with pytest.raises(ValueError):
+        s(torch.randn(4, 8))
+
+
+def test_same_seed_gives_reference_parameter_order():
+    """Parameter creation order follows the reference, so one torch.manual_seed gives the same init."""
+    torch.manual_seed(6)
+    ours = nn.ModuleList([ResEncoderBlock(emb_s=8, head_cnt=8, dp1=0.0, dp2=0.0) for _ in range(3)])
+    names = [n for n, _ in ours.named_parameters()]
+    assert names[:10] == ["0.kqv.weight", "0.proj.weight", "0.ln1.weight", "0.ln1.bias", "0.ln2.weight", "0.ln2.bias",
+                          "0.ff.0.weight", "0.ff.0.bias", "0.ff.2.weight", "0.ff.2.bias"]
+
+
+def test_compute_dtype_switch():
+    assert mmvqa_b200.compute_dtype() in (torch.bfloat16, torch.float32)
+    with mmvqa_b200.compute_dtype_scope("fp32"):
+        assert mmvqa_b200.compute_dtype() == torch.float32
+    with pytest.raises((ValueError, KeyError)):
+        mmvqa_b200.set_compute_dtype("fp16")
