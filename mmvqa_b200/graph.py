@@ -1,0 +1,59 @@
+"""CUDA-graph capture of a whole training step (forward + loss + backward + optimizer).
+
+At the flagship VQA shape (B=16, T=28) a step is ~300 short kernels; launching them from Python
+costs more than running them, so the step is captured once and replayed (no tracing compiler: the
+graph records exactly the C-ABI launches the eager path makes)."""
+from __future__ import annotations
+
+from typing import Callable, Sequence
+
+import torch
+
+from . import _lib
+from .functional import invalidate_weight_cache
+
+
+class GraphedTrainStep:
+    """``loss_fn(*inputs) -> scalar loss`` is run as zero_grad -> forward -> backward -> optimizer.step().
+
+    ``replay(*inputs)`` copies new inputs into the static buffers (device or pinned-host sources,
+    non-blocking), replays the graph and returns the static loss tensor."""
+
+    def __init__(self, loss_fn: Callable, example_inputs: Sequence[torch.Tensor], optimizer, warmup: int = 3,
+                 post_backward: Callable = None):
+        self.loss_fn = loss_fn
+        self.optimizer = optimizer
+        self.post_backward = post_backward
+        self.static_inputs = [t.clone() for t in example_inputs]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._one()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        invalidate_weight_cache()          # weight casts must be recorded inside the graph
+        self.optimizer.zero_grad(set_to_none=True)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.static_loss = self._one(zero=False)
+        self.launches_per_step = _lib.launch_count() - n0
+        invalidate_weight_cache()
+
+    def _one(self, zero: bool = True):
+        if zero:
+            self.optimizer.zero_grad(set_to_none=True)
+        loss = self.loss_fn(*self.static_inputs)
+        loss.backward()
+        if self.post_backward is not None:
+            self.post_backward()
+        self.optimizer.step()
+        return loss.detach()
+
+    def replay(self, *inputs):
+        for dst, src in zip(self.static_inputs, inputs):
+            if src is not dst:
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.static_loss

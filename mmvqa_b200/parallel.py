@@ -1,0 +1,119 @@
+"""Batch-sharded data parallelism: one process per GPU, full weight replica, two exchanges
+per step -- a bucketed gradient all-reduce and (SupCon only) an all-gather of the [N_local, D]
+embeddings with the matching gradient reduction.  torch.distributed (NCCL over NVLink 5 / NVSwitch on the
+GPU box, gloo in the CPU tests) is the transport; the reference has no distributed code at all."""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def is_dist() -> bool:
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> None:
+    """identical init on every rank (rank-0 state wins)."""
+    if not is_dist():
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src)
+
+
+class GradBuckets:
+    """Flat fp32 gradient buckets.  After backward: ``reduce()`` packs every p.grad into its bucket (in reverse
+    parameter order, so the first bucket holds the gradients that were produced last and every earlier
+    all-reduce overlaps the packing of the next bucket), launches one async all-reduce(SUM) per bucket and
+    waits.  ``grads()`` returns per-parameter views into the buckets for FusedAdam(step(grads=...)) with
+    ``grad_scale = 1/world`` -- gradients are never copied back."""
+
+    def __init__(self, params, bucket_mb: float = 64.0, dtype: torch.dtype = torch.float32):
+        self.params = [p for p in params if p.requires_grad]
+        cap = int(bucket_mb * 1024 * 1024 / 4)
+        self.buckets: List[torch.Tensor] = []
+        self.slots = []                      # (param index, bucket index, offset, numel)
+        cur, cur_n = [], 0
+        order = list(reversed(range(len(self.params))))
+        groups = []
+        for i in order:
+            n = (self.params[i].numel() + 3) // 4 * 4          # keep 16-byte alignment of every view
+            if cur and cur_n + n > cap:
+                groups.append((cur, cur_n))
+                cur, cur_n = [], 0
+            cur.append((i, cur_n, self.params[i].numel()))
+            cur_n += n
+        if cur:
+            groups.append((cur, cur_n))
+        dev = self.params[0].device
+        for bi, (items, total) in enumerate(groups):
+            self.buckets.append(torch.zeros(total, device=dev, dtype=dtype))
+            for (i, off, n) in items:
+                self.slots.append((i, bi, off, n))
+        self._views = {}
+        for (i, bi, off, n) in self.slots:
+            self._views[i] = self.buckets[bi][off:off + n].view_as(self.params[i])
+
+    def reduce(self) -> None:
+        world = dist.get_world_size() if is_dist() else 1
+        works = []
+        per_bucket = {}
+        for (i, bi, off, n) in self.slots:
+            per_bucket.setdefault(bi, []).append(i)
+        for bi, idxs in per_bucket.items():
+            dsts = [self._views[i] for i in idxs]
+            srcs = [self.params[i].grad if self.params[i].grad is not None else torch.zeros_like(self.params[i]) for i in idxs]
+            torch._foreach_copy_(dsts, srcs)
+            if world > 1:
+                works.append(dist.all_reduce(self.buckets[bi], op=dist.ReduceOp.SUM, async_op=True))
+        for w in works:
+            w.wait()
+
+    def grads(self, plist=None) -> List[torch.Tensor]:
+        idx = {id(p): i for i, p in enumerate(self.params)}
+        plist = self.params if plist is None else plist
+        return [self._views[idx[id(p)]] for p in plist]
+
+    @property
+    def grad_scale(self) -> float:
+        return 1.0 / (dist.get_world_size() if is_dist() else 1)
+
+
+class _GatherFeatures(torch.autograd.Function):
+    """all-gather of per-rank SupCon embeddings [n_local, n_views, D] -> [n_global, n_views, D] (rank-major, which
+    keeps the reference's view-major contrast order inside SupConLoss: all view-0 rows, then all view-1 rows).
+    Backward: sum the contrast-role gradients of every rank (all-reduce) and keep the local slice."""
+
+    @staticmethod
+    def forward(ctx, feat):
+        world, rank = dist.get_world_size(), dist.get_rank()
+        outs = [torch.empty_like(feat) for _ in range(world)]
+        dist.all_gather(outs, feat.contiguous())
+        ctx.meta = (rank, feat.shape[0])
+        return torch.cat(outs, dim=0)
+
+    @staticmethod
+    def backward(ctx, dgathered):
+        rank, n = ctx.meta
+        g = dgathered.contiguous()
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)
+        return g[rank * n:(rank + 1) * n]
+
+
+def gather_supcon_features(feat: torch.Tensor) -> torch.Tensor:
+    """feat [n_local, n_views, D] -> global [world * n_local, n_views, D].  The SupCon loss of the gathered tensor
+    is the same on every rank; with DP gradient averaging (sum / world) each rank back-propagates
+    world * loss / world = the global-batch loss gradient through its local slice."""
+    if not is_dist():
+        return feat
+    return _GatherFeatures.apply(feat)
+
+
+def gather_mask_rows(mask_local_rows: torch.Tensor) -> torch.Tensor:
+    """rows of the [bsz_global, bsz_global] similarity mask owned by this rank -> full mask (no gradient)."""
+    if not is_dist():
+        return mask_local_rows
+    outs = [torch.empty_like(mask_local_rows) for _ in range(dist.get_world_size())]
+    dist.all_gather(outs, mask_local_rows.contiguous())
+    return torch.cat(outs, dim=0)

@@ -18,6 +18,7 @@ if torch.cuda.is_available():
 
 DEV = "cuda"
 ACTS = {"serf": 1, "gelu": 2, "relu": 3, "none": 0}
+DTS = [pytest.param(torch.float32, id="fp32"), pytest.param(torch.bfloat16, id="bf16")]
 
 
 def rnd(*shape, scale=1.0, seed=0):
@@ -38,7 +39,7 @@ def oracle_act(name, x):
 
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("act", ["serf", "gelu", "relu"])
-@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dt", DTS)
 @pytest.mark.parametrize("shape", [(7, 768), (5, 13)])
 def test_bias_act(act, dt, shape):
     x = rnd(*shape, scale=3.0, seed=1)
@@ -68,7 +69,7 @@ def test_serf_known_answers_fp32():
     assert torch.isfinite(ops.bias_act_fwd(torch.tensor([-100.0], device=DEV), None, ACT_SERF)).all()
 
 
-@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dt", DTS)
 def test_colsum_cast_dropout(dt):
     x = rnd(333, 70, seed=4).to(dt)
     s = ops.colsum(x.to(DEV), 333, 70)
@@ -91,7 +92,7 @@ def test_colsum_cast_dropout(dt):
     close(z, torch.full((100,), 3.0), 0, 0)
 
 
-@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dt", DTS)
 @pytest.mark.parametrize("cols,eps", [(768, 1e-5), (768, 1e-12), (64, 1e-5), (36, 1e-12), (1500, 1e-5)])
 def test_layernorm(dt, cols, eps):
     rows = 37
@@ -144,7 +145,7 @@ GEMM_SHAPES = [(448, 768, 768), (448, 3072, 768), (130, 200, 96), (3584, 288, 96
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
 @pytest.mark.parametrize("a_trans,b_trans", [(False, False), (False, True), (True, True), (True, False)])
-@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dt", DTS)
 def test_gemm_store(dt, M, N, K, a_trans, b_trans):
     if dt == torch.bfloat16 and ((a_trans and M % 8) or (b_trans and N % 8) or K % 8):
         pytest.skip("TMA needs 16-byte row strides")
@@ -158,7 +159,7 @@ def test_gemm_store(dt, M, N, K, a_trans, b_trans):
         close(C, ref + bias.cpu(), **tol, msg=f"gemm {dt} {cdt} {a_trans}{b_trans}")
 
 
-@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dt", DTS)
 def test_gemm_bf16_inputs_exact_small_ints(dt):
     # integer-valued operands: every product and partial sum is exact in fp32 -> results must be bit-exact,
     # which pins the swizzle / descriptor / k-advance arithmetic of the tensor-core path
@@ -175,7 +176,7 @@ def test_gemm_bf16_inputs_exact_small_ints(dt):
         assert torch.equal(C.cpu(), ref), f"{dt} {(M, N, K, at, bt)} max err {(C.cpu() - ref).abs().max()}"
 
 
-@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dt", DTS)
 @pytest.mark.parametrize("act", ["serf", "gelu", "relu"])
 def test_gemm_epilogues(dt, act):
     M, N, K = 200, 264, 136
@@ -210,7 +211,7 @@ def test_gemm_epilogues(dt, act):
     close(C, ref * dact, **tol, msg="dact")
 
 
-@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dt", DTS)
 def test_gemm_splitk_accumulate_and_batch(dt):
     M, N, K = 136, 72, 1000
     A, lda, B, ldb, ref = _gemm_case(dt, M, N, K, True, True, seed=30)
@@ -234,7 +235,7 @@ def test_gemm_splitk_accumulate_and_batch(dt):
     close(C, ref, 1e-2 if dt == torch.bfloat16 else 1e-4, 1e-1 if dt == torch.bfloat16 else 1e-3, msg="batched store")
 
 
-@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dt", DTS)
 @pytest.mark.parametrize("act", ["serf", "relu"])
 def test_gemm_projector_epilogues(dt, act):
     # visual-token pooling: v[b, m] = mean_n act(W f_b)[m, n]  with f stored [C, HW] (MN-major B operand)
@@ -284,7 +285,7 @@ def _mask(B, T, seed):
     return m
 
 
-@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dt", DTS)
 @pytest.mark.parametrize("B,T,heads,d", [(3, 28, 8, 96), (2, 75, 8, 96), (2, 128, 2, 64), (2, 10, 8, 8), (1, 1, 1, 4)])
 def test_rf_attention(dt, B, T, heads, d):
     H = heads * d
@@ -317,7 +318,7 @@ def test_rf_attention(dt, B, T, heads, d):
     close(sc2.permute(0, 2, 3, 1), s2, 1e-5, 1e-4, msg="scores (no prev)")
 
 
-@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dt", DTS)
 @pytest.mark.parametrize("B,T,heads,d", [(3, 28, 12, 64), (2, 75, 12, 64), (2, 9, 4, 16)])
 def test_mhsa_attention(dt, B, T, heads, d):
     H = heads * d
@@ -344,7 +345,7 @@ def test_mhsa_attention(dt, B, T, heads, d):
 # ------------------------------------------------------------------------------------------
 # fusion / pooling / losses
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dt", DTS)
 def test_embed_ln_scatter(dt):
     B, T, H, V, nvis = 3, 12, 72, 50, 5
     ids = torch.randint(0, V, (B, T), generator=torch.Generator().manual_seed(70))
@@ -372,7 +373,7 @@ def test_embed_ln_scatter(dt):
         close(got, want, 1e-4, 1e-4, msg=name)
 
 
-@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dt", DTS)
 def test_masked_mean_and_l2norm(dt):
     B, T, H = 4, 28, 768
     h = rnd(B, T, H, seed=80).to(dt)
