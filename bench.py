@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""bench.py -- VQA fine-tune samples/sec of the MMBERT fusion-encoder hot path (BASELINE.json configs[1]):
+EffNetV2-M feature maps -> 5 visual tokens -> 12-layer RealFormer (8 x 96) -> heads -> ASLSingleLabel,
+forward + backward + Adam, batch 16 per GPU, T = 28, synthetic VQA-Med-shaped inputs, random-init weights.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                      (CPU arm: the oracle port on the host cores)
+
+Prints ONE JSON line (rank 0).  `value`: whole-job samples/s with inputs resident in HBM (CUDA-graph replay,
+CUDA-event timed, max over ranks).  `e2e`: the same step through the public module API with HOST inputs, the
+host->device copies and the device->host loss read inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.nn as nn  # noqa: E402
+
+HIDDEN, LAYERS, T, NUM_CLASSES, HEADS = 768, 12, 28, 1552, 8
+EFFNET_MAPS = [(24, 112), (48, 56), (80, 28), (176, 14), (512, 7)]          # (channels, side) in token order
+# algorithmic GEMM FLOPs per sample: forward 4.631 G, train step = 3 x forward
+STEP_GFLOP_PER_SAMPLE = 13.893
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        d = json.load(open(path))
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+def make_args():
+    return types.SimpleNamespace(task="VQA", clinicalbert="", transformer_model="realformer",
+                                 cnn_encoder="tf_efficientnetv2_m", num_vis=5, hidden_size=HIDDEN, use_relu=False,
+                                 heads=HEADS, hidden_dropout_prob=0.1, n_layers=LAYERS, vocab_size=30522, dataset="VQA-Med")
+
+
+def synth_batch(B, seed):
+    """SURVEY.md section 8d synthetic inputs: post-activation-like feature maps, [CLS] 5x0 [SEP] question [SEP] pad."""
+    g = torch.Generator().manual_seed(seed)
+    feats = [torch.randn(B, c, s, s, generator=g).abs_() for c, s in EFFNET_MAPS]
+    ids = torch.zeros(B, T, dtype=torch.long)
+    seg = torch.zeros(B, T, dtype=torch.long)
+    mask = torch.zeros(B, T, dtype=torch.long)
+    for b in range(B):
+        qlen = int(torch.randint(4, T - 8 + 1, (1,), generator=g))
+        ids[b, 0], ids[b, 6] = 101, 102
+        ids[b, 7:7 + qlen] = torch.randint(1000, 30522, (qlen,), generator=g)
+        ids[b, 7 + qlen] = 102
+        seg[b, 7:8 + qlen] = 1
+        mask[b, :8 + qlen] = 1
+    target = torch.randint(0, NUM_CLASSES, (B,), generator=g)
+    return feats, ids, seg, mask, target
+
+
+def build_model(seed=0):
+    """Model(args) exactly as vqamed2019/train.py builds it (incl. the classifier[2] swap, train.py:137), with the
+    two offline stand-ins: bert-base-shaped random BertEmbeddings and no backbone (inputs are feature maps)."""
+    from transformers import BertConfig, BertModel
+    from mmvqa_b200.models import image_encoding as IE
+    from mmvqa_b200.models import mmbert as MM
+    torch.manual_seed(seed)
+    old = MM.AutoModel.from_pretrained
+    MM.AutoModel.from_pretrained = staticmethod(lambda name, *a, **k: BertModel(BertConfig(num_hidden_layers=1)))
+    IE.models_dict[5]["tf_efficientnetv2_m"][0] = lambda *a, **k: nn.Identity()
+    try:
+        model = MM.Model(make_args())
+    finally:
+        MM.AutoModel.from_pretrained = old
+    model.classifier[2] = nn.Linear(HIDDEN, NUM_CLASSES)
+    return model
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_step_fn(model_state, B):
+    from oracle import mmbert_oracle as O          # CPU baseline leg: the one place bench.py executes oracle/
+    p = {k: v.detach().clone().float().requires_grad_(v.is_floating_point()) for k, v in model_state.items()}
+    params = [v for v in p.values() if v.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-5)
+    feats, ids, seg, mask, target = synth_batch(B, 1234)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        logits = O.model_forward(feats, ids, seg, mask, p, encoder="realformer", n_layers=LAYERS, dataset="VQA-Med")
+        loss = O.asl_single_label(logits, target)
+        loss.backward()
+        opt.step()
+        return float(loss.detach())
+    return step
+
+
+def run_cpu(model_state, B, steps, warmup, budget_s=None):
+    torch.set_num_threads(os.cpu_count() or 1)
+    step = cpu_step_fn(model_state, B)
+    for _ in range(warmup):
+        step()
+    t0, n = time.perf_counter(), 0
+    while n < steps:
+        step()
+        n += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return n * B / dt, dt / n * 1e3, n
+
+
+def main_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model = build_model()
+    state = {k: v for k, v in model.state_dict().items()}
+    sps, ms, n = run_cpu(state, a.batch, a.steps, min(a.warmup, 1), budget_s=150.0)
+    cores = os.cpu_count() or 1
+    line = {"impl": "reference", "metric": "vqa_finetune_samples_per_sec", "value": sps, "unit": "samples/s", "n_gpus": a.gpus,
+            "steps": n, "warmup": min(a.warmup, 1), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(a.batch, a.gpus),
+            "cpu_baseline": {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "sample": f"{n} full steps of batch {a.batch} (torch fp32 oracle port of models/*.py, {cores} threads)"},
+            "e2e": {"value": sps, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(B, n):
+    return {"workload": "configs[1]: MMBERT EfficientNetV2-M feature maps + RealFormer-12 (8 heads x 96, hidden 768) + "
+                        "ASLSingleLabel fine-tune step (fwd+bwd+Adam), T=28, num_vis=5, 1552 answer classes",
+            "batch_per_gpu": B, "global_batch": B * n, "seq_len": T, "parallelism": f"dp{n}",
+            "scope": "hot path: feature maps -> loss -> grads -> Adam (CNN backbone is library code, out of scope)",
+            "l2": "4 rotating input batches (147 MB) and 1.3 GB of weights + Adam state are streamed every step (> 126 MB L2)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def time_kernel(fn, iters=20):
+    """Average device time of one fn() launch in ms.  [L2 flush, fn] x iters is captured in a CUDA graph and timed
+    with CUDA events on the launching stream; the same graph without fn is subtracted, so neither host launch
+    latency nor the flush is in the number and every launch starts with a cold L2 (256 MB memset) as inside the step."""
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+
+    def capture(with_fn):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(iters):
+                flush.zero_()
+                if with_fn:
+                    fn()
+        return g
+
+    def run(g):
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        e1.synchronize()
+        return e0.elapsed_time(e1)
+    g1, g0 = capture(True), capture(False)
+    t = (run(g1) - run(g0)) / iters
+    del g1, g0
+    return max(t, 1e-6)
+
+
+def main_gpu(a):
+    import torch.distributed as dist
+    import mmvqa_b200
+    from mmvqa_b200 import ops
+    from mmvqa_b200.graph import GraphedTrainStep
+    from mmvqa_b200.models.asl_singlelabel import ASLSingleLabel
+    from mmvqa_b200.optim import FusedAdam
+    from mmvqa_b200.parallel import GradBuckets, broadcast_parameters
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dt = torch.bfloat16 if a.dtype == "bf16" else torch.float32
+    mmvqa_b200.set_compute_dtype(dt)
+    B = a.batch
+    model = build_model().cuda().train()
+    if world > 1:
+        broadcast_parameters(model)
+    if not a.dropout:
+        for m in model.modules():
+            if isinstance(m, nn.Dropout):
+                m.p = 0.0
+    params = [p for p in model.parameters() if p.requires_grad]
+    nparams = sum(p.numel() for p in params)
+    opt = FusedAdam(params, lr=1e-5)
+    crit = ASLSingleLabel()
+    buckets = GradBuckets(params) if world > 1 else None
+    if buckets is not None:
+        opt.grad_scale = buckets.grad_scale
+
+    def loss_fn(f0, f1, f2, f3, f4, ids, seg, mask, target):
+        logits, _, _ = model.forward_features([f0, f1, f2, f3, f4], ids, seg, mask)
+        return crit(logits, target)
+
+    NB = 4
+    host = []
+    for i in range(NB):
+        feats, ids, seg, mask, target = synth_batch(B, 1000 * rank + i)
+        host.append([t.pin_memory() for t in (*feats, ids, seg, mask, target)])
+    dev = [[t.cuda() for t in hb] for hb in host]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+
+    def step_kwargs():
+        plist = [p for p in params if p.grad is not None]
+        return dict(grads=buckets.grads(plist))
+    gs = GraphedTrainStep(loss_fn, dev[0], opt, warmup=3, post_backward=(buckets.reduce if buckets else None),
+                          step_kwargs=(step_kwargs if buckets else None))
+    launches = gs.launches_per_step
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM ----
+    for i in range(max(a.warmup, 3)):
+        gs.replay(*dev[i % NB])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        # pad the sampled window so nvidia-smi sees the load (untimed replays), then the timed region
+        t_end = time.perf_counter() + 0.6
+        while time.perf_counter() < t_end:
+            gs.replay(*dev[0])
+        barrier()
+        e0.record()
+        for i in range(a.steps):
+            gs.replay(*dev[i % NB])
+        e1.record()
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        t_end = time.perf_counter() + 0.3
+        while time.perf_counter() < t_end:
+            gs.replay(*dev[0])
+        torch.cuda.synchronize()
+    loss_val = float(gs.static_loss)
+    if world > 1:
+        tmax = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_total = float(tmax)
+    ms_step = ms_total / a.steps
+    value = B * world / (ms_step * 1e-3)
+
+    # ---- e2e: host inputs, H2D + D2H inside the timed region, every step ----
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+    for i in range(3):
+        gs.replay(*host[i % NB])
+        loss_host.copy_(gs.static_loss, non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    e0.record()
+    for i in range(a.steps):
+        gs.replay(*host[i % NB])
+        loss_host.copy_(gs.static_loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()        # the loss is read on the host every step
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+    if world > 1:
+        tmax = torch.tensor([ms_e2e], device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_e2e = float(tmax)
+    e2e_value = B * world * a.steps / (ms_e2e * 1e-3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    hbm, tf_burst, tf_sus, which = peaks()
+    # ---- roofline of the dominant kernel, measured live (CUDA events, cold L2) ----
+    M = B * T
+    x = torch.randn(M, HIDDEN, device="cuda").to(dt)
+    w = torch.randn(4 * HIDDEN, HIDDEN, device="cuda").to(dt)
+    bias = torch.randn(4 * HIDDEN, device="cuda")
+    y = torch.empty(M, 4 * HIDDEN, device="cuda", dtype=dt)
+    pre = torch.empty_like(y)
+    from mmvqa_b200._lib import ACT_SERF, EPI_ACT
+    ms_ff1 = time_kernel(lambda: ops.gemm(M, 4 * HIDDEN, HIDDEN, x, HIDDEN, False, w, HIDDEN, False, y, 4 * HIDDEN, bias=bias,
+                                          epilogue=EPI_ACT, act=ACT_SERF, aux_out=pre, ld_aux_out=4 * HIDDEN))
+    ff1_tflops = 2.0 * M * 4 * HIDDEN * HIDDEN / (ms_ff1 * 1e-3) / 1e12
+    # Adam: 16 B read (p, m, v, g) + 12 B written (p, m, v) per parameter
+    _, table, nchunks = opt._tables[0]
+    grp = opt.param_groups[0]
+    ms_adam = time_kernel(lambda: ops.adam_step(table, nchunks, grp["lr"], grp["betas"][0], grp["betas"][1], grp["eps"],
+                                                grp["weight_decay"], 0, opt._step_dev, opt.grad_scale), iters=10)
+    adam_gbs = nparams * 28 / (ms_adam * 1e-3) / 1e9
+    adam_share = ms_adam / ms_step
+    roof = {"kernel": "adam_kernel (multi-tensor Adam, %.1f M fp32 params, 28 B/param)" % (nparams / 1e6), "bound": "hbm",
+            "achieved": adam_gbs, "peak": hbm, "unit": "GB/s", "frac": adam_gbs / hbm, "traffic": None,
+            "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)", "ms_per_launch": ms_adam, "share_of_step": adam_share,
+            "tensor_kernel": {"kernel": "gemm_tc_kernel FF1 %dx%dx%d + bias + SERF epilogue" % (M, 4 * HIDDEN, HIDDEN),
+                              "achieved": ff1_tflops, "peak": tf_burst, "unit": "TFLOP/s", "frac": ff1_tflops / tf_burst,
+                              "ms_per_launch": ms_ff1},
+            "step_tensor_frac": value / world * STEP_GFLOP_PER_SAMPLE * 1e9 / (tf_burst * 1e12)}
+    cpu = None
+    if world == 1 and not a.no_cpu:
+        state = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+        sps, ms_cpu, n = run_cpu(state, B, 1000, 1, budget_s=15.0)
+        cores = os.cpu_count() or 1
+        cpu = {"value": sps, "unit": "samples/s", "cores": cores, "kind": "port", "ms_per_step": ms_cpu,
+               "sample": f"{n} full steps of the same batch-{B} workload (torch fp32 oracle port, {cores} threads)"}
+    line = {"metric": "vqa_finetune_samples_per_sec", "value": value, "unit": "samples/s", "n_gpus": world, "steps": a.steps,
+            "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": a.dtype, "data": "synthetic", "config": config_dict(B, world),
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": launches * a.steps, "gpu_launches_per_step": launches, "clocks": clocks.summary(),
+            "roofline": roof, "cpu_baseline": cpu, "loss": loss_val, "dropout": bool(a.dropout), "params": nparams}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=16, help="samples per GPU (weak scaling)")
+    ap.add_argument("--dropout", type=int, default=1, help="1: training-mode dropout on (throughput runs), 0: off")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        main_reference(a)
+    else:
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback "
+                             "(use --impl reference for the CPU arm)")
+        main_gpu(a)

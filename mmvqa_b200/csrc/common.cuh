@@ -127,6 +127,63 @@ __device__ __forceinline__ float dact_rt(int act, float x) {
 }
 
 // ---------------------------------------------------------------------------------
+// fast activations for the bf16 tensor-core epilogues (results are rounded to bf16 or pooled
+// anyway): MUFU ex2/lg2/rcp based softplus and the Abramowitz-Stegun 7.1.26 erf
+// (|abs err| < 1.5e-7 on erf, ~1e-6 relative on the activation).  The fp32 validation path
+// keeps the accurate libdevice versions above.
+// ---------------------------------------------------------------------------------
+struct ErfPos {  // erf(z) for z >= 0 and E = exp(-z^2)
+  float erf, E;
+};
+__device__ __forceinline__ ErfPos erf_pos_fast(float z) {
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  ErfPos r;
+  r.E = __expf(-z * z);
+  r.erf = fmaf(-poly, r.E, 1.0f);
+  return r;
+}
+__device__ __forceinline__ float serf_fast(float x) {
+  const float e = __expf(-fabsf(x));
+  const float sp = fmaxf(x, 0.0f) + __logf(1.0f + e);
+  return x * erf_pos_fast(sp).erf;
+}
+__device__ __forceinline__ float dserf_fast(float x) {
+  const float e = __expf(-fabsf(x));
+  const float one_e = 1.0f + e;
+  const float sp = fmaxf(x, 0.0f) + __logf(one_e);
+  const ErfPos r = erf_pos_fast(sp);
+  const float inv = __fdividef(1.0f, one_e);
+  const float sig = x >= 0.0f ? inv : e * inv;
+  // beyond the reference's clamp (x > 50) E underflows to 0 and the slope is erf(sp) = 1, as in serf.py
+  return fmaf(x * 1.1283791670955126f * r.E, sig, r.erf);
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  const ErfPos r = erf_pos_fast(fabsf(x) * 0.7071067811865476f);
+  return 0.5f * x * (1.0f + copysignf(r.erf, x));
+}
+__device__ __forceinline__ float dgelu_fast(float x) {
+  const ErfPos r = erf_pos_fast(fabsf(x) * 0.7071067811865476f);
+  return fmaf(x * 0.3989422804014327f, r.E, 0.5f * (1.0f + copysignf(r.erf, x)));
+}
+template <int ACT> __device__ __forceinline__ float act_fast(float x) {
+  if (ACT == MMVQA_ACT_SERF) return serf_fast(x);
+  if (ACT == MMVQA_ACT_GELU) return gelu_fast(x);
+  if (ACT == MMVQA_ACT_RELU) return fmaxf(x, 0.0f);
+  return x;
+}
+template <int ACT> __device__ __forceinline__ float dact_fast(float x) {
+  if (ACT == MMVQA_ACT_SERF) return dserf_fast(x);
+  if (ACT == MMVQA_ACT_GELU) return dgelu_fast(x);
+  if (ACT == MMVQA_ACT_RELU) return x > 0.0f ? 1.0f : 0.0f;
+  return 1.0f;
+}
+
+// ---------------------------------------------------------------------------------
 // reductions
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

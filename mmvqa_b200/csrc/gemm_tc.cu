@@ -9,6 +9,7 @@
 // shared-memory descriptors, so no transposed copies of weights or activations are ever made.
 #include "gemm_common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace mmvqa {
 
@@ -96,9 +97,9 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_byte
   return d;
 }
 
-template <int BN>
+template <int BN, int STAGES_>
 struct TcCfg {
-  static constexpr int STAGES = 4;
+  static constexpr int STAGES = STAGES_;
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -107,13 +108,137 @@ struct TcCfg {
 };
 
 // ---------------------------------------------------------------------------------
+// epilogue: one thread = one accumulator row (TMEM lane); 16 columns per tcgen05.ld
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ bool al16(const void* base, int64_t elem_off, int elem_bytes) {
+  return ((reinterpret_cast<uintptr_t>(base) + (uintptr_t)(elem_off * elem_bytes)) & 15) == 0;
+}
+__device__ __forceinline__ void load16_bf16(const __nv_bfloat16* src, int nvalid, float* out) {
+  if (nvalid == 16 && al16(src, 0, 2)) {
+    Vec16<__nv_bfloat16> a, b;
+    a.load(src);
+    b.load(src + 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { out[j] = a.get(j); out[8 + j] = b.get(j); }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) out[j] = j < nvalid ? __bfloat162float(src[j]) : 0.0f;
+  }
+}
+__device__ __forceinline__ void store16_bf16(__nv_bfloat16* dst, int nvalid, const float* v) {
+  if (nvalid == 16 && al16(dst, 0, 2)) {
+    Vec16<__nv_bfloat16> a, b;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a.set(j, v[j]); b.set(j, v[8 + j]); }
+    a.store(dst);
+    b.store(dst + 8);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < nvalid) dst[j] = __float2bfloat16_rn(v[j]);
+  }
+}
+__device__ __forceinline__ void store16_f32(float* dst, int nvalid, const float* v) {
+  if (nvalid == 16 && al16(dst, 0, 4)) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (j < nvalid) dst[j] = v[j];
+  }
+}
+
+template <int EPI, int ACT, int BN>
+__device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_row, int m, int n0, int bz, bool first,
+                                            bool row_ok, bool has_acc) {
+  float rowsum = 0.0f;
+  float rscale = 0.0f;
+  if (EPI == MMVQA_EPI_DACT_SCALE && row_ok) rscale = __ldg(p.rowscale + (int64_t)bz * p.M + m) * p.scale;
+  const bool use_bias = p.bias != nullptr && first;
+  const uint32_t thr = (uint32_t)(p.dropout_p * 4294967296.0);
+  const float inv_keep = p.dropout_p > 0.0f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
+#pragma unroll 1
+  for (int c = 0; c < BN; c += 16) {
+    uint32_t r[16];
+    __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
+    tmem_ld16(tmem_row + (uint32_t)c, r);
+    tmem_ld_wait();
+    const int nb = n0 + c;
+    if (row_ok && nb < p.N) {
+      const int nvalid = min(16, p.N - nb);
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = has_acc ? __uint_as_float(r[j]) : 0.0f;
+      if (use_bias) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nvalid) v[j] += __ldg(p.bias + nb + j);
+      }
+      const int64_t coff = (int64_t)bz * p.c_batch_stride + (int64_t)m * p.ldc + nb;
+      if (EPI == MMVQA_EPI_ACT_ROWSUM) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nvalid) rowsum += act_fast<ACT>(v[j]);
+        continue;
+      }
+      if (EPI == MMVQA_EPI_ACT) {
+        if (p.aux_out) store16_bf16(reinterpret_cast<__nv_bfloat16*>(p.aux_out) + (int64_t)m * p.ld_aux_out + nb, nvalid, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = act_fast<ACT>(v[j]);
+      } else if (EPI == MMVQA_EPI_RESIDUAL) {
+        float a[16];
+        load16_bf16(reinterpret_cast<const __nv_bfloat16*>(p.aux_in) + (int64_t)m * p.ld_aux_in + nb, nvalid, a);
+        if (p.dropout_p > 0.0f) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            v[j] = hash32(p.dropout_seed, (uint64_t)m * (uint64_t)p.N + (uint64_t)(nb + j)) >= thr ? v[j] * inv_keep : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] += a[j];
+      } else if (EPI == MMVQA_EPI_DACT) {
+        float a[16];
+        load16_bf16(reinterpret_cast<const __nv_bfloat16*>(p.aux_in) + (int64_t)m * p.ld_aux_in + nb, nvalid, a);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] *= dact_fast<ACT>(a[j]);
+      } else if (EPI == MMVQA_EPI_DACT_SCALE) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = dact_fast<ACT>(v[j]) * rscale;
+      }
+      if (p.accumulate) {
+        float* c32 = reinterpret_cast<float*>(p.C) + coff;
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (j < nvalid) atomicAdd(c32 + j, v[j]);
+      } else if (p.c_bf16) {
+        store16_bf16(reinterpret_cast<__nv_bfloat16*>(p.C) + coff, nvalid, v);
+      } else {
+        store16_f32(reinterpret_cast<float*>(p.C) + coff, nvalid, v);
+      }
+    }
+  }
+  if (EPI == MMVQA_EPI_ACT_ROWSUM && row_ok) atomicAdd(p.rowsum_out + (int64_t)bz * p.M + m, rowsum * p.scale);
+}
+
+template <int EPI, int BN>
+__device__ __forceinline__ void tc_epilogue_act(const EpiParams& p, uint32_t tmem_row, int m, int n0, int bz, bool first,
+                                                bool row_ok, bool has_acc) {
+  switch (p.act) {
+    case MMVQA_ACT_SERF: tc_epilogue<EPI, MMVQA_ACT_SERF, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
+    case MMVQA_ACT_GELU: tc_epilogue<EPI, MMVQA_ACT_GELU, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
+    case MMVQA_ACT_RELU: tc_epilogue<EPI, MMVQA_ACT_RELU, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
+    default: tc_epilogue<EPI, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
+  }
+}
+
+// ---------------------------------------------------------------------------------
 // kernel: one 128 x BN output tile (of one batch entry / one K split) per CTA
 // ---------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, EpiParams p,
                                                              int a_batched, int b_batched) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -205,94 +330,17 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     const bool first = (ks == 0);
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    float rowsum = 0.0f;
-    const bool row_ok = m < p.M;
-    const bool skip = (nkb == 0 && ks != 0);
-#pragma unroll 1
-    for (int c = 0; c < BN; c += 16) {
-      uint32_t r[16];
-      __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
-      tmem_ld16(tmem_acc + ((uint32_t)(g * 32) << 16) + (uint32_t)c, r);
-      tmem_ld_wait();
-      const int nb = n0 + c;
-      if (row_ok && !skip && nb < p.N) {
-      float v[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = (nkb > 0) ? __uint_as_float(r[j]) : 0.0f;
-      const bool full16 = (nb + 16 <= p.N);
-      // fast path: plain / activation / residual stores of 16 contiguous, 16-byte aligned outputs
-      const int64_t off = (int64_t)bz * p.c_batch_stride + (int64_t)m * p.ldc + nb;
-      const bool c_al = full16 && !p.accumulate &&
-                        (p.c_bf16 ? ((off & 7) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0)
-                                  : ((off & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0));
-      bool done = false;
-      if (c_al && (p.epilogue == MMVQA_EPI_STORE || p.epilogue == MMVQA_EPI_ACT || p.epilogue == MMVQA_EPI_RESIDUAL ||
-                   p.epilogue == MMVQA_EPI_DACT)) {
-        const int64_t aoff_in = (int64_t)m * p.ld_aux_in + nb, aoff_out = (int64_t)m * p.ld_aux_out + nb;
-        const bool need_in = (p.epilogue == MMVQA_EPI_RESIDUAL || p.epilogue == MMVQA_EPI_DACT);
-        const bool in_al = !need_in || ((aoff_in & 7) == 0 && (reinterpret_cast<uintptr_t>(p.aux_in) & 15) == 0);
-        const bool has_out = (p.epilogue == MMVQA_EPI_ACT && p.aux_out != nullptr);
-        const bool out_al = !has_out || ((aoff_out & 7) == 0 && (reinterpret_cast<uintptr_t>(p.aux_out) & 15) == 0);
-        if (in_al && out_al) {
-          if (p.bias && first) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] += __ldg(p.bias + nb + j);
-          }
-          if (has_out) {
-            Vec16<__nv_bfloat16> o0, o1;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { o0.set(j, v[j]); o1.set(j, v[8 + j]); }
-            __nv_bfloat16* ao = reinterpret_cast<__nv_bfloat16*>(p.aux_out) + aoff_out;
-            o0.store(ao);
-            o1.store(ao + 8);
-          }
-          if (need_in) {
-            Vec16<__nv_bfloat16> i0, i1;
-            const __nv_bfloat16* ai = reinterpret_cast<const __nv_bfloat16*>(p.aux_in) + aoff_in;
-            i0.load(ai);
-            i1.load(ai + 8);
-            if (p.epilogue == MMVQA_EPI_RESIDUAL) {
-              if (p.dropout_p > 0.0f) {
-                const uint32_t thr = (uint32_t)(p.dropout_p * 4294967296.0);
-                const float inv = 1.0f / (1.0f - p.dropout_p);
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                  v[j] = hash32(p.dropout_seed, (uint64_t)m * (uint64_t)p.N + (uint64_t)(nb + j)) >= thr ? v[j] * inv : 0.0f;
-              }
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { v[j] += i0.get(j); v[8 + j] += i1.get(j); }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) { v[j] *= dact_rt(p.act, i0.get(j)); v[8 + j] *= dact_rt(p.act, i1.get(j)); }
-            }
-          } else if (p.epilogue == MMVQA_EPI_ACT) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) v[j] = act_rt(p.act, v[j]);
-          }
-          if (p.c_bf16) {
-            Vec16<__nv_bfloat16> o0, o1;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) { o0.set(j, v[j]); o1.set(j, v[8 + j]); }
-            __nv_bfloat16* co = reinterpret_cast<__nv_bfloat16*>(p.C) + off;
-            o0.store(co);
-            o1.store(co + 8);
-          } else {
-            float4* co = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.C) + off);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) co[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          done = true;
-        }
-      }
-      if (!done) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (nb + j < p.N) rowsum += epi_element<__nv_bfloat16>(p, bz, m, nb + j, v[j], first);
-      }
-      }
+    const bool row_ok = (m < p.M) && !(nkb == 0 && ks != 0);
+    const uint32_t tmem_row = tmem_acc + ((uint32_t)(g * 32) << 16);
+    const bool has_acc = nkb > 0;
+    switch (p.epilogue) {
+      case MMVQA_EPI_ACT: tc_epilogue_act<MMVQA_EPI_ACT, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
+      case MMVQA_EPI_RESIDUAL: tc_epilogue<MMVQA_EPI_RESIDUAL, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
+      case MMVQA_EPI_DACT: tc_epilogue_act<MMVQA_EPI_DACT, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
+      case MMVQA_EPI_ACT_ROWSUM: tc_epilogue_act<MMVQA_EPI_ACT_ROWSUM, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
+      case MMVQA_EPI_DACT_SCALE: tc_epilogue_act<MMVQA_EPI_DACT_SCALE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
+      default: tc_epilogue<MMVQA_EPI_STORE, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
     }
-    if (p.epilogue == MMVQA_EPI_ACT_ROWSUM && row_ok && !skip)
-      atomicAdd(p.rowsum_out + (int64_t)bz * p.M + m, rowsum * p.scale);
   }
   tc_fence_before();
   __syncthreads();
@@ -338,9 +386,9 @@ static int make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t r
   return MMVQA_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, int STAGES>
 static int launch_tc(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, STAGES>;
   CUtensorMap tmA, tmB;
   int rc;
   // A: K-major stored [M, K] -> inner K, box 64 x 128;  MN-major stored [K, M] -> inner M, box 64 x 64
@@ -350,7 +398,7 @@ static int launch_tc(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t
   if (B_MN) rc = make_map(&tmB, a->B, a->N, a->K, a->ldb, a->batch, a->b_batch_rows, 64, 64, "B");
   else rc = make_map(&tmB, a->B, a->K, a->N, a->ldb, a->batch, a->b_batch_rows, 64, BN, "B");
   if (rc) return rc;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
     MMVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
@@ -364,37 +412,61 @@ static int launch_tc(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t
   return MMVQA_OK;
 }
 
-template <int BN>
+template <int BN, int STAGES>
 static int launch_tc_major(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st) {
-  if (a->a_trans && a->b_trans) return launch_tc<BN, true, true>(a, ep, st);
-  if (a->a_trans) return launch_tc<BN, true, false>(a, ep, st);
-  if (a->b_trans) return launch_tc<BN, false, true>(a, ep, st);
-  return launch_tc<BN, false, false>(a, ep, st);
+  if (a->a_trans && a->b_trans) return launch_tc<BN, true, true, STAGES>(a, ep, st);
+  if (a->a_trans) return launch_tc<BN, true, false, STAGES>(a, ep, st);
+  if (a->b_trans) return launch_tc<BN, false, true, STAGES>(a, ep, st);
+  return launch_tc<BN, false, false, STAGES>(a, ep, st);
+}
+
+template <int STAGES>
+static int launch_tc_bn(int bn, const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st) {
+  switch (bn) {
+    case 256: return launch_tc_major<256, STAGES>(a, ep, st);
+    case 128: return launch_tc_major<128, STAGES>(a, ep, st);
+    case 64: return launch_tc_major<64, STAGES>(a, ep, st);
+    default:
+      if (a->a_trans) return launch_tc<32, true, false, STAGES>(a, ep, st);
+      return launch_tc<32, false, false, STAGES>(a, ep, st);
+  }
+}
+
+static int env_int(const char* name) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : 0;
 }
 
 int gemm_tc_bf16(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st) {
-  // tile width: the widest BN that still gives the chip a full wave of CTAs (two for BN = 256);
-  // MN-major B needs BN % 64 == 0.
+  // Tile width: the widest BN that still gives the chip a full wave of CTAs (two for BN = 256).  Epilogues that
+  // evaluate an activation per element are bound by the epilogue warps, not the MMA: they take BN <= 128 and a
+  // 2-stage ring when the K loop is short, so that 3 CTAs (12 epilogue warps) share an SM.
+  // MN-major B needs BN % 64 == 0.  MMVQA_TC_BN / MMVQA_TC_STAGES override the choice (tuning only).
   const int sms = num_sms();
   const int64_t mt = (a->M + TC_BM - 1) / TC_BM;
   const int64_t z = (int64_t)a->batch * a->split_k;
+  const bool heavy = (a->act != MMVQA_ACT_NONE && a->act != MMVQA_ACT_RELU) &&
+                     (a->epilogue == MMVQA_EPI_ACT || a->epilogue == MMVQA_EPI_ACT_ROWSUM ||
+                      a->epilogue == MMVQA_EPI_DACT_SCALE || a->epilogue == MMVQA_EPI_DACT);
   const int cand[4] = {256, 128, 64, 32};
   const int ncand = a->b_trans ? 3 : 4;
   int bn = cand[ncand - 1];
-  for (int i = 0; i < ncand; ++i) {
+  for (int i = heavy ? 1 : 0; i < ncand; ++i) {
     const int b = cand[i];
     if (b > 32 && b / 2 >= a->N) continue;  // tile wider than twice the problem
     const int64_t ctas = mt * ((a->N + b - 1) / b) * z;
     if (ctas >= (int64_t)sms * (b == 256 ? 2 : 1)) { bn = b; break; }
   }
-  switch (bn) {
-    case 256: return launch_tc_major<256>(a, ep, st);
-    case 128: return launch_tc_major<128>(a, ep, st);
-    case 64: return launch_tc_major<64>(a, ep, st);
-    default:
-      if (a->a_trans) return launch_tc<32, true, false>(a, ep, st);
-      return launch_tc<32, false, false>(a, ep, st);
+  const int kblocks = ((a->K + TC_BK - 1) / TC_BK + a->split_k - 1) / a->split_k;
+  int stages = (kblocks <= 2) ? 2 : 4;
+  static const int env_bn = env_int("MMVQA_TC_BN"), env_st = env_int("MMVQA_TC_STAGES");
+  if (env_bn == 32 || env_bn == 64 || env_bn == 128 || env_bn == 256) {
+    bn = env_bn;
+    if (a->b_trans && bn < 64) bn = 64;
   }
+  if (env_st == 2 || env_st == 4) stages = env_st;
+  if (stages == 2) return launch_tc_bn<2>(bn, a, ep, st);
+  return launch_tc_bn<4>(bn, a, ep, st);
 }
 
 }  // namespace mmvqa

@@ -20,10 +20,11 @@ class GraphedTrainStep:
     non-blocking), replays the graph and returns the static loss tensor."""
 
     def __init__(self, loss_fn: Callable, example_inputs: Sequence[torch.Tensor], optimizer, warmup: int = 3,
-                 post_backward: Callable = None):
+                 post_backward: Callable = None, step_kwargs: Callable = None):
         self.loss_fn = loss_fn
         self.optimizer = optimizer
-        self.post_backward = post_backward
+        self.post_backward = post_backward      # e.g. GradBuckets.reduce (gradient all-reduce)
+        self.step_kwargs = step_kwargs          # e.g. lambda: dict(grads=buckets.grads(plist))
         self.static_inputs = [t.clone() for t in example_inputs]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -48,7 +49,7 @@ class GraphedTrainStep:
         loss.backward()
         if self.post_backward is not None:
             self.post_backward()
-        self.optimizer.step()
+        self.optimizer.step(**(self.step_kwargs() if self.step_kwargs is not None else {}))
         return loss.detach()
 
     def replay(self, *inputs):

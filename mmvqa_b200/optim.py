@@ -22,6 +22,7 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.grad_scale = 1.0
         self._tables = {}
+        self._keepalive = []       # pinned host tables referenced by memcpy nodes of captured graphs
         self._step_dev = None
 
     def _state_of(self, p):
@@ -51,7 +52,8 @@ class FusedAdam(torch.optim.Optimizer):
         host = torch.from_numpy(np.array(rows, dtype=_DESC).view(np.uint8).reshape(-1)).pin_memory()
         dev = torch.empty(host.numel(), dtype=torch.uint8, device=plist[0].device)
         dev.copy_(host, non_blocking=True)
-        self._tables[gi] = (key, dev, len(rows), host)
+        self._tables[gi] = (key, dev, len(rows))
+        self._keepalive.append((host, dev))
         return dev, len(rows)
 
     @torch.no_grad()
