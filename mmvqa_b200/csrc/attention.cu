@@ -19,11 +19,54 @@ struct AttnLayout {
   int q_off, k_off, v_off;
 };
 
-template <typename T>
-__device__ __forceinline__ void load_tile(float* dst, int dst_ld, const T* src, int64_t row_stride, int Tn, int d) {
-  for (int idx = threadIdx.x; idx < Tn * d; idx += blockDim.x) {
-    int t = idx / d, s = idx - t * d;
-    dst[t * dst_ld + s] = to_f(src[t * row_stride + s]);
+// Stage NT row-major [Tn, d] tiles (row strides differ) into shared memory as fp32.  VEC: 128-bit global loads,
+// every thread issues all of its loads (up to 4 per round) before the first shared-memory store, so the CTA pays
+// ONE global-memory latency for all tiles instead of one per element.
+struct TileSrc {
+  const void* src;
+  int64_t row_stride;
+  float* dst;
+  int dst_ld;
+};
+
+template <typename T, int NT>
+__device__ __forceinline__ void load_tiles(const TileSrc (&t)[NT], int Tn, int d, bool vec) {
+  if (vec) {
+    constexpr int N = Vec16<T>::N;
+    const int cpr = d / N;                // 16-byte chunks per row
+    const int per_tile = Tn * cpr;
+    const int total = NT * per_tile;
+    for (int base = threadIdx.x; base < total; base += blockDim.x * 4) {
+      Vec16<T> v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int idx = base + k * blockDim.x;
+        if (idx < total) {
+          const int ti = idx / per_tile, rem = idx - ti * per_tile;
+          const int row = rem / cpr, ch = rem - row * cpr;
+          v[k].load(reinterpret_cast<const T*>(t[ti].src) + row * t[ti].row_stride + ch * N);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int idx = base + k * blockDim.x;
+        if (idx < total) {
+          const int ti = idx / per_tile, rem = idx - ti * per_tile;
+          const int row = rem / cpr, ch = rem - row * cpr;
+          float* o = t[ti].dst + row * t[ti].dst_ld + ch * N;
+#pragma unroll
+          for (int j = 0; j < N; ++j) o[j] = v[k].get(j);
+        }
+      }
+    }
+  } else {
+    for (int ti = 0; ti < NT; ++ti) {
+      const T* src = reinterpret_cast<const T*>(t[ti].src);
+      for (int idx = threadIdx.x; idx < Tn * d; idx += blockDim.x) {
+        const int row = idx / d, c = idx - row * d;
+        t[ti].dst[row * t[ti].dst_ld + c] = to_f(src[row * t[ti].row_stride + c]);
+      }
+    }
   }
 }
 
@@ -32,7 +75,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const T* __restrict__ qkv
                                                        const float* __restrict__ prev, const float* __restrict__ mask,
                                                        T* __restrict__ out, float* __restrict__ scores,
                                                        T* __restrict__ probs, int Tn, int heads, int d, float drop_p,
-                                                       unsigned long long seed) {
+                                                       unsigned long long seed, int vec) {
   extern __shared__ float sm[];
   const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* Ks = sm;                       // [Tn][d+1]
@@ -41,9 +84,11 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const T* __restrict__ qkv
   float* Ps = Vs + Tn * d;              // [nwarp][Tn]
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const T* base = qkv + (int64_t)b * L.tok_batch + (int64_t)h * L.head_stride;
-  load_tile(Ks, d + 1, base + L.k_off, L.row_stride, Tn, d);
-  load_tile(Qs, d, base + L.q_off, L.row_stride, Tn, d);
-  load_tile(Vs, d, base + L.v_off, L.row_stride, Tn, d);
+  {
+    const TileSrc tiles[3] = {{base + L.k_off, L.row_stride, Ks, d + 1}, {base + L.q_off, L.row_stride, Qs, d},
+                              {base + L.v_off, L.row_stride, Vs, d}};
+    load_tiles<T, 3>(tiles, Tn, d, vec != 0);
+  }
   __syncthreads();
   const float sqrt_d = sqrtf((float)d);
   const int64_t sbase = ((int64_t)b * heads + h) * Tn * Tn;
@@ -62,6 +107,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const T* __restrict__ qkv
         float dot = 0.0f;
         const float* qr = Qs + i * d;
         const float* kr = Ks + j * (d + 1);
+#pragma unroll 8
         for (int s = 0; s < d; ++s) dot = fmaf(qr[s], kr[s], dot);
         float v = dot / sqrt_d;
         if (RF) {
@@ -103,6 +149,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const T* __restrict__ qkv
     for (int s = lane; s < d; s += 32) {
       float acc = 0.0f;
       const float* pw = Ps + warp * Tn;
+#pragma unroll 4
       for (int j = 0; j < Tn; ++j) acc = fmaf(pw[j], Vs[j * d + s], acc);
       out[((int64_t)b * Tn + i) * H + h * d + s] = from_f<T>(acc);
     }
@@ -115,20 +162,28 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const T* __restrict__ qkv
                                                        const float* __restrict__ scores, const T* __restrict__ probs,
                                                        const T* __restrict__ dout, const float* __restrict__ dscores_in,
                                                        T* __restrict__ dqkv, float* __restrict__ dprev, int Tn, int heads,
-                                                       int d, float drop_p, unsigned long long seed) {
+                                                       int d, float drop_p, unsigned long long seed, int vec, int resident) {
   extern __shared__ float sm[];
   const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* X = sm;                        // [Tn][d+1]  V, then K, then Q
+  float* X = sm;                        // [Tn][d+1]  V (then K, then Q when the tiles do not all fit)
   float* dO = X + Tn * (d + 1);         // [Tn][d]
   float* P = dO + Tn * d;               // [Tn][Tn]   probabilities used by dV (post-dropout for MHSA)
   float* dS = P + Tn * Tn;              // [Tn][Tn]   gradient of the pre-softmax scores
+  float* Kb = resident ? dS + Tn * Tn : X;          // resident: K and Q have their own tiles and are
+  float* Qb = resident ? Kb + Tn * (d + 1) : X;     // fetched together with V and dO (one latency)
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int H = heads * d;
   const T* base = qkv + (int64_t)b * L.tok_batch + (int64_t)h * L.head_stride;
   T* dbase = dqkv + (int64_t)b * L.tok_batch + (int64_t)h * L.head_stride;
   const int64_t sbase = ((int64_t)b * heads + h) * Tn * Tn;
-  load_tile(X, d + 1, base + L.v_off, L.row_stride, Tn, d);
-  load_tile(dO, d, dout + (int64_t)b * Tn * H + h * d, (int64_t)H, Tn, d);
+  if (resident) {
+    const TileSrc tiles[4] = {{base + L.v_off, L.row_stride, X, d + 1}, {dout + (int64_t)b * Tn * H + h * d, (int64_t)H, dO, d},
+                              {base + L.k_off, L.row_stride, Kb, d + 1}, {base + L.q_off, L.row_stride, Qb, d + 1}};
+    load_tiles<T, 4>(tiles, Tn, d, vec != 0);
+  } else {
+    const TileSrc tiles[2] = {{base + L.v_off, L.row_stride, X, d + 1}, {dout + (int64_t)b * Tn * H + h * d, (int64_t)H, dO, d}};
+    load_tiles<T, 2>(tiles, Tn, d, vec != 0);
+  }
   __syncthreads();
   const uint32_t thr = (uint32_t)(drop_p * 4294967296.0);
   const float inv_keep = drop_p > 0.0f ? 1.0f / (1.0f - drop_p) : 1.0f;
@@ -171,6 +226,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const T* __restrict__ qkv
         float acc = 0.0f;
         const float* dr = dO + i * d;
         const float* vr = X + j * (d + 1);
+#pragma unroll 8
         for (int s = 0; s < d; ++s) acc = fmaf(dr[s], vr[s], acc);
         float pd = pr[jj];
         if (!RF && drop_p > 0.0f) {
@@ -206,24 +262,30 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const T* __restrict__ qkv
     for (int i = 0; i < Tn; ++i) acc = fmaf(P[i * Tn + j], dO[i * d + s], acc);
     dbase[L.v_off + (int64_t)j * L.row_stride + s] = from_f<T>(acc);
   }
-  __syncthreads();
-  load_tile(X, d + 1, base + L.k_off, L.row_stride, Tn, d);
-  __syncthreads();
+  if (!resident) {
+    __syncthreads();
+    const TileSrc tk[1] = {{base + L.k_off, L.row_stride, X, d + 1}};
+    load_tiles<T, 1>(tk, Tn, d, vec != 0);
+    __syncthreads();
+  }
   // dQ[i][s] = sum_j dS[i][j] K[j][s] / sqrt(d)
   for (int idx = threadIdx.x; idx < Tn * d; idx += blockDim.x) {
     const int i = idx / d, s = idx - i * d;
     float acc = 0.0f;
-    for (int j = 0; j < Tn; ++j) acc = fmaf(dS[i * Tn + j], X[j * (d + 1) + s], acc);
+    for (int j = 0; j < Tn; ++j) acc = fmaf(dS[i * Tn + j], Kb[j * (d + 1) + s], acc);
     dbase[L.q_off + (int64_t)i * L.row_stride + s] = from_f<T>(acc * inv_sqrt_d);
   }
-  __syncthreads();
-  load_tile(X, d + 1, base + L.q_off, L.row_stride, Tn, d);
-  __syncthreads();
+  if (!resident) {
+    __syncthreads();
+    const TileSrc tq[1] = {{base + L.q_off, L.row_stride, X, d + 1}};
+    load_tiles<T, 1>(tq, Tn, d, vec != 0);
+    __syncthreads();
+  }
   // dK[j][s] = sum_i dS[i][j] Q[i][s] / sqrt(d)
   for (int idx = threadIdx.x; idx < Tn * d; idx += blockDim.x) {
     const int j = idx / d, s = idx - j * d;
     float acc = 0.0f;
-    for (int i = 0; i < Tn; ++i) acc = fmaf(dS[i * Tn + j], X[i * (d + 1) + s], acc);
+    for (int i = 0; i < Tn; ++i) acc = fmaf(dS[i * Tn + j], Qb[i * (d + 1) + s], acc);
     dbase[L.k_off + (int64_t)j * L.row_stride + s] = from_f<T>(acc * inv_sqrt_d);
   }
 }
@@ -242,7 +304,10 @@ static int launch_fwd(const void* qkv, const AttnLayout& L, const float* prev, c
   if (smem > 227 * 1024) return set_err(MMVQA_ERR_SMEM, "attention fwd: T=%d d=%d needs %zu bytes of shared memory", Tn, d, smem);
   auto kern = attn_fwd_kernel<T, RF>;
   if (smem > 48 * 1024) MMVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<B * heads, 256, smem, st>>>((const T*)qkv, L, prev, mask, (T*)out, scores, (T*)probs, Tn, heads, d, p, seed);
+  const int vn = 16 / (int)sizeof(T);
+  const int vec = (d % vn == 0 && L.row_stride % vn == 0 && L.head_stride % vn == 0 && L.q_off % vn == 0 && L.k_off % vn == 0 &&
+                   L.v_off % vn == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0) ? 1 : 0;
+  kern<<<B * heads, 256, smem, st>>>((const T*)qkv, L, prev, mask, (T*)out, scores, (T*)probs, Tn, heads, d, p, seed, vec);
   MMVQA_LAUNCHED("attn_fwd");
   return MMVQA_OK;
 }
@@ -252,11 +317,19 @@ static int launch_bwd(const void* qkv, const AttnLayout& L, const float* scores,
                       const float* dscores_in, void* dqkv, float* dprev, int B, int Tn, int heads, int d, float p,
                       uint64_t seed, cudaStream_t st) {
   size_t smem = sizeof(float) * ((size_t)Tn * (d + 1) + (size_t)Tn * d + 2 * (size_t)Tn * Tn);
+  const size_t smem_res = smem + sizeof(float) * 2 * (size_t)Tn * (d + 1);
+  const int resident = smem_res <= 100 * 1024 ? 1 : 0;   // K and Q tiles too when two CTAs still share an SM
+  if (resident) smem = smem_res;
   if (smem > 227 * 1024) return set_err(MMVQA_ERR_SMEM, "attention bwd: T=%d d=%d needs %zu bytes of shared memory", Tn, d, smem);
   auto kern = attn_bwd_kernel<T, RF>;
   if (smem > 48 * 1024) MMVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int vn = 16 / (int)sizeof(T);
+  const int H = heads * d;
+  const int vec = (d % vn == 0 && L.row_stride % vn == 0 && L.head_stride % vn == 0 && L.q_off % vn == 0 && L.k_off % vn == 0 &&
+                   L.v_off % vn == 0 && H % vn == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(dout) & 15) == 0) ? 1 : 0;
   kern<<<B * heads, 256, smem, st>>>((const T*)qkv, L, scores, (const T*)probs, (const T*)dout, dscores_in, (T*)dqkv, dprev,
-                                     Tn, heads, d, p, seed);
+                                     Tn, heads, d, p, seed, vec, resident);
   MMVQA_LAUNCHED("attn_bwd");
   return MMVQA_OK;
 }

@@ -99,7 +99,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, in
     float t = 0.0f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) t += red[j][tx];
-    atomicAdd(out + c, t);
+    if (gridDim.y == 1) out[c] = t;     // single row split: plain store, no zero-fill needed
+    else atomicAdd(out + c, t);
   }
 }
 
@@ -451,13 +452,16 @@ int mmvqa_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int cols,
   MMVQA_REQUIRE(out && (x || rows == 0), "colsum: null pointer");
   MMVQA_REQUIRE(cols > 0 && ldx >= cols, "colsum: bad cols/ld");
   cudaStream_t st = as_stream(stream);
-  MMVQA_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)cols, st));
-  if (rows <= 0) return MMVQA_OK;
+  if (rows <= 0) {
+    MMVQA_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)cols, st));
+    return MMVQA_OK;
+  }
   int gx = (cols + 31) / 32;
   int64_t want = ((int64_t)num_sms() * 4 + gx - 1) / gx;  // row splits to fill the chip
   int64_t rpb = (rows + want - 1) / want;
-  if (rpb < 64) rpb = 64;
+  if (rpb < 512) rpb = 512;
   int gy = (int)((rows + rpb - 1) / rpb);
+  if (gy > 1) MMVQA_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)cols, st));
   dim3 grid(gx, gy);
   if (dtype == MMVQA_F32)
     colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ldx, out, rows, cols, rpb);

@@ -36,16 +36,22 @@ def _round_up(x: int, m: int) -> int:
 class WeightCache:
     """Casts parameters to the compute dtype once per parameter version.
 
-    The key is the parameter identity; an entry is valid while every source parameter keeps its
-    ``_version`` and storage.  ``torch.optim`` steps and ``load_state_dict`` bump the version, the
-    fused Adam (mmvqa_b200.optim) refreshes the bf16 copy itself and re-validates the entry."""
+    The key is the parameter identity; an entry is valid while every source parameter keeps its ``_version`` and
+    storage and no optimizer that bypasses torch's version counters has stepped since (``epoch``).
+    ``torch.optim`` steps and ``load_state_dict`` bump the version; the fused Adam (mmvqa_b200.optim) writes the
+    bf16 copies itself in its update kernel and re-validates exactly the entries it refreshed."""
 
     def __init__(self):
         self._entries = {}
+        self.epoch = 0
+        self.generation = 0          # bumps whenever a buffer is (re)allocated or the cache is cleared
+
+    def _sig(self, params):
+        return (self.epoch, tuple((p._version, p.data_ptr()) for p in params))
 
     def get(self, params: Sequence[Tensor], dtype: torch.dtype) -> Tensor:
         key = (tuple(id(p) for p in params), dtype)
-        sig = tuple((p._version, p.data_ptr()) for p in params)
+        sig = self._sig(params)
         ent = self._entries.get(key)
         if ent is not None and ent[0] == sig:
             return ent[1]
@@ -55,28 +61,49 @@ class WeightCache:
                 out = flat[0]
             else:
                 rows = sum(f.shape[0] for f in flat)
-                out = ent[1] if ent is not None and ent[1].shape == (rows, flat[0].shape[1]) else torch.empty(
-                    rows, flat[0].shape[1], device=flat[0].device, dtype=dtype)
+                if ent is not None and ent[1].shape == (rows, flat[0].shape[1]):
+                    out = ent[1]
+                else:
+                    out = torch.empty(rows, flat[0].shape[1], device=flat[0].device, dtype=dtype)
+                    self.generation += 1
                 r = 0
                 for f in flat:
                     ops.cast(f.contiguous(), dtype, out=out[r:r + f.shape[0]])
                     r += f.shape[0]
-        self._entries[key] = (sig, out, [p for p in params])
+        self._entries[key] = (sig, out, list(params))
         return out
 
-    def bf16_target(self, p: Tensor) -> Optional[Tensor]:
-        """bf16 copy of a single parameter if one is cached (for the fused Adam to overwrite)."""
-        ent = self._entries.get(((id(p),), torch.bfloat16))
-        return None if ent is None else ent[1]
+    def bf16_view(self, p: Tensor) -> Optional[Tensor]:
+        """The bf16 copy of `p` inside the cache (a row slice of a concatenated entry if need be), or None.
+        Returns None as well if `p` appears in more than one bf16 entry (then the version check recasts)."""
+        found = None
+        for (ids, dtype), (_, out, params) in self._entries.items():
+            if dtype != torch.bfloat16 or id(p) not in ids:
+                continue
+            r = 0
+            for q in params:
+                if q is p:
+                    if found is not None:
+                        return None
+                    found = out[r:r + q.shape[0]]
+                r += q.shape[0]
+        return found
 
-    def revalidate(self, p: Tensor) -> None:
-        key = ((id(p),), torch.bfloat16)
-        ent = self._entries.get(key)
-        if ent is not None:
-            self._entries[key] = (((p._version, p.data_ptr()),), ent[1], ent[2])
+    def note_optimizer_step(self, refreshed_ids) -> None:
+        """An optimizer updated parameters behind torch's back: entries whose parameters were all refreshed in
+        the same kernel stay valid, every other entry is recast on next use."""
+        self.epoch += 1
+        for key, (sig, out, params) in list(self._entries.items()):
+            if key[1] == torch.bfloat16 and all(id(q) in refreshed_ids for q in params):
+                self._entries[key] = (self._sig(params), out, params)
+
+    def covered_by(self, refreshed_ids) -> bool:
+        return all(all(id(q) in refreshed_ids for q in params) for (ids, dtype), (_, _, params) in self._entries.items()
+                   if not (dtype == torch.float32 and len(params) == 1))
 
     def clear(self) -> None:
         self._entries.clear()
+        self.generation += 1
 
 
 weight_cache = WeightCache()
@@ -117,14 +144,14 @@ def gemm_dgrad(dy: Tensor, ld_dy: int, M: int, N: int, w: Tensor, K: int, *, epi
     return dx
 
 
-def gemm_wgrad(dy: Tensor, ld_dy: int, M: int, N: int, x: Tensor, ld_x: int, K: int) -> Tensor:
+def gemm_wgrad(dy: Tensor, ld_dy: int, M: int, N: int, x: Tensor, ld_x: int, K: int, zeroed: Optional[Tensor] = None) -> Tensor:
     """dW[N,K] (fp32) = dy[M,N]^T . x[M,K]   (both operands read MN-major); split-K when the output has
-    too few tiles to fill the chip."""
+    too few tiles to fill the chip.  `zeroed`: an already zero-filled [N,K] fp32 buffer to accumulate into."""
     tile = 128 if dy.dtype == torch.bfloat16 else 64
     tiles = ((N + tile - 1) // tile) * ((K + tile - 1) // tile)
     sk = _split_k_for(tiles, M, dy.device, 64 if dy.dtype == torch.bfloat16 else 16)
     if sk > 1:
-        dw = torch.zeros(N, K, device=dy.device, dtype=torch.float32)
+        dw = zeroed if zeroed is not None else torch.zeros(N, K, device=dy.device, dtype=torch.float32)
         ops.gemm(N, K, M, dy, ld_dy, True, x, ld_x, True, dw, K, accumulate=True, split_k=sk)
     else:
         dw = torch.empty(N, K, device=dy.device, dtype=torch.float32)
@@ -558,6 +585,9 @@ class RealFormerEncoderFn(torch.autograd.Function):
                 dx = dx.to(dt)
         ds = None if dscores is None else dscores.contiguous().float()
         grads: List[Optional[Tensor]] = [None] * len(params)
+        # one zero-filled workspace for everything that is accumulated with atomics (LN gamma/beta, split-K kqv dW)
+        per_layer = 4 * H + 3 * d * d
+        zws = torch.zeros(n_layers * per_layer, device=saved[0].device, dtype=torch.float32)
         for l in reversed(range(n_layers)):
             xin, kqv, scores, attn, y1, mean1, rstd1, x1, hpre, hact, y2, mean2, rstd2 = saved[l * nsave:(l + 1) * nsave]
             kqv_w, proj_w, g1, b1, w0, bb0, w2, bb2, g2, b2 = params[l * RF_PARAMS_PER_LAYER:(l + 1) * RF_PARAMS_PER_LAYER]
@@ -566,8 +596,8 @@ class RealFormerEncoderFn(torch.autograd.Function):
             wf0 = weight_cache.get((w0,), dt)
             wf2 = weight_cache.get((w2,), dt)
             F4 = wf0.shape[0]
-            dg2 = torch.zeros(H, device=dx.device, dtype=torch.float32)
-            db2 = torch.zeros(H, device=dx.device, dtype=torch.float32)
+            zl = zws[l * per_layer:(l + 1) * per_layer]
+            dg2, db2, dg1, db1 = zl[0:H], zl[H:2 * H], zl[2 * H:3 * H], zl[3 * H:4 * H]
             dy2 = ops.layernorm_bwd(dx, y2, g2.detach(), mean2, rstd2, None, dg2, db2)
             dff = ops.dropout(dy2, p2, seed + 2 * l + 1) if p2 > 0.0 else dy2
             dbb2 = ops.colsum(dff, M, H)
@@ -576,15 +606,13 @@ class RealFormerEncoderFn(torch.autograd.Function):
             dbb0 = ops.colsum(dhpre, M, F4)
             dw0 = gemm_wgrad(dhpre, F4, M, F4, x1, H, H)
             dx1 = gemm_dgrad(dhpre, F4, M, F4, wf0, H, epilogue=EPI_RESIDUAL, aux_in=dy2)
-            dg1 = torch.zeros(H, device=dx.device, dtype=torch.float32)
-            db1 = torch.zeros(H, device=dx.device, dtype=torch.float32)
             dy1 = ops.layernorm_bwd(dx1, y1, g1.detach(), mean1, rstd1, None, dg1, db1)
             dpr = ops.dropout(dy1, p1, seed + 2 * l) if p1 > 0.0 else dy1
             dwp = gemm_wgrad(dpr, H, M, H, attn, H, H)
             dattn = gemm_dgrad(dpr, H, M, H, wp, H)
             want_dprev = (l > 0) or (has_prev and ctx.needs_input_grad[2])
             dkqv, dprev = ops.rf_attn_bwd(kqv, scores, dattn, ds, want_dprev, B, T, heads, d)
-            dwk = gemm_wgrad(dkqv, 3 * d, M * heads, 3 * d, xin, d, d)
+            dwk = gemm_wgrad(dkqv, 3 * d, M * heads, 3 * d, xin, d, d, zeroed=zl[4 * H:].view(3 * d, d))
             # dx_in = dkqv . Wkqv (per head) + dy1 (residual around the attention block)
             dxin = torch.empty(M, H, device=dx.device, dtype=dt)
             ops.gemm(M * heads, d, 3 * d, dkqv, 3 * d, False, wk, d, True, dxin, d, epilogue=EPI_RESIDUAL, aux_in=dy1,

@@ -33,14 +33,18 @@ class GraphedTrainStep:
                 self._one()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        invalidate_weight_cache()          # weight casts must be recorded inside the graph
+        covers = getattr(self.optimizer, "covers_weight_cache", None)
+        self.casts_in_graph = not (covers is not None and covers())
+        if self.casts_in_graph:
+            invalidate_weight_cache()      # weight casts must be recorded inside the graph
         self.optimizer.zero_grad(set_to_none=True)
         self.graph = torch.cuda.CUDAGraph()
         n0 = _lib.launch_count()
         with torch.cuda.graph(self.graph):
             self.static_loss = self._one(zero=False)
         self.launches_per_step = _lib.launch_count() - n0
-        invalidate_weight_cache()
+        if self.casts_in_graph:
+            invalidate_weight_cache()
 
     def _one(self, zero: bool = True):
         if zero:

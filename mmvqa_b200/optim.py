@@ -7,6 +7,7 @@ import numpy as np
 import torch
 
 from . import ops
+from .functional import weight_cache
 
 CHUNK = 32768
 _DESC = np.dtype([("p", "<u8"), ("m", "<u8"), ("v", "<u8"), ("g", "<u8"), ("bf16_out", "<u8"), ("n", "<i8")])
@@ -23,6 +24,7 @@ class FusedAdam(torch.optim.Optimizer):
         self.grad_scale = 1.0
         self._tables = {}
         self._keepalive = []       # pinned host tables referenced by memcpy nodes of captured graphs
+        self._refreshed = {}       # group index -> ids of parameters whose bf16 cache copy the kernel rewrites
         self._step_dev = None
 
     def _state_of(self, p):
@@ -35,24 +37,31 @@ class FusedAdam(torch.optim.Optimizer):
 
     def _table(self, gi, group, grads):
         plist = [p for p in group["params"] if p.grad is not None]
-        key = tuple((p.data_ptr(), g.data_ptr()) for p, g in zip(plist, grads))
+        key = (weight_cache.generation, tuple((p.data_ptr(), g.data_ptr()) for p, g in zip(plist, grads)))
         ent = self._tables.get(gi)
         if ent is not None and ent[0] == key:
             return ent[1], ent[2]
         rows = []
+        refreshed = set()
         for p, g in zip(plist, grads):
             st = self._state_of(p)
+            bv = weight_cache.bf16_view(p)          # tensor-core operand copy, rewritten by the same kernel
+            bptr = 0
+            if bv is not None and bv.is_contiguous() and bv.numel() == p.numel():
+                bptr = bv.data_ptr()
+                refreshed.add(id(p))
             if p.dtype != torch.float32 or not p.is_contiguous() or not g.is_contiguous() or g.dtype != torch.float32:
                 raise RuntimeError("FusedAdam needs contiguous float32 parameters and gradients")
             n = p.numel()
             for off in range(0, n, CHUNK):
                 cnt = min(CHUNK, n - off)
                 rows.append((p.data_ptr() + 4 * off, st["exp_avg"].data_ptr() + 4 * off, st["exp_avg_sq"].data_ptr() + 4 * off,
-                             g.data_ptr() + 4 * off, 0, cnt))
+                             g.data_ptr() + 4 * off, (bptr + 2 * off) if bptr else 0, cnt))
         host = torch.from_numpy(np.array(rows, dtype=_DESC).view(np.uint8).reshape(-1)).pin_memory()
         dev = torch.empty(host.numel(), dtype=torch.uint8, device=plist[0].device)
         dev.copy_(host, non_blocking=True)
         self._tables[gi] = (key, dev, len(rows))
+        self._refreshed[gi] = refreshed
         self._keepalive.append((host, dev))
         return dev, len(rows)
 
@@ -77,7 +86,19 @@ class FusedAdam(torch.optim.Optimizer):
             b1, b2 = group["betas"]
             ops.adam_step(table, n, group["lr"], b1, b2, group["eps"], group["weight_decay"], 0, self._step_dev,
                           self.grad_scale)
+        ids = set()
+        for r in self._refreshed.values():
+            ids |= r
+        weight_cache.note_optimizer_step(ids)
         return loss
+
+    def covers_weight_cache(self) -> bool:
+        """True if every cached tensor-core operand copy is rewritten by this optimizer's kernel (then a captured
+        graph of the step needs no weight casts)."""
+        ids = set()
+        for r in self._refreshed.values():
+            ids |= r
+        return bool(self._tables) and weight_cache.covered_by(ids)
 
     def state_dict(self):
         if self._step_dev is not None:                  # publish the device step counter in torch's layout

@@ -1,0 +1,111 @@
+"""FusedAdam vs torch.optim.Adam, the tensor-core weight-cache refresh, and CUDA-graph replay == eager (GPU)."""
+import types
+
+import pytest
+import torch
+import torch.nn as nn
+
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    import mmvqa_b200
+    from mmvqa_b200 import functional as Fn
+    from mmvqa_b200._lib import launch_count
+    from mmvqa_b200.graph import GraphedTrainStep
+    from mmvqa_b200.models.realformer import ResEncoderBlock, run_blocks
+    from mmvqa_b200.optim import FusedAdam
+
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("wd", [0.0, 0.01])
+def test_fused_adam_matches_torch(wd):
+    torch.manual_seed(0)
+    shapes = [(3072, 768), (768,), (33, 7), (100001,)]
+    ref = [torch.randn(*s, device=DEV).requires_grad_(True) for s in shapes]
+    ours = [p.detach().clone().requires_grad_(True) for p in ref]
+    o_ref = torch.optim.Adam(ref, lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=wd)
+    o_ours = FusedAdam(ours, lr=1e-2, betas=(0.9, 0.99), eps=1e-8, weight_decay=wd)
+    for step in range(4):
+        for a, b in zip(ref, ours):
+            g = torch.randn_like(a)
+            a.grad, b.grad = g.clone(), g.clone()
+        o_ref.step()
+        o_ours.step()
+    for a, b in zip(ref, ours):
+        torch.testing.assert_close(b, a, rtol=2e-5, atol=2e-6)
+    sd = o_ours.state_dict()
+    assert float(sd["state"][0]["step"]) == 4.0
+    torch.testing.assert_close(sd["state"][0]["exp_avg"], o_ref.state_dict()["state"][0]["exp_avg"], rtol=1e-5, atol=1e-7)
+    o_ours.grad_scale = 0.5          # gradient averaging after an all-reduce SUM over 2 ranks
+    for a, b in zip(ref, ours):
+        g = torch.randn_like(a)
+        a.grad, b.grad = g.clone(), 2 * g
+    o_ref.step()
+    o_ours.step()
+    for a, b in zip(ref, ours):
+        torch.testing.assert_close(b, a, rtol=2e-5, atol=2e-6)
+
+
+def test_adam_refreshes_the_bf16_weight_cache():
+    with mmvqa_b200.compute_dtype_scope(torch.bfloat16):
+        Fn.invalidate_weight_cache()
+        lin = nn.Linear(64, 128).to(DEV)
+        opt = FusedAdam(lin.parameters(), lr=1e-1)
+        x = torch.randn(16, 64, device=DEV).bfloat16()
+        y = Fn.linear(x, lin.weight, lin.bias)
+        y.float().sum().backward()
+        opt.step()
+        assert opt.covers_weight_cache()
+        n0 = launch_count()
+        w = Fn.weight_cache.get((lin.weight,), torch.bfloat16)
+        assert launch_count() == n0, "the cache entry must still be valid: Adam rewrote the bf16 copy itself"
+        assert torch.equal(w, lin.weight.detach().bfloat16())
+        with torch.no_grad():
+            lin.weight.mul_(2.0)                       # any torch-side update bumps the version -> recast
+        w2 = Fn.weight_cache.get((lin.weight,), torch.bfloat16)
+        assert launch_count() == n0 + 1
+        assert torch.equal(w2, lin.weight.detach().bfloat16())
+        Fn.invalidate_weight_cache()
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_graph_replay_equals_eager(dt):
+    with mmvqa_b200.compute_dtype_scope(dt):
+        Fn.invalidate_weight_cache()
+
+        def make():
+            torch.manual_seed(3)
+            return nn.ModuleList([ResEncoderBlock(emb_s=16, head_cnt=8, dp1=0.0, dp2=0.0) for _ in range(2)]).to(DEV)
+        xs = [torch.randn(4, 12, 128, device=DEV) for _ in range(3)]
+        mask = torch.ones(4, 12, device=DEV, dtype=torch.long)
+        mask[1, 7:] = 0
+
+        def run(graph):
+            blocks = make()
+            opt = FusedAdam(blocks.parameters(), lr=1e-3)
+
+            def loss_fn(x):
+                h, _ = run_blocks(list(blocks), x, None, mask, False)
+                return h.float().pow(2).mean()
+            losses = []
+            if graph:
+                gs = GraphedTrainStep(loss_fn, [xs[0]], opt, warmup=0)
+                for x in xs:
+                    losses.append(float(gs.replay(x)))
+            else:
+                for x in xs:
+                    opt.zero_grad(set_to_none=True)
+                    loss = loss_fn(x)
+                    loss.backward()
+                    opt.step()
+                    losses.append(float(loss))
+            return losses, [p.detach().clone() for p in blocks.parameters()]
+        le, pe = run(False)
+        lg, pg = run(True)
+        tol = 1e-5 if dt == torch.float32 else 2e-2
+        for a, b in zip(le, lg):
+            assert abs(a - b) <= tol * max(1.0, abs(a)), (le, lg)
+        for a, b in zip(pe, pg):
+            torch.testing.assert_close(b, a, rtol=1e-3, atol=1e-4 if dt == torch.float32 else 3e-3)
+        Fn.invalidate_weight_cache()
