@@ -237,6 +237,10 @@ def main_gpu(a):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+
+    def log(msg):
+        if a.verbose:
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dt = torch.bfloat16 if a.dtype == "bf16" else torch.float32
@@ -272,8 +276,11 @@ def main_gpu(a):
     def step_kwargs():
         plist = [p for p in params if p.grad is not None]
         return dict(grads=buckets.grads(plist))
-    gs = GraphedTrainStep(loss_fn, dev[0], opt, warmup=3, post_backward=(buckets.reduce if buckets else None),
+    log("building the graphed step")
+    gs = GraphedTrainStep(loss_fn, dev[0], opt, warmup=3, post_backward=(buckets.pack if buckets else None),
+                          eager_between=(buckets.allreduce if buckets else None),
                           step_kwargs=(step_kwargs if buckets else None))
+    log("graph captured: %d launches per step" % gs.launches_per_step)
     launches = gs.launches_per_step
 
     def barrier():
@@ -281,15 +288,16 @@ def main_gpu(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    log("timing value")
     # ---- value: inputs resident in HBM ----
     for i in range(max(a.warmup, 3)):
         gs.replay(*dev[i % NB])
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
-        # pad the sampled window so nvidia-smi sees the load (untimed replays), then the timed region
-        t_end = time.perf_counter() + 0.6
-        while time.perf_counter() < t_end:
+        # pad the sampled window so nvidia-smi sees the load (untimed replays; the SAME count on every rank, the
+        # step contains a collective), then the timed region
+        for _ in range(a.pad_steps):
             gs.replay(*dev[0])
         barrier()
         e0.record()
@@ -298,8 +306,7 @@ def main_gpu(a):
         e1.record()
         barrier()
         ms_total = e0.elapsed_time(e1)
-        t_end = time.perf_counter() + 0.3
-        while time.perf_counter() < t_end:
+        for _ in range(a.pad_steps // 2):
             gs.replay(*dev[0])
         torch.cuda.synchronize()
     loss_val = float(gs.static_loss)
@@ -310,6 +317,7 @@ def main_gpu(a):
     ms_step = ms_total / a.steps
     value = B * world / (ms_step * 1e-3)
 
+    log("timing e2e")
     # ---- e2e: host inputs, H2D + D2H inside the timed region, every step ----
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     for i in range(3):
@@ -331,8 +339,10 @@ def main_gpu(a):
         ms_e2e = float(tmax)
     e2e_value = B * world * a.steps / (ms_e2e * 1e-3)
 
+    log("timed regions done")
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
     hbm, tf_burst, tf_sus, which = peaks()
@@ -377,6 +387,7 @@ def main_gpu(a):
             "roofline": roof, "cpu_baseline": cpu, "loss": loss_val, "dropout": bool(a.dropout), "params": nparams}
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -390,6 +401,8 @@ if __name__ == "__main__":
     ap.add_argument("--batch", type=int, default=16, help="samples per GPU (weak scaling)")
     ap.add_argument("--dropout", type=int, default=1, help="1: training-mode dropout on (throughput runs), 0: off")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--verbose", action="store_true", help="progress lines on stderr")
+    ap.add_argument("--pad-steps", type=int, default=100, help="untimed steps around the timed region (clock sampling)")
     a = ap.parse_args()
     if a.impl == "reference":
         main_reference(a)

@@ -14,23 +14,31 @@ from .functional import invalidate_weight_cache
 
 
 class GraphedTrainStep:
-    """``loss_fn(*inputs) -> scalar loss`` is run as zero_grad -> forward -> backward -> optimizer.step().
+    """``loss_fn(*inputs) -> scalar loss`` is run as zero_grad -> forward -> backward -> [post_backward] ->
+    [eager_between] -> optimizer.step().
 
-    ``replay(*inputs)`` copies new inputs into the static buffers (device or pinned-host sources,
-    non-blocking), replays the graph and returns the static loss tensor."""
+    Without ``eager_between`` the whole step is ONE graph.  With it (data parallel: the NCCL gradient all-reduce)
+    the step is two graphs -- forward/backward/bucket-packing and the optimizer -- with the collective launched
+    eagerly between the two replays, so no NCCL kernel is ever recorded into a graph.
+    ``replay(*inputs)`` copies new inputs into the static buffers (device or pinned-host sources, non-blocking),
+    replays and returns the static loss tensor."""
 
     def __init__(self, loss_fn: Callable, example_inputs: Sequence[torch.Tensor], optimizer, warmup: int = 3,
-                 post_backward: Callable = None, step_kwargs: Callable = None):
+                 post_backward: Callable = None, eager_between: Callable = None, step_kwargs: Callable = None):
         self.loss_fn = loss_fn
         self.optimizer = optimizer
-        self.post_backward = post_backward      # e.g. GradBuckets.reduce (gradient all-reduce)
+        self.post_backward = post_backward      # capturable, e.g. GradBuckets.pack
+        self.eager_between = eager_between      # not captured, e.g. GradBuckets.allreduce
         self.step_kwargs = step_kwargs          # e.g. lambda: dict(grads=buckets.grads(plist))
         self.static_inputs = [t.clone() for t in example_inputs]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(warmup):
-                self._one()
+                self._fwd_bwd()
+                if self.eager_between is not None:
+                    self.eager_between()
+                self._opt()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         covers = getattr(self.optimizer, "covers_weight_cache", None)
@@ -39,26 +47,41 @@ class GraphedTrainStep:
             invalidate_weight_cache()      # weight casts must be recorded inside the graph
         self.optimizer.zero_grad(set_to_none=True)
         self.graph = torch.cuda.CUDAGraph()
+        self.graph_opt = None
         n0 = _lib.launch_count()
-        with torch.cuda.graph(self.graph):
-            self.static_loss = self._one(zero=False)
+        if self.eager_between is None:
+            with torch.cuda.graph(self.graph):
+                self.static_loss = self._fwd_bwd(zero=False)
+                self._opt()
+        else:
+            with torch.cuda.graph(self.graph):
+                self.static_loss = self._fwd_bwd(zero=False)
+            self.eager_between()
+            self.graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph_opt, pool=self.graph.pool()):
+                self._opt()
         self.launches_per_step = _lib.launch_count() - n0
         if self.casts_in_graph:
             invalidate_weight_cache()
 
-    def _one(self, zero: bool = True):
+    def _fwd_bwd(self, zero: bool = True):
         if zero:
             self.optimizer.zero_grad(set_to_none=True)
         loss = self.loss_fn(*self.static_inputs)
         loss.backward()
         if self.post_backward is not None:
             self.post_backward()
-        self.optimizer.step(**(self.step_kwargs() if self.step_kwargs is not None else {}))
         return loss.detach()
+
+    def _opt(self):
+        self.optimizer.step(**(self.step_kwargs() if self.step_kwargs is not None else {}))
 
     def replay(self, *inputs):
         for dst, src in zip(self.static_inputs, inputs):
             if src is not dst:
                 dst.copy_(src, non_blocking=True)
         self.graph.replay()
+        if self.graph_opt is not None:
+            self.eager_between()
+            self.graph_opt.replay()
         return self.static_loss

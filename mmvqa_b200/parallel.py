@@ -55,9 +55,8 @@ class GradBuckets:
         for (i, bi, off, n) in self.slots:
             self._views[i] = self.buckets[bi][off:off + n].view_as(self.params[i])
 
-    def reduce(self) -> None:
-        world = dist.get_world_size() if is_dist() else 1
-        works = []
+    def pack(self) -> None:
+        """copy every p.grad into its bucket slot (pure device copies: CUDA-graph capturable)."""
         per_bucket = {}
         for (i, bi, off, n) in self.slots:
             per_bucket.setdefault(bi, []).append(i)
@@ -65,10 +64,18 @@ class GradBuckets:
             dsts = [self._views[i] for i in idxs]
             srcs = [self.params[i].grad if self.params[i].grad is not None else torch.zeros_like(self.params[i]) for i in idxs]
             torch._foreach_copy_(dsts, srcs)
-            if world > 1:
-                works.append(dist.all_reduce(self.buckets[bi], op=dist.ReduceOp.SUM, async_op=True))
+
+    def allreduce(self) -> None:
+        """one async all-reduce(SUM) per bucket, then wait (NCCL over NVLink on the GPU box, gloo in CPU tests)."""
+        if not is_dist():
+            return
+        works = [dist.all_reduce(b, op=dist.ReduceOp.SUM, async_op=True) for b in self.buckets]
         for w in works:
             w.wait()
+
+    def reduce(self) -> None:
+        self.pack()
+        self.allreduce()
 
     def grads(self, plist=None) -> List[torch.Tensor]:
         idx = {id(p): i for i, p in enumerate(self.params)}

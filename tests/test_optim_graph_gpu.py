@@ -103,7 +103,7 @@ def test_graph_replay_equals_eager(dt):
             return losses, [p.detach().clone() for p in blocks.parameters()]
         le, pe = run(False)
         lg, pg = run(True)
-        tol = 1e-5 if dt == torch.float32 else 2e-2
+        tol = 1e-4 if dt == torch.float32 else 2e-2   # atomics (split-K, LN gamma/beta) reorder fp32 sums
         for a, b in zip(le, lg):
             assert abs(a - b) <= tol * max(1.0, abs(a)), (le, lg)
         for a, b in zip(pe, pg):
