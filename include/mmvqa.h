@@ -89,6 +89,8 @@ typedef struct mmvqa_gemm_args {
   const void* aux_in; int64_t ld_aux_in;     /* dtype = `dtype` */
   void* aux_out; int64_t ld_aux_out;         /* dtype = `dtype` */
   float* rowsum_out;         /* EPI_ACT_ROWSUM */
+  float* colsum_out;         /* optional, any storing epilogue: colsum_out[n] += sum_m C[m,n] (fp32 atomics, caller
+                                zero-fills) -- the bias gradient of the layer below, fused into the dgrad GEMM */
   const float* rowscale;     /* EPI_DACT_SCALE */
   float scale;
   int accumulate;
@@ -130,10 +132,14 @@ int mmvqa_add_layernorm_fwd(const void* x, const void* res, const float* gamma, 
                             void* sum_out, float* mean, float* rstd, int64_t rows, int cols, float eps, int dtype,
                             mmvqa_stream_t stream);
 /* dx = d(LN)/d(xsum) . dy (+ dres_extra if non-NULL: an extra gradient of the same shape added into dx,
- * i.e. the residual branch); dgamma/dbeta [cols] are ACCUMULATED with atomics (caller zero-fills). */
+ * i.e. the residual branch); dgamma/dbeta [cols] are ACCUMULATED with atomics (caller zero-fills).
+ * Optional fused outputs for the branch that was added to the residual before the LayerNorm:
+ *   dx_drop (dtype `dtype`) = dropout(dx) with the forward mask of (dropout_p, dropout_seed)  [= dx if p == 0]
+ *   dxsum [cols] fp32      += column sums of dx_drop (the bias gradient of that branch's last Linear). */
 int mmvqa_layernorm_bwd(const void* dy, const void* xsum, const float* gamma, const float* mean, const float* rstd,
-                        const void* dx_extra, void* dx, float* dgamma, float* dbeta, int64_t rows, int cols,
-                        int dtype, mmvqa_stream_t stream);
+                        const void* dx_extra, void* dx, float* dgamma, float* dbeta, void* dx_drop, float* dxsum,
+                        float dropout_p, uint64_t dropout_seed, int64_t rows, int cols, int dtype,
+                        mmvqa_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Attention (short sequence: T <= 128, head dim <= 128; one CTA per (batch, head))

@@ -29,7 +29,7 @@ class GemmArgs(C.Structure):
         ("epilogue", i32), ("act", i32),
         ("aux_in", vp), ("ld_aux_in", i64),
         ("aux_out", vp), ("ld_aux_out", i64),
-        ("rowsum_out", vp), ("rowscale", vp), ("scale", f32),
+        ("rowsum_out", vp), ("colsum_out", vp), ("rowscale", vp), ("scale", f32),
         ("accumulate", i32), ("split_k", i32),
         ("batch", i32), ("a_batch_rows", i64), ("b_batch_rows", i64), ("c_batch_stride", i64),
         ("dropout_p", f32), ("dropout_seed", u64),
@@ -55,7 +55,7 @@ SIGNATURES = {
     "mmvqa_scale_by_device_scalar": (i32, [vp, i32, vp, f32, i64, vp]),
     "mmvqa_dropout": (i32, [vp, vp, i64, f32, u64, i32, vp]),
     "mmvqa_add_layernorm_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, f32, i32, vp]),
-    "mmvqa_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
+    "mmvqa_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, u64, i64, i32, i32, vp]),
     "mmvqa_mhsa_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, f32, u64, i32, vp]),
     "mmvqa_mhsa_bwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, f32, u64, i32, vp]),
     "mmvqa_rf_attn_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),

@@ -95,9 +95,29 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const T* __restrict__ qkv
   const int H = heads * d;
   const uint32_t thr = (uint32_t)(drop_p * 4294967296.0);
   const float inv_keep = drop_p > 0.0f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  // per-row global operands (prev row, query-mask term) are fetched one row ahead; the key-mask term of the
+  // MHSA variant is row independent and fetched once
+  float pn[4] = {0.0f, 0.0f, 0.0f, 0.0f}, qn = 0.0f, km[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  auto fetch = [&](int i) {
+    if (RF) {
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj) {
+        const int j = lane + 32 * jj;
+        pn[jj] = (prev && j < Tn) ? __ldg(prev + sbase + (int64_t)i * Tn + j) : 0.0f;
+      }
+      qn = mask ? -10000.0f * (1.0f - __ldg(mask + b * Tn + i)) : 0.0f;
+    }
+  };
+  if (!RF && mask) {
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) km[jj] = (lane + 32 * jj < Tn) ? -10000.0f * (1.0f - __ldg(mask + b * Tn + lane + 32 * jj)) : 0.0f;
+  }
+  if (warp < Tn) fetch(warp);
   for (int i = warp; i < Tn; i += nwarp) {
     float sc[4];
-    const float qoff = (RF && mask) ? -10000.0f * (1.0f - mask[b * Tn + i]) : 0.0f;
+    float pc[4] = {pn[0], pn[1], pn[2], pn[3]};
+    const float qoff = qn;
+    if (i + nwarp < Tn) fetch(i + nwarp);
     float mx = -INFINITY;
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
@@ -111,11 +131,11 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const T* __restrict__ qkv
         for (int s = 0; s < d; ++s) dot = fmaf(qr[s], kr[s], dot);
         float v = dot / sqrt_d;
         if (RF) {
-          if (prev) v += prev[sbase + (int64_t)i * Tn + j];
+          v += pc[jj];
           v += qoff;
           scores[sbase + (int64_t)i * Tn + j] = v;
-        } else if (mask) {
-          v -= 10000.0f * (1.0f - mask[b * Tn + j]);
+        } else {
+          v += km[jj];
         }
         sc[jj] = v;
         mx = fmaxf(mx, v);
@@ -187,22 +207,35 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const T* __restrict__ qkv
   __syncthreads();
   const uint32_t thr = (uint32_t)(drop_p * 4294967296.0);
   const float inv_keep = drop_p > 0.0f ? 1.0f / (1.0f - drop_p) : 1.0f;
-  for (int i = warp; i < Tn; i += nwarp) {
-    float pr[4], dp[4];
-    float mx = -INFINITY;
+  // score / probability rows and the incoming score gradient are fetched one row ahead
+  float sn[4], gn[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+  auto fetch = [&](int i) {
 #pragma unroll
     for (int jj = 0; jj < 4; ++jj) {
       const int j = lane + 32 * jj;
-      pr[jj] = RF ? -INFINITY : 0.0f;
+      sn[jj] = RF ? -INFINITY : 0.0f;
+      gn[jj] = 0.0f;
       if (j < Tn) {
         if (RF) {
-          pr[jj] = scores[sbase + (int64_t)i * Tn + j];
-          mx = fmaxf(mx, pr[jj]);
+          sn[jj] = __ldg(scores + sbase + (int64_t)i * Tn + j);
+          if (dscores_in) gn[jj] = __ldg(dscores_in + sbase + (int64_t)i * Tn + j);
         } else {
-          pr[jj] = to_f(probs[sbase + (int64_t)i * Tn + j]);
+          sn[jj] = to_f(probs[sbase + (int64_t)i * Tn + j]);
         }
       }
     }
+  };
+  if (warp < Tn) fetch(warp);
+  for (int i = warp; i < Tn; i += nwarp) {
+    float pr[4], dp[4], gin[4];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      pr[jj] = sn[jj];
+      gin[jj] = gn[jj];
+      if (RF) mx = fmaxf(mx, pr[jj]);
+    }
+    if (i + nwarp < Tn) fetch(i + nwarp);
     if (RF) {
       mx = warp_max(mx);
       float sum = 0.0f;
@@ -246,7 +279,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const T* __restrict__ qkv
       if (j < Tn) {
         float g = pr[jj] * (dp[jj] - rowdot);
         if (RF) {
-          if (dscores_in) g += dscores_in[sbase + (int64_t)i * Tn + j];
+          g += gin[jj];
           if (dprev) dprev[sbase + (int64_t)i * Tn + j] = g;
         }
         dS[i * Tn + j] = g;

@@ -295,32 +295,45 @@ __global__ void __launch_bounds__(128) add_ln_fwd_generic(const T* __restrict__ 
   }
 }
 
-// backward.  Each warp walks rows (grid-stride); lanes own fixed columns, so dgamma/dbeta partials
-// accumulate in registers and are flushed through shared memory with one global atomic per
-// (block, column).  CACHED = cols <= 1024.
+// backward.  Each warp walks rows (grid-stride); lanes own fixed columns, so dgamma/dbeta (and the column
+// sums of the optional dropped copy) accumulate in registers and are flushed through shared memory with one
+// global atomic per (block, column).  CACHED = cols <= 1024.
+struct LnBwdExtra {
+  void* dx_drop;            // optional: dropout(dx), same dtype
+  float* dxsum;             // optional: += column sums of dx_drop (or of dx when dx_drop == NULL)
+  float p;
+  unsigned long long seed;
+};
+
 template <typename T, bool VEC, bool CACHED>
 __global__ void __launch_bounds__(128) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ xsum,
                                                      const float* __restrict__ gamma, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, const T* __restrict__ dx_extra,
                                                      T* __restrict__ dx, float* __restrict__ dgamma,
-                                                     float* __restrict__ dbeta, int64_t rows, int cols) {
-  extern __shared__ float sm[];  // [2][cols] block partials
+                                                     float* __restrict__ dbeta, LnBwdExtra ex, int64_t rows, int cols) {
+  extern __shared__ float sm[];  // [3][cols] block partials
   constexpr int N = VEC ? Vec16<T>::N : 1;
   constexpr int ITER = LN_CACHE / N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  float dg[CACHED ? LN_CACHE : 1], db[CACHED ? LN_CACHE : 1];
+  float dg[CACHED ? LN_CACHE : 1], db[CACHED ? LN_CACHE : 1], dsum[CACHED ? LN_CACHE : 1];
   if (CACHED) {
 #pragma unroll
-    for (int k = 0; k < LN_CACHE; ++k) dg[k] = db[k] = 0.0f;
+    for (int k = 0; k < LN_CACHE; ++k) dg[k] = db[k] = dsum[k] = 0.0f;
   }
-  for (int c = threadIdx.x; c < 2 * cols; c += blockDim.x) sm[c] = 0.0f;
+  for (int c = threadIdx.x; c < 3 * cols; c += blockDim.x) sm[c] = 0.0f;
   __syncthreads();
+  T* dxd = reinterpret_cast<T*>(ex.dx_drop);
+  const bool want_sum = ex.dxsum != nullptr;
+  const bool drop = ex.p > 0.0f;
+  const uint32_t thr = (uint32_t)(ex.p * 4294967296.0);
+  const float inv_keep = drop ? 1.0f / (1.0f - ex.p) : 1.0f;
   for (int64_t row = blockIdx.x * (int64_t)nwarp + warp; row < rows; row += (int64_t)gridDim.x * nwarp) {
     const float mu = mean[row], rs = rstd[row];
     const T* dyr = dy + row * cols;
     const T* xr = xsum + row * cols;
     const T* er = dx_extra ? dx_extra + row * cols : nullptr;
     T* dxr = dx + row * cols;
+    T* ddr = dxd ? dxd + row * cols : nullptr;
     float s1 = 0.0f, s2 = 0.0f;
     if (CACHED) {
       float g_[LN_CACHE], xh_[LN_CACHE];
@@ -362,14 +375,30 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const T* __restrict__ dy, c
         const int c = (k * 32 + lane) * N;
         if (c < cols) {
           if (VEC) {
-            Vec16<T> e, o;
+            Vec16<T> e, o, od;
             if (er) e.load(er + c);
 #pragma unroll
-            for (int j = 0; j < N; ++j)
+            for (int j = 0; j < N; ++j) {
               o.set(j, rs * (g_[k * N + j] - s1 - xh_[k * N + j] * s2) + (er ? e.get(j) : 0.0f));
+              if (ddr || want_sum) {
+                float d = o.get(j);   // the stored (rounded) value is what the branch sees
+                if (drop) d = hash32(ex.seed, (uint64_t)(row * cols + c + j)) >= thr ? d * inv_keep : 0.0f;
+                od.set(j, d);
+                dsum[k * N + j] += od.get(j);
+              }
+            }
             o.store(dxr + c);
+            if (ddr) od.store(ddr + c);
           } else {
-            dxr[c] = from_f<T>(rs * (g_[k] - s1 - xh_[k] * s2) + (er ? to_f(er[c]) : 0.0f));
+            T o = from_f<T>(rs * (g_[k] - s1 - xh_[k] * s2) + (er ? to_f(er[c]) : 0.0f));
+            dxr[c] = o;
+            if (ddr || want_sum) {
+              float d = to_f(o);
+              if (drop) d = hash32(ex.seed, (uint64_t)(row * cols + c)) >= thr ? d * inv_keep : 0.0f;
+              T q = from_f<T>(d);
+              if (ddr) ddr[c] = q;
+              dsum[k] += to_f(q);
+            }
           }
         }
       }
@@ -386,11 +415,19 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const T* __restrict__ dy, c
       s2 = warp_sum(s2) / (float)cols;
       for (int c = lane; c < cols; c += 32) {
         float g = to_f(dyr[c]) * __ldg(gamma + c), xh = (to_f(xr[c]) - mu) * rs;
-        dxr[c] = from_f<T>(rs * (g - s1 - xh * s2) + (er ? to_f(er[c]) : 0.0f));
+        T o = from_f<T>(rs * (g - s1 - xh * s2) + (er ? to_f(er[c]) : 0.0f));
+        dxr[c] = o;
+        if (ddr || want_sum) {
+          float d = to_f(o);
+          if (drop) d = hash32(ex.seed, (uint64_t)(row * cols + c)) >= thr ? d * inv_keep : 0.0f;
+          T q = from_f<T>(d);
+          if (ddr) ddr[c] = q;
+          atomicAdd(&sm[2 * cols + c], to_f(q));
+        }
       }
     }
   }
-  if (dgamma == nullptr && dbeta == nullptr) return;
+  if (dgamma == nullptr && dbeta == nullptr && !want_sum) return;
   if (CACHED) {
 #pragma unroll
     for (int k = 0; k < ITER; ++k) {
@@ -400,6 +437,7 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const T* __restrict__ dy, c
         for (int j = 0; j < N; ++j) {
           atomicAdd(&sm[c + j], dg[k * N + j]);
           atomicAdd(&sm[cols + c + j], db[k * N + j]);
+          if (want_sum) atomicAdd(&sm[2 * cols + c + j], dsum[k * N + j]);
         }
       }
     }
@@ -408,6 +446,7 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const T* __restrict__ dy, c
   for (int c = threadIdx.x; c < cols; c += blockDim.x) {
     if (dgamma) atomicAdd(dgamma + c, sm[c]);
     if (dbeta) atomicAdd(dbeta + c, sm[cols + c]);
+    if (want_sum) atomicAdd(ex.dxsum + c, sm[2 * cols + c]);
   }
 }
 
@@ -586,22 +625,26 @@ int mmvqa_add_layernorm_fwd(const void* x, const void* res, const float* gamma, 
 }
 
 int mmvqa_layernorm_bwd(const void* dy, const void* xsum, const float* gamma, const float* mean, const float* rstd,
-                        const void* dx_extra, void* dx, float* dgamma, float* dbeta, int64_t rows, int cols,
-                        int dtype, mmvqa_stream_t stream) {
+                        const void* dx_extra, void* dx, float* dgamma, float* dbeta, void* dx_drop, float* dxsum,
+                        float dropout_p, uint64_t dropout_seed, int64_t rows, int cols, int dtype,
+                        mmvqa_stream_t stream) {
   MMVQA_REQUIRE(dy && xsum && gamma && mean && rstd && dx, "layernorm_bwd: null pointer");
   MMVQA_REQUIRE(cols > 0 && rows >= 0, "layernorm_bwd: bad shape");
   MMVQA_REQUIRE(dtype == MMVQA_F32 || dtype == MMVQA_BF16, "layernorm_bwd: bad dtype %d", dtype);
+  MMVQA_REQUIRE(dropout_p >= 0.0f && dropout_p < 1.0f, "layernorm_bwd: dropout_p must be in [0,1)");
   if (rows == 0) return MMVQA_OK;
   cudaStream_t st = as_stream(stream);
   int64_t want = (rows + 3) / 4, cap = (int64_t)num_sms() * 4;
   int grid = (int)(want < cap ? want : cap);
-  size_t smem = sizeof(float) * 2 * (size_t)cols;
+  size_t smem = sizeof(float) * 3 * (size_t)cols;
   MMVQA_REQUIRE(smem <= 48 * 1024, "layernorm_bwd: cols %d too large", cols);
   const int vn = dtype == MMVQA_F32 ? 4 : 8;
   const bool cached = cols <= 32 * LN_CACHE;
   const bool vec = cached && cols % vn == 0 && aligned16(dy) && aligned16(xsum) && aligned16(dx) &&
-                   (!dx_extra || aligned16(dx_extra));
-#define LN_BWD(T, V, C) ln_bwd_kernel<T, V, C><<<grid, 128, smem, st>>>((const T*)dy, (const T*)xsum, gamma, mean, rstd, (const T*)dx_extra, (T*)dx, dgamma, dbeta, rows, cols)
+                   (!dx_extra || aligned16(dx_extra)) && (!dx_drop || aligned16(dx_drop));
+  LnBwdExtra ex;
+  ex.dx_drop = dx_drop; ex.dxsum = dxsum; ex.p = dx_drop ? dropout_p : 0.0f; ex.seed = dropout_seed;
+#define LN_BWD(T, V, C) ln_bwd_kernel<T, V, C><<<grid, 128, smem, st>>>((const T*)dy, (const T*)xsum, gamma, mean, rstd, (const T*)dx_extra, (T*)dx, dgamma, dbeta, ex, rows, cols)
   if (dtype == MMVQA_F32) {
     if (vec) LN_BWD(float, true, true);
     else if (cached) LN_BWD(float, false, true);

@@ -27,6 +27,7 @@ extern "C" int mmvqa_gemm(const mmvqa_gemm_args* a, mmvqa_stream_t stream) {
     MMVQA_REQUIRE(a->aux_in != nullptr && a->ld_aux_in >= a->N, "gemm: epilogue %d needs aux_in", a->epilogue);
   if (a->epilogue == MMVQA_EPI_DACT_SCALE) MMVQA_REQUIRE(a->rowscale != nullptr, "gemm: EPI_DACT_SCALE needs rowscale");
   if (a->aux_out) MMVQA_REQUIRE(a->ld_aux_out >= a->N, "gemm: bad ld_aux_out");
+  if (a->colsum_out) MMVQA_REQUIRE(a->epilogue != MMVQA_EPI_ACT_ROWSUM && split_k == 1, "gemm: colsum_out needs a storing epilogue and split_k == 1");
   if (a->accumulate || split_k > 1) {
     MMVQA_REQUIRE(a->c_dtype == MMVQA_F32 && a->epilogue == MMVQA_EPI_STORE && (a->accumulate || split_k == 1),
                   "gemm: split_k / accumulate need an fp32 C, EPI_STORE and accumulate != 0");
@@ -44,7 +45,7 @@ extern "C" int mmvqa_gemm(const mmvqa_gemm_args* a, mmvqa_stream_t stream) {
   ep.bias = a->bias; ep.epilogue = a->epilogue; ep.act = a->act;
   ep.aux_in = a->aux_in; ep.ld_aux_in = a->ld_aux_in;
   ep.aux_out = a->aux_out; ep.ld_aux_out = a->ld_aux_out;
-  ep.rowsum_out = a->rowsum_out; ep.rowscale = a->rowscale; ep.scale = a->scale;
+  ep.rowsum_out = a->rowsum_out; ep.colsum_out = a->colsum_out; ep.rowscale = a->rowscale; ep.scale = a->scale;
   ep.accumulate = a->accumulate; ep.split_k = split_k; ep.batch = batch;
   ep.c_batch_stride = a->c_batch_stride;
   ep.dropout_p = a->dropout_p; ep.dropout_seed = a->dropout_seed;

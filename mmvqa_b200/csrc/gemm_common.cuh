@@ -11,14 +11,14 @@ struct EpiParams {
   int epilogue, act;
   const void* aux_in; int64_t ld_aux_in;      // storage type == operand type
   void* aux_out; int64_t ld_aux_out;
-  float* rowsum_out; const float* rowscale; float scale;
+  float* rowsum_out; float* colsum_out; const float* rowscale; float scale;
   int accumulate, split_k, batch;
   int64_t c_batch_stride;
   float dropout_p; unsigned long long dropout_seed;
 };
 
 // one output element; AUX = storage type of aux_in / aux_out.  `first_split` gates bias so that
-// split-K partial sums add it once.  Returns the value to add to the row sum for EPI_ACT_ROWSUM.
+// split-K partial sums add it once.  Returns the stored value (the activation for EPI_ACT_ROWSUM).
 template <typename AUX>
 __device__ __forceinline__ float epi_element(const EpiParams& p, int bz, int m, int n, float acc, bool first_split) {
   float v = acc + ((p.bias && first_split) ? __ldg(p.bias + n) : 0.0f);
@@ -54,7 +54,7 @@ __device__ __forceinline__ float epi_element(const EpiParams& p, int bz, int m, 
     reinterpret_cast<__nv_bfloat16*>(p.C)[off] = __float2bfloat16_rn(out);
   else
     reinterpret_cast<float*>(p.C)[off] = out;
-  return 0.0f;
+  return out;
 }
 
 int gemm_simt_f32(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st);

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
   }
   if (kb0 >= kb1 && ks != 0) return;  // empty split
   const bool first = (ks == 0);
+  float cs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int m = m0 + ty * 4 + i;
@@ -67,7 +68,11 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         int n = n0 + tx * 4 + j;
-        if (n < p.N) rs += epi_element<float>(p, bz, m, n, acc[i][j], first);
+        if (n < p.N) {
+          const float o = epi_element<float>(p, bz, m, n, acc[i][j], first);
+          rs += o;
+          cs[j] += o;
+        }
       }
     }
     if (p.epilogue == MMVQA_EPI_ACT_ROWSUM) {
@@ -75,6 +80,13 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
       if (tx == 0 && m < p.M) atomicAdd(p.rowsum_out + (int64_t)bz * p.M + m, rs * p.scale);
+    }
+  }
+  if (p.colsum_out && p.epilogue != MMVQA_EPI_ACT_ROWSUM) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n < p.N) atomicAdd(p.colsum_out + n, cs[j]);
     }
   }
 }

@@ -165,9 +165,11 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_ro
     tmem_ld16(tmem_row + (uint32_t)c, r);
     tmem_ld_wait();
     const int nb = n0 + c;
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = 0.0f;
     if (row_ok && nb < p.N) {
       const int nvalid = min(16, p.N - nb);
-      float v[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = has_acc ? __uint_as_float(r[j]) : 0.0f;
       if (use_bias) {
@@ -215,6 +217,51 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_ro
       } else {
         store16_f32(reinterpret_cast<float*>(p.C) + coff, nvalid, v);
       }
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        if (j >= nvalid) v[j] = 0.0f;
+    }
+    if (EPI != MMVQA_EPI_ACT_ROWSUM && p.colsum_out != nullptr && nb < p.N) {
+      // column sums over the warp's 32 rows: transposing butterfly, 16 shuffles; lane l ends with column
+      // 8*b4 + 4*b3 + 2*b2 + b1 of the chunk (b_k = bit k of l), duplicated on the lane pair (l, l^1)
+      __syncwarp();
+      const int lane = threadIdx.x & 31;
+      {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float send = hi ? v[k] : v[k + 8];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+          v[k] = (hi ? v[k + 8] : v[k]) + recv;
+        }
+      }
+      {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float send = hi ? v[k] : v[k + 4];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+          v[k] = (hi ? v[k + 4] : v[k]) + recv;
+        }
+      }
+      {
+        const bool hi = lane & 4;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const float send = hi ? v[k] : v[k + 2];
+          const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+          v[k] = (hi ? v[k + 2] : v[k]) + recv;
+        }
+      }
+      {
+        const bool hi = lane & 2;
+        const float send = hi ? v[0] : v[1];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+        v[0] = (hi ? v[1] : v[0]) + recv;
+      }
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+      const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+      if ((lane & 1) == 0 && nb + col < p.N) atomicAdd(p.colsum_out + nb + col, v[0]);
     }
   }
   if (EPI == MMVQA_EPI_ACT_ROWSUM && row_ok) atomicAdd(p.rowsum_out + (int64_t)bz * p.M + m, rowsum * p.scale);

@@ -137,10 +137,13 @@ def _split_k_for(tiles: int, k: int, device, kblock: int = 64) -> int:
 
 
 def gemm_dgrad(dy: Tensor, ld_dy: int, M: int, N: int, w: Tensor, K: int, *, epilogue=EPI_STORE, act=ACT_NONE,
-               aux_in: Optional[Tensor] = None, out_dtype: Optional[torch.dtype] = None) -> Tensor:
-    """dx[M,K] = dy[M,N] . w[N,K]   (w read MN-major: no transposed weight copy)."""
+               aux_in: Optional[Tensor] = None, out_dtype: Optional[torch.dtype] = None,
+               colsum_out: Optional[Tensor] = None) -> Tensor:
+    """dx[M,K] = dy[M,N] . w[N,K]   (w read MN-major: no transposed weight copy).  colsum_out (zero-filled fp32 [K])
+    receives the column sums of dx: the bias gradient of the layer that produced this activation."""
     dx = torch.empty(M, K, device=dy.device, dtype=out_dtype or dy.dtype)
-    ops.gemm(M, K, N, dy, ld_dy, False, w, K, True, dx, K, epilogue=epilogue, act=act, aux_in=aux_in, ld_aux_in=K)
+    ops.gemm(M, K, N, dy, ld_dy, False, w, K, True, dx, K, epilogue=epilogue, act=act, aux_in=aux_in, ld_aux_in=K,
+             colsum_out=colsum_out)
     return dx
 
 
@@ -586,7 +589,8 @@ class RealFormerEncoderFn(torch.autograd.Function):
         ds = None if dscores is None else dscores.contiguous().float()
         grads: List[Optional[Tensor]] = [None] * len(params)
         # one zero-filled workspace for everything that is accumulated with atomics (LN gamma/beta, split-K kqv dW)
-        per_layer = 4 * H + 3 * d * d
+        F4 = params[4].shape[0]
+        per_layer = 5 * H + F4 + 3 * d * d
         zws = torch.zeros(n_layers * per_layer, device=saved[0].device, dtype=torch.float32)
         for l in reversed(range(n_layers)):
             xin, kqv, scores, attn, y1, mean1, rstd1, x1, hpre, hact, y2, mean2, rstd2 = saved[l * nsave:(l + 1) * nsave]
@@ -595,24 +599,32 @@ class RealFormerEncoderFn(torch.autograd.Function):
             wp = weight_cache.get((proj_w,), dt)
             wf0 = weight_cache.get((w0,), dt)
             wf2 = weight_cache.get((w2,), dt)
-            F4 = wf0.shape[0]
             zl = zws[l * per_layer:(l + 1) * per_layer]
-            dg2, db2, dg1, db1 = zl[0:H], zl[H:2 * H], zl[2 * H:3 * H], zl[3 * H:4 * H]
-            dy2 = ops.layernorm_bwd(dx, y2, g2.detach(), mean2, rstd2, None, dg2, db2)
-            dff = ops.dropout(dy2, p2, seed + 2 * l + 1) if p2 > 0.0 else dy2
-            dbb2 = ops.colsum(dff, M, H)
+            dg2, db2, dg1, db1, dbb2 = zl[0:H], zl[H:2 * H], zl[2 * H:3 * H], zl[3 * H:4 * H], zl[4 * H:5 * H]
+            dbb0 = zl[5 * H:5 * H + F4]
+            # LN2 backward also emits dropout(dy2) for the FF branch and its column sums (= d ff.2.bias)
+            if p2 > 0.0:
+                dy2, dff = ops.layernorm_bwd(dx, y2, g2.detach(), mean2, rstd2, None, dg2, db2, want_drop=True, dxsum=dbb2,
+                                             dropout_p=p2, dropout_seed=seed + 2 * l + 1)
+            else:
+                dy2 = ops.layernorm_bwd(dx, y2, g2.detach(), mean2, rstd2, None, dg2, db2, dxsum=dbb2)
+                dff = dy2
             dw2 = gemm_wgrad(dff, H, M, H, hact, F4, F4)
-            dhpre = gemm_dgrad(dff, H, M, H, wf2, F4, epilogue=EPI_DACT, act=ACT_SERF, aux_in=hpre)
-            dbb0 = ops.colsum(dhpre, M, F4)
+            # dgrad through FF2 with act'(h_pre) in the epilogue; its column sums are d ff.0.bias
+            dhpre = gemm_dgrad(dff, H, M, H, wf2, F4, epilogue=EPI_DACT, act=ACT_SERF, aux_in=hpre, colsum_out=dbb0)
             dw0 = gemm_wgrad(dhpre, F4, M, F4, x1, H, H)
             dx1 = gemm_dgrad(dhpre, F4, M, F4, wf0, H, epilogue=EPI_RESIDUAL, aux_in=dy2)
-            dy1 = ops.layernorm_bwd(dx1, y1, g1.detach(), mean1, rstd1, None, dg1, db1)
-            dpr = ops.dropout(dy1, p1, seed + 2 * l) if p1 > 0.0 else dy1
+            if p1 > 0.0:
+                dy1, dpr = ops.layernorm_bwd(dx1, y1, g1.detach(), mean1, rstd1, None, dg1, db1, want_drop=True,
+                                             dropout_p=p1, dropout_seed=seed + 2 * l)
+            else:
+                dy1 = ops.layernorm_bwd(dx1, y1, g1.detach(), mean1, rstd1, None, dg1, db1)
+                dpr = dy1
             dwp = gemm_wgrad(dpr, H, M, H, attn, H, H)
             dattn = gemm_dgrad(dpr, H, M, H, wp, H)
             want_dprev = (l > 0) or (has_prev and ctx.needs_input_grad[2])
             dkqv, dprev = ops.rf_attn_bwd(kqv, scores, dattn, ds, want_dprev, B, T, heads, d)
-            dwk = gemm_wgrad(dkqv, 3 * d, M * heads, 3 * d, xin, d, d, zeroed=zl[4 * H:].view(3 * d, d))
+            dwk = gemm_wgrad(dkqv, 3 * d, M * heads, 3 * d, xin, d, d, zeroed=zl[5 * H + F4:].view(3 * d, d))
             # dx_in = dkqv . Wkqv (per head) + dy1 (residual around the attention block)
             dxin = torch.empty(M, H, device=dx.device, dtype=dt)
             ops.gemm(M * heads, d, 3 * d, dkqv, 3 * d, False, wk, d, True, dxin, d, epilogue=EPI_RESIDUAL, aux_in=dy1,

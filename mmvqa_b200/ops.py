@@ -60,7 +60,8 @@ def _cont(t: Tensor, name: str) -> Tensor:
 def gemm(M: int, N: int, K: int, A: Tensor, lda: int, a_trans: bool, B: Tensor, ldb: int, b_trans: bool,
          Cout: Optional[Tensor], ldc: int, *, bias: Optional[Tensor] = None, epilogue: int = EPI_STORE,
          act: int = ACT_NONE, aux_in: Optional[Tensor] = None, ld_aux_in: int = 0, aux_out: Optional[Tensor] = None,
-         ld_aux_out: int = 0, rowsum_out: Optional[Tensor] = None, rowscale: Optional[Tensor] = None,
+         ld_aux_out: int = 0, rowsum_out: Optional[Tensor] = None, colsum_out: Optional[Tensor] = None,
+         rowscale: Optional[Tensor] = None,
          scale: float = 1.0, accumulate: bool = False, split_k: int = 1, batch: int = 1, a_batch_rows: int = 0,
          b_batch_rows: int = 0, c_batch_stride: int = 0, dropout_p: float = 0.0, dropout_seed: int = 0) -> None:
     """C[M,N] = epilogue(sum_k opA(A)[m,k] opB(B)[n,k]); see include/mmvqa.h for the epilogues."""
@@ -79,7 +80,7 @@ def gemm(M: int, N: int, K: int, A: Tensor, lda: int, a_trans: bool, B: Tensor, 
     a.epilogue, a.act = epilogue, act
     a.aux_in, a.ld_aux_in = _p(aux_in), ld_aux_in
     a.aux_out, a.ld_aux_out = _p(aux_out), ld_aux_out
-    a.rowsum_out, a.rowscale, a.scale = _p(rowsum_out), _p(rowscale), scale
+    a.rowsum_out, a.colsum_out, a.rowscale, a.scale = _p(rowsum_out), _p(colsum_out), _p(rowscale), scale
     a.accumulate, a.split_k = int(accumulate), split_k
     a.batch, a.a_batch_rows, a.b_batch_rows, a.c_batch_stride = batch, a_batch_rows, b_batch_rows, c_batch_stride
     a.dropout_p, a.dropout_seed = dropout_p, dropout_seed
@@ -166,15 +167,19 @@ def add_layernorm_fwd(x: Tensor, res: Optional[Tensor], gamma: Tensor, beta: Ten
 
 
 def layernorm_bwd(dy: Tensor, xsum: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor, dx_extra: Optional[Tensor],
-                  dgamma: Tensor, dbeta: Tensor) -> Tensor:
-    """dgamma / dbeta are ACCUMULATED into (caller zero-fills)."""
+                  dgamma: Tensor, dbeta: Tensor, *, want_drop: bool = False, dxsum: Optional[Tensor] = None,
+                  dropout_p: float = 0.0, dropout_seed: int = 0):
+    """dgamma / dbeta (and dxsum) are ACCUMULATED into (caller zero-fills).  Returns dx, or (dx, dropout(dx)) when
+    want_drop."""
     _cont(dy, "dy"), _cont(xsum, "xsum")
     cols = dy.shape[-1]
     rows = dy.numel() // cols
     dx = torch.empty_like(dy)
+    dxd = torch.empty_like(dy) if want_drop else None
     L.check(L.lib().mmvqa_layernorm_bwd(_p(dy), _p(xsum), _p(gamma), _p(mean), _p(rstd), _p(dx_extra), _p(dx), _p(dgamma),
-                                       _p(dbeta), rows, cols, dtype_code(dy), _stream()), "layernorm_bwd")
-    return dx
+                                       _p(dbeta), _p(dxd), _p(dxsum), dropout_p, dropout_seed, rows, cols, dtype_code(dy),
+                                       _stream()), "layernorm_bwd")
+    return (dx, dxd) if want_drop else dx
 
 
 # ------------------------------------------------------------------------------- attention

@@ -125,6 +125,17 @@ def test_layernorm(dt, cols, eps):
         close(dx, gx + extra, **btol, msg="ln dx")
         close(dg, gg, 1e-4, 1e-3 if dt == torch.float32 else 5e-2, msg="dgamma")
         close(db, gb, 1e-4, 1e-4, msg="dbeta")
+        # fused extras: dropout(dx) with the library mask and its column sums (bias gradient of the branch)
+        dg2, db2, dsum = torch.zeros(cols, device=DEV), torch.zeros(cols, device=DEV), torch.zeros(cols, device=DEV)
+        dx2, dxd = ops.layernorm_bwd(dy.to(dt).to(DEV), xs_dev, gamma.to(DEV), mean, rstd, extra.to(dt).to(DEV), dg2, db2,
+                                     want_drop=True, dxsum=dsum, dropout_p=0.25, dropout_seed=5)
+        assert torch.equal(dx2, dx)
+        assert torch.equal(dxd, ops.dropout(dx, 0.25, 5))
+        close(dsum, dxd.float().sum(0), 1e-4, 1e-3, msg="dxsum")
+        dsum0 = torch.zeros(cols, device=DEV)
+        ops.layernorm_bwd(dy.to(dt).to(DEV), xs_dev, gamma.to(DEV), mean, rstd, None, dg2, db2, dxsum=dsum0)
+        dx_plain = ops.layernorm_bwd(dy.to(dt).to(DEV), xs_dev, gamma.to(DEV), mean, rstd, None, dg2, db2)
+        close(dsum0, dx_plain.float().sum(0), 1e-4, 1e-3, msg="dxsum (no dropout)")
 
 
 # ------------------------------------------------------------------------------------------
@@ -207,8 +218,11 @@ def test_gemm_epilogues(dt, act):
     # EPI_DACT
     aux = rnd(M, N, seed=23, scale=2.0).to(dt)
     _, dact = oracle_act(act, aux.float())
-    ops.gemm(M, N, K, A, lda, False, B, ldb, False, C, N, epilogue=EPI_DACT, act=ACTS[act], aux_in=aux.to(DEV), ld_aux_in=N)
+    cs = torch.zeros(N, device=DEV)
+    ops.gemm(M, N, K, A, lda, False, B, ldb, False, C, N, epilogue=EPI_DACT, act=ACTS[act], aux_in=aux.to(DEV), ld_aux_in=N,
+             colsum_out=cs)
     close(C, ref * dact, **tol, msg="dact")
+    close(cs, (ref * dact).sum(0), 1e-3 if dt == torch.float32 else 2e-2, 1e-2 if dt == torch.float32 else 0.3, msg="fused colsum")
 
 
 @pytest.mark.parametrize("dt", DTS)
