@@ -70,8 +70,35 @@ __device__ __forceinline__ void load_tiles(const TileSrc (&t)[NT], int Tn, int d
   }
 }
 
+// dot product of two shared-memory rows with four independent accumulators (breaks the FMA dependency chain)
+__device__ __forceinline__ float dot_rows(const float* __restrict__ a, const float* __restrict__ b, int n) {
+  float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, d3 = 0.0f;
+  int s = 0;
+#pragma unroll 2
+  for (; s + 3 < n; s += 4) {
+    d0 = fmaf(a[s], b[s], d0);
+    d1 = fmaf(a[s + 1], b[s + 1], d1);
+    d2 = fmaf(a[s + 2], b[s + 2], d2);
+    d3 = fmaf(a[s + 3], b[s + 3], d3);
+  }
+  for (; s < n; ++s) d0 = fmaf(a[s], b[s], d0);
+  return (d0 + d1) + (d2 + d3);
+}
+// sum_k a[k * lda] * b[k * ldb], two accumulators
+__device__ __forceinline__ float dot_strided(const float* __restrict__ a, int lda, const float* __restrict__ b, int ldb, int n) {
+  float d0 = 0.0f, d1 = 0.0f;
+  int k = 0;
+#pragma unroll 2
+  for (; k + 1 < n; k += 2) {
+    d0 = fmaf(a[k * lda], b[k * ldb], d0);
+    d1 = fmaf(a[(k + 1) * lda], b[(k + 1) * ldb], d1);
+  }
+  if (k < n) d0 = fmaf(a[k * lda], b[k * ldb], d0);
+  return d0 + d1;
+}
+
 template <typename T, bool RF>
-__global__ void __launch_bounds__(256) attn_fwd_kernel(const T* __restrict__ qkv, AttnLayout L,
+__global__ void __launch_bounds__(1024) attn_fwd_kernel(const T* __restrict__ qkv, AttnLayout L,
                                                        const float* __restrict__ prev, const float* __restrict__ mask,
                                                        T* __restrict__ out, float* __restrict__ scores,
                                                        T* __restrict__ probs, int Tn, int heads, int d, float drop_p,
@@ -124,11 +151,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const T* __restrict__ qkv
       const int j = lane + 32 * jj;
       sc[jj] = -INFINITY;
       if (j < Tn) {
-        float dot = 0.0f;
-        const float* qr = Qs + i * d;
-        const float* kr = Ks + j * (d + 1);
-#pragma unroll 8
-        for (int s = 0; s < d; ++s) dot = fmaf(qr[s], kr[s], dot);
+        const float dot = dot_rows(Qs + i * d, Ks + j * (d + 1), d);
         float v = dot / sqrt_d;
         if (RF) {
           v += pc[jj];
@@ -167,10 +190,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const T* __restrict__ qkv
     }
     __syncwarp();
     for (int s = lane; s < d; s += 32) {
-      float acc = 0.0f;
-      const float* pw = Ps + warp * Tn;
-#pragma unroll 4
-      for (int j = 0; j < Tn; ++j) acc = fmaf(pw[j], Vs[j * d + s], acc);
+      const float acc = dot_strided(Ps + warp * Tn, 1, Vs + s, d, Tn);
       out[((int64_t)b * Tn + i) * H + h * d + s] = from_f<T>(acc);
     }
     __syncwarp();
@@ -178,7 +198,7 @@ __global__ void __launch_bounds__(256) attn_fwd_kernel(const T* __restrict__ qkv
 }
 
 template <typename T, bool RF>
-__global__ void __launch_bounds__(256) attn_bwd_kernel(const T* __restrict__ qkv, AttnLayout L,
+__global__ void __launch_bounds__(1024) attn_bwd_kernel(const T* __restrict__ qkv, AttnLayout L,
                                                        const float* __restrict__ scores, const T* __restrict__ probs,
                                                        const T* __restrict__ dout, const float* __restrict__ dscores_in,
                                                        T* __restrict__ dqkv, float* __restrict__ dprev, int Tn, int heads,
@@ -256,11 +276,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const T* __restrict__ qkv
       const int j = lane + 32 * jj;
       dp[jj] = 0.0f;
       if (j < Tn) {
-        float acc = 0.0f;
-        const float* dr = dO + i * d;
-        const float* vr = X + j * (d + 1);
-#pragma unroll 8
-        for (int s = 0; s < d; ++s) acc = fmaf(dr[s], vr[s], acc);
+        float acc = dot_rows(dO + i * d, X + j * (d + 1), d);
         float pd = pr[jj];
         if (!RF && drop_p > 0.0f) {
           const bool keep = hash32(seed, (uint64_t)(sbase + (int64_t)i * Tn + j)) >= thr;
@@ -291,8 +307,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const T* __restrict__ qkv
   // dV[j][s] = sum_i P[i][j] dO[i][s]
   for (int idx = threadIdx.x; idx < Tn * d; idx += blockDim.x) {
     const int j = idx / d, s = idx - j * d;
-    float acc = 0.0f;
-    for (int i = 0; i < Tn; ++i) acc = fmaf(P[i * Tn + j], dO[i * d + s], acc);
+    const float acc = dot_strided(P + j, Tn, dO + s, d, Tn);
     dbase[L.v_off + (int64_t)j * L.row_stride + s] = from_f<T>(acc);
   }
   if (!resident) {
@@ -304,8 +319,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const T* __restrict__ qkv
   // dQ[i][s] = sum_j dS[i][j] K[j][s] / sqrt(d)
   for (int idx = threadIdx.x; idx < Tn * d; idx += blockDim.x) {
     const int i = idx / d, s = idx - i * d;
-    float acc = 0.0f;
-    for (int j = 0; j < Tn; ++j) acc = fmaf(dS[i * Tn + j], Kb[j * (d + 1) + s], acc);
+    const float acc = dot_strided(dS + i * Tn, 1, Kb + s, d + 1, Tn);
     dbase[L.q_off + (int64_t)i * L.row_stride + s] = from_f<T>(acc * inv_sqrt_d);
   }
   if (!resident) {
@@ -317,8 +331,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const T* __restrict__ qkv
   // dK[j][s] = sum_i dS[i][j] Q[i][s] / sqrt(d)
   for (int idx = threadIdx.x; idx < Tn * d; idx += blockDim.x) {
     const int j = idx / d, s = idx - j * d;
-    float acc = 0.0f;
-    for (int i = 0; i < Tn; ++i) acc = fmaf(dS[i * Tn + j], Qb[i * (d + 1) + s], acc);
+    const float acc = dot_strided(dS + j, Tn, Qb + s, d + 1, Tn);
     dbase[L.k_off + (int64_t)j * L.row_stride + s] = from_f<T>(acc * inv_sqrt_d);
   }
 }
@@ -333,14 +346,15 @@ static int check_shape(const char* name, int B, int T, int heads, int d) {
 template <typename T, bool RF>
 static int launch_fwd(const void* qkv, const AttnLayout& L, const float* prev, const float* mask, void* out, float* scores,
                       void* probs, int B, int Tn, int heads, int d, float p, uint64_t seed, cudaStream_t st) {
-  size_t smem = sizeof(float) * ((size_t)Tn * (d + 1) + 2 * (size_t)Tn * d + 8 * (size_t)Tn);
+  const int nthreads = 32 * (Tn < 8 ? 8 : (Tn > 32 ? 32 : Tn));   // one warp per query row, 8..32 warps
+  size_t smem = sizeof(float) * ((size_t)Tn * (d + 1) + 2 * (size_t)Tn * d + (size_t)(nthreads / 32) * Tn);
   if (smem > 227 * 1024) return set_err(MMVQA_ERR_SMEM, "attention fwd: T=%d d=%d needs %zu bytes of shared memory", Tn, d, smem);
   auto kern = attn_fwd_kernel<T, RF>;
   if (smem > 48 * 1024) MMVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int vn = 16 / (int)sizeof(T);
   const int vec = (d % vn == 0 && L.row_stride % vn == 0 && L.head_stride % vn == 0 && L.q_off % vn == 0 && L.k_off % vn == 0 &&
                    L.v_off % vn == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0) ? 1 : 0;
-  kern<<<B * heads, 256, smem, st>>>((const T*)qkv, L, prev, mask, (T*)out, scores, (T*)probs, Tn, heads, d, p, seed, vec);
+  kern<<<B * heads, nthreads, smem, st>>>((const T*)qkv, L, prev, mask, (T*)out, scores, (T*)probs, Tn, heads, d, p, seed, vec);
   MMVQA_LAUNCHED("attn_fwd");
   return MMVQA_OK;
 }
@@ -361,7 +375,8 @@ static int launch_bwd(const void* qkv, const AttnLayout& L, const float* scores,
   const int vec = (d % vn == 0 && L.row_stride % vn == 0 && L.head_stride % vn == 0 && L.q_off % vn == 0 && L.k_off % vn == 0 &&
                    L.v_off % vn == 0 && H % vn == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(dout) & 15) == 0) ? 1 : 0;
-  kern<<<B * heads, 256, smem, st>>>((const T*)qkv, L, scores, (const T*)probs, (const T*)dout, dscores_in, (T*)dqkv, dprev,
+  const int nthreads = 32 * (Tn < 8 ? 8 : (Tn > 32 ? 32 : Tn));
+  kern<<<B * heads, nthreads, smem, st>>>((const T*)qkv, L, scores, (const T*)probs, (const T*)dout, dscores_in, (T*)dqkv, dprev,
                                      Tn, heads, d, p, seed, vec, resident);
   MMVQA_LAUNCHED("attn_bwd");
   return MMVQA_OK;

@@ -13,386 +13,12 @@
 
 namespace mmvqa {
 
-constexpr int TC_BM = 128;      // UMMA M (cta_group::1)
-constexpr int TC_BK = 64;       // 64 bf16 = one 128-byte swizzle row
-constexpr int TC_UK = 16;       // UMMA K for 16-bit inputs
-constexpr int TC_THREADS = 192;
+constexpr int TC_BM = 128, TC_BK = 64;
 
-// ---------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// bounded wait: a protocol bug traps (launch error) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  if (mbar_try(bar, parity)) return;
-  long long t0 = clock64();
-  while (!mbar_try(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
-  }
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// UMMA shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, version 1):
-//  [0,14) start >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 |
-//  [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
-__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
-}
-
-template <int BN, int STAGES_>
-struct TcCfg {
-  static constexpr int STAGES = STAGES_;
-  static constexpr int A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
-  static constexpr int B_BYTES = BN * TC_BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-};
-
-// ---------------------------------------------------------------------------------
-// epilogue: one thread = one accumulator row (TMEM lane); 16 columns per tcgen05.ld
-// ---------------------------------------------------------------------------------
-__device__ __forceinline__ bool al16(const void* base, int64_t elem_off, int elem_bytes) {
-  return ((reinterpret_cast<uintptr_t>(base) + (uintptr_t)(elem_off * elem_bytes)) & 15) == 0;
-}
-__device__ __forceinline__ void load16_bf16(const __nv_bfloat16* src, int nvalid, float* out) {
-  if (nvalid == 16 && al16(src, 0, 2)) {
-    Vec16<__nv_bfloat16> a, b;
-    a.load(src);
-    b.load(src + 8);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { out[j] = a.get(j); out[8 + j] = b.get(j); }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 16; ++j) out[j] = j < nvalid ? __bfloat162float(src[j]) : 0.0f;
-  }
-}
-__device__ __forceinline__ void store16_bf16(__nv_bfloat16* dst, int nvalid, const float* v) {
-  if (nvalid == 16 && al16(dst, 0, 2)) {
-    Vec16<__nv_bfloat16> a, b;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { a.set(j, v[j]); b.set(j, v[8 + j]); }
-    a.store(dst);
-    b.store(dst + 8);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (j < nvalid) dst[j] = __float2bfloat16_rn(v[j]);
-  }
-}
-__device__ __forceinline__ void store16_f32(float* dst, int nvalid, const float* v) {
-  if (nvalid == 16 && al16(dst, 0, 4)) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 16; ++j)
-      if (j < nvalid) dst[j] = v[j];
-  }
-}
-
-template <int EPI, int ACT, int BN>
-__device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_row, int m, int n0, int bz, bool first,
-                                            bool row_ok, bool has_acc) {
-  float rowsum = 0.0f;
-  float rscale = 0.0f;
-  if (EPI == MMVQA_EPI_DACT_SCALE && row_ok) rscale = __ldg(p.rowscale + (int64_t)bz * p.M + m) * p.scale;
-  const bool use_bias = p.bias != nullptr && first;
-  const uint32_t thr = (uint32_t)(p.dropout_p * 4294967296.0);
-  const float inv_keep = p.dropout_p > 0.0f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
-#pragma unroll 1
-  for (int c = 0; c < BN; c += 16) {
-    uint32_t r[16];
-    __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
-    tmem_ld16(tmem_row + (uint32_t)c, r);
-    tmem_ld_wait();
-    const int nb = n0 + c;
-    float v[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = 0.0f;
-    if (row_ok && nb < p.N) {
-      const int nvalid = min(16, p.N - nb);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = has_acc ? __uint_as_float(r[j]) : 0.0f;
-      if (use_bias) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j < nvalid) v[j] += __ldg(p.bias + nb + j);
-      }
-      const int64_t coff = (int64_t)bz * p.c_batch_stride + (int64_t)m * p.ldc + nb;
-      if (EPI == MMVQA_EPI_ACT_ROWSUM) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j < nvalid) rowsum += act_fast<ACT>(v[j]);
-        continue;
-      }
-      if (EPI == MMVQA_EPI_ACT) {
-        if (p.aux_out) store16_bf16(reinterpret_cast<__nv_bfloat16*>(p.aux_out) + (int64_t)m * p.ld_aux_out + nb, nvalid, v);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = act_fast<ACT>(v[j]);
-      } else if (EPI == MMVQA_EPI_RESIDUAL) {
-        float a[16];
-        load16_bf16(reinterpret_cast<const __nv_bfloat16*>(p.aux_in) + (int64_t)m * p.ld_aux_in + nb, nvalid, a);
-        if (p.dropout_p > 0.0f) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            v[j] = hash32(p.dropout_seed, (uint64_t)m * (uint64_t)p.N + (uint64_t)(nb + j)) >= thr ? v[j] * inv_keep : 0.0f;
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] += a[j];
-      } else if (EPI == MMVQA_EPI_DACT) {
-        float a[16];
-        load16_bf16(reinterpret_cast<const __nv_bfloat16*>(p.aux_in) + (int64_t)m * p.ld_aux_in + nb, nvalid, a);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] *= dact_fast<ACT>(a[j]);
-      } else if (EPI == MMVQA_EPI_DACT_SCALE) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = dact_fast<ACT>(v[j]) * rscale;
-      }
-      if (p.accumulate) {
-        float* c32 = reinterpret_cast<float*>(p.C) + coff;
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j < nvalid) atomicAdd(c32 + j, v[j]);
-      } else if (p.c_bf16) {
-        store16_bf16(reinterpret_cast<__nv_bfloat16*>(p.C) + coff, nvalid, v);
-      } else {
-        store16_f32(reinterpret_cast<float*>(p.C) + coff, nvalid, v);
-      }
-#pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (j >= nvalid) v[j] = 0.0f;
-    }
-    if (EPI != MMVQA_EPI_ACT_ROWSUM && p.colsum_out != nullptr && nb < p.N) {
-      // column sums over the warp's 32 rows: transposing butterfly, 16 shuffles; lane l ends with column
-      // 8*b4 + 4*b3 + 2*b2 + b1 of the chunk (b_k = bit k of l), duplicated on the lane pair (l, l^1)
-      __syncwarp();
-      const int lane = threadIdx.x & 31;
-      {
-        const bool hi = lane & 16;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float send = hi ? v[k] : v[k + 8];
-          const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
-          v[k] = (hi ? v[k + 8] : v[k]) + recv;
-        }
-      }
-      {
-        const bool hi = lane & 8;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float send = hi ? v[k] : v[k + 4];
-          const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
-          v[k] = (hi ? v[k + 4] : v[k]) + recv;
-        }
-      }
-      {
-        const bool hi = lane & 4;
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const float send = hi ? v[k] : v[k + 2];
-          const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
-          v[k] = (hi ? v[k + 2] : v[k]) + recv;
-        }
-      }
-      {
-        const bool hi = lane & 2;
-        const float send = hi ? v[0] : v[1];
-        const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
-        v[0] = (hi ? v[1] : v[0]) + recv;
-      }
-      v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-      const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-      if ((lane & 1) == 0 && nb + col < p.N) atomicAdd(p.colsum_out + nb + col, v[0]);
-    }
-  }
-  if (EPI == MMVQA_EPI_ACT_ROWSUM && row_ok) atomicAdd(p.rowsum_out + (int64_t)bz * p.M + m, rowsum * p.scale);
-}
-
-template <int EPI, int BN>
-__device__ __forceinline__ void tc_epilogue_act(const EpiParams& p, uint32_t tmem_row, int m, int n0, int bz, bool first,
-                                                bool row_ok, bool has_acc) {
-  switch (p.act) {
-    case MMVQA_ACT_SERF: tc_epilogue<EPI, MMVQA_ACT_SERF, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
-    case MMVQA_ACT_GELU: tc_epilogue<EPI, MMVQA_ACT_GELU, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
-    case MMVQA_ACT_RELU: tc_epilogue<EPI, MMVQA_ACT_RELU, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
-    default: tc_epilogue<EPI, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
-  }
-}
-
-// ---------------------------------------------------------------------------------
-// kernel: one 128 x BN output tile (of one batch entry / one K split) per CTA
-// ---------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                             const __grid_constant__ CUtensorMap tmB, EpiParams p,
-                                                             int a_batched, int b_batched) {
-  using Cfg = TcCfg<BN, STAGES>;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
-  // barriers: full[s] at +8*s, empty[s] at +8*(STAGES+s), tmem_full at +8*2*STAGES, tmem ptr after
-  const uint32_t tmem_full_bar = bar_base + 8 * 2 * Cfg::STAGES;
-  const uint32_t tmem_ptr_addr = tmem_full_bar + 8;
-  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + 8 * 2 * Cfg::STAGES + 8);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * TC_BM;
-  const int bz = blockIdx.z / p.split_k, ks = blockIdx.z % p.split_k;
-  const int kblocks = (p.K + TC_BK - 1) / TC_BK;
-  const int kb_per = (kblocks + p.split_k - 1) / p.split_k;
-  const int kb0 = ks * kb_per;
-  const int kb1 = min(kblocks, kb0 + kb_per);
-  const int nkb = max(0, kb1 - kb0);
-
-  if (warp == 0) {
-    tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
-  } else if (warp == 1 && lane == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) {
-      mbar_init(bar_base + 8 * s, 1);
-      mbar_init(bar_base + 8 * (Cfg::STAGES + s), 1);
-    }
-    mbar_init(tmem_full_bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_acc = *tmem_ptr_gen;
-
-  if (warp == 0) {
-    // ===== TMA producer =====
-    if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % Cfg::STAGES;
-        const uint32_t ph = (uint32_t)(i / Cfg::STAGES) & 1u;
-        mbar_wait(bar_base + 8 * (Cfg::STAGES + s), ph ^ 1u);
-        const uint32_t full = bar_base + 8 * s;
-        mbar_expect_tx(full, Cfg::STAGE_BYTES);
-        const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
-        const int k0 = (kb0 + i) * TC_BK;
-        if (A_MN) {  // stored [K, M]: two boxes of 64 (m) x 64 (k)
-          tma_load_3d(sa, &tmA, full, m0, k0, a_batched ? bz : 0);
-          tma_load_3d(sa + 8192, &tmA, full, m0 + 64, k0, a_batched ? bz : 0);
-        } else {     // stored [M, K]: one box of 64 (k) x 128 (m)
-          tma_load_3d(sa, &tmA, full, k0, m0, a_batched ? bz : 0);
-        }
-        if (B_MN) {  // stored [K, N]: BN/64 boxes of 64 (n) x 64 (k)
-#pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_3d(sb + j * 8192, &tmB, full, n0 + j * 64, k0, b_batched ? bz : 0);
-        } else {     // stored [N, K]: one box of 64 (k) x BN (n)
-          tma_load_3d(sb, &tmB, full, k0, n0, b_batched ? bz : 0);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, majors, N>>3, M>>4
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      for (int i = 0; i < nkb; ++i) {
-        const int s = i % Cfg::STAGES;
-        const uint32_t ph = (uint32_t)(i / Cfg::STAGES) & 1u;
-        mbar_wait(bar_base + 8 * s, ph);
-        tc_fence_after();
-        const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
-#pragma unroll
-        for (int j = 0; j < TC_BK / TC_UK; ++j) {
-          // K-major: 16 bf16 = 32 bytes inside the swizzled 128-byte row; SBO = 8 rows * 128 B.
-          // MN-major: 16 k-rows = 2 groups of 8 rows (1024 B each); LBO = next 64-wide MN group.
-          const uint64_t ad = A_MN ? make_sdesc(sa + j * 2048, 8192, 1024) : make_sdesc(sa + j * 32, 16, 1024);
-          const uint64_t bd = B_MN ? make_sdesc(sb + j * 2048, 8192, 1024) : make_sdesc(sb + j * 32, 16, 1024);
-          umma_bf16(tmem_acc, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
-        }
-        umma_commit(bar_base + 8 * (Cfg::STAGES + s));  // frees the smem slot when these MMAs retire
-      }
-      umma_commit(tmem_full_bar);                       // accumulator complete
-    }
-  } else {
-    // ===== epilogue: TMEM -> registers -> global =====
-    const int g = warp & 3;                 // TMEM lane group this warp may read
-    const int m = m0 + g * 32 + lane;
-    const bool first = (ks == 0);
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const bool row_ok = (m < p.M) && !(nkb == 0 && ks != 0);
-    const uint32_t tmem_row = tmem_acc + ((uint32_t)(g * 32) << 16);
-    const bool has_acc = nkb > 0;
-    switch (p.epilogue) {
-      case MMVQA_EPI_ACT: tc_epilogue_act<MMVQA_EPI_ACT, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
-      case MMVQA_EPI_RESIDUAL: tc_epilogue<MMVQA_EPI_RESIDUAL, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
-      case MMVQA_EPI_DACT: tc_epilogue_act<MMVQA_EPI_DACT, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
-      case MMVQA_EPI_ACT_ROWSUM: tc_epilogue_act<MMVQA_EPI_ACT_ROWSUM, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
-      case MMVQA_EPI_DACT_SCALE: tc_epilogue_act<MMVQA_EPI_DACT_SCALE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
-      default: tc_epilogue<MMVQA_EPI_STORE, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem_acc, Cfg::TMEM_COLS);
-}
+int launch_tc_bn32(int stages, const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st);
+int launch_tc_bn64(int stages, const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st);
+int launch_tc_bn128(int stages, const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st);
+int launch_tc_bn256(int stages, const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------
 // host: tensor maps + dispatch
@@ -414,7 +40,7 @@ static EncodeTiledFn get_encode() {
 }
 
 // 3-D map over a stored [rows, inner] bf16 matrix with `nbatch` slabs `batch_rows` rows apart.
-static int make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t rows, int64_t ld, int nbatch,
+int tc_make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t rows, int64_t ld, int nbatch,
                     int64_t batch_rows, int box_inner, int box_rows, const char* what) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_err(MMVQA_ERR_CUDA, "gemm(bf16): cuTensorMapEncodeTiled unavailable");
@@ -433,52 +59,6 @@ static int make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t r
   return MMVQA_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, int STAGES>
-static int launch_tc(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st) {
-  using Cfg = TcCfg<BN, STAGES>;
-  CUtensorMap tmA, tmB;
-  int rc;
-  // A: K-major stored [M, K] -> inner K, box 64 x 128;  MN-major stored [K, M] -> inner M, box 64 x 64
-  if (A_MN) rc = make_map(&tmA, a->A, a->M, a->K, a->lda, a->batch, a->a_batch_rows, 64, 64, "A");
-  else rc = make_map(&tmA, a->A, a->K, a->M, a->lda, a->batch, a->a_batch_rows, 64, TC_BM, "A");
-  if (rc) return rc;
-  if (B_MN) rc = make_map(&tmB, a->B, a->N, a->K, a->ldb, a->batch, a->b_batch_rows, 64, 64, "B");
-  else rc = make_map(&tmB, a->B, a->K, a->N, a->ldb, a->batch, a->b_batch_rows, 64, BN, "B");
-  if (rc) return rc;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MMVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
-    attr_set = true;
-  }
-  dim3 grid((a->N + BN - 1) / BN, (a->M + TC_BM - 1) / TC_BM, a->batch * a->split_k);
-  MMVQA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm(bf16): grid too large");
-  kern<<<grid, TC_THREADS, Cfg::SMEM, st>>>(tmA, tmB, ep, (a->batch > 1 && a->a_batch_rows > 0) ? 1 : 0,
-                                            (a->batch > 1 && a->b_batch_rows > 0) ? 1 : 0);
-  MMVQA_LAUNCHED("gemm_tc_bf16");
-  return MMVQA_OK;
-}
-
-template <int BN, int STAGES>
-static int launch_tc_major(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st) {
-  if (a->a_trans && a->b_trans) return launch_tc<BN, true, true, STAGES>(a, ep, st);
-  if (a->a_trans) return launch_tc<BN, true, false, STAGES>(a, ep, st);
-  if (a->b_trans) return launch_tc<BN, false, true, STAGES>(a, ep, st);
-  return launch_tc<BN, false, false, STAGES>(a, ep, st);
-}
-
-template <int STAGES>
-static int launch_tc_bn(int bn, const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st) {
-  switch (bn) {
-    case 256: return launch_tc_major<256, STAGES>(a, ep, st);
-    case 128: return launch_tc_major<128, STAGES>(a, ep, st);
-    case 64: return launch_tc_major<64, STAGES>(a, ep, st);
-    default:
-      if (a->a_trans) return launch_tc<32, true, false, STAGES>(a, ep, st);
-      return launch_tc<32, false, false, STAGES>(a, ep, st);
-  }
-}
-
 static int env_int(const char* name) {
   const char* v = getenv(name);
   return v ? atoi(v) : 0;
@@ -486,9 +66,12 @@ static int env_int(const char* name) {
 
 int gemm_tc_bf16(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st) {
   // Tile width: the widest BN that still gives the chip a full wave of CTAs (two for BN = 256).  Epilogues that
-  // evaluate an activation per element are bound by the epilogue warps, not the MMA: they take BN <= 128 and a
-  // 2-stage ring when the K loop is short, so that 3 CTAs (12 epilogue warps) share an SM.
-  // MN-major B needs BN % 64 == 0.  MMVQA_TC_BN / MMVQA_TC_STAGES override the choice (tuning only).
+  // evaluate an activation per element are bound by the epilogue warps, not the MMA: they take BN <= 128.
+  // MN-major B needs BN % 64 == 0.
+  // Ring depth: a small-M problem (one wave or less) is bound by how many bytes each SM keeps in flight from
+  // L2 / HBM, so it takes the deepest ring that fits (up to 8 stages, ~190 KB); multi-wave problems take 4 stages
+  // so two CTAs share an SM (the epilogue of one overlaps the main loop of the other), and 2 when the K loop is
+  // that short.  MMVQA_TC_BN / MMVQA_TC_STAGES override the choice (tuning only).
   const int sms = num_sms();
   const int64_t mt = (a->M + TC_BM - 1) / TC_BM;
   const int64_t z = (int64_t)a->batch * a->split_k;
@@ -504,16 +87,27 @@ int gemm_tc_bf16(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st)
     const int64_t ctas = mt * ((a->N + b - 1) / b) * z;
     if (ctas >= (int64_t)sms * (b == 256 ? 2 : 1)) { bn = b; break; }
   }
-  const int kblocks = ((a->K + TC_BK - 1) / TC_BK + a->split_k - 1) / a->split_k;
-  int stages = (kblocks <= 2) ? 2 : 4;
   static const int env_bn = env_int("MMVQA_TC_BN"), env_st = env_int("MMVQA_TC_STAGES");
   if (env_bn == 32 || env_bn == 64 || env_bn == 128 || env_bn == 256) {
     bn = env_bn;
     if (a->b_trans && bn < 64) bn = 64;
   }
-  if (env_st == 2 || env_st == 4) stages = env_st;
-  if (stages == 2) return launch_tc_bn<2>(bn, a, ep, st);
-  return launch_tc_bn<4>(bn, a, ep, st);
+  const int kblocks = ((a->K + TC_BK - 1) / TC_BK + a->split_k - 1) / a->split_k;
+  const int64_t ctas = mt * ((a->N + bn - 1) / bn) * z;
+  const int deep = bn == 256 ? 4 : (bn == 128 ? 6 : 8);
+  int stages;
+  if (kblocks <= 2) stages = 2;
+  else if (ctas <= sms && kblocks > 4) stages = deep;
+  else stages = 4;
+  if (env_st == 2 || env_st == 4 || env_st == 6 || env_st == 8) stages = env_st > deep ? deep : env_st;
+  if (stages == 6 && bn != 128) stages = 4;
+  if (stages == 8 && bn > 64) stages = deep;
+  switch (bn) {
+    case 256: return launch_tc_bn256(stages, a, ep, st);
+    case 128: return launch_tc_bn128(stages, a, ep, st);
+    case 64: return launch_tc_bn64(stages, a, ep, st);
+    default: return launch_tc_bn32(stages, a, ep, st);
+  }
 }
 
 }  // namespace mmvqa

@@ -1,0 +1,13 @@
+#include "gemm_tc_kernel.cuh"
+
+namespace mmvqa {
+
+int launch_tc_bn256(int stages, const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st) {
+  switch (stages) {
+    case 2: return launch_tc_major<256, 2>(a, ep, st);
+    case 4: return launch_tc_major<256, 4>(a, ep, st);
+    default: return set_err(MMVQA_ERR_ARG, "gemm(bf16): no %d-stage kernel for this tile", stages);
+  }
+}
+
+}  // namespace mmvqa
