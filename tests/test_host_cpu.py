@@ -132,3 +132,22 @@ def test_compute_dtype_switch():
         assert mmvqa_b200.compute_dtype() == torch.float32
     with pytest.raises((ValueError, KeyError)):
         mmvqa_b200.set_compute_dtype("fp16")
+
+
+def test_shim_aliases_reference_import_paths():
+    import sys
+    import mmvqa_b200.shim as shim
+    saved = {k: v for k, v in sys.modules.items() if k == "models" or k.startswith("models.")}
+    try:
+        shim.install()
+        from models.mmbert import Model, get_transformer_model, mean_pooling  # noqa: F401  (vqamed2019/train.py:21)
+        from models.asl_singlelabel import ASLSingleLabel as A2               # noqa: F401  (train.py:22)
+        from models.SupConLoss.loss import SupConLoss as S2                   # noqa: F401  (roco_supcon_train.py)
+        from models.realformer import ResEncoderBlock as R2                   # noqa: F401
+        from models.transformer import BertLayer as B2, gelu                  # noqa: F401
+        from models.image_encoding import get_transfer, models_dict          # noqa: F401
+        from models.serf import SERF as SF2                                   # noqa: F401
+        assert Model is MM.Model and A2 is ASLSingleLabel and S2 is SupConLoss
+    finally:
+        shim.uninstall()
+        sys.modules.update(saved)
