@@ -346,7 +346,22 @@ def main_gpu(a):
             dist.destroy_process_group()
         return
     hbm, tf_burst, tf_sus, which = peaks()
-    # ---- roofline of the dominant kernel, measured live (CUDA events, cold L2) ----
+    log("roofline measurements")
+    # ---- roofline of the dominant kernel, measured live with CUDA events on the launching stream ----
+    # (1) the tcgen05 GEMM family (gemm_tc_kernel): one eager forward+backward with an event pair around every
+    #     mmvqa_gemm launch, queued behind a 100 ms spin so the device never waits for the host between launches.
+    from mmvqa_b200 import ops as _ops
+    opt.zero_grad(set_to_none=True)
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(2e8))
+    _ops.gemm_timing(True)
+    loss_fn(*dev[0]).backward()
+    rec = _ops.gemm_timing(False)
+    torch.cuda.synchronize()
+    g_ms = [e0.elapsed_time(e1) for (_, _, e0, e1) in rec]
+    g_flops = sum(f for (f, _, _, _) in rec)
+    gemm_ms, gemm_n = sum(g_ms), len(g_ms)
+    gemm_tflops = g_flops / (gemm_ms * 1e-3) / 1e12
     M = B * T
     x = torch.randn(M, HIDDEN, device="cuda").to(dt)
     w = torch.randn(4 * HIDDEN, HIDDEN, device="cuda").to(dt)
@@ -357,19 +372,29 @@ def main_gpu(a):
     ms_ff1 = time_kernel(lambda: ops.gemm(M, 4 * HIDDEN, HIDDEN, x, HIDDEN, False, w, HIDDEN, False, y, 4 * HIDDEN, bias=bias,
                                           epilogue=EPI_ACT, act=ACT_SERF, aux_out=pre, ld_aux_out=4 * HIDDEN))
     ff1_tflops = 2.0 * M * 4 * HIDDEN * HIDDEN / (ms_ff1 * 1e-3) / 1e12
-    # Adam: 16 B read (p, m, v, g) + 12 B written (p, m, v) per parameter
+    xb_, wb_ = torch.randn(8192, 8192, device="cuda").to(dt), torch.randn(8192, 8192, device="cuda").to(dt)
+    yb_ = torch.empty(8192, 8192, device="cuda", dtype=dt)
+    ms_big = time_kernel(lambda: ops.gemm(8192, 8192, 8192, xb_, 8192, False, wb_, 8192, False, yb_, 8192), iters=5)
+    big_tflops = 2.0 * 8192 ** 3 / (ms_big * 1e-3) / 1e12
+    del xb_, wb_, yb_
+    # (2) Adam: 16 B read (p, m, v, g) + 12 B written (p, m, v) per parameter (+2 B bf16 operand copy where cached)
     _, table, nchunks = opt._tables[0]
     grp = opt.param_groups[0]
     ms_adam = time_kernel(lambda: ops.adam_step(table, nchunks, grp["lr"], grp["betas"][0], grp["betas"][1], grp["eps"],
                                                 grp["weight_decay"], 0, opt._step_dev, opt.grad_scale), iters=10)
     adam_gbs = nparams * 28 / (ms_adam * 1e-3) / 1e9
-    adam_share = ms_adam / ms_step
-    roof = {"kernel": "adam_kernel (multi-tensor Adam, %.1f M fp32 params, 28 B/param)" % (nparams / 1e6), "bound": "hbm",
-            "achieved": adam_gbs, "peak": hbm, "unit": "GB/s", "frac": adam_gbs / hbm, "traffic": None,
-            "peak_source": which + " (MEASURED_PEAKS.json hbm_gbs)", "ms_per_launch": ms_adam, "share_of_step": adam_share,
-            "tensor_kernel": {"kernel": "gemm_tc_kernel FF1 %dx%dx%d + bias + SERF epilogue" % (M, 4 * HIDDEN, HIDDEN),
-                              "achieved": ff1_tflops, "peak": tf_burst, "unit": "TFLOP/s", "frac": ff1_tflops / tf_burst,
-                              "ms_per_launch": ms_ff1},
+    roof = {"kernel": "gemm_tc_kernel (tcgen05/TMEM/TMA bf16 GEMM family: %d launches per step, %.0f%% of the step time)"
+                      % (gemm_n, 100.0 * gemm_ms / ms_step),
+            "bound": "tensor", "achieved": gemm_tflops, "peak": tf_burst, "unit": "TFLOP/s", "frac": gemm_tflops / tf_burst,
+            "traffic": None, "peak_source": which + " (MEASURED_PEAKS.json bf16_tflops, burst: kernels timed alone)",
+            "flops_per_launch": g_flops / max(gemm_n, 1), "ms_per_launch": gemm_ms / max(gemm_n, 1),
+            "how": "CUDA events around every mmvqa_gemm launch of one forward+backward at the bench shape; algorithmic 2MNK",
+            "same_kernel_other_shapes": {
+                "ff1_448x3072x768_bias_serf": {"achieved": ff1_tflops, "frac": ff1_tflops / tf_burst, "ms_per_launch": ms_ff1},
+                "square_8192": {"achieved": big_tflops, "frac": big_tflops / tf_burst, "ms_per_launch": ms_big}},
+            "hbm_kernel": {"kernel": "adam_kernel (multi-tensor Adam, %.1f M fp32 params, 28 B/param)" % (nparams / 1e6),
+                           "bound": "hbm", "achieved": adam_gbs, "peak": hbm, "unit": "GB/s", "frac": adam_gbs / hbm,
+                           "ms_per_launch": ms_adam, "share_of_step": ms_adam / ms_step},
             "step_tensor_frac": value / world * STEP_GFLOP_PER_SAMPLE * 1e9 / (tf_burst * 1e12)}
     cpu = None
     if world == 1 and not a.no_cpu:

@@ -60,14 +60,16 @@ int64_t mmvqa_launch_count(void);
  *   models/realformer.py:33,45,22-26, models/mmbert.py:133-148,164-166, image_encoding.py:74-113
  *   (1x1 conv), SupConLoss/loss.py:69-71, and their autograd backward (dgrad / wgrad).
  * Epilogues (acc = fp32 accumulator, bias fp32 [N] optional everywhere):
- *   EPI_STORE      C = acc + bias
+ *   EPI_STORE      C = (acc + bias) * (rowscale ? rowscale[batch*M + m] * scale : 1)
  *   EPI_ACT        aux_out = acc + bias (pre-activation, optional) ; C = act(acc + bias)
  *   EPI_RESIDUAL   C = dropout(acc + bias) + aux_in[m,n]   (nn.Dropout on the branch output,
  *                  realformer.py:45,26 / transformer.py:79,86; dropout_p = 0 -> identity.  The keep
  *                  decision is a counter hash of (dropout_seed, m*N+n), reproduced by mmvqa_dropout)
  *   EPI_DACT       C = acc * act'(aux_in[m,n])          (dgrad through an activation)
  *   EPI_ACT_ROWSUM rowsum_out[batch*M + m] += scale * sum_n act(acc)   (visual-token pooling;
- *                  C unused; columns n >= N contribute act(0) = 0)
+ *                  C unused; columns n >= N are masked).  If aux_out != NULL, act'(acc) is stored at
+ *                  aux_out[(batch*M + m) * ld_aux_out + n] for the backward pass (the [B,hidden,H,W]
+ *                  activation map itself is never written)
  *   EPI_DACT_SCALE C = act'(acc) * rowscale[batch*M + m] * scale  (projector backward recompute)
  * c_dtype may differ from dtype (fp32 output for weight gradients / logits).
  * accumulate != 0: C += result with fp32 atomics (C must be fp32; used with split_k > 1

@@ -147,20 +147,59 @@ __device__ __forceinline__ ErfPos erf_pos_fast(float z) {
   r.erf = fmaf(-poly, r.E, 1.0f);
   return r;
 }
+// erf(z), z >= 0, without an exponential: Abramowitz-Stegun 7.1.28, 1 - (1 + a1 z + ... + a6 z^6)^-16
+// (|err| <= 3e-7): 6 FMA + 4 squarings + ONE MUFU (rcp).  p^16 overflows to +inf for z > ~9 -> erf = 1.
+__device__ __forceinline__ float erf_pos_rcp16(float z) {
+  float p = fmaf(0.0000430638f, z, 0.0002765672f);
+  p = fmaf(p, z, 0.0001520143f);
+  p = fmaf(p, z, 0.0092705272f);
+  p = fmaf(p, z, 0.0422820123f);
+  p = fmaf(p, z, 0.0705230784f);
+  p = fmaf(p, z, 1.0f);
+  p *= p;
+  p *= p;
+  p *= p;
+  p *= p;
+  return 1.0f - __fdividef(1.0f, p);
+}
+// log1p(u) for u in [0, 1] = u * q(u), degree-7 minimax-like fit (rel err 3.6e-7): no MUFU
+__device__ __forceinline__ float log1p_unit(float u) {
+  float q = fmaf(-0.0085746762f, u, 0.0442141923f);
+  q = fmaf(q, u, -0.107853679f);
+  q = fmaf(q, u, 0.17757024f);
+  q = fmaf(q, u, -0.244996117f);
+  q = fmaf(q, u, 0.332761766f);
+  q = fmaf(q, u, -0.499974494f);
+  q = fmaf(q, u, 0.99999981f);
+  return q * u;
+}
+// SERF with 2 MUFU ops (ex2, rcp): softplus(x) = max(x,0) + log1p(exp(-|x|)), erf by 7.1.28.  |abs err| < 2e-5.
 __device__ __forceinline__ float serf_fast(float x) {
   const float e = __expf(-fabsf(x));
-  const float sp = fmaxf(x, 0.0f) + __logf(1.0f + e);
-  return x * erf_pos_fast(sp).erf;
+  const float sp = fmaxf(x, 0.0f) + log1p_unit(e);
+  return x * erf_pos_rcp16(sp);
 }
+// SERF' with 4 MUFU ops (ex2, rcp, rcp, ex2).  |abs err| < 3e-6.
 __device__ __forceinline__ float dserf_fast(float x) {
   const float e = __expf(-fabsf(x));
-  const float one_e = 1.0f + e;
-  const float sp = fmaxf(x, 0.0f) + __logf(one_e);
-  const ErfPos r = erf_pos_fast(sp);
-  const float inv = __fdividef(1.0f, one_e);
+  const float sp = fmaxf(x, 0.0f) + log1p_unit(e);
+  const float er = erf_pos_rcp16(sp);
+  const float E = __expf(-sp * sp);
+  const float inv = __fdividef(1.0f, 1.0f + e);
   const float sig = x >= 0.0f ? inv : e * inv;
   // beyond the reference's clamp (x > 50) E underflows to 0 and the slope is erf(sp) = 1, as in serf.py
-  return fmaf(x * 1.1283791670955126f * r.E, sig, r.erf);
+  return fmaf(x * 1.1283791670955126f * E, sig, er);
+}
+// SERF and SERF' together (shared softplus / erf): 4 MUFU for both
+__device__ __forceinline__ void serf_both_fast(float x, float& a, float& d) {
+  const float e = __expf(-fabsf(x));
+  const float sp = fmaxf(x, 0.0f) + log1p_unit(e);
+  const float er = erf_pos_rcp16(sp);
+  const float E = __expf(-sp * sp);
+  const float inv = __fdividef(1.0f, 1.0f + e);
+  const float sig = x >= 0.0f ? inv : e * inv;
+  a = x * er;
+  d = fmaf(x * 1.1283791670955126f * E, sig, er);
 }
 __device__ __forceinline__ float gelu_fast(float x) {
   const ErfPos r = erf_pos_fast(fabsf(x) * 0.7071067811865476f);
@@ -175,6 +214,16 @@ template <int ACT> __device__ __forceinline__ float act_fast(float x) {
   if (ACT == MMVQA_ACT_GELU) return gelu_fast(x);
   if (ACT == MMVQA_ACT_RELU) return fmaxf(x, 0.0f);
   return x;
+}
+template <int ACT> __device__ __forceinline__ void act_both_fast(float x, float& a, float& d) {
+  if (ACT == MMVQA_ACT_SERF) {
+    serf_both_fast(x, a, d);
+  } else {
+    a = act_fast<ACT>(x);
+    if (ACT == MMVQA_ACT_GELU) d = dgelu_fast(x);
+    else if (ACT == MMVQA_ACT_RELU) d = x > 0.0f ? 1.0f : 0.0f;
+    else d = 1.0f;
+  }
 }
 template <int ACT> __device__ __forceinline__ float dact_fast(float x) {
   if (ACT == MMVQA_ACT_SERF) return dserf_fast(x);

@@ -2,6 +2,7 @@
 // tcgen05 / TMEM / TMA kernel (dtype BF16).  There is no fallback between the two: a bf16 problem
 // that violates the TMA alignment rules is an error, not a silent SIMT run.
 #include "gemm_common.cuh"
+#include <stdlib.h>
 
 using namespace mmvqa;
 
@@ -26,6 +27,8 @@ extern "C" int mmvqa_gemm(const mmvqa_gemm_args* a, mmvqa_stream_t stream) {
   if (a->epilogue == MMVQA_EPI_RESIDUAL || a->epilogue == MMVQA_EPI_DACT)
     MMVQA_REQUIRE(a->aux_in != nullptr && a->ld_aux_in >= a->N, "gemm: epilogue %d needs aux_in", a->epilogue);
   if (a->epilogue == MMVQA_EPI_DACT_SCALE) MMVQA_REQUIRE(a->rowscale != nullptr, "gemm: EPI_DACT_SCALE needs rowscale");
+  if (a->rowscale != nullptr)
+    MMVQA_REQUIRE(a->epilogue == MMVQA_EPI_DACT_SCALE || a->epilogue == MMVQA_EPI_STORE, "gemm: rowscale only with EPI_STORE / EPI_DACT_SCALE");
   if (a->aux_out) MMVQA_REQUIRE(a->ld_aux_out >= a->N, "gemm: bad ld_aux_out");
   if (a->colsum_out) MMVQA_REQUIRE(a->epilogue != MMVQA_EPI_ACT_ROWSUM && split_k == 1, "gemm: colsum_out needs a storing epilogue and split_k == 1");
   if (a->accumulate || split_k > 1) {
@@ -53,5 +56,7 @@ extern "C" int mmvqa_gemm(const mmvqa_gemm_args* a, mmvqa_stream_t stream) {
   int sm = mmvqa_device_sm();
   if (sm < 0) return sm;
   if (sm / 10 != 10) return set_err(MMVQA_ERR_ARCH, "gemm(bf16): tcgen05 path needs sm_100, device is sm_%d", sm);
+  static const bool no_vistok = getenv("MMVQA_NO_VISTOK") != nullptr;   // A/B switch for tuning runs
+  if (!no_vistok && vistok_applicable(&v)) return vistok_launch(&v, ep, as_stream(stream));
   return gemm_tc_bf16(&v, ep, as_stream(stream));
 }

@@ -40,12 +40,14 @@ __device__ __forceinline__ float epi_element(const EpiParams& p, int bz, int m, 
       out = v * dact_rt(p.act, to_f(reinterpret_cast<const AUX*>(p.aux_in)[(int64_t)m * p.ld_aux_in + n]));
       break;
     case MMVQA_EPI_ACT_ROWSUM:
+      if (p.aux_out)   // act'(.) kept for the backward pass: [batch, M, ld_aux_out]
+        reinterpret_cast<AUX*>(p.aux_out)[((int64_t)bz * p.M + m) * p.ld_aux_out + n] = from_f<AUX>(dact_rt(p.act, v));
       return act_rt(p.act, v);
     case MMVQA_EPI_DACT_SCALE:
       out = dact_rt(p.act, v) * __ldg(p.rowscale + (int64_t)bz * p.M + m) * p.scale;
       break;
     default:
-      out = v;
+      out = p.rowscale ? v * __ldg(p.rowscale + (int64_t)bz * p.M + m) * p.scale : v;
   }
   int64_t off = (int64_t)bz * p.c_batch_stride + (int64_t)m * p.ldc + n;
   if (p.accumulate)
@@ -59,5 +61,7 @@ __device__ __forceinline__ float epi_element(const EpiParams& p, int bz, int m, 
 
 int gemm_simt_f32(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st);
 int gemm_tc_bf16(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st);
+bool vistok_applicable(const mmvqa_gemm_args* a);
+int vistok_launch(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st);
 
 }  // namespace mmvqa

@@ -14,7 +14,7 @@ int tc_make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t rows,
 constexpr int TC_BM = 128;      // UMMA M (cta_group::1)
 constexpr int TC_BK = 64;       // 64 bf16 = one 128-byte swizzle row
 constexpr int TC_UK = 16;       // UMMA K for 16-bit inputs
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;   // TMA warp + MMA warp + 8 epilogue warps
 
 // ---------------------------------------------------------------------------------
 // PTX wrappers
@@ -149,15 +149,16 @@ __device__ __forceinline__ void store16_f32(float* dst, int nvalid, const float*
 
 template <int EPI, int ACT, int BN>
 __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_row, int m, int n0, int bz, bool first,
-                                            bool row_ok, bool has_acc) {
+                                            bool row_ok, bool has_acc, int c_begin) {
   float rowsum = 0.0f;
   float rscale = 0.0f;
-  if (EPI == MMVQA_EPI_DACT_SCALE && row_ok) rscale = __ldg(p.rowscale + (int64_t)bz * p.M + m) * p.scale;
+  if ((EPI == MMVQA_EPI_DACT_SCALE || (EPI == MMVQA_EPI_STORE && p.rowscale != nullptr)) && row_ok)
+    rscale = __ldg(p.rowscale + (int64_t)bz * p.M + m) * p.scale;
   const bool use_bias = p.bias != nullptr && first;
   const uint32_t thr = (uint32_t)(p.dropout_p * 4294967296.0);
   const float inv_keep = p.dropout_p > 0.0f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
 #pragma unroll 1
-  for (int c = 0; c < BN; c += 16) {
+  for (int c = c_begin; c < c_begin + BN / 2; c += 16) {
     uint32_t r[16];
     __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
     tmem_ld16(tmem_row + (uint32_t)c, r);
@@ -177,10 +178,25 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_ro
       }
       const int64_t coff = (int64_t)bz * p.c_batch_stride + (int64_t)m * p.ldc + nb;
       if (EPI == MMVQA_EPI_ACT_ROWSUM) {
+        if (p.aux_out) {
+          float dv_[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j < nvalid) rowsum += act_fast<ACT>(v[j]);
+          for (int j = 0; j < 16; ++j) {
+            float a_;
+            act_both_fast<ACT>(v[j], a_, dv_[j]);
+            if (j < nvalid) rowsum += a_;
+          }
+          store16_bf16(reinterpret_cast<__nv_bfloat16*>(p.aux_out) + ((int64_t)bz * p.M + m) * p.ld_aux_out + nb, nvalid, dv_);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nvalid) rowsum += act_fast<ACT>(v[j]);
+        }
         continue;
+      }
+      if (EPI == MMVQA_EPI_STORE && p.rowscale != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] *= rscale;
       }
       if (EPI == MMVQA_EPI_ACT) {
         if (p.aux_out) store16_bf16(reinterpret_cast<__nv_bfloat16*>(p.aux_out) + (int64_t)m * p.ld_aux_out + nb, nvalid, v);
@@ -267,12 +283,12 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_ro
 
 template <int EPI, int BN>
 __device__ __forceinline__ void tc_epilogue_act(const EpiParams& p, uint32_t tmem_row, int m, int n0, int bz, bool first,
-                                                bool row_ok, bool has_acc) {
+                                                bool row_ok, bool has_acc, int c_begin) {
   switch (p.act) {
-    case MMVQA_ACT_SERF: tc_epilogue<EPI, MMVQA_ACT_SERF, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
-    case MMVQA_ACT_GELU: tc_epilogue<EPI, MMVQA_ACT_GELU, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
-    case MMVQA_ACT_RELU: tc_epilogue<EPI, MMVQA_ACT_RELU, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
-    default: tc_epilogue<EPI, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
+    case MMVQA_ACT_SERF: tc_epilogue<EPI, MMVQA_ACT_SERF, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin); break;
+    case MMVQA_ACT_GELU: tc_epilogue<EPI, MMVQA_ACT_GELU, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin); break;
+    case MMVQA_ACT_RELU: tc_epilogue<EPI, MMVQA_ACT_RELU, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin); break;
+    default: tc_epilogue<EPI, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin); break;
   }
 }
 
@@ -369,8 +385,9 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
       umma_commit(tmem_full_bar);                       // accumulator complete
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> global =====
+    // ===== epilogue: TMEM -> registers -> global.  8 warps: two per TMEM lane group, each takes half the columns =====
     const int g = warp & 3;                 // TMEM lane group this warp may read
+    const int c_begin = ((warp - 2) >> 2) * (BN / 2);
     const int m = m0 + g * 32 + lane;
     const bool first = (ks == 0);
     mbar_wait(tmem_full_bar, 0);
@@ -379,12 +396,12 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     const uint32_t tmem_row = tmem_acc + ((uint32_t)(g * 32) << 16);
     const bool has_acc = nkb > 0;
     switch (p.epilogue) {
-      case MMVQA_EPI_ACT: tc_epilogue_act<MMVQA_EPI_ACT, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
-      case MMVQA_EPI_RESIDUAL: tc_epilogue<MMVQA_EPI_RESIDUAL, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
-      case MMVQA_EPI_DACT: tc_epilogue_act<MMVQA_EPI_DACT, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
-      case MMVQA_EPI_ACT_ROWSUM: tc_epilogue_act<MMVQA_EPI_ACT_ROWSUM, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
-      case MMVQA_EPI_DACT_SCALE: tc_epilogue_act<MMVQA_EPI_DACT_SCALE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
-      default: tc_epilogue<MMVQA_EPI_STORE, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc); break;
+      case MMVQA_EPI_ACT: tc_epilogue_act<MMVQA_EPI_ACT, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin); break;
+      case MMVQA_EPI_RESIDUAL: tc_epilogue<MMVQA_EPI_RESIDUAL, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin); break;
+      case MMVQA_EPI_DACT: tc_epilogue_act<MMVQA_EPI_DACT, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin); break;
+      case MMVQA_EPI_ACT_ROWSUM: tc_epilogue_act<MMVQA_EPI_ACT_ROWSUM, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin); break;
+      case MMVQA_EPI_DACT_SCALE: tc_epilogue_act<MMVQA_EPI_DACT_SCALE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin); break;
+      default: tc_epilogue<MMVQA_EPI_STORE, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin); break;
     }
   }
   tc_fence_before();

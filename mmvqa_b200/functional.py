@@ -343,8 +343,9 @@ class L2NormFn(torch.autograd.Function):
 # visual-token projector: v[b,:] = mean_hw act(W . f[b,:,hw])     (image_encoding.py:74,103)
 # --------------------------------------------------------------------------------------
 class VisTokFn(torch.autograd.Function):
-    """One pyramid level.  The [B, hidden, H, W] activation map is never materialised in forward;
-    backward recomputes the projection and materialises only G = act'(.) * dv / HW."""
+    """One pyramid level.  The [B, hidden, H, W] activation map is never materialised; when a gradient is needed the
+    forward epilogue also stores act'(.) (compute dtype), so backward is two plain GEMMs with no transcendental:
+    dW = sum_b (dv_b / HW) . (act'_b f_b^T)   and   df_b = (W * dv_b / HW)^T act'_b."""
 
     @staticmethod
     def forward(ctx, feat: Tensor, conv_w: Tensor, act: int, dtype: torch.dtype):
@@ -355,32 +356,35 @@ class VisTokFn(torch.autograd.Function):
         f2 = feat.detach().reshape(B * Cc, HW)
         fb, ld = _pad_ld(f2, dtype)                         # compute dtype, ld % 8 == 0 for bf16
         v = torch.zeros(B, hidden, device=feat.device, dtype=torch.float32)
+        need_bwd = ctx.needs_input_grad[0] or ctx.needs_input_grad[1]
+        actp = torch.empty(B, hidden, ld, device=feat.device, dtype=dtype) if need_bwd else None
         ops.gemm(hidden, HW, Cc, w, Cc, False, fb, ld, True, None, 0, epilogue=EPI_ACT_ROWSUM, act=act, rowsum_out=v,
-                 scale=1.0 / HW, batch=B, a_batch_rows=0, b_batch_rows=Cc)
-        ctx.save_for_backward(fb, conv_w)
+                 scale=1.0 / HW, batch=B, a_batch_rows=0, b_batch_rows=Cc, aux_out=actp, ld_aux_out=ld)
+        ctx.save_for_backward(fb, conv_w, actp)
         ctx.meta = (act, dtype, B, Cc, Hh, Ww, ld, hidden, feat.dtype)
         return v
 
     @staticmethod
     def backward(ctx, dv: Tensor):
-        fb, conv_w = ctx.saved_tensors
+        fb, conv_w, actp = ctx.saved_tensors
         act, dtype, B, Cc, Hh, Ww, ld, hidden, fdt = ctx.meta
         HW = Hh * Ww
-        w = weight_cache.get((conv_w,), dtype)
-        dv = dv.contiguous().float()
-        G = torch.empty(B, hidden, ld, device=fb.device, dtype=dtype)
-        ops.gemm(hidden, HW, Cc, w, Cc, False, fb, ld, True, G, ld, epilogue=EPI_DACT_SCALE, act=act, rowscale=dv,
-                 scale=1.0 / HW, batch=B, a_batch_rows=0, b_batch_rows=Cc, c_batch_stride=hidden * ld)
+        dvs = dv.contiguous().float()
         dw = dfeat = None
         if ctx.needs_input_grad[1]:
             dw = torch.zeros(hidden, Cc, device=fb.device, dtype=torch.float32)
-            ops.gemm(hidden, Cc, HW, G, ld, False, fb, ld, False, dw, Cc, accumulate=True, batch=B, a_batch_rows=hidden,
-                     b_batch_rows=Cc, c_batch_stride=0)
+            tiles = ((hidden + 127) // 128) * B
+            kblocks = (HW + 63) // 64
+            sk = max(1, min(4, (2 * _sms(fb.device)) // max(tiles, 1), kblocks // 16))
+            ops.gemm(hidden, Cc, HW, actp, ld, False, fb, ld, False, dw, Cc, accumulate=True, split_k=sk, batch=B,
+                     a_batch_rows=hidden, b_batch_rows=Cc, c_batch_stride=0, rowscale=dvs, scale=1.0 / HW)
             dw = dw.view(conv_w.shape)
         if ctx.needs_input_grad[0]:
+            w32 = conv_w.detach().reshape(hidden, Cc).float()
+            wb = (w32.unsqueeze(0) * (dvs / HW).unsqueeze(-1)).to(dtype).contiguous()       # [B, hidden, C]
             dfeat = torch.empty(B, Cc, HW, device=fb.device, dtype=torch.float32)
-            ops.gemm(Cc, HW, hidden, w, Cc, True, G, ld, True, dfeat, HW, batch=B, a_batch_rows=0, b_batch_rows=hidden,
-                     c_batch_stride=Cc * HW)
+            ops.gemm(Cc, HW, hidden, wb, Cc, True, actp, ld, True, dfeat, HW, batch=B, a_batch_rows=hidden,
+                     b_batch_rows=hidden, c_batch_stride=Cc * HW)
             dfeat = dfeat.view(B, Cc, Hh, Ww).to(fdt)
         return dfeat, dw, None, None
 

@@ -461,3 +461,49 @@ def test_supcon_rows_against_oracle(golden):
         want = r[tag + "_grad"].float()
         want_vm = torch.cat([want[:, v] for v in range(nv)], 0)
         close(dF, want_vm, 1e-3, 1e-5, msg=tag + " grad")
+
+
+@pytest.mark.parametrize("Cc,HW,hidden,Bn", [(24, 1000, 256, 3), (48, 3136, 768, 2), (80, 784, 136, 2), (128, 520, 128, 1)])
+@pytest.mark.parametrize("act", ["serf", "relu"])
+def test_persistent_projector_kernel(Cc, HW, hidden, Bn, act):
+    """vistok.cu (bf16, C <= 128, >= 2 pixel tiles): pooled forward and the recompute backward vs torch."""
+    dt = torch.bfloat16
+    ld = (HW + 7) // 8 * 8
+    W = (rnd(hidden, Cc, seed=100) * 0.3).to(dt)
+    f = rnd(Bn, Cc, HW, seed=101).abs().to(dt)
+    fpad = torch.zeros(Bn, Cc, ld, dtype=dt)
+    fpad[:, :, :HW] = f
+    Y = torch.einsum("mc,bcn->bmn", W.float(), f.float())
+    v_ref = O.activation(act, Y).mean(-1)
+    v = torch.zeros(Bn, hidden, device=DEV)
+    ops.gemm(hidden, HW, Cc, W.to(DEV), Cc, False, fpad.to(DEV), ld, True, None, 0, epilogue=EPI_ACT_ROWSUM, act=ACTS[act],
+             rowsum_out=v, scale=1.0 / HW, batch=Bn, a_batch_rows=0, b_batch_rows=Cc)
+    close(v, v_ref, 1e-2, 2e-3, msg="pooled forward")
+    dv = rnd(Bn, hidden, seed=102)
+    _, dact = oracle_act(act, Y)
+    # forward that also keeps act'(.) for the backward pass, then dW = sum_b (dv_b/HW) . act'_b f_b^T
+    v2 = torch.zeros(Bn, hidden, device=DEV)
+    actp = torch.full((Bn, hidden, ld), float("nan"), device=DEV, dtype=dt)
+    ops.gemm(hidden, HW, Cc, W.to(DEV), Cc, False, fpad.to(DEV), ld, True, None, 0, epilogue=EPI_ACT_ROWSUM, act=ACTS[act],
+             rowsum_out=v2, scale=1.0 / HW, batch=Bn, a_batch_rows=0, b_batch_rows=Cc, aux_out=actp, ld_aux_out=ld)
+    close(v2, v_ref, 1e-2, 2e-3, msg="pooled forward (+act')")
+    ap = actp[:, :, :HW].float().cpu()
+    assert torch.isfinite(ap).all()
+    sel = (Y.abs() > 0.05) if act == "relu" else torch.ones_like(Y, dtype=torch.bool)
+    close(ap[sel], dact[sel], 2e-2, 1e-2, msg="stored act'")
+    dw = torch.zeros(hidden, Cc, device=DEV)
+    ops.gemm(hidden, Cc, HW, actp, ld, False, fpad.to(DEV), ld, False, dw, Cc, accumulate=True, split_k=2, batch=Bn,
+             a_batch_rows=hidden, b_batch_rows=Cc, c_batch_stride=0, rowscale=dv.to(DEV), scale=1.0 / HW)
+    dw_ref = torch.einsum("bmn,bcn,bm->mc", ap, f.float(), dv) / HW
+    close(dw, dw_ref, 2e-2, 2e-3 * float(dw_ref.abs().max()), msg="row-scaled batched accumulate")
+    G_ref = dact * dv[:, :, None] / HW
+    G = torch.full((Bn, hidden, ld), float("nan"), device=DEV, dtype=dt)
+    ops.gemm(hidden, HW, Cc, W.to(DEV), Cc, False, fpad.to(DEV), ld, True, G, ld, epilogue=EPI_DACT_SCALE, act=ACTS[act],
+             rowscale=dv.to(DEV), scale=1.0 / HW, batch=Bn, a_batch_rows=0, b_batch_rows=Cc, c_batch_stride=hidden * ld)
+    got = G[:, :, :HW].float().cpu()
+    assert torch.isfinite(got).all()
+    if act == "relu":       # act' flips where the bf16 product crosses 0: compare away from the kink
+        sel = Y.abs() > 0.05
+        close(got[sel], G_ref[sel], 2e-2, 1e-6, msg="recompute backward (relu)")
+    else:
+        close(got, G_ref, 2e-2, 2e-3 * float(G_ref.abs().max()), msg="recompute backward")

@@ -88,6 +88,14 @@ gemm_case("proj wgrad", H, H, M, at=True, bt=True, cdt=torch.float32)
 gemm_case("proj wgrad split4", H, H, M, at=True, bt=True, cdt=torch.float32, accumulate=True, split_k=4)
 gemm_case("kqv wgrad", 3 * d, d, M * heads, at=True, bt=True, cdt=torch.float32)
 gemm_case("kqv wgrad split14", 3 * d, d, M * heads, at=True, bt=True, cdt=torch.float32, accumulate=True, split_k=14)
+for sk in (2, 3, 4, 6, 8):
+    gemm_case(f"ff2 fwd split{sk} (fp32 atomics)", M, H, F4, cdt=torch.float32, accumulate=True, split_k=sk)
+for sk in (2, 3, 4):
+    gemm_case(f"proj fwd split{sk} (fp32 atomics)", M, H, H, cdt=torch.float32, accumulate=True, split_k=sk)
+for sk in (2, 3):
+    gemm_case(f"ff1 fwd split{sk} (fp32 atomics)", M, F4, H, cdt=torch.float32, accumulate=True, split_k=sk)
+if os.environ.get("KB_ONLY_SPLIT"):
+    sys.exit(0)
 gemm_case("big 8192^3", 8192, 8192, 8192)
 gemm_case("big 4096x3072x768", 4096, 3072, 768)
 
