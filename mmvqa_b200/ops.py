@@ -17,16 +17,21 @@ from ._lib import (ACT_GELU, ACT_NONE, ACT_RELU, ACT_SERF, BF16, EPI_ACT, EPI_AC
 
 Tensor = torch.Tensor
 ACT_CODES = {"none": ACT_NONE, "serf": ACT_SERF, "gelu": ACT_GELU, "relu": ACT_RELU}
-_GEMM_TIMING = None     # bench.py instrumentation: list of (flops, start_event, end_event) per mmvqa_gemm launch
+_GEMM_RECORD = None     # bench.py instrumentation: list of (signature, flops, GemmArgs, keep-alive tensors)
 
 
-def gemm_timing(enable: bool):
-    """Start / stop recording a CUDA-event pair around every mmvqa_gemm launch (roofline measurement in bench.py).
-    Returns the recorded list when stopping."""
-    global _GEMM_TIMING
-    out = _GEMM_TIMING
-    _GEMM_TIMING = [] if enable else None
+def gemm_record(enable: bool):
+    """Start / stop recording every mmvqa_gemm launch (its argument struct and the tensors it points to) so that
+    bench.py can replay each distinct problem in isolation and time it (roofline measurement).  Returns the list
+    when stopping."""
+    global _GEMM_RECORD
+    out = _GEMM_RECORD
+    _GEMM_RECORD = [] if enable else None
     return out
+
+
+def gemm_replay(args) -> None:
+    L.check(L.lib().mmvqa_gemm(C.byref(args), _stream()), "mmvqa_gemm")
 
 
 def dtype_code(t) -> int:
@@ -87,13 +92,11 @@ def gemm(M: int, N: int, K: int, A: Tensor, lda: int, a_trans: bool, B: Tensor, 
     for t in (aux_in, aux_out):
         if t is not None and t.dtype != A.dtype:
             raise L.MMVQAError("gemm aux tensors must have the operand dtype")
-    if _GEMM_TIMING is not None:
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        L.check(L.lib().mmvqa_gemm(C.byref(a), _stream()), "mmvqa_gemm")
-        e1.record()
-        _GEMM_TIMING.append((2.0 * M * N * K * max(batch, 1), A.dtype, e0, e1))
-        return
+    if _GEMM_RECORD is not None:
+        sig = (a.dtype, M, N, K, int(a_trans), int(b_trans), epilogue, act, batch, split_k, int(accumulate), a.c_dtype,
+               bias is not None, aux_out is not None, colsum_out is not None, rowscale is not None, dropout_p > 0)
+        _GEMM_RECORD.append((sig, 2.0 * M * N * K * max(batch, 1), a,
+                             (A, B, Cout, bias, aux_in, aux_out, rowsum_out, colsum_out, rowscale)))
     L.check(L.lib().mmvqa_gemm(C.byref(a), _stream()), "mmvqa_gemm")
 
 
