@@ -68,10 +68,9 @@ int gemm_tc_bf16(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st)
   // Tile width: the widest BN that still gives the chip a full wave of CTAs (two for BN = 256).  Epilogues that
   // evaluate an activation per element are bound by the epilogue warps, not the MMA: they take BN <= 128.
   // MN-major B needs BN % 64 == 0.
-  // Ring depth: a small-M problem (one wave or less) is bound by how many bytes each SM keeps in flight from
-  // L2 / HBM, so it takes the deepest ring that fits (up to 8 stages, ~190 KB); multi-wave problems take 4 stages
-  // so two CTAs share an SM (the epilogue of one overlaps the main loop of the other), and 2 when the K loop is
-  // that short.  MMVQA_TC_BN / MMVQA_TC_STAGES override the choice (tuning only).
+  // Ring depth: a problem of one wave or less takes the deepest ring that fits (up to 8 stages, ~190 KB);
+  // multi-wave problems take a 2-stage ring so that 2-3 CTAs share an SM and the epilogue of one CTA overlaps the
+  // main loop of the others (measured at M = 28672: FF1 + SERF 466 -> 270 us, plain GEMMs unchanged or faster).  MMVQA_TC_BN / MMVQA_TC_STAGES override the choice (tuning only).
   const int sms = num_sms();
   const int64_t mt = (a->M + TC_BM - 1) / TC_BM;
   const int64_t z = (int64_t)a->batch * a->split_k;
@@ -98,6 +97,7 @@ int gemm_tc_bf16(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st)
   int stages;
   if (kblocks <= 2) stages = 2;
   else if (ctas <= sms && kblocks > 4) stages = deep;
+  else if (ctas > 2 * (int64_t)sms) stages = 2;   // multi-wave: 2-3 CTAs per SM, epilogue of one hides under the main loop of the others
   else stages = 4;
   if (env_st == 2 || env_st == 4 || env_st == 6 || env_st == 8) stages = env_st > deep ? deep : env_st;
   if (stages == 6 && bn != 128) stages = 4;
