@@ -111,6 +111,8 @@ __global__ void __launch_bounds__(1024) attn_fwd_kernel(const T* __restrict__ qk
   float* Ps = Vs + Tn * d;              // [nwarp][Tn]
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const T* base = qkv + (int64_t)b * L.tok_batch + (int64_t)h * L.head_stride;
+  pdl_wait();
+  pdl_trigger();
   {
     const TileSrc tiles[3] = {{base + L.k_off, L.row_stride, Ks, d + 1}, {base + L.q_off, L.row_stride, Qs, d},
                               {base + L.v_off, L.row_stride, Vs, d}};
@@ -216,6 +218,8 @@ __global__ void __launch_bounds__(1024) attn_bwd_kernel(const T* __restrict__ qk
   const T* base = qkv + (int64_t)b * L.tok_batch + (int64_t)h * L.head_stride;
   T* dbase = dqkv + (int64_t)b * L.tok_batch + (int64_t)h * L.head_stride;
   const int64_t sbase = ((int64_t)b * heads + h) * Tn * Tn;
+  pdl_wait();
+  pdl_trigger();
   if (resident) {
     const TileSrc tiles[4] = {{base + L.v_off, L.row_stride, X, d + 1}, {dout + (int64_t)b * Tn * H + h * d, (int64_t)H, dO, d},
                               {base + L.k_off, L.row_stride, Kb, d + 1}, {base + L.q_off, L.row_stride, Qb, d + 1}};
@@ -354,7 +358,8 @@ static int launch_fwd(const void* qkv, const AttnLayout& L, const float* prev, c
   const int vn = 16 / (int)sizeof(T);
   const int vec = (d % vn == 0 && L.row_stride % vn == 0 && L.head_stride % vn == 0 && L.q_off % vn == 0 && L.k_off % vn == 0 &&
                    L.v_off % vn == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0) ? 1 : 0;
-  kern<<<B * heads, nthreads, smem, st>>>((const T*)qkv, L, prev, mask, (T*)out, scores, (T*)probs, Tn, heads, d, p, seed, vec);
+  MMVQA_CUDA(launch_pdl(kern, dim3(B * heads), dim3(nthreads), smem, st, (const T*)qkv, L, prev, mask, (T*)out, scores, (T*)probs, Tn, heads, d, p,
+                        (unsigned long long)seed, vec));
   MMVQA_LAUNCHED("attn_fwd");
   return MMVQA_OK;
 }
@@ -376,8 +381,8 @@ static int launch_bwd(const void* qkv, const AttnLayout& L, const float* scores,
                    L.v_off % vn == 0 && H % vn == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(dout) & 15) == 0) ? 1 : 0;
   const int nthreads = 32 * (Tn < 8 ? 8 : (Tn > 32 ? 32 : Tn));
-  kern<<<B * heads, nthreads, smem, st>>>((const T*)qkv, L, scores, (const T*)probs, (const T*)dout, dscores_in, (T*)dqkv, dprev,
-                                     Tn, heads, d, p, seed, vec, resident);
+  MMVQA_CUDA(launch_pdl(kern, dim3(B * heads), dim3(nthreads), smem, st, (const T*)qkv, L, scores, (const T*)probs, (const T*)dout,
+                        dscores_in, (T*)dqkv, dprev, Tn, heads, d, p, (unsigned long long)seed, vec, resident));
   MMVQA_LAUNCHED("attn_bwd");
   return MMVQA_OK;
 }

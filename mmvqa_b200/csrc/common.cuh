@@ -38,6 +38,32 @@ int set_err(int code, const char* fmt, ...);
 
 static inline cudaStream_t as_stream(mmvqa_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 int num_sms();
+bool pdl_enabled();
+
+// Programmatic dependent launch: the kernel may be scheduled while the previous kernel on the stream is still
+// draining; it must call pdl_wait() before touching any global memory a predecessor may have written (or that a
+// predecessor may still be reading and this kernel overwrites).  Everything before pdl_wait() -- shared-memory
+// carve-up, mbarrier init, TMEM allocation, tensor-map prefetch -- overlaps the predecessor's tail.
+// Also valid inside stream capture (becomes a programmatic edge of the CUDA graph).
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#if defined(__CUDACC__)
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 // ---------------------------------------------------------------------------------
 // element access templated on storage type

@@ -3,6 +3,7 @@
 // the row length and pointers allow it and fall back to scalar accesses otherwise.
 #include "common.cuh"
 #include <stdarg.h>
+#include <stdlib.h>
 
 namespace mmvqa {
 
@@ -25,6 +26,13 @@ int num_sms() {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
   }
   return n;
+}
+
+bool pdl_enabled() {
+  // Off by default: measured on B200 the captured step is kernel-bound, not launch-gap-bound (3.85 ms with
+  // programmatic dependent launch vs 3.82 ms without); MMVQA_PDL=1 turns it on for experiments.
+  static const bool on = getenv("MMVQA_PDL") != nullptr;
+  return on;
 }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -179,6 +187,8 @@ __global__ void __launch_bounds__(128) add_ln_fwd_kernel(const T* __restrict__ x
   constexpr int ITER = LN_CACHE / N;
   const int lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  pdl_wait();
+  pdl_trigger();
   if (row >= rows) return;
   const T* xr = x + row * cols;
   const T* rr = res ? res + row * cols : nullptr;
@@ -264,6 +274,8 @@ __global__ void __launch_bounds__(128) add_ln_fwd_generic(const T* __restrict__ 
                                                           int64_t rows, int cols, float eps) {
   const int lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  pdl_wait();
+  pdl_trigger();
   if (row >= rows) return;
   const T* xr = x + row * cols;
   const T* rr = res ? res + row * cols : nullptr;
@@ -322,6 +334,8 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const T* __restrict__ dy, c
   }
   for (int c = threadIdx.x; c < 3 * cols; c += blockDim.x) sm[c] = 0.0f;
   __syncthreads();
+  pdl_wait();
+  pdl_trigger();
   T* dxd = reinterpret_cast<T*>(ex.dx_drop);
   const bool want_sum = ex.dxsum != nullptr;
   const bool drop = ex.p > 0.0f;
@@ -608,7 +622,7 @@ int mmvqa_add_layernorm_fwd(const void* x, const void* res, const float* gamma, 
   const bool cached = cols <= 32 * LN_CACHE;
   const bool vec = cached && cols % vn == 0 && aligned16(x) && aligned16(y) && (!res || aligned16(res)) &&
                    (!sum_out || aligned16(sum_out));
-#define LN_FWD(T, K) K<<<grid, 128, 0, st>>>((const T*)x, (const T*)res, gamma, beta, (T*)y, (T*)sum_out, mean, rstd, rows, cols, eps)
+#define LN_FWD(T, K) launch_pdl(K, dim3(grid), dim3(128), 0, st, (const T*)x, (const T*)res, gamma, beta, (T*)y, (T*)sum_out, mean, rstd, rows, cols, eps)
   if (dtype == MMVQA_F32) {
     if (vec) LN_FWD(float, (add_ln_fwd_kernel<float, true>));
     else if (cached) LN_FWD(float, (add_ln_fwd_kernel<float, false>));
@@ -644,7 +658,7 @@ int mmvqa_layernorm_bwd(const void* dy, const void* xsum, const float* gamma, co
                    (!dx_extra || aligned16(dx_extra)) && (!dx_drop || aligned16(dx_drop));
   LnBwdExtra ex;
   ex.dx_drop = dx_drop; ex.dxsum = dxsum; ex.p = dx_drop ? dropout_p : 0.0f; ex.seed = dropout_seed;
-#define LN_BWD(T, V, C) ln_bwd_kernel<T, V, C><<<grid, 128, smem, st>>>((const T*)dy, (const T*)xsum, gamma, mean, rstd, (const T*)dx_extra, (T*)dx, dgamma, dbeta, ex, rows, cols)
+#define LN_BWD(T, V, C) launch_pdl(ln_bwd_kernel<T, V, C>, dim3(grid), dim3(128), smem, st, (const T*)dy, (const T*)xsum, gamma, mean, rstd, (const T*)dx_extra, (T*)dx, dgamma, dbeta, ex, rows, cols)
   if (dtype == MMVQA_F32) {
     if (vec) LN_BWD(float, true, true);
     else if (cached) LN_BWD(float, false, true);

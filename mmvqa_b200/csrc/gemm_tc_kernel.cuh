@@ -332,6 +332,8 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_ptr_gen;
+  pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched below
+  pdl_trigger();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -429,8 +431,8 @@ static int launch_tc(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t
   }
   dim3 grid((a->N + BN - 1) / BN, (a->M + TC_BM - 1) / TC_BM, a->batch * a->split_k);
   MMVQA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm(bf16): grid too large");
-  kern<<<grid, TC_THREADS, Cfg::SMEM, st>>>(tmA, tmB, ep, (a->batch > 1 && a->a_batch_rows > 0) ? 1 : 0,
-                                            (a->batch > 1 && a->b_batch_rows > 0) ? 1 : 0);
+  MMVQA_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), (size_t)Cfg::SMEM, st, tmA, tmB, ep,
+                        (a->batch > 1 && a->a_batch_rows > 0) ? 1 : 0, (a->batch > 1 && a->b_batch_rows > 0) ? 1 : 0));
   MMVQA_LAUNCHED("gemm_tc_bf16");
   return MMVQA_OK;
 }

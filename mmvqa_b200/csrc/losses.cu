@@ -157,6 +157,8 @@ __device__ __forceinline__ void adam_one(float& p, float& m, float& v, float g, 
 __global__ void __launch_bounds__(256) adam_kernel(const mmvqa_adam_desc* __restrict__ table, float lr, float beta1,
                                                    float beta2, float eps, float wd, float bc1, float bc2_sqrt,
                                                    float grad_scale, const int* __restrict__ step_dev) {
+  pdl_wait();
+  pdl_trigger();
   const mmvqa_adam_desc d = table[blockIdx.x];
   if (step_dev) {  // step counter lives on the device (CUDA-graph replay safe)
     const float t = (float)(*step_dev);
@@ -255,7 +257,8 @@ int mmvqa_adam_step(const mmvqa_adam_desc* table, int n_chunks, float lr, float 
   if (n_chunks == 0) return MMVQA_OK;
   const float bc1 = 1.0f - powf(beta1, (float)step);
   const float bc2 = 1.0f - powf(beta2, (float)step);
-  adam_kernel<<<n_chunks, 256, 0, as_stream(stream)>>>(table, lr, beta1, beta2, eps, weight_decay, bc1, sqrtf(bc2), grad_scale, step_dev);
+  MMVQA_CUDA(launch_pdl(adam_kernel, dim3(n_chunks), dim3(256), 0, as_stream(stream), table, lr, beta1, beta2, eps, weight_decay, bc1,
+                        sqrtf(bc2), grad_scale, step_dev));
   MMVQA_LAUNCHED("adam_step");
   return MMVQA_OK;
 }

@@ -104,6 +104,8 @@ __global__ void __launch_bounds__(VT_THREADS) vistok_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_ptr_gen;
+  pdl_wait();
+  pdl_trigger();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -203,7 +205,7 @@ static int launch_vt(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t
   if (nsplit < 1) nsplit = 1;
   dim3 grid(nsplit, mt, a->batch);
   MMVQA_REQUIRE(grid.z <= 65535 && grid.y <= 65535, "vistok: grid too large");
-  kern<<<grid, VT_THREADS, Cfg::SMEM, st>>>(tmA, tmB, ep, n_tiles);
+  MMVQA_CUDA(launch_pdl(kern, grid, dim3(VT_THREADS), (size_t)Cfg::SMEM, st, tmA, tmB, ep, n_tiles));
   MMVQA_LAUNCHED("vistok_kernel");
   return MMVQA_OK;
 }

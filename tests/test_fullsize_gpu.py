@@ -96,3 +96,86 @@ def test_dp_gradients_equal_big_batch_fullsize(c2):
         e = (avg - full[n]).abs().max() / full[n].abs().max()
         assert e < 1e-4, (n, float(e))
     model.cpu()
+
+
+def _mlm_model(supcon):
+    import types
+    from transformers import BertConfig, BertModel
+    from mmvqa_b200.models import image_encoding as IE
+    from mmvqa_b200.models import mmbert as MM
+    import torch.nn as nn
+    args = types.SimpleNamespace(task="MLM", clinicalbert="", transformer_model="realformer", cnn_encoder="tf_efficientnetv2_m",
+                                 num_vis=5, hidden_size=768, use_relu=False, heads=8, hidden_dropout_prob=0.1, n_layers=2,
+                                 vocab_size=30522, dataset="roco", supcon=supcon)
+    old = MM.AutoModel.from_pretrained
+    MM.AutoModel.from_pretrained = staticmethod(lambda name, *a, **k: BertModel(BertConfig(num_hidden_layers=1)))
+    IE.models_dict[5]["tf_efficientnetv2_m"][0] = lambda *a, **k: nn.Identity()
+    try:
+        torch.manual_seed(5)
+        return MM.Model(args).eval()
+    finally:
+        MM.AutoModel.from_pretrained = old
+
+
+def test_mlm_supcon_full_width_vs_oracle():
+    """BASELINE configs[2]/[3] shapes at full width (hidden 768, T=75, V=30522, feat 128; 2 layers and B=8 so the CPU
+    oracle finishes in seconds): MLM logits [B,75,30522], SupCon features, fused CE == log_softmax+NLL, SupCon loss."""
+    from mmvqa_b200 import functional as Fn
+    from mmvqa_b200.models.SupConLoss.loss import SupConLoss
+    B, Tn, V = 8, 75, 30522
+    model = _mlm_model(True)
+    g = torch.Generator().manual_seed(11)
+    feats = [torch.randn(B, c, s, s, generator=g).abs() for c, s in bench.EFFNET_MAPS]
+    ids = torch.randint(1000, V, (B, Tn), generator=g)
+    ids[:, :5] = 0
+    seg = torch.zeros(B, Tn, dtype=torch.long)
+    mask = torch.ones(B, Tn, dtype=torch.long)
+    mask[:, 60:] = 0
+    target = torch.where(torch.rand(B, Tn, generator=g) < 0.15, ids, torch.zeros_like(ids))
+    p = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        ref_logits, ref_feat = O.model_forward(feats, ids, seg, mask, p, encoder="realformer", n_layers=2, dataset="roco",
+                                               supcon=True)
+        ref_mlm = O.mlm_nll(ref_logits, target)
+        pairs = ref_feat.view(B // 2, 2, -1)
+        ref_sc = O.supcon_loss(pairs)
+    model = model.to(DEV)
+    for dt, tol in ((torch.float32, 2e-4), (torch.bfloat16, 6e-2)):
+        with mmvqa_b200.compute_dtype_scope(dt):
+            logits, feat = model.forward_features([f.to(DEV) for f in feats], ids.to(DEV), seg.to(DEV), mask.to(DEV))
+            assert logits.shape == (B, Tn, V) and logits.dtype == torch.float32 and feat.shape == (B, 128)
+            err = (logits.cpu() - ref_logits).abs().max() / ref_logits.abs().max()
+            assert err < tol, (dt, float(err))
+            ferr = (feat.cpu() - ref_feat).abs().max()
+            assert ferr < (1e-4 if dt == torch.float32 else 3e-2), (dt, float(ferr))
+            rows = Fn.CrossEntropyRowsFn.apply(logits.view(B * Tn, V), target.view(-1).to(DEV))
+            assert abs(rows.mean().item() - ref_mlm.item()) < (1e-4 if dt == torch.float32 else 3e-2) * ref_mlm.item()
+            sc = SupConLoss()(feat.view(B // 2, 2, -1))
+            assert abs(sc.item() - ref_sc.item()) < (1e-4 if dt == torch.float32 else 5e-2) * abs(ref_sc.item())
+            if dt == torch.float32:
+                assert torch.equal(logits.argmax(-1).cpu(), ref_logits.argmax(-1))
+            (rows.mean() + sc).backward()
+            gsum = sum(float(q.grad.abs().sum()) for q in model.parameters() if q.grad is not None)
+            assert gsum > 0 and gsum == gsum
+            model.zero_grad(set_to_none=True)
+
+
+def test_supcon_global_batch_2048():
+    """BASELINE configs[3]: N = 2048 contrast rows (1024 pairs), D = 128, soft jaccard-shaped mask, vs the oracle."""
+    from mmvqa_b200.models.SupConLoss.loss import SupConLoss
+    g = torch.Generator().manual_seed(12)
+    f = torch.randn(1024, 2, 128, generator=g)
+    f = f / f.norm(dim=-1, keepdim=True)
+    soft = torch.rand(1024, 1024, generator=g)
+    soft.fill_diagonal_(1.0)
+    fl = f.clone().requires_grad_(True)
+    ref = O.supcon_loss(fl, mask=soft)
+    (gref,) = torch.autograd.grad(ref, fl)
+    for dt, tol in ((torch.float32, 1e-4), (torch.bfloat16, 3e-2)):
+        with mmvqa_b200.compute_dtype_scope(dt):
+            fd = f.to(DEV).requires_grad_(True)
+            loss = SupConLoss()(fd, mask=soft.to(DEV))
+            loss.backward()
+            assert abs(loss.item() - ref.item()) < tol * abs(ref.item()), (dt, loss.item(), ref.item())
+            e = (fd.grad.cpu() - gref).abs().max() / gref.abs().max()
+            assert e < (1e-3 if dt == torch.float32 else 0.15), (dt, float(e))
