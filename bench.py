@@ -257,7 +257,8 @@ def main_gpu(a):
     nparams = sum(p.numel() for p in params)
     opt = FusedAdam(params, lr=1e-5)
     crit = ASLSingleLabel()
-    buckets = GradBuckets(params) if world > 1 else None
+    # bf16 buckets halve the all-reduce volume (364 -> 182 MB) on the bf16 path; the fp32 path keeps fp32 buckets
+    buckets = GradBuckets(params, dtype=(torch.bfloat16 if (dt == torch.bfloat16 and a.bf16_buckets) else torch.float32)) if world > 1 else None
     if buckets is not None:
         opt.grad_scale = buckets.grad_scale
 
@@ -456,6 +457,7 @@ if __name__ == "__main__":
     ap.add_argument("--dropout", type=int, default=1, help="1: training-mode dropout on (throughput runs), 0: off")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--verbose", action="store_true", help="progress lines on stderr")
+    ap.add_argument("--bf16-buckets", type=int, default=1, help="data parallel: all-reduce gradients as bf16 (bf16 path only)")
     ap.add_argument("--pad-steps", type=int, default=100, help="untimed steps around the timed region (clock sampling)")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -220,7 +220,8 @@ int mmvqa_supcon_rows(const float* logits, const float* mask, float* loss_rows, 
  * bf16 (refreshes the tensor-core weight cache in the same pass).
  * ---------------------------------------------------------------------------------- */
 typedef struct mmvqa_adam_desc {
-  float* p; float* m; float* v; const float* g; void* bf16_out; int64_t n;
+  float* p; float* m; float* v; const void* g; void* bf16_out; int64_t n;
+  int64_t flags;             /* bit 0: g is bf16 (all-reduced bf16 gradient bucket) instead of fp32 */
 } mmvqa_adam_desc;
 /* `step` (1-based) sets the bias corrections; if step_dev != NULL the kernel reads the step from
  * that device int instead, so a captured CUDA graph can be replayed while the host bumps it. */

@@ -37,7 +37,7 @@ class GemmArgs(C.Structure):
 
 
 class AdamDesc(C.Structure):
-    _fields_ = [("p", vp), ("m", vp), ("v", vp), ("g", vp), ("bf16_out", vp), ("n", i64)]
+    _fields_ = [("p", vp), ("m", vp), ("v", vp), ("g", vp), ("bf16_out", vp), ("n", i64), ("flags", i64)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/mmvqa.h

@@ -166,8 +166,11 @@ __global__ void __launch_bounds__(256) adam_kernel(const mmvqa_adam_desc* __rest
     bc2_sqrt = sqrtf(1.0f - powf(beta2, t));
   }
   const float step = lr / bc1;
-  const bool vec = ((reinterpret_cast<uintptr_t>(d.p) | reinterpret_cast<uintptr_t>(d.m) | reinterpret_cast<uintptr_t>(d.v) |
-                     reinterpret_cast<uintptr_t>(d.g)) & 15) == 0 &&
+  const bool g16 = (d.flags & 1) != 0;
+  const float* g32 = reinterpret_cast<const float*>(d.g);
+  const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(d.g);
+  const bool vec = ((reinterpret_cast<uintptr_t>(d.p) | reinterpret_cast<uintptr_t>(d.m) | reinterpret_cast<uintptr_t>(d.v)) & 15) == 0 &&
+                   (reinterpret_cast<uintptr_t>(d.g) & (g16 ? 7 : 15)) == 0 &&
                    (d.bf16_out == nullptr || (reinterpret_cast<uintptr_t>(d.bf16_out) & 7) == 0);
   int64_t done = 0;
   if (vec) {
@@ -175,7 +178,14 @@ __global__ void __launch_bounds__(256) adam_kernel(const mmvqa_adam_desc* __rest
     for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
       float4 p = reinterpret_cast<float4*>(d.p)[i], m = reinterpret_cast<float4*>(d.m)[i];
       float4 v = reinterpret_cast<float4*>(d.v)[i];
-      const float4 g = reinterpret_cast<const float4*>(d.g)[i];
+      float4 g;
+      if (g16) {
+        const uint2 raw = reinterpret_cast<const uint2*>(gb)[i];
+        g.x = __uint_as_float(raw.x << 16); g.y = __uint_as_float(raw.x & 0xffff0000u);
+        g.z = __uint_as_float(raw.y << 16); g.w = __uint_as_float(raw.y & 0xffff0000u);
+      } else {
+        g = reinterpret_cast<const float4*>(g32)[i];
+      }
       adam_one(p.x, m.x, v.x, g.x, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
       adam_one(p.y, m.y, v.y, g.y, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
       adam_one(p.z, m.z, v.z, g.z, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
@@ -195,7 +205,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const mmvqa_adam_desc* __rest
   }
   for (int64_t i = done + threadIdx.x; i < d.n; i += blockDim.x) {
     float p = d.p[i], m = d.m[i], v = d.v[i];
-    adam_one(p, m, v, d.g[i], beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
+    adam_one(p, m, v, g16 ? __bfloat162float(gb[i]) : g32[i], beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
     d.p[i] = p;
     d.m[i] = m;
     d.v[i] = v;

@@ -10,7 +10,7 @@ from . import ops
 from .functional import weight_cache
 
 CHUNK = 32768
-_DESC = np.dtype([("p", "<u8"), ("m", "<u8"), ("v", "<u8"), ("g", "<u8"), ("bf16_out", "<u8"), ("n", "<i8")])
+_DESC = np.dtype([("p", "<u8"), ("m", "<u8"), ("v", "<u8"), ("g", "<u8"), ("bf16_out", "<u8"), ("n", "<i8"), ("flags", "<i8")])
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -50,13 +50,15 @@ class FusedAdam(torch.optim.Optimizer):
             if bv is not None and bv.is_contiguous() and bv.numel() == p.numel():
                 bptr = bv.data_ptr()
                 refreshed.add(id(p))
-            if p.dtype != torch.float32 or not p.is_contiguous() or not g.is_contiguous() or g.dtype != torch.float32:
-                raise RuntimeError("FusedAdam needs contiguous float32 parameters and gradients")
+            if p.dtype != torch.float32 or not p.is_contiguous() or not g.is_contiguous() or \
+                    g.dtype not in (torch.float32, torch.bfloat16):
+                raise RuntimeError("FusedAdam needs contiguous float32 parameters and float32 / bfloat16 gradients")
             n = p.numel()
+            gsz = g.element_size()
             for off in range(0, n, CHUNK):
                 cnt = min(CHUNK, n - off)
                 rows.append((p.data_ptr() + 4 * off, st["exp_avg"].data_ptr() + 4 * off, st["exp_avg_sq"].data_ptr() + 4 * off,
-                             g.data_ptr() + 4 * off, (bptr + 2 * off) if bptr else 0, cnt))
+                             g.data_ptr() + gsz * off, (bptr + 2 * off) if bptr else 0, cnt, 1 if gsz == 2 else 0))
         host = torch.from_numpy(np.array(rows, dtype=_DESC).view(np.uint8).reshape(-1)).pin_memory()
         dev = torch.empty(host.numel(), dtype=torch.uint8, device=plist[0].device)
         dev.copy_(host, non_blocking=True)

@@ -31,14 +31,14 @@ class GradBuckets:
 
     def __init__(self, params, bucket_mb: float = 64.0, dtype: torch.dtype = torch.float32):
         self.params = [p for p in params if p.requires_grad]
-        cap = int(bucket_mb * 1024 * 1024 / 4)
+        cap = int(bucket_mb * 1024 * 1024 / (2 if dtype == torch.bfloat16 else 4))
         self.buckets: List[torch.Tensor] = []
         self.slots = []                      # (param index, bucket index, offset, numel)
         cur, cur_n = [], 0
         order = list(reversed(range(len(self.params))))
         groups = []
         for i in order:
-            n = (self.params[i].numel() + 3) // 4 * 4          # keep 16-byte alignment of every view
+            n = (self.params[i].numel() + 7) // 8 * 8          # keep 16-byte alignment of every view (fp32 and bf16)
             if cur and cur_n + n > cap:
                 groups.append((cur, cur_n))
                 cur, cur_n = [], 0

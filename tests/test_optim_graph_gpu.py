@@ -47,6 +47,20 @@ def test_fused_adam_matches_torch(wd):
         torch.testing.assert_close(b, a, rtol=2e-5, atol=2e-6)
 
 
+def test_fused_adam_bf16_gradient_buckets():
+    torch.manual_seed(1)
+    ref = [torch.randn(1000, 64, device=DEV).requires_grad_(True), torch.randn(77, device=DEV).requires_grad_(True)]
+    ours = [p.detach().clone().requires_grad_(True) for p in ref]
+    o_ref, o_ours = torch.optim.Adam(ref, lr=1e-2), FusedAdam(ours, lr=1e-2)
+    gb = [torch.randn_like(p).bfloat16() for p in ref]
+    for a, b, g in zip(ref, ours, gb):
+        a.grad, b.grad = g.float(), torch.zeros_like(b)          # p.grad only marks "has a gradient"
+    o_ref.step()
+    o_ours.step(grads=gb)
+    for a, b in zip(ref, ours):
+        torch.testing.assert_close(b, a, rtol=2e-5, atol=2e-6)
+
+
 def test_adam_refreshes_the_bf16_weight_cache():
     with mmvqa_b200.compute_dtype_scope(torch.bfloat16):
         Fn.invalidate_weight_cache()
