@@ -442,6 +442,39 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const T* __restrict__ dy, c
     }
   }
   if (dgamma == nullptr && dbeta == nullptr && !want_sum) return;
+  if (CACHED && VEC) {
+    // each warp parks its register partials in a private shared-memory slab (plain 128-bit stores, no atomics),
+    // then the CTA sums the slabs and issues ONE 128-bit vector atomic per 4 columns and output
+    __syncthreads();                      // sm[] was only used as zero-filled scratch so far
+    float* slab = sm + (size_t)warp * 3 * cols;
+#pragma unroll
+    for (int k = 0; k < ITER; ++k) {
+      const int c = (k * 32 + lane) * N;
+      if (c < cols) {
+#pragma unroll
+        for (int j = 0; j < N; j += 4) {
+          *reinterpret_cast<float4*>(slab + c + j) = make_float4(dg[k * N + j], dg[k * N + j + 1], dg[k * N + j + 2], dg[k * N + j + 3]);
+          *reinterpret_cast<float4*>(slab + cols + c + j) = make_float4(db[k * N + j], db[k * N + j + 1], db[k * N + j + 2], db[k * N + j + 3]);
+          if (want_sum)
+            *reinterpret_cast<float4*>(slab + 2 * cols + c + j) = make_float4(dsum[k * N + j], dsum[k * N + j + 1], dsum[k * N + j + 2], dsum[k * N + j + 3]);
+        }
+      }
+    }
+    __syncthreads();
+    const int nv = cols / 4;
+    for (int i = threadIdx.x; i < 3 * nv; i += blockDim.x) {
+      const int which = i / nv, c4 = (i - which * nv) * 4;
+      float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : ex.dxsum);
+      if (dst == nullptr) continue;
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int w = 0; w < nwarp; ++w) {
+        const float4 t = *reinterpret_cast<const float4*>(sm + (size_t)w * 3 * cols + which * cols + c4);
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+      }
+      atomicAdd(reinterpret_cast<float4*>(dst + c4), acc);
+    }
+    return;
+  }
   if (CACHED) {
 #pragma unroll
     for (int k = 0; k < ITER; ++k) {
@@ -650,12 +683,13 @@ int mmvqa_layernorm_bwd(const void* dy, const void* xsum, const float* gamma, co
   cudaStream_t st = as_stream(stream);
   int64_t want = (rows + 3) / 4, cap = (int64_t)num_sms() * 4;
   int grid = (int)(want < cap ? want : cap);
-  size_t smem = sizeof(float) * 3 * (size_t)cols;
-  MMVQA_REQUIRE(smem <= 48 * 1024, "layernorm_bwd: cols %d too large", cols);
   const int vn = dtype == MMVQA_F32 ? 4 : 8;
   const bool cached = cols <= 32 * LN_CACHE;
   const bool vec = cached && cols % vn == 0 && aligned16(dy) && aligned16(xsum) && aligned16(dx) &&
-                   (!dx_extra || aligned16(dx_extra)) && (!dx_drop || aligned16(dx_drop));
+                   (!dx_extra || aligned16(dx_extra)) && (!dx_drop || aligned16(dx_drop)) &&
+                   (!dgamma || aligned16(dgamma)) && (!dbeta || aligned16(dbeta)) && (!dxsum || aligned16(dxsum));
+  size_t smem = sizeof(float) * 3 * (size_t)cols * (vec ? 4 : 1);     // vec path: one slab per warp
+  MMVQA_REQUIRE(smem <= 48 * 1024, "layernorm_bwd: cols %d too large", cols);
   LnBwdExtra ex;
   ex.dx_drop = dx_drop; ex.dxsum = dxsum; ex.p = dx_drop ? dropout_p : 0.0f; ex.seed = dropout_seed;
 #define LN_BWD(T, V, C) launch_pdl(ln_bwd_kernel<T, V, C>, dim3(grid), dim3(128), smem, st, (const T*)dy, (const T*)xsum, gamma, mean, rstd, (const T*)dx_extra, (T*)dx, dgamma, dbeta, ex, rows, cols)
