@@ -8,16 +8,11 @@
 // K/Q/V of the (batch, head) are staged once in shared memory as fp32; the T x T score tile never
 // leaves the SM except for the tensors the reference itself materialises; softmax is a
 // warp-shuffle reduction with the mask applied in registers.
-#include "common.cuh"
+#include "attention_tc.cuh"
+#include <stdlib.h>
+#include <type_traits>
 
 namespace mmvqa {
-
-struct AttnLayout {
-  int64_t row_stride;   // elements between consecutive tokens of the same head
-  int64_t head_stride;  // elements between heads of the same token
-  int64_t tok_batch;    // elements between batches (= T * row_stride)
-  int q_off, k_off, v_off;
-};
 
 // Stage NT row-major [Tn, d] tiles (row strides differ) into shared memory as fp32.  VEC: 128-bit global loads,
 // every thread issues all of its loads (up to 4 per round) before the first shared-memory store, so the CTA pays
@@ -340,6 +335,16 @@ __global__ void __launch_bounds__(1024) attn_bwd_kernel(const T* __restrict__ qk
   }
 }
 
+// the tensor-core variant needs 16-byte aligned rows (d, strides and offsets multiples of 8 bf16) and d % 16 == 0
+static bool tc_attention_ok(const void* qkv, const AttnLayout& L, const void* dout, int Tn, int heads, int d) {
+  static const bool off = getenv("MMVQA_NO_TC_ATTN") != nullptr;
+  if (off || d % 16 != 0 || d > 128 || Tn > 128) return false;
+  if (L.row_stride % 8 || L.head_stride % 8 || L.q_off % 8 || L.k_off % 8 || L.v_off % 8) return false;
+  if (reinterpret_cast<uintptr_t>(qkv) & 15) return false;
+  if (dout && ((reinterpret_cast<uintptr_t>(dout) & 15) || (heads * d) % 8)) return false;
+  return true;
+}
+
 static int check_shape(const char* name, int B, int T, int heads, int d) {
   MMVQA_REQUIRE(B > 0 && T > 0 && heads > 0 && d > 0, "%s: bad shape", name);
   MMVQA_REQUIRE(T <= 128, "%s: sequence length %d > 128 (short-sequence kernel)", name, T);
@@ -350,6 +355,24 @@ static int check_shape(const char* name, int B, int T, int heads, int d) {
 template <typename T, bool RF>
 static int launch_fwd(const void* qkv, const AttnLayout& L, const float* prev, const float* mask, void* out, float* scores,
                       void* probs, int B, int Tn, int heads, int d, float p, uint64_t seed, cudaStream_t st) {
+  if (std::is_same<T, __nv_bfloat16>::value && tc_attention_ok(qkv, L, nullptr, Tn, heads, d)) {
+    const int Tp = (Tn + 15) & ~15, ldn = d + 8, ldt = Tp + 8;
+    const size_t smem_tc = (size_t)(2 * Tp * ldn + d * ldt) * 2;
+    if (smem_tc <= 227 * 1024) {
+      const int nthr = 32 * (Tp / 16 < 4 ? 4 : Tp / 16);
+#define TC_FWD(TPV)                                                                                                     \
+  do {                                                                                                                  \
+    auto k = attn_tc_fwd_kernel<RF, TPV>;                                                                               \
+    if (smem_tc > 48 * 1024) MMVQA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc)); \
+    MMVQA_CUDA(launch_pdl(k, dim3(B * heads), dim3(nthr), smem_tc, st, (const bf16*)qkv, L, prev, mask, (bf16*)out, scores, \
+                          (bf16*)probs, Tn, heads, d, p, (unsigned long long)seed));                                    \
+  } while (0)
+      if (Tp <= 32) TC_FWD(32); else if (Tp <= 64) TC_FWD(64); else if (Tp <= 96) TC_FWD(96); else TC_FWD(128);
+#undef TC_FWD
+      MMVQA_LAUNCHED("attn_tc_fwd");
+      return MMVQA_OK;
+    }
+  }
   const int nthreads = 32 * (Tn < 8 ? 8 : (Tn > 32 ? 32 : Tn));   // one warp per query row, 8..32 warps
   size_t smem = sizeof(float) * ((size_t)Tn * (d + 1) + 2 * (size_t)Tn * d + (size_t)(nthreads / 32) * Tn);
   if (smem > 227 * 1024) return set_err(MMVQA_ERR_SMEM, "attention fwd: T=%d d=%d needs %zu bytes of shared memory", Tn, d, smem);
@@ -368,6 +391,25 @@ template <typename T, bool RF>
 static int launch_bwd(const void* qkv, const AttnLayout& L, const float* scores, const void* probs, const void* dout,
                       const float* dscores_in, void* dqkv, float* dprev, int B, int Tn, int heads, int d, float p,
                       uint64_t seed, cudaStream_t st) {
+  if (std::is_same<T, __nv_bfloat16>::value && tc_attention_ok(qkv, L, dout, Tn, heads, d) &&
+      (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0) {
+    const int Tp = (Tn + 15) & ~15, ldn = d + 8, ldt = Tp + 8;
+    const size_t smem_tc = (size_t)(2 * Tp * ldn + 3 * d * ldt + 2 * Tp * ldt) * 2;
+    if (smem_tc <= 227 * 1024) {
+      const int nthr = 32 * (Tp / 16 < 4 ? 4 : Tp / 16);
+#define TC_BWD(TPV)                                                                                                     \
+  do {                                                                                                                  \
+    auto k = attn_tc_bwd_kernel<RF, TPV>;                                                                               \
+    if (smem_tc > 48 * 1024) MMVQA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc)); \
+    MMVQA_CUDA(launch_pdl(k, dim3(B * heads), dim3(nthr), smem_tc, st, (const bf16*)qkv, L, scores, (const bf16*)probs,  \
+                          (const bf16*)dout, dscores_in, (bf16*)dqkv, dprev, Tn, heads, d, p, (unsigned long long)seed)); \
+  } while (0)
+      if (Tp <= 32) TC_BWD(32); else if (Tp <= 64) TC_BWD(64); else if (Tp <= 96) TC_BWD(96); else TC_BWD(128);
+#undef TC_BWD
+      MMVQA_LAUNCHED("attn_tc_bwd");
+      return MMVQA_OK;
+    }
+  }
   size_t smem = sizeof(float) * ((size_t)Tn * (d + 1) + (size_t)Tn * d + 2 * (size_t)Tn * Tn);
   const size_t smem_res = smem + sizeof(float) * 2 * (size_t)Tn * (d + 1);
   const int resident = smem_res <= 100 * 1024 ? 1 : 0;   // K and Q tiles too when two CTAs still share an SM

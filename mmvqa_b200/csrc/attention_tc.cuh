@@ -1,0 +1,463 @@
+// attention_tc.cuh -- bf16 tensor-core variant of the fused short-sequence attention kernels (T <= 128,
+// d % 16 == 0, d <= 128).  One CTA per (batch, head); one warp per 16-query-row strip.
+//   forward : S = Q K^T (mma.sync m16n8k16, fp32 accumulators stay in registers) -> scale, + prev, mask in
+//             registers -> scores written once (fp32) -> warp-shuffle softmax on the accumulator fragments -> the P
+//             fragments are re-packed in registers as the A operand of O = P V (V staged transposed) -> bf16 out.
+//   backward: per strip P (recomputed from the stored scores), dP = dO V^T, dS = P (dP - rowdot) + dS_next (the
+//             running RealFormer score gradient, written once as dprev), dQ = dS K from registers; P and dS strips
+//             are parked transposed in shared memory, then the warps re-partition over key strips for
+//             dV = P^T dO and dK = dS^T Q.
+// The T x T tile never exists in shared or global memory except for the tensors the reference itself materialises.
+#pragma once
+#include "common.cuh"
+
+namespace mmvqa {
+
+struct AttnLayout {
+  int64_t row_stride;   // elements between consecutive tokens of the same head
+  int64_t head_stride;  // elements between heads of the same token
+  int64_t tok_batch;    // elements between batches (= T * row_stride)
+  int q_off, k_off, v_off;
+};
+
+using bf16 = __nv_bfloat16;
+
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);   // .x (low 16 bits) = lo
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t lds32(const bf16* p) { return *reinterpret_cast<const uint32_t*>(p); }
+
+// A fragment (16 rows x 16 k) from a row-major [row][k] bf16 tile
+__device__ __forceinline__ void load_a(uint32_t (&a)[4], const bf16* X, int ld, int r0, int k0, int g, int t) {
+  a[0] = lds32(X + (r0 + g) * ld + k0 + 2 * t);
+  a[1] = lds32(X + (r0 + g + 8) * ld + k0 + 2 * t);
+  a[2] = lds32(X + (r0 + g) * ld + k0 + 2 * t + 8);
+  a[3] = lds32(X + (r0 + g + 8) * ld + k0 + 2 * t + 8);
+}
+// B fragment (16 k x 8 n) from a [n][k] bf16 tile (k contiguous)
+__device__ __forceinline__ void load_b(uint32_t (&b)[2], const bf16* Y, int ld, int n0, int k0, int g, int t) {
+  b[0] = lds32(Y + (n0 + g) * ld + k0 + 2 * t);
+  b[1] = lds32(Y + (n0 + g) * ld + k0 + 2 * t + 8);
+}
+
+// global [Tn, d] bf16 tile (row stride in elements) -> natural [row][d+8] and/or transposed [col][Tp+8] smem copies
+__device__ __forceinline__ void stage_tile(const bf16* __restrict__ src, int64_t row_stride, int Tn, int d, bf16* nat,
+                                           int ldn, bf16* tr, int ldt) {
+  const int cpr = d / 8;
+  const int total = Tn * cpr;
+  for (int base = threadIdx.x; base < total; base += blockDim.x * 4) {
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int idx = base + k * blockDim.x;
+      if (idx < total) {
+        const int row = idx / cpr, ch = idx - row * cpr;
+        v[k] = *reinterpret_cast<const uint4*>(src + row * row_stride + ch * 8);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int idx = base + k * blockDim.x;
+      if (idx < total) {
+        const int row = idx / cpr, ch = idx - row * cpr;
+        if (nat) *reinterpret_cast<uint4*>(nat + row * ldn + ch * 8) = v[k];
+        if (tr) {
+          const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const unsigned short bits = (unsigned short)((e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xffffu));
+            reinterpret_cast<unsigned short*>(tr)[(ch * 8 + e) * ldt + row] = bits;
+          }
+        }
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void zero_smem(void* base, int bytes) {
+  uint4* p = reinterpret_cast<uint4*>(base);
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) p[i] = z;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward.  TP = register-array bound on the padded sequence (32 / 64 / 96 / 128)
+// ---------------------------------------------------------------------------------------------------
+template <bool RF, int TP>
+__global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const bf16* __restrict__ qkv, AttnLayout L,
+                                                          const float* __restrict__ prev, const float* __restrict__ mask,
+                                                          bf16* __restrict__ out, float* __restrict__ scores,
+                                                          bf16* __restrict__ probs, int Tn, int heads, int d, float drop_p,
+                                                          unsigned long long seed) {
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  constexpr int NT = TP / 8, KS = TP / 16;
+  const int Tp = (Tn + 15) & ~15;            // rows / keys padded to the mma tile
+  const int ldn = d + 8, ldt = Tp + 8;
+  bf16* Qs = reinterpret_cast<bf16*>(smem_attn);     // [Tp][d+8]
+  bf16* Ks = Qs + Tp * ldn;                          // [Tp][d+8]
+  bf16* Vt = Ks + Tp * ldn;                          // [d][Tp+8]   V transposed: B operand of P V
+  const int smem_bytes = (2 * Tp * ldn + d * ldt) * 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const bf16* base = qkv + (int64_t)b * L.tok_batch + (int64_t)h * L.head_stride;
+  zero_smem(smem_attn, smem_bytes);
+  __syncthreads();
+  pdl_wait();
+  pdl_trigger();
+  stage_tile(base + L.q_off, L.row_stride, Tn, d, Qs, ldn, nullptr, 0);
+  stage_tile(base + L.k_off, L.row_stride, Tn, d, Ks, ldn, nullptr, 0);
+  stage_tile(base + L.v_off, L.row_stride, Tn, d, nullptr, 0, Vt, ldt);
+  __syncthreads();
+  const int r0 = warp * 16;
+  if (r0 >= Tp) return;
+  const int nt_n = Tp / 8, ks_n = Tp / 16, kd_n = d / 16, nd_n = d / 8;
+  const int iA = r0 + g, iB = r0 + g + 8;
+  const int64_t sbase = ((int64_t)b * heads + h) * Tn * Tn;
+  const int H = heads * d;
+  // ---- S = Q K^T
+  float s[NT][4];
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.0f;
+  for (int kd = 0; kd < kd_n; ++kd) {
+    uint32_t a[4];
+    load_a(a, Qs, ldn, r0, kd * 16, g, t);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      if (nt < nt_n) {
+        uint32_t bb[2];
+        load_b(bb, Ks, ldn, nt * 8, kd * 16, g, t);
+        mma_bf16_16816(s[nt], a, bb);
+      }
+    }
+  }
+  // ---- scale, residual scores, mask, write scores, softmax (rows iA: c0,c1; iB: c2,c3; cols j0, j0+1)
+  const float inv_sqrt_d = 1.0f / sqrtf((float)d);
+  float qoffA = 0.0f, qoffB = 0.0f;
+  if (RF && mask) {
+    if (iA < Tn) qoffA = -10000.0f * (1.0f - __ldg(mask + b * Tn + iA));
+    if (iB < Tn) qoffB = -10000.0f * (1.0f - __ldg(mask + b * Tn + iB));
+  }
+  float mxA = -INFINITY, mxB = -INFINITY;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    if (nt < nt_n) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = (e < 2) ? iA : iB;
+        const int j = nt * 8 + 2 * t + (e & 1);
+        float v = -INFINITY;
+        if (i < Tn && j < Tn) {
+          v = s[nt][e] * inv_sqrt_d;
+          if (RF) {
+            if (prev) v += __ldg(prev + sbase + (int64_t)i * Tn + j);
+            v += (e < 2) ? qoffA : qoffB;
+            scores[sbase + (int64_t)i * Tn + j] = v;
+          } else if (mask) {
+            v -= 10000.0f * (1.0f - __ldg(mask + b * Tn + j));
+          }
+        }
+        s[nt][e] = v;
+        if (e < 2) mxA = fmaxf(mxA, v); else mxB = fmaxf(mxB, v);
+      }
+    }
+  }
+  mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, 1));
+  mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, 2));
+  mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, 1));
+  mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, 2));
+  float sumA = 0.0f, sumB = 0.0f;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    if (nt < nt_n) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float m = (e < 2) ? mxA : mxB;
+        const float p = (s[nt][e] == -INFINITY) ? 0.0f : expf(s[nt][e] - m);
+        s[nt][e] = p;
+        if (e < 2) sumA += p; else sumB += p;
+      }
+    }
+  }
+  sumA += __shfl_xor_sync(0xffffffffu, sumA, 1);
+  sumA += __shfl_xor_sync(0xffffffffu, sumA, 2);
+  sumB += __shfl_xor_sync(0xffffffffu, sumB, 1);
+  sumB += __shfl_xor_sync(0xffffffffu, sumB, 2);
+  const float invA = sumA > 0.0f ? 1.0f / sumA : 0.0f, invB = sumB > 0.0f ? 1.0f / sumB : 0.0f;
+  const uint32_t thr = (uint32_t)(drop_p * 4294967296.0);
+  const float inv_keep = drop_p > 0.0f ? 1.0f / (1.0f - drop_p) : 1.0f;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    if (nt < nt_n) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = (e < 2) ? iA : iB;
+        const int j = nt * 8 + 2 * t + (e & 1);
+        float p = s[nt][e] * ((e < 2) ? invA : invB);
+        if (!RF && i < Tn && j < Tn) {
+          probs[sbase + (int64_t)i * Tn + j] = __float2bfloat16_rn(p);
+          if (drop_p > 0.0f) p = hash32(seed, (uint64_t)(sbase + (int64_t)i * Tn + j)) >= thr ? p * inv_keep : 0.0f;
+        }
+        s[nt][e] = p;
+      }
+    }
+  }
+  // ---- O = P V : the accumulator fragments of P are the A fragments of the second GEMM
+  constexpr int ND = 16;                       // d <= 128
+  float o[ND][4];
+#pragma unroll
+  for (int nd = 0; nd < ND; ++nd) o[nd][0] = o[nd][1] = o[nd][2] = o[nd][3] = 0.0f;
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks) {
+    if (ks < ks_n) {
+      uint32_t a[4];
+      a[0] = pack2(s[2 * ks][0], s[2 * ks][1]);
+      a[1] = pack2(s[2 * ks][2], s[2 * ks][3]);
+      a[2] = pack2(s[2 * ks + 1][0], s[2 * ks + 1][1]);
+      a[3] = pack2(s[2 * ks + 1][2], s[2 * ks + 1][3]);
+#pragma unroll
+      for (int nd = 0; nd < ND; ++nd) {
+        if (nd < nd_n) {
+          uint32_t bb[2];
+          load_b(bb, Vt, ldt, nd * 8, ks * 16, g, t);
+          mma_bf16_16816(o[nd], a, bb);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int nd = 0; nd < ND; ++nd) {
+    if (nd < nd_n) {
+      const int sc = nd * 8 + 2 * t;
+      if (iA < Tn) *reinterpret_cast<uint32_t*>(out + ((int64_t)b * Tn + iA) * H + h * d + sc) = pack2(o[nd][0], o[nd][1]);
+      if (iB < Tn) *reinterpret_cast<uint32_t*>(out + ((int64_t)b * Tn + iB) * H + h * d + sc) = pack2(o[nd][2], o[nd][3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------------
+template <bool RF, int TP>
+__global__ void __launch_bounds__(256) attn_tc_bwd_kernel(const bf16* __restrict__ qkv, AttnLayout L,
+                                                          const float* __restrict__ scores, const bf16* __restrict__ probs,
+                                                          const bf16* __restrict__ dout, const float* __restrict__ dscores_in,
+                                                          bf16* __restrict__ dqkv, float* __restrict__ dprev, int Tn, int heads,
+                                                          int d, float drop_p, unsigned long long seed) {
+  extern __shared__ __align__(16) uint8_t smem_attn[];
+  constexpr int NT = TP / 8, KS = TP / 16, ND = 16;
+  const int Tp = (Tn + 15) & ~15;
+  const int ldn = d + 8, ldt = Tp + 8;
+  bf16* Vs = reinterpret_cast<bf16*>(smem_attn);     // [Tp][d+8]   B of dP = dO V^T
+  bf16* dOs = Vs + Tp * ldn;                         // [Tp][d+8]   A of dP
+  bf16* Kt = dOs + Tp * ldn;                         // [d][Tp+8]   B of dQ = dS K
+  bf16* dOt = Kt + d * ldt;                          // [d][Tp+8]   B of dV = P^T dO
+  bf16* Qt = dOt + d * ldt;                          // [d][Tp+8]   B of dK = dS^T Q
+  bf16* Pt = Qt + d * ldt;                           // [Tp][Tp+8]  P^T  (A of dV)
+  bf16* dSt = Pt + Tp * ldt;                         // [Tp][Tp+8]  dS^T (A of dK)
+  const int smem_bytes = (2 * Tp * ldn + 3 * d * ldt + 2 * Tp * ldt) * 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int H = heads * d;
+  const bf16* base = qkv + (int64_t)b * L.tok_batch + (int64_t)h * L.head_stride;
+  bf16* dbase = dqkv + (int64_t)b * L.tok_batch + (int64_t)h * L.head_stride;
+  const int64_t sbase = ((int64_t)b * heads + h) * Tn * Tn;
+  zero_smem(smem_attn, smem_bytes);
+  __syncthreads();
+  pdl_wait();
+  pdl_trigger();
+  stage_tile(base + L.v_off, L.row_stride, Tn, d, Vs, ldn, nullptr, 0);
+  stage_tile(dout + (int64_t)b * Tn * H + h * d, (int64_t)H, Tn, d, dOs, ldn, dOt, ldt);
+  stage_tile(base + L.k_off, L.row_stride, Tn, d, nullptr, 0, Kt, ldt);
+  stage_tile(base + L.q_off, L.row_stride, Tn, d, nullptr, 0, Qt, ldt);
+  __syncthreads();
+  const int r0 = warp * 16;
+  const int nt_n = Tp / 8, ks_n = Tp / 16, kd_n = d / 16, nd_n = d / 8;
+  const float inv_sqrt_d = 1.0f / sqrtf((float)d);
+  const uint32_t thr = (uint32_t)(drop_p * 4294967296.0);
+  const float inv_keep = drop_p > 0.0f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  if (r0 < Tp) {
+    const int iA = r0 + g, iB = r0 + g + 8;
+    // ---- P strip
+    float p[NT][4];
+    float mxA = -INFINITY, mxB = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = (e < 2) ? iA : iB;
+        const int j = nt * 8 + 2 * t + (e & 1);
+        float v = RF ? -INFINITY : 0.0f;
+        if (nt < nt_n && i < Tn && j < Tn) {
+          if (RF) v = __ldg(scores + sbase + (int64_t)i * Tn + j);
+          else v = __bfloat162float(probs[sbase + (int64_t)i * Tn + j]);
+        }
+        p[nt][e] = v;
+        if (RF) { if (e < 2) mxA = fmaxf(mxA, v); else mxB = fmaxf(mxB, v); }
+      }
+    }
+    if (RF) {
+      mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, 1));
+      mxA = fmaxf(mxA, __shfl_xor_sync(0xffffffffu, mxA, 2));
+      mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, 1));
+      mxB = fmaxf(mxB, __shfl_xor_sync(0xffffffffu, mxB, 2));
+      float sumA = 0.0f, sumB = 0.0f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float m = (e < 2) ? mxA : mxB;
+          const float q = (p[nt][e] == -INFINITY) ? 0.0f : expf(p[nt][e] - m);
+          p[nt][e] = q;
+          if (e < 2) sumA += q; else sumB += q;
+        }
+      }
+      sumA += __shfl_xor_sync(0xffffffffu, sumA, 1);
+      sumA += __shfl_xor_sync(0xffffffffu, sumA, 2);
+      sumB += __shfl_xor_sync(0xffffffffu, sumB, 1);
+      sumB += __shfl_xor_sync(0xffffffffu, sumB, 2);
+      const float invA = sumA > 0.0f ? 1.0f / sumA : 0.0f, invB = sumB > 0.0f ? 1.0f / sumB : 0.0f;
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        p[nt][0] *= invA; p[nt][1] *= invA; p[nt][2] *= invB; p[nt][3] *= invB;
+      }
+    }
+    // ---- dP = dO V^T
+    float dp[NT][4];
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.0f;
+    for (int kd = 0; kd < kd_n; ++kd) {
+      uint32_t a[4];
+      load_a(a, dOs, ldn, r0, kd * 16, g, t);
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        if (nt < nt_n) {
+          uint32_t bb[2];
+          load_b(bb, Vs, ldn, nt * 8, kd * 16, g, t);
+          mma_bf16_16816(dp[nt], a, bb);
+        }
+      }
+    }
+    // ---- dS = P (dP - rowdot) + dS_next ; park P^T (post-dropout for MHSA) and dS^T
+    float rdA = 0.0f, rdB = 0.0f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = (e < 2) ? iA : iB;
+        const int j = nt * 8 + 2 * t + (e & 1);
+        float pd = p[nt][e];
+        if (!RF && drop_p > 0.0f && nt < nt_n && i < Tn && j < Tn) {
+          const bool keep = hash32(seed, (uint64_t)(sbase + (int64_t)i * Tn + j)) >= thr;
+          dp[nt][e] = keep ? dp[nt][e] * inv_keep : 0.0f;
+          pd = keep ? pd * inv_keep : 0.0f;
+        }
+        if (nt < nt_n) Pt[j * ldt + i] = __float2bfloat16_rn(pd);
+        const float contrib = p[nt][e] * dp[nt][e];
+        if (e < 2) rdA += contrib; else rdB += contrib;
+      }
+    }
+    rdA += __shfl_xor_sync(0xffffffffu, rdA, 1);
+    rdA += __shfl_xor_sync(0xffffffffu, rdA, 2);
+    rdB += __shfl_xor_sync(0xffffffffu, rdB, 1);
+    rdB += __shfl_xor_sync(0xffffffffu, rdB, 2);
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = (e < 2) ? iA : iB;
+        const int j = nt * 8 + 2 * t + (e & 1);
+        float gsc = p[nt][e] * (dp[nt][e] - ((e < 2) ? rdA : rdB));
+        if (nt < nt_n && i < Tn && j < Tn) {
+          if (RF) {
+            if (dscores_in) gsc += __ldg(dscores_in + sbase + (int64_t)i * Tn + j);
+            if (dprev) dprev[sbase + (int64_t)i * Tn + j] = gsc;
+          }
+        } else {
+          gsc = 0.0f;
+        }
+        dp[nt][e] = gsc;                                   // dp now holds dS
+        if (nt < nt_n) dSt[j * ldt + i] = __float2bfloat16_rn(gsc);
+      }
+    }
+    // ---- dQ = dS K / sqrt(d)  (A from registers)
+    float dq[ND][4];
+#pragma unroll
+    for (int nd = 0; nd < ND; ++nd) dq[nd][0] = dq[nd][1] = dq[nd][2] = dq[nd][3] = 0.0f;
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      if (ks < ks_n) {
+        uint32_t a[4];
+        a[0] = pack2(dp[2 * ks][0], dp[2 * ks][1]);
+        a[1] = pack2(dp[2 * ks][2], dp[2 * ks][3]);
+        a[2] = pack2(dp[2 * ks + 1][0], dp[2 * ks + 1][1]);
+        a[3] = pack2(dp[2 * ks + 1][2], dp[2 * ks + 1][3]);
+#pragma unroll
+        for (int nd = 0; nd < ND; ++nd) {
+          if (nd < nd_n) {
+            uint32_t bb[2];
+            load_b(bb, Kt, ldt, nd * 8, ks * 16, g, t);
+            mma_bf16_16816(dq[nd], a, bb);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int nd = 0; nd < ND; ++nd) {
+      if (nd < nd_n) {
+        const int sc = nd * 8 + 2 * t;
+        if (iA < Tn) *reinterpret_cast<uint32_t*>(dbase + L.q_off + (int64_t)iA * L.row_stride + sc) = pack2(dq[nd][0] * inv_sqrt_d, dq[nd][1] * inv_sqrt_d);
+        if (iB < Tn) *reinterpret_cast<uint32_t*>(dbase + L.q_off + (int64_t)iB * L.row_stride + sc) = pack2(dq[nd][2] * inv_sqrt_d, dq[nd][3] * inv_sqrt_d);
+      }
+    }
+  }
+  __syncthreads();
+  if (r0 >= Tp) return;
+  // ---- phase 2: this warp now owns KEY rows j in [r0, r0+16): dV = P^T dO, dK = dS^T Q / sqrt(d)
+  {
+    const int jA = r0 + g, jB = r0 + g + 8;
+    float dv[ND][4], dk[ND][4];
+#pragma unroll
+    for (int nd = 0; nd < ND; ++nd) {
+      dv[nd][0] = dv[nd][1] = dv[nd][2] = dv[nd][3] = 0.0f;
+      dk[nd][0] = dk[nd][1] = dk[nd][2] = dk[nd][3] = 0.0f;
+    }
+    for (int ks = 0; ks < ks_n; ++ks) {
+      uint32_t ap[4], as[4];
+      load_a(ap, Pt, ldt, r0, ks * 16, g, t);
+      load_a(as, dSt, ldt, r0, ks * 16, g, t);
+#pragma unroll
+      for (int nd = 0; nd < ND; ++nd) {
+        if (nd < nd_n) {
+          uint32_t bb[2];
+          load_b(bb, dOt, ldt, nd * 8, ks * 16, g, t);
+          mma_bf16_16816(dv[nd], ap, bb);
+          load_b(bb, Qt, ldt, nd * 8, ks * 16, g, t);
+          mma_bf16_16816(dk[nd], as, bb);
+        }
+      }
+    }
+#pragma unroll
+    for (int nd = 0; nd < ND; ++nd) {
+      if (nd < nd_n) {
+        const int sc = nd * 8 + 2 * t;
+        if (jA < Tn) {
+          *reinterpret_cast<uint32_t*>(dbase + L.v_off + (int64_t)jA * L.row_stride + sc) = pack2(dv[nd][0], dv[nd][1]);
+          *reinterpret_cast<uint32_t*>(dbase + L.k_off + (int64_t)jA * L.row_stride + sc) = pack2(dk[nd][0] * inv_sqrt_d, dk[nd][1] * inv_sqrt_d);
+        }
+        if (jB < Tn) {
+          *reinterpret_cast<uint32_t*>(dbase + L.v_off + (int64_t)jB * L.row_stride + sc) = pack2(dv[nd][2], dv[nd][3]);
+          *reinterpret_cast<uint32_t*>(dbase + L.k_off + (int64_t)jB * L.row_stride + sc) = pack2(dk[nd][2] * inv_sqrt_d, dk[nd][3] * inv_sqrt_d);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace mmvqa

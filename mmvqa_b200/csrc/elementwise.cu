@@ -265,6 +265,91 @@ __global__ void __launch_bounds__(128) add_ln_fwd_kernel(const T* __restrict__ x
   }
 }
 
+// Vector path used whenever cols % (16 B) == 0 and cols <= 1024: the row stays in registers as the RAW 128-bit
+// vectors (12 registers for a 768-wide bf16 row instead of 24-32 floats) and is converted on the fly in each of the
+// three passes -- the ALU has slack, HBM does not.  Low register count -> 8 warps x 8 CTAs per SM in flight.
+template <typename T>
+__global__ void __launch_bounds__(256) add_ln_fwd_packed(const T* __restrict__ x, const T* __restrict__ res,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         T* __restrict__ y, T* __restrict__ sum_out,
+                                                         float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                         int64_t rows, int cols, float eps) {
+  constexpr int N = Vec16<T>::N;
+  constexpr int ITER = LN_CACHE / N;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  pdl_wait();
+  pdl_trigger();
+  if (row >= rows) return;
+  const T* xr = x + row * cols;
+  const T* rr = res ? res + row * cols : nullptr;
+  T* so = sum_out ? sum_out + row * cols : nullptr;
+  Vec16<T> raw[ITER];
+  float s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < ITER; ++k) {
+    const int c = (k * 32 + lane) * N;
+    if (c < cols) raw[k].load(xr + c);
+  }
+  if (rr) {
+#pragma unroll
+    for (int k = 0; k < ITER; ++k) {
+      const int c = (k * 32 + lane) * N;
+      if (c < cols) {
+        Vec16<T> b;
+        b.load(rr + c);
+#pragma unroll
+        for (int j = 0; j < N; ++j) raw[k].set(j, raw[k].get(j) + b.get(j));   // the stored (rounded) sum is what is normalised
+        if (so) raw[k].store(so + c);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < ITER; ++k) {
+    const int c = (k * 32 + lane) * N;
+    if (c < cols) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) s += raw[k].get(j);
+    }
+  }
+  const float mean = warp_sum(s) / (float)cols;
+  float q = 0.0f;
+#pragma unroll
+  for (int k = 0; k < ITER; ++k) {
+    const int c = (k * 32 + lane) * N;
+    if (c < cols) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const float d = raw[k].get(j) - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)cols + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  T* yr = y + row * cols;
+#pragma unroll
+  for (int k = 0; k < ITER; ++k) {
+    const int c = (k * 32 + lane) * N;
+    if (c < cols) {
+      Vec16<T> o;
+#pragma unroll
+      for (int j = 0; j < N; j += 4) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c + j));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c + j));
+        o.set(j, (raw[k].get(j) - mean) * rstd * g4.x + b4.x);
+        o.set(j + 1, (raw[k].get(j + 1) - mean) * rstd * g4.y + b4.y);
+        o.set(j + 2, (raw[k].get(j + 2) - mean) * rstd * g4.z + b4.z);
+        o.set(j + 3, (raw[k].get(j + 3) - mean) * rstd * g4.w + b4.w);
+      }
+      o.store(yr + c);
+    }
+  }
+}
+
 // generic (any cols): re-reads the row from global memory
 template <typename T>
 __global__ void __launch_bounds__(128) add_ln_fwd_generic(const T* __restrict__ x, const T* __restrict__ res,
@@ -307,9 +392,6 @@ __global__ void __launch_bounds__(128) add_ln_fwd_generic(const T* __restrict__ 
   }
 }
 
-// backward.  Each warp walks rows (grid-stride); lanes own fixed columns, so dgamma/dbeta (and the column
-// sums of the optional dropped copy) accumulate in registers and are flushed through shared memory with one
-// global atomic per (block, column).  CACHED = cols <= 1024.
 struct LnBwdExtra {
   void* dx_drop;            // optional: dropout(dx), same dtype
   float* dxsum;             // optional: += column sums of dx_drop (or of dx when dx_drop == NULL)
@@ -317,6 +399,116 @@ struct LnBwdExtra {
   unsigned long long seed;
 };
 
+// Packed backward (vector path): the two input rows stay in registers as raw 128-bit vectors and are re-expanded in
+// the second pass instead of keeping 2 x 32 floats; KU = number of 32-lane vector slots actually used by `cols`
+// (3 for a 768-wide bf16 row), so the gamma / beta / bias-gradient accumulators are 3 x KU x N registers.
+template <typename T, int KU>
+__global__ void __launch_bounds__(128) ln_bwd_packed(const T* __restrict__ dy, const T* __restrict__ xsum,
+                                                     const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                     const float* __restrict__ rstd, const T* __restrict__ dx_extra,
+                                                     T* __restrict__ dx, float* __restrict__ dgamma,
+                                                     float* __restrict__ dbeta, LnBwdExtra ex, int64_t rows, int cols) {
+  extern __shared__ float sm[];  // [nwarp][3][cols] slabs for the final flush
+  constexpr int N = Vec16<T>::N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  float dg[KU * N], db[KU * N], dsum[KU * N];
+#pragma unroll
+  for (int k = 0; k < KU * N; ++k) dg[k] = db[k] = dsum[k] = 0.0f;
+  pdl_wait();
+  pdl_trigger();
+  T* dxd = reinterpret_cast<T*>(ex.dx_drop);
+  const bool want_sum = ex.dxsum != nullptr;
+  const bool drop = ex.p > 0.0f;
+  const uint32_t thr = (uint32_t)(ex.p * 4294967296.0);
+  const float inv_keep = drop ? 1.0f / (1.0f - ex.p) : 1.0f;
+  for (int64_t row = blockIdx.x * (int64_t)nwarp + warp; row < rows; row += (int64_t)gridDim.x * nwarp) {
+    const float mu = mean[row], rs = rstd[row];
+    const T* dyr = dy + row * cols;
+    const T* xr = xsum + row * cols;
+    const T* er = dx_extra ? dx_extra + row * cols : nullptr;
+    T* dxr = dx + row * cols;
+    T* ddr = dxd ? dxd + row * cols : nullptr;
+    Vec16<T> a[KU], b[KU];
+#pragma unroll
+    for (int k = 0; k < KU; ++k) {
+      const int c = (k * 32 + lane) * N;
+      if (c < cols) {
+        a[k].load(dyr + c);
+        b[k].load(xr + c);
+      }
+    }
+    float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < KU; ++k) {
+      const int c = (k * 32 + lane) * N;
+      if (c < cols) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const float g = a[k].get(j), xh = (b[k].get(j) - mu) * rs;
+          dg[k * N + j] += g * xh;
+          db[k * N + j] += g;
+          const float gg = g * __ldg(gamma + c + j);
+          s1 += gg;
+          s2 += gg * xh;
+        }
+      }
+    }
+    s1 = warp_sum(s1) / (float)cols;
+    s2 = warp_sum(s2) / (float)cols;
+#pragma unroll
+    for (int k = 0; k < KU; ++k) {
+      const int c = (k * 32 + lane) * N;
+      if (c < cols) {
+        Vec16<T> e, o, od;
+        if (er) e.load(er + c);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+          const float gg = a[k].get(j) * __ldg(gamma + c + j), xh = (b[k].get(j) - mu) * rs;
+          o.set(j, rs * (gg - s1 - xh * s2) + (er ? e.get(j) : 0.0f));
+          if (ddr || want_sum) {
+            float d = o.get(j);   // the stored (rounded) value is what the branch sees
+            if (drop) d = hash32(ex.seed, (uint64_t)(row * cols + c + j)) >= thr ? d * inv_keep : 0.0f;
+            od.set(j, d);
+            dsum[k * N + j] += od.get(j);
+          }
+        }
+        o.store(dxr + c);
+        if (ddr) od.store(ddr + c);
+      }
+    }
+  }
+  if (dgamma == nullptr && dbeta == nullptr && !want_sum) return;
+  float* slab = sm + (size_t)warp * 3 * cols;
+#pragma unroll
+  for (int k = 0; k < KU; ++k) {
+    const int c = (k * 32 + lane) * N;
+    if (c < cols) {
+#pragma unroll
+      for (int j = 0; j < N; j += 4) {
+        *reinterpret_cast<float4*>(slab + c + j) = make_float4(dg[k * N + j], dg[k * N + j + 1], dg[k * N + j + 2], dg[k * N + j + 3]);
+        *reinterpret_cast<float4*>(slab + cols + c + j) = make_float4(db[k * N + j], db[k * N + j + 1], db[k * N + j + 2], db[k * N + j + 3]);
+        *reinterpret_cast<float4*>(slab + 2 * cols + c + j) = make_float4(dsum[k * N + j], dsum[k * N + j + 1], dsum[k * N + j + 2], dsum[k * N + j + 3]);
+      }
+    }
+  }
+  __syncthreads();
+  const int nv = cols / 4;
+  for (int i = threadIdx.x; i < 3 * nv; i += blockDim.x) {
+    const int which = i / nv, c4 = (i - which * nv) * 4;
+    float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : ex.dxsum);
+    if (dst == nullptr) continue;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int w = 0; w < nwarp; ++w) {
+      const float4 t = *reinterpret_cast<const float4*>(sm + (size_t)w * 3 * cols + which * cols + c4);
+      acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    atomicAdd(reinterpret_cast<float4*>(dst + c4), acc);
+  }
+}
+
+// backward.  Each warp walks rows (grid-stride); lanes own fixed columns, so dgamma/dbeta (and the column
+// sums of the optional dropped copy) accumulate in registers and are flushed through shared memory with one
+// global atomic per (block, column).  CACHED = cols <= 1024.
 template <typename T, bool VEC, bool CACHED>
 __global__ void __launch_bounds__(128) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ xsum,
                                                      const float* __restrict__ gamma, const float* __restrict__ mean,
@@ -656,7 +848,12 @@ int mmvqa_add_layernorm_fwd(const void* x, const void* res, const float* gamma, 
   const bool vec = cached && cols % vn == 0 && aligned16(x) && aligned16(y) && (!res || aligned16(res)) &&
                    (!sum_out || aligned16(sum_out));
 #define LN_FWD(T, K) launch_pdl(K, dim3(grid), dim3(128), 0, st, (const T*)x, (const T*)res, gamma, beta, (T*)y, (T*)sum_out, mean, rstd, rows, cols, eps)
-  if (dtype == MMVQA_F32) {
+#define LN_FWD_PACKED(T) launch_pdl(add_ln_fwd_packed<T>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, st, (const T*)x, (const T*)res, gamma, beta, (T*)y, (T*)sum_out, mean, rstd, rows, cols, eps)
+  const bool gb_al = aligned16(gamma) && aligned16(beta);
+  if (vec && gb_al) {
+    if (dtype == MMVQA_F32) LN_FWD_PACKED(float);
+    else LN_FWD_PACKED(__nv_bfloat16);
+  } else if (dtype == MMVQA_F32) {
     if (vec) LN_FWD(float, (add_ln_fwd_kernel<float, true>));
     else if (cached) LN_FWD(float, (add_ln_fwd_kernel<float, false>));
     else LN_FWD(float, add_ln_fwd_generic<float>);
@@ -667,6 +864,7 @@ int mmvqa_add_layernorm_fwd(const void* x, const void* res, const float* gamma, 
     else LN_FWD(B, add_ln_fwd_generic<B>);
   }
 #undef LN_FWD
+#undef LN_FWD_PACKED
   MMVQA_LAUNCHED("add_layernorm_fwd");
   return MMVQA_OK;
 }
@@ -692,6 +890,30 @@ int mmvqa_layernorm_bwd(const void* dy, const void* xsum, const float* gamma, co
   MMVQA_REQUIRE(smem <= 48 * 1024, "layernorm_bwd: cols %d too large", cols);
   LnBwdExtra ex;
   ex.dx_drop = dx_drop; ex.dxsum = dxsum; ex.p = dx_drop ? dropout_p : 0.0f; ex.seed = dropout_seed;
+  // packed kernel: 4-warp CTAs (one row per warp) when the problem is small, 8-warp CTAs with a row loop otherwise
+  if (vec && aligned16(gamma)) {
+    const int vnn = dtype == MMVQA_F32 ? 4 : 8;
+    const int ku = (cols + 32 * vnn - 1) / (32 * vnn);
+    const int nthr = 128;
+    const int nw = nthr / 32;
+    int64_t want2 = (rows + nw - 1) / nw, cap2 = (int64_t)num_sms() * 12;
+    const int grid2 = (int)(want2 < cap2 ? want2 : cap2);
+    const size_t smem2 = sizeof(float) * 3 * (size_t)cols * nw;
+    bool launched = true;
+    if (smem2 > 48 * 1024) launched = false;
+#define LN_BWDP(T, KU) MMVQA_CUDA(launch_pdl(ln_bwd_packed<T, KU>, dim3(grid2), dim3(nthr), smem2, st, (const T*)dy, (const T*)xsum, gamma, mean, rstd, (const T*)dx_extra, (T*)dx, dgamma, dbeta, ex, rows, cols))
+    if (launched) {
+      if (dtype == MMVQA_BF16) {
+        using B = __nv_bfloat16;
+        if (ku <= 1) LN_BWDP(B, 1); else if (ku == 2) LN_BWDP(B, 2); else if (ku == 3) LN_BWDP(B, 3); else LN_BWDP(B, 4);
+      } else {
+        if (ku <= 2) LN_BWDP(float, 2); else if (ku <= 4) LN_BWDP(float, 4); else if (ku <= 6) LN_BWDP(float, 6); else LN_BWDP(float, 8);
+      }
+      MMVQA_LAUNCHED("layernorm_bwd");
+      return MMVQA_OK;
+    }
+#undef LN_BWDP
+  }
 #define LN_BWD(T, V, C) launch_pdl(ln_bwd_kernel<T, V, C>, dim3(grid), dim3(128), smem, st, (const T*)dy, (const T*)xsum, gamma, mean, rstd, (const T*)dx_extra, (T*)dx, dgamma, dbeta, ex, rows, cols)
   if (dtype == MMVQA_F32) {
     if (vec) LN_BWD(float, true, true);
