@@ -31,6 +31,45 @@ def _round_up(x: int, m: int) -> int:
 
 
 # --------------------------------------------------------------------------------------
+# side stream for work that is off the critical path (weight-gradient GEMMs): it forks from / joins the current
+# stream with events, so inside a CUDA-graph capture it becomes a parallel branch of the graph
+# --------------------------------------------------------------------------------------
+import os as _os
+
+_SIDE = {}
+_OVERLAP = _os.environ.get("MMVQA_NO_OVERLAP") is None
+
+
+class SideBranch:
+    """`with branch.after_now(): ...` runs the body on the side stream once everything enqueued so far on the main
+    stream has finished; `join()` makes the main stream wait for the branch.  Tensors touched by the branch must be
+    kept alive by the caller until join() (the caching allocator only tracks the allocating stream)."""
+
+    def __init__(self, device):
+        self.main = torch.cuda.current_stream(device)
+        key = (device.index if device.index is not None else torch.cuda.current_device(), self.main.cuda_stream)
+        if key not in _SIDE:
+            _SIDE[key] = torch.cuda.Stream(device)
+        self.side = _SIDE[key] if _OVERLAP else self.main
+        self.used = False
+
+    def after_now(self):
+        if self.side is not self.main:
+            ev = torch.cuda.Event()
+            ev.record(self.main)
+            self.side.wait_event(ev)
+            self.used = True
+        return torch.cuda.stream(self.side)
+
+    def join(self):
+        if self.used:
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            self.main.wait_event(ev)
+            self.used = False
+
+
+# --------------------------------------------------------------------------------------
 # weight cache: fp32 master parameters -> compute-dtype GEMM operands (optionally concatenated)
 # --------------------------------------------------------------------------------------
 class WeightCache:
@@ -395,6 +434,92 @@ def vistok_project(feat: Tensor, conv_w: Tensor, act: int) -> Tensor:
     return VisTokFn.apply(feat, conv_w, act, compute_dtype())
 
 
+class VisTokAllFn(torch.autograd.Function):
+    """All pyramid levels in one autograd node: v[n] = mean_hw act(W_n . f_n).  The levels are independent, so the
+    largest one runs on the main stream and the others on a side branch (parallel graph branches when captured);
+    returns the stacked [num_vis, B, hidden] fp32 tokens that the fused embedding kernel consumes."""
+
+    @staticmethod
+    def forward(ctx, act: int, dtype: torch.dtype, nlev: int, *tensors):
+        feats, convs = tensors[:nlev], tensors[nlev:]
+        B = feats[0].shape[0]
+        hidden = convs[0].shape[0]
+        dev = feats[0].device
+        vis = torch.zeros(nlev, B, hidden, device=dev, dtype=torch.float32)
+        order = sorted(range(nlev), key=lambda n: -feats[n][0].numel())          # biggest level first, on main
+        branch = SideBranch(dev)
+        saved, metas = [None] * (3 * nlev), [None] * nlev
+        keep = []
+
+        def run(n):
+            f, cw = feats[n], convs[n]
+            _, Cc, Hh, Ww = f.shape
+            HW = Hh * Ww
+            w = weight_cache.get((cw,), dtype)
+            fb, ld = _pad_ld(f.detach().reshape(B * Cc, HW), dtype)
+            need_bwd = ctx.needs_input_grad[3 + n] or ctx.needs_input_grad[3 + nlev + n]
+            actp = torch.empty(B, hidden, ld, device=dev, dtype=dtype) if need_bwd else None
+            ops.gemm(hidden, HW, Cc, w, Cc, False, fb, ld, True, None, 0, epilogue=EPI_ACT_ROWSUM, act=act, rowsum_out=vis[n],
+                     scale=1.0 / HW, batch=B, a_batch_rows=0, b_batch_rows=Cc, aux_out=actp, ld_aux_out=ld)
+            saved[3 * n:3 * n + 3] = [fb, cw, actp]
+            metas[n] = (Cc, Hh, Ww, ld, f.dtype)
+            keep.append((fb, actp))
+        run(order[0])
+        if nlev > 1:
+            with branch.after_now():
+                for n in order[1:]:
+                    run(n)
+        branch.join()
+        ctx.save_for_backward(*saved)
+        ctx.meta = (act, dtype, nlev, B, hidden, metas, order)
+        return vis
+
+    @staticmethod
+    def backward(ctx, dvis: Tensor):
+        act, dtype, nlev, B, hidden, metas, order = ctx.meta
+        saved = ctx.saved_tensors
+        dev = dvis.device
+        dvs = dvis.contiguous().float()
+        dfeats, dws = [None] * nlev, [None] * nlev
+        branch = SideBranch(dev)
+        keep = []
+
+        def run(n):
+            fb, cw, actp = saved[3 * n:3 * n + 3]
+            Cc, Hh, Ww, ld, fdt = metas[n]
+            HW = Hh * Ww
+            dv = dvs[n]
+            if ctx.needs_input_grad[3 + nlev + n]:
+                dw = torch.zeros(hidden, Cc, device=dev, dtype=torch.float32)
+                tiles = ((hidden + 127) // 128) * B
+                kblocks = (HW + 63) // 64
+                sk = max(1, min(4, (2 * _sms(dev)) // max(tiles, 1), kblocks // 16))
+                ops.gemm(hidden, Cc, HW, actp, ld, False, fb, ld, False, dw, Cc, accumulate=True, split_k=sk, batch=B,
+                         a_batch_rows=hidden, b_batch_rows=Cc, c_batch_stride=0, rowscale=dv, scale=1.0 / HW)
+                dws[n] = dw.view(cw.shape)
+            if ctx.needs_input_grad[3 + n]:
+                w32 = cw.detach().reshape(hidden, Cc).float()
+                wb = (w32.unsqueeze(0) * (dv / HW).unsqueeze(-1)).to(dtype).contiguous()
+                df = torch.empty(B, Cc, HW, device=dev, dtype=torch.float32)
+                ops.gemm(Cc, HW, hidden, wb, Cc, True, actp, ld, True, df, HW, batch=B, a_batch_rows=hidden, b_batch_rows=hidden,
+                         c_batch_stride=Cc * HW)
+                dfeats[n] = df.view(B, Cc, Hh, Ww).to(fdt)
+                keep.append(wb)
+        run(order[0])
+        if nlev > 1:
+            with branch.after_now():
+                for n in order[1:]:
+                    run(n)
+        branch.join()
+        return (None, None, None, *dfeats, *dws)
+
+
+def vistok_project_all(feats: Sequence[Tensor], conv_ws: Sequence[Tensor], act: int) -> Tensor:
+    """[num_vis, B, hidden] fp32 visual tokens."""
+    fs = [f if f.dtype in (torch.float32, torch.bfloat16) else f.float() for f in feats]
+    return VisTokAllFn.apply(act, compute_dtype(), len(fs), *fs, *conv_ws)
+
+
 # --------------------------------------------------------------------------------------
 # BertEmbeddings + visual-token scatter  (mmbert.py:60-67)
 # --------------------------------------------------------------------------------------
@@ -596,6 +721,10 @@ class RealFormerEncoderFn(torch.autograd.Function):
         F4 = params[4].shape[0]
         per_layer = 5 * H + F4 + 3 * d * d
         zws = torch.zeros(n_layers * per_layer, device=saved[0].device, dtype=torch.float32)
+        # weight-gradient GEMMs are off the critical path (nothing in this backward reads them): they run on a side
+        # branch and overlap the dgrad -> LayerNorm -> attention chain of the same and the following layers
+        branch = SideBranch(saved[0].device)
+        keep = []
         for l in reversed(range(n_layers)):
             xin, kqv, scores, attn, y1, mean1, rstd1, x1, hpre, hact, y2, mean2, rstd2 = saved[l * nsave:(l + 1) * nsave]
             kqv_w, proj_w, g1, b1, w0, bb0, w2, bb2, g2, b2 = params[l * RF_PARAMS_PER_LAYER:(l + 1) * RF_PARAMS_PER_LAYER]
@@ -613,10 +742,12 @@ class RealFormerEncoderFn(torch.autograd.Function):
             else:
                 dy2 = ops.layernorm_bwd(dx, y2, g2.detach(), mean2, rstd2, None, dg2, db2, dxsum=dbb2)
                 dff = dy2
-            dw2 = gemm_wgrad(dff, H, M, H, hact, F4, F4)
+            with branch.after_now():
+                dw2 = gemm_wgrad(dff, H, M, H, hact, F4, F4)
             # dgrad through FF2 with act'(h_pre) in the epilogue; its column sums are d ff.0.bias
             dhpre = gemm_dgrad(dff, H, M, H, wf2, F4, epilogue=EPI_DACT, act=ACT_SERF, aux_in=hpre, colsum_out=dbb0)
-            dw0 = gemm_wgrad(dhpre, F4, M, F4, x1, H, H)
+            with branch.after_now():
+                dw0 = gemm_wgrad(dhpre, F4, M, F4, x1, H, H)
             dx1 = gemm_dgrad(dhpre, F4, M, F4, wf0, H, epilogue=EPI_RESIDUAL, aux_in=dy2)
             if p1 > 0.0:
                 dy1, dpr = ops.layernorm_bwd(dx1, y1, g1.detach(), mean1, rstd1, None, dg1, db1, want_drop=True,
@@ -624,11 +755,14 @@ class RealFormerEncoderFn(torch.autograd.Function):
             else:
                 dy1 = ops.layernorm_bwd(dx1, y1, g1.detach(), mean1, rstd1, None, dg1, db1)
                 dpr = dy1
-            dwp = gemm_wgrad(dpr, H, M, H, attn, H, H)
+            with branch.after_now():
+                dwp = gemm_wgrad(dpr, H, M, H, attn, H, H)
             dattn = gemm_dgrad(dpr, H, M, H, wp, H)
             want_dprev = (l > 0) or (has_prev and ctx.needs_input_grad[2])
             dkqv, dprev = ops.rf_attn_bwd(kqv, scores, dattn, ds, want_dprev, B, T, heads, d)
-            dwk = gemm_wgrad(dkqv, 3 * d, M * heads, 3 * d, xin, d, d, zeroed=zl[5 * H + F4:].view(3 * d, d))
+            with branch.after_now():
+                dwk = gemm_wgrad(dkqv, 3 * d, M * heads, 3 * d, xin, d, d, zeroed=zl[5 * H + F4:].view(3 * d, d))
+            keep.append((dff, dhpre, dpr, dkqv, dy2, dy1))
             # dx_in = dkqv . Wkqv (per head) + dy1 (residual around the attention block)
             dxin = torch.empty(M, H, device=dx.device, dtype=dt)
             ops.gemm(M * heads, d, 3 * d, dkqv, 3 * d, False, wk, d, True, dxin, d, epilogue=EPI_RESIDUAL, aux_in=dy1,
@@ -637,6 +771,8 @@ class RealFormerEncoderFn(torch.autograd.Function):
             grads[base:base + RF_PARAMS_PER_LAYER] = [dwk.view(kqv_w.shape), dwp, dg1, db1, dw0, dbb0, dw2, dbb2, dg2, db2]
             dx = dxin
             ds = dprev
+        branch.join()
+        del keep
         dprev_out = ds if (has_prev and ctx.needs_input_grad[2]) else None
         return (dx.view(B, T, H), None, dprev_out, None, None, None, None, *grads)
 

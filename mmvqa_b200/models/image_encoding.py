@@ -89,10 +89,15 @@ class Transfer(nn.Module):
     def _convs(self):
         return (self.conv2, self.conv3, self.conv4, self.conv5, self.conv7)
 
+    def project_stacked(self, feats):
+        """feature maps (token order) -> [num_vis, B, hidden] fp32 visual tokens (one autograd node, levels overlapped)."""
+        act = ACT_RELU if self.args.use_relu else ACT_SERF
+        feats = list(feats)
+        return Fn.vistok_project_all(feats, [c.weight for c in self._convs()][:len(feats)], act)
+
     def project(self, feats):
         """feature maps (token order) -> tuple of [B, hidden] fp32 visual tokens."""
-        act = ACT_RELU if self.args.use_relu else ACT_SERF
-        return tuple(Fn.vistok_project(f, c.weight, act) for f, c in zip(feats, self._convs()))
+        return tuple(self.project_stacked(feats).unbind(0))
 
 
 class ResNetTransfer(Transfer):

@@ -59,7 +59,10 @@ class TransformerAbstract(nn.Module):
 
     def fuse(self, vizs, input_ids, token_type_ids):
         emb = self.bert_embedding
-        vis = torch.stack([v.float() for v in vizs], dim=0) if len(vizs) > 0 else None       # [nvis, B, H]
+        if torch.is_tensor(vizs):
+            vis = vizs                                                                        # already [nvis, B, H]
+        else:
+            vis = torch.stack([v.float() for v in vizs], dim=0) if len(vizs) > 0 else None   # [nvis, B, H]
         p = emb.dropout.p if self.training else 0.0
         pad = emb.word_embeddings.padding_idx
         return Fn.EmbedFuseFn.apply(input_ids, token_type_ids, emb.word_embeddings.weight,
@@ -157,7 +160,7 @@ class Model(nn.Module):
         """Hot path only: backbone feature maps (token order) -> outputs.  Same arithmetic as forward()
         after the CNN; used by bench.py and the parity tests, whose inputs start at the feature maps."""
         tr = self.transformer
-        h = tr.fuse(list(tr.trans.project(feats)), input_ids, segment_ids)
+        h = tr.fuse(tr.trans.project_stacked(feats), input_ids, segment_ids)
         return self.heads(tr.encode(h, input_mask), input_mask)
 
 
