@@ -70,6 +70,26 @@ class SideBranch:
 
 
 # --------------------------------------------------------------------------------------
+# gradient sink: lets an optimizer / data-parallel engine consume parameter gradients the moment a layer's backward
+# has enqueued them, instead of after the whole backward (autograd only publishes .grad when a node returns)
+# --------------------------------------------------------------------------------------
+_GRAD_SINK = None
+
+
+def set_grad_sink(fn) -> None:
+    """``fn(params, grads, side_stream) -> bool`` is called from inside multi-layer backward nodes with the
+    parameters of ONE layer and their final fp32 gradients; work producing them is enqueued on the current stream
+    and on `side_stream`.  Returning True means the sink took the gradients (it may set ``p.grad`` itself): the node
+    then returns None for them.  ``None`` removes the sink."""
+    global _GRAD_SINK
+    _GRAD_SINK = fn
+
+
+def grad_sink():
+    return _GRAD_SINK
+
+
+# --------------------------------------------------------------------------------------
 # weight cache: fp32 master parameters -> compute-dtype GEMM operands (optionally concatenated)
 # --------------------------------------------------------------------------------------
 class WeightCache:
@@ -464,11 +484,12 @@ class VisTokAllFn(torch.autograd.Function):
             saved[3 * n:3 * n + 3] = [fb, cw, actp]
             metas[n] = (Cc, Hh, Ww, ld, f.dtype)
             keep.append((fb, actp))
-        run(order[0])
+        # fork BEFORE the big level is enqueued: the side branch only depends on what precedes this node
         if nlev > 1:
             with branch.after_now():
                 for n in order[1:]:
                     run(n)
+        run(order[0])
         branch.join()
         ctx.save_for_backward(*saved)
         ctx.meta = (act, dtype, nlev, B, hidden, metas, order)
@@ -505,11 +526,11 @@ class VisTokAllFn(torch.autograd.Function):
                          c_batch_stride=Cc * HW)
                 dfeats[n] = df.view(B, Cc, Hh, Ww).to(fdt)
                 keep.append(wb)
-        run(order[0])
         if nlev > 1:
             with branch.after_now():
                 for n in order[1:]:
                     run(n)
+        run(order[0])
         branch.join()
         return (None, None, None, *dfeats, *dws)
 
@@ -725,6 +746,7 @@ class RealFormerEncoderFn(torch.autograd.Function):
         # branch and overlap the dgrad -> LayerNorm -> attention chain of the same and the following layers
         branch = SideBranch(saved[0].device)
         keep = []
+        sink = _GRAD_SINK
         for l in reversed(range(n_layers)):
             xin, kqv, scores, attn, y1, mean1, rstd1, x1, hpre, hact, y2, mean2, rstd2 = saved[l * nsave:(l + 1) * nsave]
             kqv_w, proj_w, g1, b1, w0, bb0, w2, bb2, g2, b2 = params[l * RF_PARAMS_PER_LAYER:(l + 1) * RF_PARAMS_PER_LAYER]
@@ -768,7 +790,14 @@ class RealFormerEncoderFn(torch.autograd.Function):
             ops.gemm(M * heads, d, 3 * d, dkqv, 3 * d, False, wk, d, True, dxin, d, epilogue=EPI_RESIDUAL, aux_in=dy1,
                      ld_aux_in=d)
             base = l * RF_PARAMS_PER_LAYER
-            grads[base:base + RF_PARAMS_PER_LAYER] = [dwk.view(kqv_w.shape), dwp, dg1, db1, dw0, dbb0, dw2, dbb2, dg2, db2]
+            gl = [dwk.view(kqv_w.shape), dwp.view(proj_w.shape), dg1, db1, dw0.view(w0.shape), dbb0, dw2.view(w2.shape), dbb2,
+                  dg2, db2]
+            pl = params[base:base + RF_PARAMS_PER_LAYER]
+            if sink is not None and all(ctx.needs_input_grad[7 + base + i] for i in range(RF_PARAMS_PER_LAYER)) and \
+                    sink(pl, gl, branch.side):
+                keep.append(gl)
+            else:
+                grads[base:base + RF_PARAMS_PER_LAYER] = gl
             dx = dxin
             ds = dprev
         branch.join()

@@ -31,6 +31,8 @@ class GraphedTrainStep:
         self.eager_between = eager_between      # not captured, e.g. GradBuckets.allreduce
         self.step_kwargs = step_kwargs          # e.g. lambda: dict(grads=buckets.grads(plist))
         self.static_inputs = [t.clone() for t in example_inputs]
+        if hasattr(optimizer, "init_state"):
+            optimizer.init_state()              # optimizer state must not be born inside the capture
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):

@@ -6,6 +6,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
+from . import functional as Fn
 from . import ops
 from .functional import weight_cache
 
@@ -19,13 +20,33 @@ class FusedAdam(torch.optim.Optimizer):
     ``grad_scale`` multiplies every gradient inside the kernel (1/world_size after an all-reduce SUM).
     The step counter lives on the device, so a captured CUDA graph of ``step()`` can be replayed."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, overlap_backward=False):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.grad_scale = 1.0
         self._tables = {}
         self._keepalive = []       # pinned host tables referenced by memcpy nodes of captured graphs
         self._refreshed = {}       # group index -> ids of parameters whose bf16 cache copy the kernel rewrites
         self._step_dev = None
+        # overlap_backward: layers whose backward node offers its gradients early (functional.set_grad_sink) are
+        # updated on a separate stream while the rest of the backward pass runs -- Adam is pure HBM traffic, the
+        # small-batch backward is latency bound, so the two overlap almost for free.  step() updates what is left.
+        self._stepped = False      # device step counter already advanced in this iteration
+        self._early_ids = set()    # parameters already updated in this iteration
+        self._early_keep = []      # gradients read by the optimizer stream (kept alive until step() joins it)
+        self._opt_stream = None
+        self._group_of = {id(p): gi for gi, g in enumerate(self.param_groups) for p in g["params"]}
+        if overlap_backward:
+            Fn.set_grad_sink(self._sink)
+        self._init_step_counter()
+
+    def _init_step_counter(self):
+        """the device step counter must exist before any CUDA-graph capture (a tensor created inside a capture is
+        re-initialised by every replay)."""
+        p0 = self.param_groups[0]["params"][0]
+        if p0.is_cuda:
+            st = self.state.get(p0, {})
+            s0 = int(st["step"].item()) if "step" in st else 0
+            self._step_dev = torch.full((1,), s0, dtype=torch.int32, device=p0.device)
 
     def _state_of(self, p):
         st = self.state[p]
@@ -35,8 +56,17 @@ class FusedAdam(torch.optim.Optimizer):
             st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
         return st
 
-    def _table(self, gi, group, grads):
-        plist = [p for p in group["params"] if p.grad is not None]
+    def init_state(self) -> None:
+        """allocate exp_avg / exp_avg_sq of every parameter now.  Must run before a CUDA-graph capture of step():
+        state created inside a capture lives in the graph's pool and would be re-zeroed by every replay."""
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.requires_grad:
+                    self._state_of(p)
+        if self._step_dev is None:
+            self._init_step_counter()
+
+    def _table(self, gi, plist, grads):
         key = (weight_cache.generation, tuple((p.data_ptr(), g.data_ptr()) for p, g in zip(plist, grads)))
         ent = self._tables.get(gi)
         if ent is not None and ent[0] == key:
@@ -67,6 +97,50 @@ class FusedAdam(torch.optim.Optimizer):
         self._keepalive.append((host, dev))
         return dev, len(rows)
 
+    def _advance(self, device):
+        if self._step_dev is None:
+            st0 = self._state_of(self.param_groups[0]["params"][0])
+            self._step_dev = torch.full((1,), int(st0["step"].item()), dtype=torch.int32, device=device)
+        if not self._stepped:
+            self._step_dev += 1
+            self._stepped = True
+
+    def _launch(self, gi, key, plist, grads):
+        group = self.param_groups[gi]
+        table, n = self._table(key, plist, grads)
+        b1, b2 = group["betas"]
+        ops.adam_step(table, n, group["lr"], b1, b2, group["eps"], group["weight_decay"], 0, self._step_dev,
+                      self.grad_scale)
+
+    @torch.no_grad()
+    def _sink(self, params, grads, side_stream) -> bool:
+        """functional.set_grad_sink target: update one layer's parameters now, on the optimizer stream."""
+        gis = {self._group_of.get(id(p)) for p in params}
+        if len(gis) != 1 or None in gis or any(p.grad is not None for p in params) or \
+                any(id(p) in self._early_ids for p in params):
+            return False            # unknown / shared / accumulating parameters: leave them to autograd + step()
+        gi = gis.pop()
+        dev = params[0].device
+        main = torch.cuda.current_stream(dev)
+        if self._opt_stream is None:
+            self._opt_stream = torch.cuda.Stream(dev)
+        self._advance(dev)          # on the main stream: ordered before every update of this iteration
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._opt_stream.wait_event(ev)
+        if side_stream is not None and side_stream is not main:
+            ev2 = torch.cuda.Event()
+            ev2.record(side_stream)
+            self._opt_stream.wait_event(ev2)
+        gs = [g.contiguous() for g in grads]
+        with torch.cuda.stream(self._opt_stream):
+            self._launch(gi, ("early", id(params[0])), list(params), gs)
+        for p, g in zip(params, gs):
+            p.grad = g              # visible to hooks / loggers exactly as after a normal backward
+            self._early_ids.add(id(p))
+        self._early_keep.append(gs)
+        return True
+
     @torch.no_grad()
     def step(self, closure=None, grads=None):
         """`grads` (optional): list aligned with the parameters that have gradients, to read the gradients from
@@ -75,24 +149,33 @@ class FusedAdam(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        if grads is not None and self._early_ids:
+            raise RuntimeError("FusedAdam: step(grads=...) cannot be combined with overlap_backward")
         for gi, group in enumerate(self.param_groups):
-            plist = [p for p in group["params"] if p.grad is not None]
+            plist = [p for p in group["params"] if p.grad is not None and id(p) not in self._early_ids]
             if not plist:
                 continue
             g = [p.grad for p in plist] if grads is None else grads
-            table, n = self._table(gi, group, g)
-            if self._step_dev is None:
-                st0 = self._state_of(plist[0])
-                self._step_dev = torch.full((1,), int(st0["step"].item()), dtype=torch.int32, device=plist[0].device)
-            self._step_dev += 1
-            b1, b2 = group["betas"]
-            ops.adam_step(table, n, group["lr"], b1, b2, group["eps"], group["weight_decay"], 0, self._step_dev,
-                          self.grad_scale)
+            self._advance(plist[0].device)
+            self._launch(gi, gi, plist, g)
+        if self._early_ids:         # join the optimizer stream; its gradient buffers may be released after this point
+            dev = self._opt_stream.device
+            ev = torch.cuda.Event()
+            ev.record(self._opt_stream)
+            torch.cuda.current_stream(dev).wait_event(ev)
+            self._early_ids = set()
+            self._early_keep = []
+        self._stepped = False
         ids = set()
         for r in self._refreshed.values():
             ids |= r
         weight_cache.note_optimizer_step(ids)
         return loss
+
+    def close(self) -> None:
+        """remove this optimizer's gradient sink (overlap_backward)."""
+        if Fn.grad_sink() == self._sink:
+            Fn.set_grad_sink(None)
 
     def covers_weight_cache(self) -> bool:
         """True if every cached tensor-core operand copy is rewritten by this optimizer's kernel (then a captured
@@ -114,3 +197,4 @@ class FusedAdam(torch.optim.Optimizer):
         super().load_state_dict(sd)
         self._tables.clear()
         self._step_dev = None
+        self._init_step_counter()

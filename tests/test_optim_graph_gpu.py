@@ -125,3 +125,48 @@ def test_graph_replay_equals_eager(dt):
         for a, b in zip(pe, pg):
             torch.testing.assert_close(b, a, rtol=1e-3, atol=6.5e-3)
         Fn.invalidate_weight_cache()
+
+
+@pytest.mark.parametrize("graph", [False, True], ids=["eager", "graph"])
+def test_overlapped_adam_equals_plain(graph):
+    """overlap_backward: every encoder layer is updated on the optimizer stream from inside the backward node; the
+    result must be the update a plain step() after backward makes (same kernel, same gradients)."""
+    with mmvqa_b200.compute_dtype_scope(torch.bfloat16):
+        Fn.invalidate_weight_cache()
+        xs = [torch.randn(4, 12, 128, device=DEV) for _ in range(3)]
+        mask = torch.ones(4, 12, device=DEV, dtype=torch.long)
+
+        def run(overlap):
+            torch.manual_seed(5)
+            blocks = nn.ModuleList([ResEncoderBlock(emb_s=16, head_cnt=8, dp1=0.0, dp2=0.0) for _ in range(3)]).to(DEV)
+            head = nn.Linear(128, 8).to(DEV)                     # a parameter that does NOT go through the sink
+            params = list(blocks.parameters()) + list(head.parameters())
+            opt = FusedAdam(params, lr=1e-3, overlap_backward=overlap)
+
+            def loss_fn(x):
+                h, _ = run_blocks(list(blocks), x, None, mask, False)
+                return Fn.linear(h, head.weight, head.bias).float().pow(2).mean()
+            try:
+                if graph:
+                    gs = GraphedTrainStep(loss_fn, [xs[0]], opt, warmup=0)
+                    for x in xs:
+                        gs.replay(x)
+                else:
+                    for x in xs:
+                        opt.zero_grad(set_to_none=True)
+                        loss_fn(x).backward()
+                        if overlap:
+                            assert len(opt._early_ids) == 3 * 10, "all three layers must have gone through the sink"
+                            assert all(p.grad is not None for p in params)
+                        opt.step()
+                torch.cuda.synchronize()
+                sd = opt.state_dict()
+                assert float(sd["state"][0]["step"]) == 3.0
+            finally:
+                opt.close()
+            return [p.detach().clone() for p in params]
+        plain, over = run(False), run(True)
+        assert Fn.grad_sink() is None
+        for a, b in zip(plain, over):
+            torch.testing.assert_close(b, a, rtol=1e-3, atol=6.5e-3)
+        Fn.invalidate_weight_cache()
