@@ -242,6 +242,8 @@ def main_gpu(a):
         if a.verbose:
             print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
     if world > 1:
+        if a.nccl_channels > 0:       # the exchange shares the SMs with the backward pass: fewer, fatter channels
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", str(a.nccl_channels))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dt = torch.bfloat16 if a.dtype == "bf16" else torch.float32
     mmvqa_b200.set_compute_dtype(dt)
@@ -255,14 +257,22 @@ def main_gpu(a):
                 m.p = 0.0
     params = [p for p in model.parameters() if p.requires_grad]
     nparams = sum(p.numel() for p in params)
-    # one GPU: Adam of each encoder layer runs on its own stream under the rest of the backward pass (needs no
-    # collective); data parallel: the all-reduced buckets are consumed by one Adam launch after the exchange
-    opt = FusedAdam(params, lr=1e-5, overlap_backward=(world == 1 and bool(a.overlap_adam)))
+    # Adam of each encoder layer runs on its own stream under the rest of the backward pass.  Data parallel
+    # (--dp-mode overlapped): the layer's gradient bucket is all-reduced on that stream first, so the NVLink exchange
+    # overlaps the backward too and the whole step -- NCCL kernels included -- is ONE CUDA graph.
+    # --dp-mode twograph: forward/backward graph, eager bucketed all-reduce, optimizer graph (no overlap).
+    from mmvqa_b200.parallel import LayerwiseReducer
+    bucket_dt = torch.bfloat16 if (dt == torch.bfloat16 and a.bf16_buckets) else torch.float32
+    overlapped_dp = world > 1 and a.dp_mode == "overlapped"
+    reducer = LayerwiseReducer(bucket_dt) if overlapped_dp else None
+    opt = FusedAdam(params, lr=1e-5, overlap_backward=((world == 1 or overlapped_dp) and bool(a.overlap_adam)),
+                    reduce_fn=reducer, early_groups=[list(model.transformer.bert_embedding.parameters())])
     crit = ASLSingleLabel()
-    # bf16 buckets halve the all-reduce volume (364 -> 182 MB) on the bf16 path; the fp32 path keeps fp32 buckets
-    buckets = GradBuckets(params, dtype=(torch.bfloat16 if (dt == torch.bfloat16 and a.bf16_buckets) else torch.float32)) if world > 1 else None
+    buckets = GradBuckets(params, dtype=bucket_dt) if (world > 1 and not overlapped_dp) else None
     if buckets is not None:
         opt.grad_scale = buckets.grad_scale
+    if reducer is not None:
+        opt.grad_scale = reducer.grad_scale
 
     def loss_fn(f0, f1, f2, f3, f4, ids, seg, mask, target):
         logits, _, _ = model.forward_features([f0, f1, f2, f3, f4], ids, seg, mask)
@@ -282,7 +292,8 @@ def main_gpu(a):
     log("building the graphed step")
     gs = GraphedTrainStep(loss_fn, dev[0], opt, warmup=3, post_backward=(buckets.pack if buckets else None),
                           eager_between=(buckets.allreduce if buckets else None),
-                          step_kwargs=(step_kwargs if buckets else None))
+                          step_kwargs=(step_kwargs if buckets else None),
+                          capture_error_mode=("thread_local" if world > 1 else "global"))
     log("graph captured: %d launches per step" % gs.launches_per_step)
     launches = gs.launches_per_step
 
@@ -365,10 +376,20 @@ def main_gpu(a):
     e2e_value = B * world * a.steps / (ms_e2e * 1e-3)
 
     log("timed regions done")
-    if rank != 0:
+    def finish():
+        """leave the job: a CUDA graph that holds captured NCCL kernels must be gone before the communicator is
+        torn down (destroy_process_group otherwise waits forever on the graph's work handles)."""
+        nonlocal gs
         if world > 1:
             dist.barrier()
+            torch.cuda.synchronize()
+            if overlapped_dp:
+                sys.stdout.flush()
+                sys.stderr.flush()
+                os._exit(0)
             dist.destroy_process_group()
+    if rank != 0:
+        finish()
         return
     hbm, tf_burst, tf_sus, which = peaks()
     log("roofline measurements")
@@ -377,6 +398,8 @@ def main_gpu(a):
     #     mmvqa_gemm launch of the step; each DISTINCT problem is then replayed alone (graph-captured back-to-back
     #     launches, cold L2, CUDA events) and the per-step total is sum(count x time).
     from mmvqa_b200 import ops as _ops
+    opt.close()                    # rank 0 works alone from here on: no gradient sink, no collective
+    opt.reduce_fn = None
     opt.zero_grad(set_to_none=True)
     _ops.gemm_record(True)
     loss_fn(*dev[0]).backward()
@@ -443,9 +466,7 @@ def main_gpu(a):
             "gpu_launches": launches * a.steps, "gpu_launches_per_step": launches, "clocks": clocks.summary(),
             "roofline": roof, "cpu_baseline": cpu, "loss": loss_val, "dropout": bool(a.dropout), "params": nparams}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    finish()
 
 
 if __name__ == "__main__":
@@ -461,8 +482,13 @@ if __name__ == "__main__":
     ap.add_argument("--verbose", action="store_true", help="progress lines on stderr")
     ap.add_argument("--bf16-buckets", type=int, default=1, help="data parallel: all-reduce gradients as bf16 (bf16 path only)")
     ap.add_argument("--overlap-adam", type=int, default=1, help="1 GPU: update each layer under the rest of the backward pass")
+    ap.add_argument("--nccl-channels", type=int, default=0, help="cap NCCL channels (CTAs) per collective; 0 = NCCL default")
+    ap.add_argument("--dp-mode", default="overlapped", choices=["overlapped", "twograph"])
     ap.add_argument("--pad-steps", type=int, default=100, help="untimed steps around the timed region (clock sampling)")
     a = ap.parse_args()
+    if os.environ.get("MMVQA_BENCH_WATCHDOG"):      # debugging aid: dump every thread's stack and exit if the run hangs
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["MMVQA_BENCH_WATCHDOG"]), exit=True)
     if a.impl == "reference":
         main_reference(a)
     else:

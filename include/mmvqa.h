@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MMVQA_ABI_VERSION 1
+#define MMVQA_ABI_VERSION 2
 
 enum { MMVQA_F32 = 0, MMVQA_BF16 = 1 };
 enum { MMVQA_ACT_NONE = 0, MMVQA_ACT_SERF = 1, MMVQA_ACT_GELU = 2, MMVQA_ACT_RELU = 3 };
@@ -99,6 +99,15 @@ typedef struct mmvqa_gemm_args {
   int split_k;               /* >= 1 */
   int batch; int64_t a_batch_rows, b_batch_rows, c_batch_stride;
   float dropout_p; uint64_t dropout_seed;    /* EPI_RESIDUAL only: C = dropout(acc + bias) + aux_in */
+  int64_t c_split_stride;    /* split_k > 1 without accumulate: split s stores its fp32 partial tile at
+                                C + s * c_split_stride (no atomics, no zero-fill; bias goes into split 0).  The
+                                consumer sums the slabs: mmvqa_add_layernorm_fwd_parts / mmvqa_layernorm_bwd_parts */
+  int b_static;              /* non-zero: B (a weight matrix) is not written by the kernel that precedes this one on the
+                                stream, so with programmatic dependent launch its first tiles may be fetched while
+                                that kernel is still running */
+  uint64_t* trace;           /* optional (tuning only): [ctas, 16] device buffer; the bf16 kernel stores %globaltimer stamps
+                                of its phases per CTA (entry, setup, dependency wait, loads issued, first tile landed,
+                                last MMA issued, accumulator ready, epilogue done) */
 } mmvqa_gemm_args;
 
 int mmvqa_gemm(const mmvqa_gemm_args* args, mmvqa_stream_t stream);
@@ -142,6 +151,21 @@ int mmvqa_layernorm_bwd(const void* dy, const void* xsum, const float* gamma, co
                         const void* dx_extra, void* dx, float* dgamma, float* dbeta, void* dx_drop, float* dxsum,
                         float dropout_p, uint64_t dropout_seed, int64_t rows, int cols, int dtype,
                         mmvqa_stream_t stream);
+
+/* The same two LayerNorm passes fed by the fp32 split-K partial tiles of mmvqa_gemm (c_split_stride): at the
+ * reference's fine-tune shape (M = 16 x 28 = 448 rows) a K = 3072 GEMM only fills the chip when K is split, and the
+ * slab reduction rides on the LayerNorm pass that follows it in realformer.py:49-50 instead of atomics.
+ *   fwd:  s = dropout_p(sum_i parts[i]) + res (rounded to `dtype`, stored in sum_out);  y = LN(s) * gamma + beta
+ *   bwd:  dy = sum_i dy_parts[i] + dy_res (dy_res may be NULL); everything else as mmvqa_layernorm_bwd.
+ * parts[i] = parts + i * part_stride, each [rows, cols] fp32 contiguous.  cols % 8 == 0 (bf16) / % 4 (f32), <= 1024. */
+int mmvqa_add_layernorm_fwd_parts(const float* parts, int nparts, int64_t part_stride, const void* res,
+                                  const float* gamma, const float* beta, void* y, void* sum_out, float* mean,
+                                  float* rstd, int64_t rows, int cols, float eps, float dropout_p,
+                                  uint64_t dropout_seed, int dtype, mmvqa_stream_t stream);
+int mmvqa_layernorm_bwd_parts(const float* dy_parts, int nparts, int64_t part_stride, const void* dy_res,
+                              const void* xsum, const float* gamma, const float* mean, const float* rstd, void* dx,
+                              float* dgamma, float* dbeta, void* dx_drop, float* dxsum, float dropout_p,
+                              uint64_t dropout_seed, int64_t rows, int cols, int dtype, mmvqa_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Attention (short sequence: T <= 128, head dim <= 128; one CTA per (batch, head))

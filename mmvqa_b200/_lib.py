@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libmmvqa_sm100.so")
 F32, BF16 = 0, 1
 ACT_NONE, ACT_SERF, ACT_GELU, ACT_RELU = 0, 1, 2, 3
 EPI_STORE, EPI_ACT, EPI_RESIDUAL, EPI_DACT, EPI_ACT_ROWSUM, EPI_DACT_SCALE = range(6)
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 vp, i64, i32, f32, u64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64
 
@@ -33,6 +33,7 @@ class GemmArgs(C.Structure):
         ("accumulate", i32), ("split_k", i32),
         ("batch", i32), ("a_batch_rows", i64), ("b_batch_rows", i64), ("c_batch_stride", i64),
         ("dropout_p", f32), ("dropout_seed", u64),
+        ("c_split_stride", i64), ("b_static", i32), ("trace", vp),
     ]
 
 
@@ -56,6 +57,8 @@ SIGNATURES = {
     "mmvqa_dropout": (i32, [vp, vp, i64, f32, u64, i32, vp]),
     "mmvqa_add_layernorm_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, f32, i32, vp]),
     "mmvqa_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, u64, i64, i32, i32, vp]),
+    "mmvqa_add_layernorm_fwd_parts": (i32, [vp, i32, i64, vp, vp, vp, vp, vp, vp, vp, i64, i32, f32, f32, u64, i32, vp]),
+    "mmvqa_layernorm_bwd_parts": (i32, [vp, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, f32, u64, i64, i32, i32, vp]),
     "mmvqa_mhsa_fwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, f32, u64, i32, vp]),
     "mmvqa_mhsa_bwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, f32, u64, i32, vp]),
     "mmvqa_rf_attn_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),

@@ -29,9 +29,12 @@ int num_sms() {
 }
 
 bool pdl_enabled() {
-  // Off by default: measured on B200 the captured step is kernel-bound, not launch-gap-bound (3.85 ms with
-  // programmatic dependent launch vs 3.82 ms without); MMVQA_PDL=1 turns it on for experiments.
-  static const bool on = getenv("MMVQA_PDL") != nullptr;
+  // Programmatic dependent launch (griddepcontrol): every kernel of the library is launched so that it may become
+  // resident while its predecessor on the stream is still running; set-up (barriers, TMEM allocation, tensor-map
+  // and weight-tile prefetch) overlaps the predecessor, dependent memory is touched only after griddepcontrol.wait.
+  // Measured on the captured B=16 step: 3.31 -> 3.24 ms once the GEMM rings are capped so two CTAs share an SM.
+  // MMVQA_NO_PDL=1 turns it off (A/B runs).
+  static const bool on = getenv("MMVQA_NO_PDL") == nullptr;
   return on;
 }
 
@@ -350,6 +353,97 @@ __global__ void __launch_bounds__(256) add_ln_fwd_packed(const T* __restrict__ x
   }
 }
 
+// LayerNorm over the sum of fp32 split-K partial tiles (mmvqa_gemm with c_split_stride): the reduction of the
+// slabs, the dropout of the branch, the residual add and the normalisation are ONE pass, so a K = 3072 GEMM at
+// M = 448 can spread over every SM without an atomic or a second sweep.  s = dropout(sum_i parts[i]) + res is
+// rounded to T and stored (sum_out) -- it is what the backward pass normalises again.
+template <typename T>
+__global__ void __launch_bounds__(256) add_ln_fwd_parts(const float* __restrict__ parts, int nparts, int64_t part_stride,
+                                                        const T* __restrict__ res, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, T* __restrict__ y,
+                                                        T* __restrict__ sum_out, float* __restrict__ mean_out,
+                                                        float* __restrict__ rstd_out, int64_t rows, int cols, float eps,
+                                                        float p, unsigned long long seed) {
+  constexpr int N = Vec16<T>::N;
+  constexpr int ITER = LN_CACHE / N;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  pdl_wait();
+  pdl_trigger();
+  if (row >= rows) return;
+  const bool drop = p > 0.0f;
+  const uint32_t thr = (uint32_t)(p * 4294967296.0);
+  const float inv_keep = drop ? 1.0f / (1.0f - p) : 1.0f;
+  const T* rr = res ? res + row * cols : nullptr;
+  T* so = sum_out ? sum_out + row * cols : nullptr;
+  Vec16<T> raw[ITER];
+  float s = 0.0f;
+#pragma unroll
+  for (int k = 0; k < ITER; ++k) {
+    const int c = (k * 32 + lane) * N;
+    if (c < cols) {
+      float acc[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) acc[j] = 0.0f;
+      for (int i = 0; i < nparts; ++i) {
+        const float* pr = parts + (int64_t)i * part_stride + row * cols + c;
+#pragma unroll
+        for (int j = 0; j < N; j += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(pr + j);
+          acc[j] += t.x; acc[j + 1] += t.y; acc[j + 2] += t.z; acc[j + 3] += t.w;
+        }
+      }
+      Vec16<T> b;
+      if (rr) b.load(rr + c);
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        float v = acc[j];
+        if (drop) v = hash32(seed, (uint64_t)(row * cols + c + j)) >= thr ? v * inv_keep : 0.0f;
+        raw[k].set(j, v + (rr ? b.get(j) : 0.0f));
+      }
+      if (so) raw[k].store(so + c);
+#pragma unroll
+      for (int j = 0; j < N; ++j) s += raw[k].get(j);
+    }
+  }
+  const float mean = warp_sum(s) / (float)cols;
+  float q = 0.0f;
+#pragma unroll
+  for (int k = 0; k < ITER; ++k) {
+    const int c = (k * 32 + lane) * N;
+    if (c < cols) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const float d = raw[k].get(j) - mean;
+        q += d * d;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)cols + eps);
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+  T* yr = y + row * cols;
+#pragma unroll
+  for (int k = 0; k < ITER; ++k) {
+    const int c = (k * 32 + lane) * N;
+    if (c < cols) {
+      Vec16<T> o;
+#pragma unroll
+      for (int j = 0; j < N; j += 4) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + c + j));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + c + j));
+        o.set(j, (raw[k].get(j) - mean) * rstd * g4.x + b4.x);
+        o.set(j + 1, (raw[k].get(j + 1) - mean) * rstd * g4.y + b4.y);
+        o.set(j + 2, (raw[k].get(j + 2) - mean) * rstd * g4.z + b4.z);
+        o.set(j + 3, (raw[k].get(j + 3) - mean) * rstd * g4.w + b4.w);
+      }
+      o.store(yr + c);
+    }
+  }
+}
+
 // generic (any cols): re-reads the row from global memory
 template <typename T>
 __global__ void __launch_bounds__(128) add_ln_fwd_generic(const T* __restrict__ x, const T* __restrict__ res,
@@ -397,6 +491,11 @@ struct LnBwdExtra {
   float* dxsum;             // optional: += column sums of dx_drop (or of dx when dx_drop == NULL)
   float p;
   unsigned long long seed;
+  // optional (packed kernel only): the incoming gradient is sum_i dy_parts[i] (fp32 split-K slabs of the dgrad GEMM)
+  // + dy (the residual branch, may be NULL), rounded to T -- exactly what a dgrad GEMM with a residual epilogue stores
+  const float* dy_parts;
+  int nparts;
+  long long part_stride;
 };
 
 // Packed backward (vector path): the two input rows stay in registers as raw 128-bit vectors and are re-expanded in
@@ -429,12 +528,41 @@ __global__ void __launch_bounds__(128) ln_bwd_packed(const T* __restrict__ dy, c
     T* dxr = dx + row * cols;
     T* ddr = dxd ? dxd + row * cols : nullptr;
     Vec16<T> a[KU], b[KU];
+    if (ex.dy_parts == nullptr) {
 #pragma unroll
-    for (int k = 0; k < KU; ++k) {
-      const int c = (k * 32 + lane) * N;
-      if (c < cols) {
-        a[k].load(dyr + c);
-        b[k].load(xr + c);
+      for (int k = 0; k < KU; ++k) {
+        const int c = (k * 32 + lane) * N;
+        if (c < cols) {
+          a[k].load(dyr + c);
+          b[k].load(xr + c);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < KU; ++k) {
+        const int c = (k * 32 + lane) * N;
+        if (c < cols) {
+          b[k].load(xr + c);
+          float acc[N];
+#pragma unroll
+          for (int j = 0; j < N; ++j) acc[j] = 0.0f;
+          for (int i = 0; i < ex.nparts; ++i) {
+            const float* pr = ex.dy_parts + (int64_t)i * ex.part_stride + row * cols + c;
+#pragma unroll
+            for (int j = 0; j < N; j += 4) {
+              const float4 t = *reinterpret_cast<const float4*>(pr + j);
+              acc[j] += t.x; acc[j + 1] += t.y; acc[j + 2] += t.z; acc[j + 3] += t.w;
+            }
+          }
+          if (dy) {
+            Vec16<T> r;
+            r.load(dyr + c);
+#pragma unroll
+            for (int j = 0; j < N; ++j) acc[j] += r.get(j);
+          }
+#pragma unroll
+          for (int j = 0; j < N; ++j) a[k].set(j, acc[j]);
+        }
       }
     }
     float s1 = 0.0f, s2 = 0.0f;
@@ -869,11 +997,11 @@ int mmvqa_add_layernorm_fwd(const void* x, const void* res, const float* gamma, 
   return MMVQA_OK;
 }
 
-int mmvqa_layernorm_bwd(const void* dy, const void* xsum, const float* gamma, const float* mean, const float* rstd,
-                        const void* dx_extra, void* dx, float* dgamma, float* dbeta, void* dx_drop, float* dxsum,
-                        float dropout_p, uint64_t dropout_seed, int64_t rows, int cols, int dtype,
-                        mmvqa_stream_t stream) {
-  MMVQA_REQUIRE(dy && xsum && gamma && mean && rstd && dx, "layernorm_bwd: null pointer");
+static int layernorm_bwd_impl(const void* dy, const float* dy_parts, int nparts, int64_t part_stride, const void* xsum,
+                              const float* gamma, const float* mean, const float* rstd, const void* dx_extra, void* dx,
+                              float* dgamma, float* dbeta, void* dx_drop, float* dxsum, float dropout_p,
+                              uint64_t dropout_seed, int64_t rows, int cols, int dtype, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE((dy || dy_parts) && xsum && gamma && mean && rstd && dx, "layernorm_bwd: null pointer");
   MMVQA_REQUIRE(cols > 0 && rows >= 0, "layernorm_bwd: bad shape");
   MMVQA_REQUIRE(dtype == MMVQA_F32 || dtype == MMVQA_BF16, "layernorm_bwd: bad dtype %d", dtype);
   MMVQA_REQUIRE(dropout_p >= 0.0f && dropout_p < 1.0f, "layernorm_bwd: dropout_p must be in [0,1)");
@@ -883,13 +1011,15 @@ int mmvqa_layernorm_bwd(const void* dy, const void* xsum, const float* gamma, co
   int grid = (int)(want < cap ? want : cap);
   const int vn = dtype == MMVQA_F32 ? 4 : 8;
   const bool cached = cols <= 32 * LN_CACHE;
-  const bool vec = cached && cols % vn == 0 && aligned16(dy) && aligned16(xsum) && aligned16(dx) &&
+  const bool vec = cached && cols % vn == 0 && (!dy || aligned16(dy)) && aligned16(xsum) && aligned16(dx) &&
                    (!dx_extra || aligned16(dx_extra)) && (!dx_drop || aligned16(dx_drop)) &&
-                   (!dgamma || aligned16(dgamma)) && (!dbeta || aligned16(dbeta)) && (!dxsum || aligned16(dxsum));
+                   (!dgamma || aligned16(dgamma)) && (!dbeta || aligned16(dbeta)) && (!dxsum || aligned16(dxsum)) &&
+                   (!dy_parts || (aligned16(dy_parts) && part_stride % 4 == 0));
   size_t smem = sizeof(float) * 3 * (size_t)cols * (vec ? 4 : 1);     // vec path: one slab per warp
   MMVQA_REQUIRE(smem <= 48 * 1024, "layernorm_bwd: cols %d too large", cols);
   LnBwdExtra ex;
   ex.dx_drop = dx_drop; ex.dxsum = dxsum; ex.p = dx_drop ? dropout_p : 0.0f; ex.seed = dropout_seed;
+  ex.dy_parts = dy_parts; ex.nparts = nparts; ex.part_stride = part_stride;
   // packed kernel: 4-warp CTAs (one row per warp) when the problem is small, 8-warp CTAs with a row loop otherwise
   if (vec && aligned16(gamma)) {
     const int vnn = dtype == MMVQA_F32 ? 4 : 8;
@@ -914,6 +1044,7 @@ int mmvqa_layernorm_bwd(const void* dy, const void* xsum, const float* gamma, co
     }
 #undef LN_BWDP
   }
+  MMVQA_REQUIRE(dy_parts == nullptr, "layernorm_bwd_parts: needs cols %% %d == 0, cols <= 1024 and 16-byte aligned buffers", vn);
 #define LN_BWD(T, V, C) launch_pdl(ln_bwd_kernel<T, V, C>, dim3(grid), dim3(128), smem, st, (const T*)dy, (const T*)xsum, gamma, mean, rstd, (const T*)dx_extra, (T*)dx, dgamma, dbeta, ex, rows, cols)
   if (dtype == MMVQA_F32) {
     if (vec) LN_BWD(float, true, true);
@@ -927,6 +1058,52 @@ int mmvqa_layernorm_bwd(const void* dy, const void* xsum, const float* gamma, co
   }
 #undef LN_BWD
   MMVQA_LAUNCHED("layernorm_bwd");
+  return MMVQA_OK;
+}
+
+int mmvqa_layernorm_bwd(const void* dy, const void* xsum, const float* gamma, const float* mean, const float* rstd,
+                        const void* dx_extra, void* dx, float* dgamma, float* dbeta, void* dx_drop, float* dxsum,
+                        float dropout_p, uint64_t dropout_seed, int64_t rows, int cols, int dtype,
+                        mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(dy != nullptr, "layernorm_bwd: null pointer");
+  return layernorm_bwd_impl(dy, nullptr, 0, 0, xsum, gamma, mean, rstd, dx_extra, dx, dgamma, dbeta, dx_drop, dxsum,
+                            dropout_p, dropout_seed, rows, cols, dtype, stream);
+}
+
+int mmvqa_layernorm_bwd_parts(const float* dy_parts, int nparts, int64_t part_stride, const void* dy_res,
+                              const void* xsum, const float* gamma, const float* mean, const float* rstd, void* dx,
+                              float* dgamma, float* dbeta, void* dx_drop, float* dxsum, float dropout_p,
+                              uint64_t dropout_seed, int64_t rows, int cols, int dtype, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(dy_parts != nullptr && nparts >= 1 && part_stride >= rows * cols, "layernorm_bwd_parts: bad partials");
+  return layernorm_bwd_impl(dy_res, dy_parts, nparts, part_stride, xsum, gamma, mean, rstd, nullptr, dx, dgamma, dbeta,
+                            dx_drop, dxsum, dropout_p, dropout_seed, rows, cols, dtype, stream);
+}
+
+int mmvqa_add_layernorm_fwd_parts(const float* parts, int nparts, int64_t part_stride, const void* res,
+                                  const float* gamma, const float* beta, void* y, void* sum_out, float* mean,
+                                  float* rstd, int64_t rows, int cols, float eps, float dropout_p,
+                                  uint64_t dropout_seed, int dtype, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(parts && gamma && beta && y, "add_layernorm_fwd_parts: null pointer");
+  MMVQA_REQUIRE(nparts >= 1 && part_stride >= rows * cols && part_stride % 4 == 0, "add_layernorm_fwd_parts: bad partials");
+  MMVQA_REQUIRE(cols > 0 && rows >= 0, "add_layernorm_fwd_parts: bad shape");
+  MMVQA_REQUIRE(dtype == MMVQA_F32 || dtype == MMVQA_BF16, "add_layernorm_fwd_parts: bad dtype %d", dtype);
+  MMVQA_REQUIRE(dropout_p >= 0.0f && dropout_p < 1.0f, "add_layernorm_fwd_parts: dropout_p must be in [0,1)");
+  if (rows == 0) return MMVQA_OK;
+  const int vn = dtype == MMVQA_F32 ? 4 : 8;
+  MMVQA_REQUIRE(cols <= 32 * LN_CACHE && cols % vn == 0 && aligned16(parts) && aligned16(y) && (!res || aligned16(res)) &&
+                    (!sum_out || aligned16(sum_out)) && aligned16(gamma) && aligned16(beta),
+                "add_layernorm_fwd_parts: needs cols %% %d == 0, cols <= %d and 16-byte aligned buffers", vn, 32 * LN_CACHE);
+  cudaStream_t st = as_stream(stream);
+  const dim3 grid((unsigned)((rows + 7) / 8));
+  if (dtype == MMVQA_F32)
+    MMVQA_CUDA(launch_pdl(add_ln_fwd_parts<float>, grid, dim3(256), 0, st, parts, nparts, part_stride, (const float*)res, gamma,
+                          beta, (float*)y, (float*)sum_out, mean, rstd, rows, cols, eps, dropout_p,
+                          (unsigned long long)dropout_seed));
+  else
+    MMVQA_CUDA(launch_pdl(add_ln_fwd_parts<__nv_bfloat16>, grid, dim3(256), 0, st, parts, nparts, part_stride,
+                          (const __nv_bfloat16*)res, gamma, beta, (__nv_bfloat16*)y, (__nv_bfloat16*)sum_out, mean, rstd, rows,
+                          cols, eps, dropout_p, (unsigned long long)dropout_seed));
+  MMVQA_LAUNCHED("add_layernorm_fwd_parts");
   return MMVQA_OK;
 }
 

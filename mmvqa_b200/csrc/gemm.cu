@@ -32,8 +32,11 @@ extern "C" int mmvqa_gemm(const mmvqa_gemm_args* a, mmvqa_stream_t stream) {
   if (a->aux_out) MMVQA_REQUIRE(a->ld_aux_out >= a->N, "gemm: bad ld_aux_out");
   if (a->colsum_out) MMVQA_REQUIRE(a->epilogue != MMVQA_EPI_ACT_ROWSUM && split_k == 1, "gemm: colsum_out needs a storing epilogue and split_k == 1");
   if (a->accumulate || split_k > 1) {
-    MMVQA_REQUIRE(a->c_dtype == MMVQA_F32 && a->epilogue == MMVQA_EPI_STORE && (a->accumulate || split_k == 1),
-                  "gemm: split_k / accumulate need an fp32 C, EPI_STORE and accumulate != 0");
+    const bool slabs = !a->accumulate && split_k > 1 && a->c_split_stride > 0;
+    MMVQA_REQUIRE(a->c_dtype == MMVQA_F32 && a->epilogue == MMVQA_EPI_STORE && (a->accumulate || split_k == 1 || slabs),
+                  "gemm: split_k / accumulate need an fp32 C, EPI_STORE and accumulate != 0 or c_split_stride > 0");
+    if (slabs) MMVQA_REQUIRE(a->c_split_stride >= (int64_t)(a->M - 1) * a->ldc + a->N && batch == 1 && a->rowscale == nullptr,
+                             "gemm: split-K slabs need batch == 1, no rowscale and c_split_stride >= one C matrix");
   }
   MMVQA_REQUIRE(a->dropout_p >= 0.0f && a->dropout_p < 1.0f, "gemm: dropout_p must be in [0,1)");
   if (batch > 1 && !a->accumulate && a->epilogue != MMVQA_EPI_ACT_ROWSUM)
@@ -51,7 +54,9 @@ extern "C" int mmvqa_gemm(const mmvqa_gemm_args* a, mmvqa_stream_t stream) {
   ep.rowsum_out = a->rowsum_out; ep.colsum_out = a->colsum_out; ep.rowscale = a->rowscale; ep.scale = a->scale;
   ep.accumulate = a->accumulate; ep.split_k = split_k; ep.batch = batch;
   ep.c_batch_stride = a->c_batch_stride;
+  ep.c_split_stride = (!a->accumulate && split_k > 1) ? a->c_split_stride : 0;
   ep.dropout_p = a->dropout_p; ep.dropout_seed = a->dropout_seed;
+  ep.trace = reinterpret_cast<unsigned long long*>(a->trace);
   if (a->dtype == MMVQA_F32) return gemm_simt_f32(&v, ep, as_stream(stream));
   int sm = mmvqa_device_sm();
   if (sm < 0) return sm;

@@ -14,13 +14,16 @@ struct EpiParams {
   float* rowsum_out; float* colsum_out; const float* rowscale; float scale;
   int accumulate, split_k, batch;
   int64_t c_batch_stride;
+  int64_t c_split_stride;
   float dropout_p; unsigned long long dropout_seed;
+  unsigned long long* trace;
 };
 
 // one output element; AUX = storage type of aux_in / aux_out.  `first_split` gates bias so that
 // split-K partial sums add it once.  Returns the stored value (the activation for EPI_ACT_ROWSUM).
 template <typename AUX>
-__device__ __forceinline__ float epi_element(const EpiParams& p, int bz, int m, int n, float acc, bool first_split) {
+__device__ __forceinline__ float epi_element(const EpiParams& p, int bz, int m, int n, float acc, bool first_split,
+                                             int64_t c_split_off = 0) {
   float v = acc + ((p.bias && first_split) ? __ldg(p.bias + n) : 0.0f);
   float out;
   switch (p.epilogue) {
@@ -49,7 +52,7 @@ __device__ __forceinline__ float epi_element(const EpiParams& p, int bz, int m, 
     default:
       out = p.rowscale ? v * __ldg(p.rowscale + (int64_t)bz * p.M + m) * p.scale : v;
   }
-  int64_t off = (int64_t)bz * p.c_batch_stride + (int64_t)m * p.ldc + n;
+  int64_t off = (int64_t)bz * p.c_batch_stride + c_split_off + (int64_t)m * p.ldc + n;
   if (p.accumulate)
     atomicAdd(reinterpret_cast<float*>(p.C) + off, out);
   else if (p.c_bf16)

@@ -57,7 +57,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
     }
     __syncthreads();
   }
-  if (kb0 >= kb1 && ks != 0) return;  // empty split
+  if (kb0 >= kb1 && ks != 0 && p.c_split_stride == 0) return;  // empty split (a slab still gets its zeros)
+  const int64_t c_split_off = (int64_t)ks * p.c_split_stride;
   const bool first = (ks == 0);
   float cs[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
       for (int j = 0; j < 4; ++j) {
         int n = n0 + tx * 4 + j;
         if (n < p.N) {
-          const float o = epi_element<float>(p, bz, m, n, acc[i][j], first);
+          const float o = epi_element<float>(p, bz, m, n, acc[i][j], first, c_split_off);
           rs += o;
           cs[j] += o;
         }

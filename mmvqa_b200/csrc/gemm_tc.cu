@@ -84,7 +84,7 @@ int gemm_tc_bf16(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st)
     const int b = cand[i];
     if (b > 32 && b / 2 >= a->N) continue;  // tile wider than twice the problem
     const int64_t ctas = mt * ((a->N + b - 1) / b) * z;
-    if (ctas >= (int64_t)sms * (b == 256 ? 2 : 1)) { bn = b; break; }
+    if (ctas * 10 >= (int64_t)sms * 9 * (b == 256 ? 2 : 1)) { bn = b; break; }   // >= 90 % of a wave
   }
   static const int env_bn = env_int("MMVQA_TC_BN"), env_st = env_int("MMVQA_TC_STAGES");
   if (env_bn == 32 || env_bn == 64 || env_bn == 128 || env_bn == 256) {
@@ -102,6 +102,12 @@ int gemm_tc_bf16(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st)
   if (env_st == 2 || env_st == 4 || env_st == 6 || env_st == 8) stages = env_st > deep ? deep : env_st;
   if (stages == 6 && bn != 128) stages = 4;
   if (stages == 8 && bn > 64) stages = deep;
+  // Programmatic dependent launch only overlaps kernels whose CTAs fit on an SM together (and the side-branch
+  // weight-gradient GEMMs share SMs with the main chain the same way): rings of <= ~96 KB, two CTAs per SM.
+  if (pdl_enabled() && env_st == 0) {
+    const int cap = bn == 128 ? 3 : (bn == 256 ? 2 : 4);
+    if (stages > cap) stages = cap;
+  }
   switch (bn) {
     case 256: return launch_tc_bn256(stages, a, ep, st);
     case 128: return launch_tc_bn128(stages, a, ep, st);

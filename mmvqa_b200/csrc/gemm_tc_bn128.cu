@@ -5,6 +5,7 @@ namespace mmvqa {
 int launch_tc_bn128(int stages, const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st) {
   switch (stages) {
     case 2: return launch_tc_major<128, 2>(a, ep, st);
+    case 3: return launch_tc_major<128, 3>(a, ep, st);
     case 4: return launch_tc_major<128, 4>(a, ep, st);
     case 6: return launch_tc_major<128, 6>(a, ep, st);
     default: return set_err(MMVQA_ERR_ARG, "gemm(bf16): no %d-stage kernel for this tile", stages);

@@ -81,6 +81,15 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// same, and ties the 16 destination registers of an earlier tcgen05.ld to the wait: nothing that reads them can be
+// scheduled above it (needed when other work sits between the load and the wait)
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 
 // UMMA shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, version 1):
 //  [0,14) start >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 |
@@ -94,6 +103,16 @@ __device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_byte
   d |= (uint64_t)2 << 61;
   return d;
 }
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TC_TRACE(slot)                                                                              \
+  do {                                                                                              \
+    if (p.trace) p.trace[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = gtime(); \
+  } while (0)
 
 template <int BN, int STAGES_>
 struct TcCfg {
@@ -147,9 +166,31 @@ __device__ __forceinline__ void store16_f32(float* dst, int nvalid, const float*
   }
 }
 
+// chunk `ci` (16 bf16 = two 128-bit registers) of a prefetched row slice -> 16 floats; the chunk index is
+// resolved with selects so the array stays in registers
+template <int NV>
+__device__ __forceinline__ void unpack_pre(const uint4* pre, int ci, float* out) {
+  uint4 lo = pre[0], hi = pre[NV > 1 ? 1 : 0];
+#pragma unroll
+  for (int q = 1; q < NV / 2; ++q) {
+    if (ci == q) { lo = pre[2 * q]; hi = pre[2 * q + 1]; }
+  }
+  const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    out[2 * j] = __uint_as_float(w[j] << 16);
+    out[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+  }
+}
+
 template <int EPI, int ACT, int BN>
 __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_row, int m, int n0, int bz, bool first,
-                                            bool row_ok, bool has_acc, int c_begin) {
+                                            bool row_ok, bool has_acc, int c_begin, int64_t c_split_off,
+                                            uint32_t tmem_full_bar) {
+  constexpr int NCH = BN / 2 / 16;                 // 16-column chunks this warp owns
+  constexpr int NBQ = (BN / 2 + 31) / 32;
+  constexpr bool PRE = (EPI == MMVQA_EPI_RESIDUAL || EPI == MMVQA_EPI_DACT) && BN <= 128;
+  const int lane = threadIdx.x & 31;
   float rowsum = 0.0f;
   float rscale = 0.0f;
   if ((EPI == MMVQA_EPI_DACT_SCALE || (EPI == MMVQA_EPI_STORE && p.rowscale != nullptr)) && row_ok)
@@ -157,26 +198,49 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_ro
   const bool use_bias = p.bias != nullptr && first;
   const uint32_t thr = (uint32_t)(p.dropout_p * 4294967296.0);
   const float inv_keep = p.dropout_p > 0.0f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
+  // ---- everything that does not depend on the accumulator is fetched NOW, while the main loop is still running:
+  // this thread's slice of the residual / pre-activation row (128-bit loads) and the bias (one column per lane,
+  // broadcast with shuffles later).  The epilogue then starts with its operands in registers.
+  uint4 pre[PRE ? NCH * 2 : 1];
+  bool pre_ok = false;
+  if (PRE) {
+    const __nv_bfloat16* ax = reinterpret_cast<const __nv_bfloat16*>(p.aux_in) + (int64_t)m * p.ld_aux_in + n0 + c_begin;
+    pre_ok = row_ok && (n0 + c_begin + BN / 2 <= p.N) && al16(ax, 0, 2);
+    if (pre_ok) {
+#pragma unroll
+      for (int i = 0; i < NCH * 2; ++i) pre[i] = __ldg(reinterpret_cast<const uint4*>(ax) + i);
+    }
+  }
+  float bias_l[NBQ];
+#pragma unroll
+  for (int q = 0; q < NBQ; ++q) {
+    const int col = n0 + c_begin + q * 32 + lane;
+    bias_l[q] = (use_bias && q * 32 + lane < BN / 2 && col < p.N) ? __ldg(p.bias + col) : 0.0f;
+  }
+  mbar_wait(tmem_full_bar, 0);
+  tc_fence_after();
+  if (threadIdx.x == 64) TC_TRACE(6);
 #pragma unroll 1
-  for (int c = c_begin; c < c_begin + BN / 2; c += 16) {
+  for (int ci = 0; ci < NCH; ++ci) {
+    const int c = c_begin + ci * 16;
     uint32_t r[16];
     __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
     tmem_ld16(tmem_row + (uint32_t)c, r);
     tmem_ld_wait();
+    if (threadIdx.x == 64 && ci == 0) TC_TRACE(9);
     const int nb = n0 + c;
     float v[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) v[j] = 0.0f;
+    for (int j = 0; j < 16; ++j) {   // accumulator + bias; warp-uniform shuffles, outside the per-row predicate below
+      const int o = ci * 16 + j;
+      float src = bias_l[0];
+#pragma unroll
+      for (int q = 1; q < NBQ; ++q) src = (o >> 5) == q ? bias_l[q] : src;
+      v[j] = (has_acc ? __uint_as_float(r[j]) : 0.0f) + __shfl_sync(0xffffffffu, src, o & 31);
+    }
     if (row_ok && nb < p.N) {
       const int nvalid = min(16, p.N - nb);
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = has_acc ? __uint_as_float(r[j]) : 0.0f;
-      if (use_bias) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j < nvalid) v[j] += __ldg(p.bias + nb + j);
-      }
-      const int64_t coff = (int64_t)bz * p.c_batch_stride + (int64_t)m * p.ldc + nb;
+      const int64_t coff = (int64_t)bz * p.c_batch_stride + c_split_off + (int64_t)m * p.ldc + nb;
       if (EPI == MMVQA_EPI_ACT_ROWSUM) {
         if (p.aux_out) {
           float dv_[16];
@@ -192,7 +256,7 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_ro
           for (int j = 0; j < 16; ++j)
             if (j < nvalid) rowsum += act_fast<ACT>(v[j]);
         }
-        continue;
+        goto next_chunk;
       }
       if (EPI == MMVQA_EPI_STORE && p.rowscale != nullptr) {
 #pragma unroll
@@ -204,7 +268,8 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_ro
         for (int j = 0; j < 16; ++j) v[j] = act_fast<ACT>(v[j]);
       } else if (EPI == MMVQA_EPI_RESIDUAL) {
         float a[16];
-        load16_bf16(reinterpret_cast<const __nv_bfloat16*>(p.aux_in) + (int64_t)m * p.ld_aux_in + nb, nvalid, a);
+        if (PRE && pre_ok) unpack_pre<PRE ? NCH * 2 : 1>(pre, ci, a);
+        else load16_bf16(reinterpret_cast<const __nv_bfloat16*>(p.aux_in) + (int64_t)m * p.ld_aux_in + nb, nvalid, a);
         if (p.dropout_p > 0.0f) {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
@@ -214,7 +279,8 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_ro
         for (int j = 0; j < 16; ++j) v[j] += a[j];
       } else if (EPI == MMVQA_EPI_DACT) {
         float a[16];
-        load16_bf16(reinterpret_cast<const __nv_bfloat16*>(p.aux_in) + (int64_t)m * p.ld_aux_in + nb, nvalid, a);
+        if (PRE && pre_ok) unpack_pre<PRE ? NCH * 2 : 1>(pre, ci, a);
+        else load16_bf16(reinterpret_cast<const __nv_bfloat16*>(p.aux_in) + (int64_t)m * p.ld_aux_in + nb, nvalid, a);
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] *= dact_fast<ACT>(a[j]);
       } else if (EPI == MMVQA_EPI_DACT_SCALE) {
@@ -223,9 +289,15 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_ro
       }
       if (p.accumulate) {
         float* c32 = reinterpret_cast<float*>(p.C) + coff;
+        if (nvalid == 16 && al16(c32, 0, 4)) {   // 128-bit vector reductions (red.global.add.v4.f32): 4x fewer L2 atomics
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (j < nvalid) atomicAdd(c32 + j, v[j]);
+          for (int j = 0; j < 4; ++j)
+            atomicAdd(reinterpret_cast<float4*>(c32) + j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j < nvalid) atomicAdd(c32 + j, v[j]);
+        }
       } else if (p.c_bf16) {
         store16_bf16(reinterpret_cast<__nv_bfloat16*>(p.C) + coff, nvalid, v);
       } else {
@@ -234,7 +306,11 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_ro
 #pragma unroll
       for (int j = 0; j < 16; ++j)
         if (j >= nvalid) v[j] = 0.0f;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = 0.0f;   // rows / columns outside the problem add nothing to the column sums
     }
+    if (threadIdx.x == 64 && c == c_begin) TC_TRACE(10);
     if (EPI != MMVQA_EPI_ACT_ROWSUM && p.colsum_out != nullptr && nb < p.N) {
       // column sums over the warp's 32 rows: transposing butterfly, 16 shuffles; lane l ends with column
       // 8*b4 + 4*b3 + 2*b2 + b1 of the chunk (b_k = bit k of l), duplicated on the lane pair (l, l^1)
@@ -277,18 +353,20 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_ro
       const int col = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
       if ((lane & 1) == 0 && nb + col < p.N) atomicAdd(p.colsum_out + nb + col, v[0]);
     }
+  next_chunk:;
   }
   if (EPI == MMVQA_EPI_ACT_ROWSUM && row_ok) atomicAdd(p.rowsum_out + (int64_t)bz * p.M + m, rowsum * p.scale);
 }
 
 template <int EPI, int BN>
 __device__ __forceinline__ void tc_epilogue_act(const EpiParams& p, uint32_t tmem_row, int m, int n0, int bz, bool first,
-                                                bool row_ok, bool has_acc, int c_begin) {
+                                                bool row_ok, bool has_acc, int c_begin, uint32_t tmem_full_bar) {
+  const int64_t c_split_off = 0;   // activation epilogues never run split-K
   switch (p.act) {
-    case MMVQA_ACT_SERF: tc_epilogue<EPI, MMVQA_ACT_SERF, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin); break;
-    case MMVQA_ACT_GELU: tc_epilogue<EPI, MMVQA_ACT_GELU, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin); break;
-    case MMVQA_ACT_RELU: tc_epilogue<EPI, MMVQA_ACT_RELU, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin); break;
-    default: tc_epilogue<EPI, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin); break;
+    case MMVQA_ACT_SERF: tc_epilogue<EPI, MMVQA_ACT_SERF, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, c_split_off, tmem_full_bar); break;
+    case MMVQA_ACT_GELU: tc_epilogue<EPI, MMVQA_ACT_GELU, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, c_split_off, tmem_full_bar); break;
+    case MMVQA_ACT_RELU: tc_epilogue<EPI, MMVQA_ACT_RELU, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, c_split_off, tmem_full_bar); break;
+    default: tc_epilogue<EPI, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, c_split_off, tmem_full_bar); break;
   }
 }
 
@@ -296,9 +374,9 @@ __device__ __forceinline__ void tc_epilogue_act(const EpiParams& p, uint32_t tme
 // kernel: one 128 x BN output tile (of one batch entry / one K split) per CTA
 // ---------------------------------------------------------------------------------
 template <int BN, bool A_MN, bool B_MN, int STAGES>
-__global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, EpiParams p,
-                                                             int a_batched, int b_batched) {
+                                                             int a_batched, int b_batched, int b_static) {
   using Cfg = TcCfg<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -317,6 +395,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
   const int kb0 = ks * kb_per;
   const int kb1 = min(kblocks, kb0 + kb_per);
   const int nkb = max(0, kb1 - kb0);
+  if (threadIdx.x == 0) TC_TRACE(0);
 
   if (warp == 0) {
     tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
@@ -332,22 +411,54 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_ptr_gen;
-  pdl_wait();      // everything above overlapped the previous kernel's tail; global memory is touched below
+  // Programmatic dependent launch: this CTA may be resident while the previous kernel on the stream is still running.
+  // The weight operand (b_static) does not depend on that kernel, so its first ring slots are requested now; the
+  // activation operand, the epilogue inputs and every store wait for griddepcontrol.wait below.
+  int b_ahead = 0;
+  if (threadIdx.x == 0) TC_TRACE(1);
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    if (b_static) {
+      b_ahead = nkb < Cfg::STAGES ? nkb : Cfg::STAGES;
+      for (int i = 0; i < b_ahead; ++i) {
+        const uint32_t full = bar_base + 8 * i;
+        mbar_expect_tx(full, Cfg::STAGE_BYTES);
+        const uint32_t sb = smem_base + i * Cfg::STAGE_BYTES + Cfg::A_BYTES;
+        const int k0 = (kb0 + i) * TC_BK;
+        if (B_MN) {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) tma_load_3d(sb + j * 8192, &tmB, full, n0 + j * 64, k0, b_batched ? bz : 0);
+        } else {
+          tma_load_3d(sb, &tmB, full, k0, n0, b_batched ? bz : 0);
+        }
+      }
+    }
+  }
+  pdl_wait();      // everything above overlapped the previous kernel; dependent global memory is touched below
   pdl_trigger();
+  if (threadIdx.x == 0) TC_TRACE(2);
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
       for (int i = 0; i < nkb; ++i) {
         const int s = i % Cfg::STAGES;
         const uint32_t ph = (uint32_t)(i / Cfg::STAGES) & 1u;
-        mbar_wait(bar_base + 8 * (Cfg::STAGES + s), ph ^ 1u);
         const uint32_t full = bar_base + 8 * s;
-        mbar_expect_tx(full, Cfg::STAGE_BYTES);
         const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
         const int k0 = (kb0 + i) * TC_BK;
+        if (i < b_ahead) {   // slot armed and its B tile already in flight: only A is missing
+          if (A_MN) {
+            tma_load_3d(sa, &tmA, full, m0, k0, a_batched ? bz : 0);
+            tma_load_3d(sa + 8192, &tmA, full, m0 + 64, k0, a_batched ? bz : 0);
+          } else {
+            tma_load_3d(sa, &tmA, full, k0, m0, a_batched ? bz : 0);
+          }
+          continue;
+        }
+        mbar_wait(bar_base + 8 * (Cfg::STAGES + s), ph ^ 1u);
+        mbar_expect_tx(full, Cfg::STAGE_BYTES);
         if (A_MN) {  // stored [K, M]: two boxes of 64 (m) x 64 (k)
           tma_load_3d(sa, &tmA, full, m0, k0, a_batched ? bz : 0);
           tma_load_3d(sa + 8192, &tmA, full, m0 + 64, k0, a_batched ? bz : 0);
@@ -361,6 +472,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
           tma_load_3d(sb, &tmB, full, k0, n0, b_batched ? bz : 0);
         }
       }
+      TC_TRACE(3);
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -373,6 +485,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
         const uint32_t ph = (uint32_t)(i / Cfg::STAGES) & 1u;
         mbar_wait(bar_base + 8 * s, ph);
         tc_fence_after();
+        if (i == 0) TC_TRACE(4);
         const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
 #pragma unroll
         for (int j = 0; j < TC_BK / TC_UK; ++j) {
@@ -385,6 +498,7 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
         umma_commit(bar_base + 8 * (Cfg::STAGES + s));  // frees the smem slot when these MMAs retire
       }
       umma_commit(tmem_full_bar);                       // accumulator complete
+      TC_TRACE(5);
     }
   } else {
     // ===== epilogue: TMEM -> registers -> global.  8 warps: two per TMEM lane group, each takes half the columns =====
@@ -392,22 +506,24 @@ __global__ void __launch_bounds__(TC_THREADS) gemm_tc_kernel(const __grid_consta
     const int c_begin = ((warp - 2) >> 2) * (BN / 2);
     const int m = m0 + g * 32 + lane;
     const bool first = (ks == 0);
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const bool row_ok = (m < p.M) && !(nkb == 0 && ks != 0);
+    // (the wait for the accumulator barrier is inside tc_epilogue, after its operand prefetch)
+    const bool row_ok = (m < p.M) && !(nkb == 0 && ks != 0 && p.c_split_stride == 0);
+    const int64_t c_split_off = (int64_t)ks * p.c_split_stride;
     const uint32_t tmem_row = tmem_acc + ((uint32_t)(g * 32) << 16);
     const bool has_acc = nkb > 0;
     switch (p.epilogue) {
-      case MMVQA_EPI_ACT: tc_epilogue_act<MMVQA_EPI_ACT, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin); break;
-      case MMVQA_EPI_RESIDUAL: tc_epilogue<MMVQA_EPI_RESIDUAL, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin); break;
-      case MMVQA_EPI_DACT: tc_epilogue_act<MMVQA_EPI_DACT, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin); break;
-      case MMVQA_EPI_ACT_ROWSUM: tc_epilogue_act<MMVQA_EPI_ACT_ROWSUM, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin); break;
-      case MMVQA_EPI_DACT_SCALE: tc_epilogue_act<MMVQA_EPI_DACT_SCALE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin); break;
-      default: tc_epilogue<MMVQA_EPI_STORE, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin); break;
+      case MMVQA_EPI_ACT: tc_epilogue_act<MMVQA_EPI_ACT, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, tmem_full_bar); break;
+      case MMVQA_EPI_RESIDUAL: tc_epilogue<MMVQA_EPI_RESIDUAL, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, c_split_off, tmem_full_bar); break;
+      case MMVQA_EPI_DACT: tc_epilogue_act<MMVQA_EPI_DACT, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, tmem_full_bar); break;
+      case MMVQA_EPI_ACT_ROWSUM: tc_epilogue_act<MMVQA_EPI_ACT_ROWSUM, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, tmem_full_bar); break;
+      case MMVQA_EPI_DACT_SCALE: tc_epilogue_act<MMVQA_EPI_DACT_SCALE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, tmem_full_bar); break;
+      default: tc_epilogue<MMVQA_EPI_STORE, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, c_split_off, tmem_full_bar); break;
     }
+    if (threadIdx.x == 64) TC_TRACE(7);
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) TC_TRACE(8);
   if (warp == 0) tmem_dealloc(tmem_acc, Cfg::TMEM_COLS);
 }
 
@@ -432,7 +548,8 @@ static int launch_tc(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t
   dim3 grid((a->N + BN - 1) / BN, (a->M + TC_BM - 1) / TC_BM, a->batch * a->split_k);
   MMVQA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm(bf16): grid too large");
   MMVQA_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), (size_t)Cfg::SMEM, st, tmA, tmB, ep,
-                        (a->batch > 1 && a->a_batch_rows > 0) ? 1 : 0, (a->batch > 1 && a->b_batch_rows > 0) ? 1 : 0));
+                        (a->batch > 1 && a->a_batch_rows > 0) ? 1 : 0, (a->batch > 1 && a->b_batch_rows > 0) ? 1 : 0,
+                        (a->b_static && pdl_enabled()) ? 1 : 0));
   MMVQA_LAUNCHED("gemm_tc_bf16");
   return MMVQA_OK;
 }

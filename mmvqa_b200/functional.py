@@ -195,6 +195,23 @@ def _split_k_for(tiles: int, k: int, device, kblock: int = 64) -> int:
     return max(1, min(sms // max(tiles, 1), kblocks // 4 if kblocks >= 8 else 1))
 
 
+def split_k_slabs(M: int, N: int, K: int, device, dtype: torch.dtype) -> int:
+    """How many fp32 split-K slabs a [M, N] = [M, K] x [K, N] GEMM should write so that it covers the chip (1 = the
+    plain fused-epilogue GEMM).  Small-batch problems only: with M = 448 a K = 3072 contraction has 48 output tiles
+    for 148 SMs, and each CTA would pull its whole K range through one SM's L2 port."""
+    if dtype != torch.bfloat16 or N % 8 != 0 or N > 1024:
+        return 1
+    sms = _sms(device)
+    tiles = ((M + 127) // 128) * ((N + 63) // 64)
+    kblocks = (K + 63) // 64
+    if tiles * 2 > sms or kblocks < 24:
+        return 1
+    ns = min(sms // tiles, kblocks // 8)
+    while ns > 1 and kblocks % ns:
+        ns -= 1
+    return max(ns, 1)
+
+
 def gemm_dgrad(dy: Tensor, ld_dy: int, M: int, N: int, w: Tensor, K: int, *, epilogue=EPI_STORE, act=ACT_NONE,
                aux_in: Optional[Tensor] = None, out_dtype: Optional[torch.dtype] = None,
                colsum_out: Optional[Tensor] = None) -> Tensor:
@@ -202,7 +219,7 @@ def gemm_dgrad(dy: Tensor, ld_dy: int, M: int, N: int, w: Tensor, K: int, *, epi
     receives the column sums of dx: the bias gradient of the layer that produced this activation."""
     dx = torch.empty(M, K, device=dy.device, dtype=out_dtype or dy.dtype)
     ops.gemm(M, K, N, dy, ld_dy, False, w, K, True, dx, K, epilogue=epilogue, act=act, aux_in=aux_in, ld_aux_in=K,
-             colsum_out=colsum_out)
+             colsum_out=colsum_out, b_static=True)
     return dx
 
 
@@ -214,10 +231,10 @@ def gemm_wgrad(dy: Tensor, ld_dy: int, M: int, N: int, x: Tensor, ld_x: int, K: 
     sk = _split_k_for(tiles, M, dy.device, 64 if dy.dtype == torch.bfloat16 else 16)
     if sk > 1:
         dw = zeroed if zeroed is not None else torch.zeros(N, K, device=dy.device, dtype=torch.float32)
-        ops.gemm(N, K, M, dy, ld_dy, True, x, ld_x, True, dw, K, accumulate=True, split_k=sk)
+        ops.gemm(N, K, M, dy, ld_dy, True, x, ld_x, True, dw, K, accumulate=True, split_k=sk, b_static=True)
     else:
         dw = torch.empty(N, K, device=dy.device, dtype=torch.float32)
-        ops.gemm(N, K, M, dy, ld_dy, True, x, ld_x, True, dw, K)
+        ops.gemm(N, K, M, dy, ld_dy, True, x, ld_x, True, dw, K, b_static=True)
     return dw
 
 
@@ -274,15 +291,16 @@ class LinearFn(torch.autograd.Function):
             if residual is not None:
                 raise MMVQAError("LinearFn: activation and residual are exclusive")
             pre = torch.empty(M, N, device=x.device, dtype=dt)
-            ops.gemm(M, N, K, x2, K, False, w, K, False, y, N, bias=b, epilogue=EPI_ACT, act=act, aux_out=pre, ld_aux_out=N)
+            ops.gemm(M, N, K, x2, K, False, w, K, False, y, N, bias=b, epilogue=EPI_ACT, act=act, aux_out=pre, ld_aux_out=N,
+                     b_static=True)
         elif residual is not None:
             r2 = residual.reshape(M, N)
             if not r2.is_contiguous():
                 r2 = r2.contiguous()
             ops.gemm(M, N, K, x2, K, False, w, K, False, y, N, bias=b, epilogue=EPI_RESIDUAL, aux_in=r2, ld_aux_in=N,
-                     dropout_p=dropout_p, dropout_seed=seed)
+                     dropout_p=dropout_p, dropout_seed=seed, b_static=True)
         else:
-            ops.gemm(M, N, K, x2, K, False, w, K, False, y, N, bias=b)
+            ops.gemm(M, N, K, x2, K, False, w, K, False, y, N, bias=b, b_static=True)
         ctx.save_for_backward(x2, weight, pre)
         ctx.meta = (act, dropout_p, seed, bias is not None, residual is not None, x.shape, weight.shape, dt)
         return y.view(*x.shape[:-1], N)
@@ -592,7 +610,7 @@ class MHSAFn(torch.autograd.Function):
         if not x2.is_contiguous():
             x2 = x2.contiguous()
         qkv = torch.empty(B * T, 3 * H, device=x.device, dtype=dt)
-        ops.gemm(B * T, 3 * H, H, x2, H, False, w, H, False, qkv, 3 * H, bias=bias)
+        ops.gemm(B * T, 3 * H, H, x2, H, False, w, H, False, qkv, 3 * H, bias=bias, b_static=True)
         out, probs = ops.mhsa_fwd(qkv, maskf, B, T, heads, d, p, seed)
         ctx.save_for_backward(x2, qkv, probs, wq, wk, wv)
         ctx.meta = (B, T, H, heads, d, p, seed, dt)
@@ -643,7 +661,7 @@ class RFAttentionFn(torch.autograd.Function):
         if not xin.is_contiguous():
             xin = xin.contiguous()
         kqv = torch.empty(M * heads, 3 * d, device=x.device, dtype=dt)
-        ops.gemm(M * heads, 3 * d, d, xin, d, False, wk, d, False, kqv, 3 * d)
+        ops.gemm(M * heads, 3 * d, d, xin, d, False, wk, d, False, kqv, 3 * d, b_static=True)
         prevc = None if prev is None else prev.contiguous().float()
         attn, scores = ops.rf_attn_fwd(kqv, prevc, maskf, B, T, heads, d)
         ctx.save_for_backward(xin, kqv, scores, kqv_w)
@@ -665,7 +683,7 @@ class RFAttentionFn(torch.autograd.Function):
         dkqv, dprev = ops.rf_attn_bwd(kqv, scores, da, ds, want_dprev, B, T, heads, d)
         dwk = gemm_wgrad(dkqv, 3 * d, M * heads, 3 * d, xin, d, d).view(kqv_w.shape)
         dx = torch.empty(M, H, device=xin.device, dtype=dt)
-        ops.gemm(M * heads, d, 3 * d, dkqv, 3 * d, False, wk, d, True, dx, d)
+        ops.gemm(M * heads, d, 3 * d, dkqv, 3 * d, False, wk, d, True, dx, d, b_static=True)
         return dx.view(B, T, H), None, dprev, dwk, None
 
 
@@ -695,6 +713,7 @@ class RealFormerEncoderFn(torch.autograd.Function):
             prev = prev.contiguous().float()
         saved: List[Tensor] = []
         scores = prev
+        parts = None
         for l in range(n_layers):
             kqv_w, proj_w, g1, b1, w0, bb0, w2, bb2, g2, b2 = params[l * RF_PARAMS_PER_LAYER:(l + 1) * RF_PARAMS_PER_LAYER]
             wk = weight_cache.get((kqv_w,), dt)
@@ -702,21 +721,31 @@ class RealFormerEncoderFn(torch.autograd.Function):
             wf0 = weight_cache.get((w0,), dt)
             wf2 = weight_cache.get((w2,), dt)
             kqv = torch.empty(M * heads, 3 * d, device=x.device, dtype=dt)
-            ops.gemm(M * heads, 3 * d, d, xin, d, False, wk, d, False, kqv, 3 * d)
+            ops.gemm(M * heads, 3 * d, d, xin, d, False, wk, d, False, kqv, 3 * d, b_static=True)
             attn, scores = ops.rf_attn_fwd(kqv, scores, maskf, B, T, heads, d)
             y1 = torch.empty(M, H, device=x.device, dtype=dt)
             ops.gemm(M, H, H, attn, H, False, wp, H, False, y1, H, epilogue=EPI_RESIDUAL, aux_in=xin, ld_aux_in=H,
-                     dropout_p=p1, dropout_seed=seed + 2 * l)
+                     dropout_p=p1, dropout_seed=seed + 2 * l, b_static=True)
             x1, _, mean1, rstd1 = ops.add_layernorm_fwd(y1, None, g1.detach(), b1.detach(), 1e-5, want_sum=False)
             F4 = wf0.shape[0]
             hpre = torch.empty(M, F4, device=x.device, dtype=dt)
             hact = torch.empty(M, F4, device=x.device, dtype=dt)
             ops.gemm(M, F4, H, x1, H, False, wf0, H, False, hact, F4, bias=bb0.detach(), epilogue=EPI_ACT, act=ACT_SERF,
-                     aux_out=hpre, ld_aux_out=F4)
-            y2 = torch.empty(M, H, device=x.device, dtype=dt)
-            ops.gemm(M, H, F4, hact, F4, False, wf2, F4, False, y2, H, bias=bb2.detach(), epilogue=EPI_RESIDUAL, aux_in=x1,
-                     ld_aux_in=H, dropout_p=p2, dropout_seed=seed + 2 * l + 1)
-            x2, _, mean2, rstd2 = ops.add_layernorm_fwd(y2, None, g2.detach(), b2.detach(), 1e-5, want_sum=False)
+                     aux_out=hpre, ld_aux_out=F4, b_static=True)
+            ns = split_k_slabs(M, H, F4, x.device, dt)
+            if ns > 1:
+                # FF2 as split-K slabs: bias in slab 0; reduction + dropout + residual + LN2 in one pass
+                if parts is None:
+                    parts = torch.empty(ns, M, H, device=x.device, dtype=torch.float32)
+                ops.gemm(M, H, F4, hact, F4, False, wf2, F4, False, parts, H, bias=bb2.detach(), split_k=ns,
+                         c_split_stride=M * H, b_static=True)
+                x2, y2, mean2, rstd2 = ops.add_layernorm_fwd_parts(parts, x1, g2.detach(), b2.detach(), 1e-5, dt, p2,
+                                                                   seed + 2 * l + 1)
+            else:
+                y2 = torch.empty(M, H, device=x.device, dtype=dt)
+                ops.gemm(M, H, F4, hact, F4, False, wf2, F4, False, y2, H, bias=bb2.detach(), epilogue=EPI_RESIDUAL, aux_in=x1,
+                         ld_aux_in=H, dropout_p=p2, dropout_seed=seed + 2 * l + 1, b_static=True)
+                x2, _, mean2, rstd2 = ops.add_layernorm_fwd(y2, None, g2.detach(), b2.detach(), 1e-5, want_sum=False)
             saved += [xin, kqv, scores, attn, y1, mean1, rstd1, x1, hpre, hact, y2, mean2, rstd2]
             xin = x2
         ctx.save_for_backward(*saved, *params)
@@ -746,6 +775,7 @@ class RealFormerEncoderFn(torch.autograd.Function):
         # branch and overlap the dgrad -> LayerNorm -> attention chain of the same and the following layers
         branch = SideBranch(saved[0].device)
         keep = []
+        parts = None
         sink = _GRAD_SINK
         for l in reversed(range(n_layers)):
             xin, kqv, scores, attn, y1, mean1, rstd1, x1, hpre, hact, y2, mean2, rstd2 = saved[l * nsave:(l + 1) * nsave]
@@ -770,13 +800,26 @@ class RealFormerEncoderFn(torch.autograd.Function):
             dhpre = gemm_dgrad(dff, H, M, H, wf2, F4, epilogue=EPI_DACT, act=ACT_SERF, aux_in=hpre, colsum_out=dbb0)
             with branch.after_now():
                 dw0 = gemm_wgrad(dhpre, F4, M, F4, x1, H, H)
-            dx1 = gemm_dgrad(dhpre, F4, M, F4, wf0, H, epilogue=EPI_RESIDUAL, aux_in=dy2)
-            if p1 > 0.0:
-                dy1, dpr = ops.layernorm_bwd(dx1, y1, g1.detach(), mean1, rstd1, None, dg1, db1, want_drop=True,
-                                             dropout_p=p1, dropout_seed=seed + 2 * l)
+            ns = split_k_slabs(M, H, F4, dx.device, dt)
+            if ns > 1:
+                # dgrad through FF1 as split-K slabs; LN1 backward sums them and adds the residual gradient dy2
+                if parts is None:
+                    parts = torch.empty(ns, M, H, device=dx.device, dtype=torch.float32)
+                ops.gemm(M, H, F4, dhpre, F4, False, wf0, H, True, parts, H, split_k=ns, c_split_stride=M * H, b_static=True)
+                if p1 > 0.0:
+                    dy1, dpr = ops.layernorm_bwd_parts(parts, dy2, y1, g1.detach(), mean1, rstd1, dg1, db1, want_drop=True,
+                                                       dropout_p=p1, dropout_seed=seed + 2 * l)
+                else:
+                    dy1 = ops.layernorm_bwd_parts(parts, dy2, y1, g1.detach(), mean1, rstd1, dg1, db1)
+                    dpr = dy1
             else:
-                dy1 = ops.layernorm_bwd(dx1, y1, g1.detach(), mean1, rstd1, None, dg1, db1)
-                dpr = dy1
+                dx1 = gemm_dgrad(dhpre, F4, M, F4, wf0, H, epilogue=EPI_RESIDUAL, aux_in=dy2)
+                if p1 > 0.0:
+                    dy1, dpr = ops.layernorm_bwd(dx1, y1, g1.detach(), mean1, rstd1, None, dg1, db1, want_drop=True,
+                                                 dropout_p=p1, dropout_seed=seed + 2 * l)
+                else:
+                    dy1 = ops.layernorm_bwd(dx1, y1, g1.detach(), mean1, rstd1, None, dg1, db1)
+                    dpr = dy1
             with branch.after_now():
                 dwp = gemm_wgrad(dpr, H, M, H, attn, H, H)
             dattn = gemm_dgrad(dpr, H, M, H, wp, H)
@@ -788,7 +831,7 @@ class RealFormerEncoderFn(torch.autograd.Function):
             # dx_in = dkqv . Wkqv (per head) + dy1 (residual around the attention block)
             dxin = torch.empty(M, H, device=dx.device, dtype=dt)
             ops.gemm(M * heads, d, 3 * d, dkqv, 3 * d, False, wk, d, True, dxin, d, epilogue=EPI_RESIDUAL, aux_in=dy1,
-                     ld_aux_in=d)
+                     ld_aux_in=d, b_static=True)
             base = l * RF_PARAMS_PER_LAYER
             gl = [dwk.view(kqv_w.shape), dwp.view(proj_w.shape), dg1, db1, dw0.view(w0.shape), dbb0, dw2.view(w2.shape), dbb2,
                   dg2, db2]

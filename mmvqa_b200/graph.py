@@ -24,7 +24,8 @@ class GraphedTrainStep:
     replays and returns the static loss tensor."""
 
     def __init__(self, loss_fn: Callable, example_inputs: Sequence[torch.Tensor], optimizer, warmup: int = 3,
-                 post_backward: Callable = None, eager_between: Callable = None, step_kwargs: Callable = None):
+                 post_backward: Callable = None, eager_between: Callable = None, step_kwargs: Callable = None,
+                 capture_error_mode: str = "global"):
         self.loss_fn = loss_fn
         self.optimizer = optimizer
         self.post_backward = post_backward      # capturable, e.g. GradBuckets.pack
@@ -52,7 +53,9 @@ class GraphedTrainStep:
         self.graph_opt = None
         n0 = _lib.launch_count()
         if self.eager_between is None:
-            with torch.cuda.graph(self.graph):
+            # capture_error_mode="thread_local": needed when collectives are captured (the NCCL watchdog thread
+            # polls events of earlier eager collectives while this thread captures)
+            with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
                 self.static_loss = self._fwd_bwd(zero=False)
                 self._opt()
         else:

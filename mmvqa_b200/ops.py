@@ -68,7 +68,8 @@ def gemm(M: int, N: int, K: int, A: Tensor, lda: int, a_trans: bool, B: Tensor, 
          ld_aux_out: int = 0, rowsum_out: Optional[Tensor] = None, colsum_out: Optional[Tensor] = None,
          rowscale: Optional[Tensor] = None,
          scale: float = 1.0, accumulate: bool = False, split_k: int = 1, batch: int = 1, a_batch_rows: int = 0,
-         b_batch_rows: int = 0, c_batch_stride: int = 0, dropout_p: float = 0.0, dropout_seed: int = 0) -> None:
+         b_batch_rows: int = 0, c_batch_stride: int = 0, dropout_p: float = 0.0, dropout_seed: int = 0,
+         c_split_stride: int = 0, b_static: bool = False, trace: Optional[Tensor] = None) -> None:
     """C[M,N] = epilogue(sum_k opA(A)[m,k] opB(B)[n,k]); see include/mmvqa.h for the epilogues."""
     if A.dtype != B.dtype:
         raise L.MMVQAError(f"gemm operands differ in dtype: {A.dtype} vs {B.dtype}")
@@ -89,11 +90,14 @@ def gemm(M: int, N: int, K: int, A: Tensor, lda: int, a_trans: bool, B: Tensor, 
     a.accumulate, a.split_k = int(accumulate), split_k
     a.batch, a.a_batch_rows, a.b_batch_rows, a.c_batch_stride = batch, a_batch_rows, b_batch_rows, c_batch_stride
     a.dropout_p, a.dropout_seed = dropout_p, dropout_seed
+    a.c_split_stride = c_split_stride
+    a.b_static = int(b_static)
+    a.trace = _p(trace)
     for t in (aux_in, aux_out):
         if t is not None and t.dtype != A.dtype:
             raise L.MMVQAError("gemm aux tensors must have the operand dtype")
     if _GEMM_RECORD is not None:
-        sig = (a.dtype, M, N, K, int(a_trans), int(b_trans), epilogue, act, batch, split_k, int(accumulate), a.c_dtype,
+        sig = (a.dtype, M, N, K, int(a_trans), int(b_trans), epilogue, act, batch, split_k, int(accumulate), a.c_dtype, c_split_stride,
                bias is not None, aux_out is not None, colsum_out is not None, rowscale is not None, dropout_p > 0)
         _GEMM_RECORD.append((sig, 2.0 * M * N * K * max(batch, 1), a,
                              (A, B, Cout, bias, aux_in, aux_out, rowsum_out, colsum_out, rowscale)))
@@ -182,6 +186,37 @@ def layernorm_bwd(dy: Tensor, xsum: Tensor, gamma: Tensor, mean: Tensor, rstd: T
     L.check(L.lib().mmvqa_layernorm_bwd(_p(dy), _p(xsum), _p(gamma), _p(mean), _p(rstd), _p(dx_extra), _p(dx), _p(dgamma),
                                        _p(dbeta), _p(dxd), _p(dxsum), dropout_p, dropout_seed, rows, cols, dtype_code(dy),
                                        _stream()), "layernorm_bwd")
+    return (dx, dxd) if want_drop else dx
+
+
+def add_layernorm_fwd_parts(parts: Tensor, res: Optional[Tensor], gamma: Tensor, beta: Tensor, eps: float,
+                            out_dtype: torch.dtype, dropout_p: float = 0.0, dropout_seed: int = 0):
+    """parts [nparts, rows, cols] fp32 split-K slabs -> (y, s, mean, rstd) with s = dropout(sum parts) + res."""
+    _cont(parts, "parts")
+    nparts, rows, cols = parts.shape
+    if parts.dtype != torch.float32:
+        raise L.MMVQAError("split-K partials must be float32")
+    y = torch.empty(rows, cols, device=parts.device, dtype=out_dtype)
+    s = torch.empty_like(y)
+    mean = torch.empty(rows, device=parts.device, dtype=torch.float32)
+    rstd = torch.empty(rows, device=parts.device, dtype=torch.float32)
+    L.check(L.lib().mmvqa_add_layernorm_fwd_parts(_p(parts), nparts, rows * cols, _p(res), _p(gamma), _p(beta), _p(y), _p(s),
+                                                 _p(mean), _p(rstd), rows, cols, eps, dropout_p, dropout_seed,
+                                                 dtype_code(out_dtype), _stream()), "add_layernorm_fwd_parts")
+    return y, s, mean, rstd
+
+
+def layernorm_bwd_parts(dy_parts: Tensor, dy_res: Optional[Tensor], xsum: Tensor, gamma: Tensor, mean: Tensor, rstd: Tensor,
+                        dgamma: Tensor, dbeta: Tensor, *, want_drop: bool = False, dxsum: Optional[Tensor] = None,
+                        dropout_p: float = 0.0, dropout_seed: int = 0):
+    """layernorm_bwd whose incoming gradient is sum(dy_parts [nparts, rows, cols] fp32) + dy_res."""
+    _cont(dy_parts, "dy_parts"), _cont(xsum, "xsum")
+    nparts, rows, cols = dy_parts.shape
+    dx = torch.empty_like(xsum)
+    dxd = torch.empty_like(xsum) if want_drop else None
+    L.check(L.lib().mmvqa_layernorm_bwd_parts(_p(dy_parts), nparts, rows * cols, _p(dy_res), _p(xsum), _p(gamma), _p(mean),
+                                             _p(rstd), _p(dx), _p(dgamma), _p(dbeta), _p(dxd), _p(dxsum), dropout_p,
+                                             dropout_seed, rows, cols, dtype_code(xsum), _stream()), "layernorm_bwd_parts")
     return (dx, dxd) if want_drop else dx
 
 

@@ -20,7 +20,8 @@ class FusedAdam(torch.optim.Optimizer):
     ``grad_scale`` multiplies every gradient inside the kernel (1/world_size after an all-reduce SUM).
     The step counter lives on the device, so a captured CUDA graph of ``step()`` can be replayed."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, overlap_backward=False):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, overlap_backward=False,
+                 reduce_fn=None, early_groups=None):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.grad_scale = 1.0
         self._tables = {}
@@ -30,14 +31,35 @@ class FusedAdam(torch.optim.Optimizer):
         # overlap_backward: layers whose backward node offers its gradients early (functional.set_grad_sink) are
         # updated on a separate stream while the rest of the backward pass runs -- Adam is pure HBM traffic, the
         # small-batch backward is latency bound, so the two overlap almost for free.  step() updates what is left.
+        # reduce_fn(params, grads) -> grads' (data parallel): called right before the update of a set of parameters,
+        # on the stream that update runs on; packs / all-reduces and returns the tensors Adam should read
+        # (mmvqa_b200.parallel.LayerwiseReducer).  With overlap_backward each layer's exchange overlaps the backward.
+        self.reduce_fn = reduce_fn
         self._stepped = False      # device step counter already advanced in this iteration
         self._early_ids = set()    # parameters already updated in this iteration
         self._early_keep = []      # gradients read by the optimizer stream (kept alive until step() joins it)
         self._opt_stream = None
         self._group_of = {id(p): gi for gi, g in enumerate(self.param_groups) for p in g["params"]}
+        self._comm_stream = None
+        self._hook_groups = []
         if overlap_backward:
             Fn.set_grad_sink(self._sink)
+            # early_groups: lists of ordinary parameters (e.g. the BertEmbeddings tables, whose gradients appear before
+            # the projector backward starts) that are updated as soon as autograd has accumulated the whole list
+            for grp in (early_groups or []):
+                grp = [p for p in grp if p.requires_grad]
+                if not grp:
+                    continue
+                st = {"n": 0, "params": grp}
+                self._hook_groups.append(st)
+                st["handles"] = [p.register_post_accumulate_grad_hook(lambda _p, st=st: self._arrived(st)) for p in grp]
         self._init_step_counter()
+
+    def _arrived(self, st) -> None:
+        st["n"] += 1
+        if st["n"] == len(st["params"]):
+            st["n"] = 0
+            self._sink(st["params"], [p.grad for p in st["params"]], None, from_hook=True)
 
     def _init_step_counter(self):
         """the device step counter must exist before any CUDA-graph capture (a tensor created inside a capture is
@@ -113,30 +135,42 @@ class FusedAdam(torch.optim.Optimizer):
                       self.grad_scale)
 
     @torch.no_grad()
-    def _sink(self, params, grads, side_stream) -> bool:
-        """functional.set_grad_sink target: update one layer's parameters now, on the optimizer stream."""
+    def _sink(self, params, grads, side_stream, from_hook: bool = False) -> bool:
+        """functional.set_grad_sink target (and the early_groups hook): update one set of parameters now, on the
+        optimizer stream; with reduce_fn the exchange runs on a communication stream ahead of it, so the all-reduce
+        of the next set overlaps this set's update."""
         gis = {self._group_of.get(id(p)) for p in params}
-        if len(gis) != 1 or None in gis or any(p.grad is not None for p in params) or \
-                any(id(p) in self._early_ids for p in params):
+        if len(gis) != 1 or None in gis or any(id(p) in self._early_ids for p in params) or \
+                (not from_hook and any(p.grad is not None for p in params)):
             return False            # unknown / shared / accumulating parameters: leave them to autograd + step()
         gi = gis.pop()
         dev = params[0].device
         main = torch.cuda.current_stream(dev)
         if self._opt_stream is None:
             self._opt_stream = torch.cuda.Stream(dev)
+            self._comm_stream = torch.cuda.Stream(dev)
         self._advance(dev)          # on the main stream: ordered before every update of this iteration
+        first = self._comm_stream if self.reduce_fn is not None else self._opt_stream
         ev = torch.cuda.Event()
         ev.record(main)
-        self._opt_stream.wait_event(ev)
+        first.wait_event(ev)
         if side_stream is not None and side_stream is not main:
             ev2 = torch.cuda.Event()
             ev2.record(side_stream)
-            self._opt_stream.wait_event(ev2)
+            first.wait_event(ev2)
         gs = [g.contiguous() for g in grads]
+        gr = gs
+        if self.reduce_fn is not None:
+            with torch.cuda.stream(self._comm_stream):
+                gr = self.reduce_fn(list(params), gs)
+            ev3 = torch.cuda.Event()
+            ev3.record(self._comm_stream)
+            self._opt_stream.wait_event(ev3)
         with torch.cuda.stream(self._opt_stream):
-            self._launch(gi, ("early", id(params[0])), list(params), gs)
+            self._launch(gi, ("early", id(params[0])), list(params), gr)
         for p, g in zip(params, gs):
-            p.grad = g              # visible to hooks / loggers exactly as after a normal backward
+            if not from_hook:
+                p.grad = g          # visible to hooks / loggers exactly as after a normal backward
             self._early_ids.add(id(p))
         self._early_keep.append(gs)
         return True
@@ -156,6 +190,8 @@ class FusedAdam(torch.optim.Optimizer):
             if not plist:
                 continue
             g = [p.grad for p in plist] if grads is None else grads
+            if self.reduce_fn is not None and grads is None:
+                g = self.reduce_fn(plist, g)
             self._advance(plist[0].device)
             self._launch(gi, gi, plist, g)
         if self._early_ids:         # join the optimizer stream; its gradient buffers may be released after this point
@@ -165,6 +201,8 @@ class FusedAdam(torch.optim.Optimizer):
             torch.cuda.current_stream(dev).wait_event(ev)
             self._early_ids = set()
             self._early_keep = []
+        for st in self._hook_groups:
+            st["n"] = 0
         self._stepped = False
         ids = set()
         for r in self._refreshed.values():
@@ -176,6 +214,10 @@ class FusedAdam(torch.optim.Optimizer):
         """remove this optimizer's gradient sink (overlap_backward)."""
         if Fn.grad_sink() == self._sink:
             Fn.set_grad_sink(None)
+        for st in self._hook_groups:
+            for h in st["handles"]:
+                h.remove()
+        self._hook_groups = []
 
     def covers_weight_cache(self) -> bool:
         """True if every cached tensor-core operand copy is rewritten by this optimizer's kernel (then a captured

@@ -87,6 +87,44 @@ class GradBuckets:
         return 1.0 / (dist.get_world_size() if is_dist() else 1)
 
 
+class LayerwiseReducer:
+    """Gradient exchange at layer granularity, for ``FusedAdam(reduce_fn=...)``.
+
+    ``reducer(params, grads)`` packs the gradients of one set of parameters (one encoder layer when it is called
+    from the backward gradient sink, everything else at ``step()``) into that set's persistent flat bucket
+    (fp32 -> bf16 cast fused into the pack when ``dtype`` is bfloat16), all-reduces the bucket (SUM; the caller
+    sets ``FusedAdam.grad_scale = 1 / world``) and returns per-parameter views of it.  Called on the stream the
+    update runs on, so with ``overlap_backward`` the all-reduce of layer l travels over NVLink while layers
+    l-1 ... 0 are still in backward; the whole data-parallel step (NCCL kernels included) is one CUDA graph."""
+
+    def __init__(self, dtype: torch.dtype = torch.float32):
+        self.dtype = dtype
+        self._buckets = {}
+        self.bytes_per_step = 0
+
+    def __call__(self, params, grads):
+        key = (id(params[0]), len(params))
+        ent = self._buckets.get(key)
+        if ent is None:
+            offs, total = [], 0
+            for g in grads:
+                offs.append(total)
+                total += (g.numel() + 7) // 8 * 8          # 16-byte aligned views for fp32 and bf16
+            flat = torch.zeros(total, device=grads[0].device, dtype=self.dtype)
+            views = [flat[o:o + g.numel()].view_as(g) for o, g in zip(offs, grads)]
+            ent = self._buckets[key] = (flat, views)
+            self.bytes_per_step += flat.numel() * flat.element_size()
+        flat, views = ent
+        torch._foreach_copy_(views, list(grads))
+        if is_dist():
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        return views
+
+    @property
+    def grad_scale(self) -> float:
+        return 1.0 / (dist.get_world_size() if is_dist() else 1)
+
+
 class _GatherFeatures(torch.autograd.Function):
     """all-gather of per-rank SupCon embeddings [n_local, n_views, D] -> [n_global, n_views, D] (rank-major, which
     keeps the reference's view-major contrast order inside SupConLoss: all view-0 rows, then all view-1 rows).

@@ -507,3 +507,57 @@ def test_persistent_projector_kernel(Cc, HW, hidden, Bn, act):
         close(got[sel], G_ref[sel], 2e-2, 1e-6, msg="recompute backward (relu)")
     else:
         close(got, G_ref, 2e-2, 2e-3 * float(G_ref.abs().max()), msg="recompute backward")
+
+
+# ------------------------------------------------------------------------------------------
+# split-K slabs: GEMM partial tiles reduced by the LayerNorm pass that follows (realformer.py:49-50 at M = 448)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("M,N,K,ns,b_trans", [(448, 768, 3072, 3, False), (448, 768, 3072, 4, True), (37, 128, 1000, 5, False),
+                                              (130, 72, 64, 3, False)])
+def test_gemm_splitk_slabs(dt, M, N, K, ns, b_trans):
+    A, lda, B, ldb, ref = _gemm_case(dt, M, N, K, False, b_trans, seed=40)
+    bias = rnd(N, seed=41)
+    parts = torch.full((ns, M, N), float("nan"), device=DEV)         # every slab element must be written (no zero-fill)
+    ops.gemm(M, N, K, A, lda, False, B, ldb, b_trans, parts, N, bias=bias.to(DEV), split_k=ns, c_split_stride=M * N)
+    assert torch.isfinite(parts).all()
+    close(parts.sum(0), ref + bias, 1e-3, 3e-2 if dt == torch.bfloat16 else 2e-3, msg="sum of slabs")
+    with pytest.raises(MMVQAError):                                  # split-K without accumulate needs a slab stride
+        ops.gemm(M, N, K, A, lda, False, B, ldb, b_trans, parts, N, split_k=ns)
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("cols,p", [(768, 0.0), (768, 0.1), (128, 0.3), (256, 0.0)])
+def test_layernorm_over_splitk_partials(dt, cols, p):
+    rows, ns, eps, seed = 37, 3, 1e-5, 11
+    parts = torch.stack([rnd(rows, cols, seed=50 + i) for i in range(ns)]).to(DEV)
+    res = rnd(rows, cols, seed=60).to(dt).to(DEV)
+    gamma, beta = (1 + 0.1 * rnd(cols, seed=61)).to(DEV), (0.1 * rnd(cols, seed=62)).to(DEV)
+    # reference composition with the library's own pieces: sum -> (round) -> dropout -> + residual -> LN
+    tot = parts.sum(0)
+    dropped = ops.dropout(tot.contiguous(), p, seed) if p > 0 else tot          # fp32 dropout of the fp32 sum
+    s_ref = (dropped + res.float()).to(dt)
+    y_ref, _, mean_ref, rstd_ref = ops.add_layernorm_fwd(s_ref, None, gamma, beta, eps, want_sum=False)
+    y, s, mean, rstd = ops.add_layernorm_fwd_parts(parts, res, gamma, beta, eps, dt, p, seed)
+    tol = dict(rtol=1e-5, atol=1e-5) if dt == torch.float32 else dict(rtol=1e-2, atol=1e-2)
+    close(s, s_ref, **tol, msg="stored sum")
+    close(y, y_ref, **(dict(rtol=1e-4, atol=1e-4) if dt == torch.float32 else dict(rtol=2e-2, atol=3e-2)), msg="ln(parts)")
+    close(mean, mean_ref, 1e-3, 1e-3)
+    # backward: dy = sum(parts) + dy_res
+    dres = rnd(rows, cols, seed=63).to(dt).to(DEV)
+    dy_ref = (tot + dres.float()).to(dt)
+    dg0, db0, ds0 = (torch.zeros(cols, device=DEV) for _ in range(3))
+    dg1, db1, ds1 = (torch.zeros(cols, device=DEV) for _ in range(3))
+    dx_ref, dxd_ref = ops.layernorm_bwd(dy_ref, s_ref, gamma, mean_ref, rstd_ref, None, dg0, db0, want_drop=True, dxsum=ds0,
+                                        dropout_p=0.2, dropout_seed=3)
+    dx, dxd = ops.layernorm_bwd_parts(parts, dres, s_ref, gamma, mean_ref, rstd_ref, dg1, db1, want_drop=True, dxsum=ds1,
+                                      dropout_p=0.2, dropout_seed=3)
+    btol = dict(rtol=1e-4, atol=1e-4) if dt == torch.float32 else dict(rtol=2e-2, atol=3e-2)
+    close(dx, dx_ref, **btol, msg="dx")
+    close(dxd, dxd_ref, **btol, msg="dropout(dx)")
+    close(dg1, dg0, 1e-3, 5e-2, msg="dgamma")
+    close(db1, db0, 1e-3, 5e-2, msg="dbeta")
+    close(ds1, ds0, 1e-3, 5e-2, msg="dxsum")
+    dx_nores = ops.layernorm_bwd_parts(parts, None, s_ref, gamma, mean_ref, rstd_ref, dg1, db1)
+    dx_nores_ref = ops.layernorm_bwd(tot.to(dt), s_ref, gamma, mean_ref, rstd_ref, None, dg0, db0)
+    close(dx_nores, dx_nores_ref, **btol, msg="dx (no residual)")

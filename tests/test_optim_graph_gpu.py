@@ -139,13 +139,15 @@ def test_overlapped_adam_equals_plain(graph):
         def run(overlap):
             torch.manual_seed(5)
             blocks = nn.ModuleList([ResEncoderBlock(emb_s=16, head_cnt=8, dp1=0.0, dp2=0.0) for _ in range(3)]).to(DEV)
-            head = nn.Linear(128, 8).to(DEV)                     # a parameter that does NOT go through the sink
-            params = list(blocks.parameters()) + list(head.parameters())
-            opt = FusedAdam(params, lr=1e-3, overlap_backward=overlap)
+            head = nn.Linear(128, 8).to(DEV)
+            late = nn.Parameter(torch.ones(8, device=DEV))       # a parameter that is left to the ordinary step()
+            params = list(blocks.parameters()) + list(head.parameters()) + [late]
+            # `head` also goes early, through the post-accumulate hooks (early_groups) instead of the sink
+            opt = FusedAdam(params, lr=1e-3, overlap_backward=overlap, early_groups=[list(head.parameters())])
 
             def loss_fn(x):
                 h, _ = run_blocks(list(blocks), x, None, mask, False)
-                return Fn.linear(h, head.weight, head.bias).float().pow(2).mean()
+                return (Fn.linear(h, head.weight, head.bias).float() * late).pow(2).mean()
             try:
                 if graph:
                     gs = GraphedTrainStep(loss_fn, [xs[0]], opt, warmup=0)
@@ -156,7 +158,7 @@ def test_overlapped_adam_equals_plain(graph):
                         opt.zero_grad(set_to_none=True)
                         loss_fn(x).backward()
                         if overlap:
-                            assert len(opt._early_ids) == 3 * 10, "all three layers must have gone through the sink"
+                            assert len(opt._early_ids) == 3 * 10 + 2, "three layers through the sink + the hooked head"
                             assert all(p.grad is not None for p in params)
                         opt.step()
                 torch.cuda.synchronize()

@@ -23,7 +23,8 @@ def _free_port():
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from mmvqa_b200.parallel import GradBuckets, broadcast_parameters, gather_mask_rows, gather_supcon_features
+    from mmvqa_b200.parallel import (GradBuckets, LayerwiseReducer, broadcast_parameters, gather_mask_rows,
+                                     gather_supcon_features)
     torch.manual_seed(100 + rank)                      # different init per rank on purpose
     model = nn.Sequential(nn.Linear(6, 5), nn.Tanh(), nn.Linear(5, 3))
     broadcast_parameters(model)
@@ -36,6 +37,14 @@ def _worker(rank, world, port, q):
     assert len(buckets.buckets) > 1
     buckets.reduce()
     avg = [gv * buckets.grad_scale for gv in buckets.grads()]
+    # layer-granular exchange (the backward gradient sink calls it once per layer, step() once for the rest)
+    red = LayerwiseReducer(torch.float32)
+    plist = list(model.parameters())
+    lay = []
+    for grp in (plist[2:], plist[:2]):                                    # last layer first, as in backward
+        lay = [v.clone() * red.grad_scale for v in red(grp, [p.grad for p in grp])] + lay
+    again = red(plist[2:], [p.grad for p in plist[2:]])                   # second step reuses the same bucket
+    assert len(red._buckets) == 2 and again[0].data_ptr() == red._buckets[(id(plist[2]), 2)][1][0].data_ptr()
     # SupCon: each rank holds 3 samples x 2 views; gathered batch = 6 samples
     F = torch.randn(6, 2, 8, generator=g)
     F = F / F.norm(dim=-1, keepdim=True)
@@ -48,6 +57,7 @@ def _worker(rank, world, port, q):
     sl.backward()
     if rank == 0:
         q.put({"state": {k: v.clone() for k, v in model.state_dict().items()}, "avg": [a.clone() for a in avg],
+               "lay": lay,
                "gathered": gathered.detach().clone(), "supcon": sl.detach().clone(), "mask": full_mask.clone()})
     q.put({"rank": rank, "df": f_local.grad.clone()})
     dist.barrier()
@@ -74,6 +84,8 @@ def test_dp_world2_gloo():
     X, Y = torch.randn(8, 6, generator=g), torch.randn(8, 3, generator=g)
     ((model(X) - Y) ** 2).mean().backward()
     for a, p in zip(main["avg"], model.parameters()):
+        torch.testing.assert_close(a, p.grad, rtol=1e-5, atol=1e-6)
+    for a, p in zip(main["lay"], model.parameters()):
         torch.testing.assert_close(a, p.grad, rtol=1e-5, atol=1e-6)
     F = torch.randn(6, 2, 8, generator=g)
     F = (F / F.norm(dim=-1, keepdim=True)).requires_grad_(True)

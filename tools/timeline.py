@@ -31,7 +31,8 @@ def main():
             if isinstance(m, torch.nn.Dropout):
                 m.p = 0.0
     params = [p for p in model.parameters() if p.requires_grad]
-    opt = FusedAdam(params, lr=1e-5, overlap_backward=bool(a.overlap))
+    opt = FusedAdam(params, lr=1e-5, overlap_backward=bool(a.overlap),
+                    early_groups=[list(model.transformer.bert_embedding.parameters())])
     crit = ASLSingleLabel()
 
     def loss_fn(f0, f1, f2, f3, f4, ids, seg, mask, target):
