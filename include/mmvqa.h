@@ -53,6 +53,16 @@ int mmvqa_device_sm(void);
 int64_t mmvqa_launch_count(void);
 
 /* ------------------------------------------------------------------------------------
+ * Caption-similarity mask.  replaces SimilarityCalculator.jaccard /
+ * jaccard_similarity, models/SupConLoss/supcon_utils.py:110-138 (two nested Python loops over word sets).
+ * ids_a / ids_b: [n, lmax] int32, each row the SORTED UNIQUE word ids of one document (padding ignored),
+ * len_a / len_b: [n] int32 set sizes.  mask[c1, c2] = 1 if c1 == c2 else |A_c1 & B_c2| / |A_c1 | B_c2| (0 when the
+ * union is empty), fp32, computed as the reference does (double division, rounded once): bit-exact.
+ * ---------------------------------------------------------------------------------- */
+int mmvqa_jaccard_mask(const int* ids_a, const int* len_a, const int* ids_b, const int* len_b, float* mask, int na,
+                       int nb, int lmax, mmvqa_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * GEMM:  C[M,N] = epilogue( sum_k opA(A)[m,k] * opB(B)[n,k] )
  *   a_trans = 0: A stored [M,K] row-major (K contiguous);  1: stored [K,M] (M contiguous)
  *   b_trans = 0: B stored [N,K] row-major (nn.Linear weight layout); 1: stored [K,N]
@@ -248,9 +258,12 @@ typedef struct mmvqa_adam_desc {
   int64_t flags;             /* bit 0: g is bf16 (all-reduced bf16 gradient bucket) instead of fp32 */
 } mmvqa_adam_desc;
 /* `step` (1-based) sets the bias corrections; if step_dev != NULL the kernel reads the step from
- * that device int instead, so a captured CUDA graph can be replayed while the host bumps it. */
+ * that device int instead, so a captured CUDA graph can be replayed while the host bumps it.
+ * max_ctas > 0 caps the grid (the CTAs stride over the table): an update that runs underneath the backward pass
+ * then takes a bounded share of the HBM bandwidth. */
 int mmvqa_adam_step(const mmvqa_adam_desc* table, int n_chunks, float lr, float beta1, float beta2, float eps,
-                    float weight_decay, int step, const int* step_dev, float grad_scale, mmvqa_stream_t stream);
+                    float weight_decay, int step, const int* step_dev, float grad_scale, int max_ctas,
+                    mmvqa_stream_t stream);
 
 #ifdef __cplusplus
 }

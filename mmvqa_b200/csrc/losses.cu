@@ -156,16 +156,19 @@ __device__ __forceinline__ void adam_one(float& p, float& m, float& v, float g, 
 
 __global__ void __launch_bounds__(256) adam_kernel(const mmvqa_adam_desc* __restrict__ table, float lr, float beta1,
                                                    float beta2, float eps, float wd, float bc1, float bc2_sqrt,
-                                                   float grad_scale, const int* __restrict__ step_dev) {
+                                                   float grad_scale, const int* __restrict__ step_dev, int n_chunks) {
   pdl_wait();
   pdl_trigger();
-  const mmvqa_adam_desc d = table[blockIdx.x];
   if (step_dev) {  // step counter lives on the device (CUDA-graph replay safe)
     const float t = (float)(*step_dev);
     bc1 = 1.0f - powf(beta1, t);
     bc2_sqrt = sqrtf(1.0f - powf(beta2, t));
   }
   const float step = lr / bc1;
+  // grid-stride over the chunk table: a capped grid bounds the HBM bandwidth this launch takes while it runs
+  // concurrently with the latency-bound backward kernels
+  for (int ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
+  const mmvqa_adam_desc d = table[ch];
   const bool g16 = (d.flags & 1) != 0;
   const float* g32 = reinterpret_cast<const float*>(d.g);
   const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(d.g);
@@ -210,6 +213,7 @@ __global__ void __launch_bounds__(256) adam_kernel(const mmvqa_adam_desc* __rest
     d.m[i] = m;
     d.v[i] = v;
     if (d.bf16_out) reinterpret_cast<__nv_bfloat16*>(d.bf16_out)[i] = __float2bfloat16_rn(p);
+  }
   }
 }
 
@@ -261,14 +265,16 @@ int mmvqa_supcon_rows(const float* logits, const float* mask, float* loss_rows, 
 }
 
 int mmvqa_adam_step(const mmvqa_adam_desc* table, int n_chunks, float lr, float beta1, float beta2, float eps,
-                    float weight_decay, int step, const int* step_dev, float grad_scale, mmvqa_stream_t stream) {
+                    float weight_decay, int step, const int* step_dev, float grad_scale, int max_ctas,
+                    mmvqa_stream_t stream) {
   MMVQA_REQUIRE(table && n_chunks >= 0 && (step >= 1 || step_dev), "adam: bad args");
   if (step < 1) step = 1;
   if (n_chunks == 0) return MMVQA_OK;
   const float bc1 = 1.0f - powf(beta1, (float)step);
   const float bc2 = 1.0f - powf(beta2, (float)step);
-  MMVQA_CUDA(launch_pdl(adam_kernel, dim3(n_chunks), dim3(256), 0, as_stream(stream), table, lr, beta1, beta2, eps, weight_decay, bc1,
-                        sqrtf(bc2), grad_scale, step_dev));
+  const int grid = (max_ctas > 0 && max_ctas < n_chunks) ? max_ctas : n_chunks;
+  MMVQA_CUDA(launch_pdl(adam_kernel, dim3(grid), dim3(256), 0, as_stream(stream), table, lr, beta1, beta2, eps, weight_decay, bc1,
+                        sqrtf(bc2), grad_scale, step_dev, n_chunks));
   MMVQA_LAUNCHED("adam_step");
   return MMVQA_OK;
 }

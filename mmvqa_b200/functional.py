@@ -43,11 +43,12 @@ _OVERLAP = _os.environ.get("MMVQA_NO_OVERLAP") is None
 class SideBranch:
     """`with branch.after_now(): ...` runs the body on the side stream once everything enqueued so far on the main
     stream has finished; `join()` makes the main stream wait for the branch.  Tensors touched by the branch must be
-    kept alive by the caller until join() (the caching allocator only tracks the allocating stream)."""
+    kept alive by the caller until join() (the caching allocator only tracks the allocating stream).
+    `index` selects one of several side streams (independent branches that may all run at once)."""
 
-    def __init__(self, device):
+    def __init__(self, device, index: int = 0):
         self.main = torch.cuda.current_stream(device)
-        key = (device.index if device.index is not None else torch.cuda.current_device(), self.main.cuda_stream)
+        key = (device.index if device.index is not None else torch.cuda.current_device(), self.main.cuda_stream, index)
         if key not in _SIDE:
             _SIDE[key] = torch.cuda.Stream(device)
         self.side = _SIDE[key] if _OVERLAP else self.main
@@ -544,12 +545,14 @@ class VisTokAllFn(torch.autograd.Function):
                          c_batch_stride=Cc * HW)
                 dfeats[n] = df.view(B, Cc, Hh, Ww).to(fdt)
                 keep.append(wb)
-        if nlev > 1:
-            with branch.after_now():
-                for n in order[1:]:
-                    run(n)
+        # every level is an independent pair of small GEMMs (atomics / latency bound): one branch per level
+        branches = [SideBranch(dev, index=1 + i) for i in range(max(nlev - 1, 0))]
+        for br, n in zip(branches, order[1:]):
+            with br.after_now():
+                run(n)
         run(order[0])
-        branch.join()
+        for br in branches:
+            br.join()
         return (None, None, None, *dfeats, *dws)
 
 

@@ -336,6 +336,24 @@ def supcon_rows(raw: Tensor, mask: Optional[Tensor], bsz: int, row_offset: int, 
 
 
 def adam_step(table: Tensor, n_chunks: int, lr: float, beta1: float, beta2: float, eps: float, weight_decay: float,
-              step: int, step_dev: Optional[Tensor], grad_scale: float = 1.0) -> None:
+              step: int, step_dev: Optional[Tensor], grad_scale: float = 1.0, max_ctas: int = 0) -> None:
     L.check(L.lib().mmvqa_adam_step(C.cast(table.data_ptr(), C.POINTER(L.AdamDesc)), n_chunks, lr, beta1, beta2, eps,
-                                   weight_decay, step, _p(step_dev), grad_scale, _stream()), "adam_step")
+                                   weight_decay, step, _p(step_dev), grad_scale, max_ctas, _stream()), "adam_step")
+
+
+# ------------------------------------------------------------------------------- caption similarity
+def jaccard_mask(ids_a: Tensor, len_a: Tensor, ids_b: Tensor, len_b: Tensor) -> Tensor:
+    """ids_* [n, lmax] int32 sorted unique word ids per document, len_* [n] int32 -> [na, nb] fp32 Jaccard mask with
+    ones on the diagonal (supcon_utils.py:110-138)."""
+    for t in (ids_a, len_a, ids_b, len_b):
+        _cont(t, "jaccard input")
+        if t.dtype != torch.int32:
+            raise L.MMVQAError("jaccard_mask takes int32 tensors")
+    na, lmax = ids_a.shape
+    nb = ids_b.shape[0]
+    if ids_b.shape[1] != lmax:
+        raise L.MMVQAError("jaccard_mask: both id matrices need the same row length")
+    mask = torch.empty(na, nb, device=ids_a.device, dtype=torch.float32)
+    L.check(L.lib().mmvqa_jaccard_mask(_p(ids_a), _p(len_a), _p(ids_b), _p(len_b), _p(mask), na, nb, lmax, _stream()),
+            "jaccard_mask")
+    return mask

@@ -3,6 +3,8 @@ kernel launch over every parameter, with a state_dict compatible with torch.opti
 reference's ``recorder_2.pt`` checkpoints round-trip (pretrain/roco_train.py:164-171)."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -35,6 +37,8 @@ class FusedAdam(torch.optim.Optimizer):
         # on the stream that update runs on; packs / all-reduces and returns the tensors Adam should read
         # (mmvqa_b200.parallel.LayerwiseReducer).  With overlap_backward each layer's exchange overlaps the backward.
         self.reduce_fn = reduce_fn
+        # grid cap of the updates that run underneath the backward pass (0 = one CTA per 32768-element chunk)
+        self.early_ctas = int(os.environ.get("MMVQA_ADAM_EARLY_CTAS", "0"))
         self._stepped = False      # device step counter already advanced in this iteration
         self._early_ids = set()    # parameters already updated in this iteration
         self._early_keep = []      # gradients read by the optimizer stream (kept alive until step() joins it)
@@ -127,12 +131,12 @@ class FusedAdam(torch.optim.Optimizer):
             self._step_dev += 1
             self._stepped = True
 
-    def _launch(self, gi, key, plist, grads):
+    def _launch(self, gi, key, plist, grads, max_ctas: int = 0):
         group = self.param_groups[gi]
         table, n = self._table(key, plist, grads)
         b1, b2 = group["betas"]
         ops.adam_step(table, n, group["lr"], b1, b2, group["eps"], group["weight_decay"], 0, self._step_dev,
-                      self.grad_scale)
+                      self.grad_scale, max_ctas)
 
     @torch.no_grad()
     def _sink(self, params, grads, side_stream, from_hook: bool = False) -> bool:
@@ -167,7 +171,7 @@ class FusedAdam(torch.optim.Optimizer):
             ev3.record(self._comm_stream)
             self._opt_stream.wait_event(ev3)
         with torch.cuda.stream(self._opt_stream):
-            self._launch(gi, ("early", id(params[0])), list(params), gr)
+            self._launch(gi, ("early", id(params[0])), list(params), gr, self.early_ctas)
         for p, g in zip(params, gs):
             if not from_hook:
                 p.grad = g          # visible to hooks / loggers exactly as after a normal backward

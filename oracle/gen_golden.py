@@ -341,6 +341,39 @@ def case_models():
     save("models", out)
 
 
+def case_jaccard():
+    """SimilarityCalculator.jaccard (models/SupConLoss/supcon_utils.py:110-138).  The module itself cannot be imported
+    here (sentence_transformers / bert_score / googletrans are missing), so the two methods are lifted out of the
+    reference file with ``ast`` at generation time and executed unmodified on seeded captions."""
+    import ast
+    import random
+    path = os.path.join(REF, "models", "SupConLoss", "supcon_utils.py")
+    tree = ast.parse(open(path).read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "SimilarityCalculator")
+    fns = [n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name in ("jaccard", "jaccard_similarity")]
+    assert len(fns) == 2
+    holder = ast.ClassDef(name="RefJaccard", bases=[], keywords=[], body=fns, decorator_list=[], type_params=[])
+    mod = ast.Module(body=[holder], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    ns = {"torch": torch}
+    exec(compile(mod, path, "exec"), ns)
+    ref = ns["RefJaccard"]()
+    rng = random.Random(0)
+    words = ["chest", "x-ray", "CT", "scan", "of", "the", "left", "right", "lung", "showing", "a", "Nodule", "mass", "MRI",
+             "brain", "axial", "view", "with", "contrast", "no", "fracture", "Pleural", "effusion", "normal", "heart"]
+    out = {}
+    for name, bsz in (("small", 6), ("medium", 33)):
+        cap = [" ".join(rng.choice(words) for _ in range(rng.randint(0 if name == "small" else 1, 14))) for _ in range(bsz)]
+        aug = [" ".join(rng.choice(words) for _ in range(rng.randint(1, 14))) for _ in range(bsz)]
+        if name == "small":
+            cap[0], aug[1] = "", ""                # empty documents: union == 0 -> 0.0 (supcon_utils.py:136-138)
+            cap[2] = "Lung  LUNG\tlung mass"       # case folding, repeated words, mixed whitespace
+        with quiet():
+            mask = ref.jaccard(cap, aug, bsz)
+        out[name] = {"caption": cap, "aug": aug, "mask": mask.clone()}
+    save("jaccard", out)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     if REF not in sys.path:
@@ -350,3 +383,4 @@ if __name__ == "__main__":
     case_transformer()
     case_realformer()
     case_models()
+    case_jaccard()

@@ -332,3 +332,25 @@ def mlm_nll(logits: Tensor, target: Tensor) -> Tensor:
     target 0 is a real class (pretrain/roco_utils.py:235-236)."""
     lp = torch.log_softmax(logits, dim=-1)
     return -lp.gather(-1, target.long().unsqueeze(-1)).mean()
+
+
+# ----------------------------------------------------------------------------------
+# caption-similarity mask  (models/SupConLoss/supcon_utils.py:110-138)
+# ----------------------------------------------------------------------------------
+def jaccard_similarity(doc1: str, doc2: str) -> float:
+    """SimilarityCalculator.jaccard_similarity, supcon_utils.py:120-138: |words1 & words2| / |words1 | words2| over the
+    lower-cased whitespace-split word sets; 0.0 when both documents are empty."""
+    w1, w2 = set(doc1.lower().split()), set(doc2.lower().split())
+    union = w1 | w2
+    if len(union) == 0:
+        return 0.0
+    return float(len(w1 & w2)) / len(union)
+
+
+def jaccard_mask(caption, aug, bsz: int) -> Tensor:
+    """SimilarityCalculator.jaccard, supcon_utils.py:110-118: [bsz, bsz] float32, ones on the diagonal."""
+    mask = torch.zeros(bsz, bsz, dtype=torch.float)
+    for c1 in range(len(caption)):
+        for c2 in range(len(aug)):
+            mask[c1, c2] = jaccard_similarity(caption[c1], aug[c2]) if c1 != c2 else 1.0
+    return mask

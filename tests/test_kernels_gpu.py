@@ -561,3 +561,25 @@ def test_layernorm_over_splitk_partials(dt, cols, p):
     dx_nores = ops.layernorm_bwd_parts(parts, None, s_ref, gamma, mean_ref, rstd_ref, dg1, db1)
     dx_nores_ref = ops.layernorm_bwd(tot.to(dt), s_ref, gamma, mean_ref, rstd_ref, None, dg0, db0)
     close(dx_nores, dx_nores_ref, **btol, msg="dx (no residual)")
+
+
+# ------------------------------------------------------------------------------------------
+# caption-similarity mask (supcon_utils.py:110-138)
+# ------------------------------------------------------------------------------------------
+def test_jaccard_mask_against_golden_and_oracle(golden):
+    import random
+
+    from mmvqa_b200.similarity import build_mask, jaccard_mask
+    for name, case in golden("jaccard").items():
+        got = jaccard_mask(case["caption"], case["aug"])
+        assert got.dtype == torch.float32 and torch.equal(got.cpu(), case["mask"]), name      # integer work: bit-exact
+    rng = random.Random(1)
+    words = [f"w{i}" for i in range(60)]
+    bsz = 257                                                                                # ragged sizes, > one CTA row group
+    cap = [" ".join(rng.choice(words) for _ in range(rng.randint(0, 40))) for _ in range(bsz)]
+    aug = [" ".join(rng.choice(words) for _ in range(rng.randint(0, 40))) for _ in range(bsz)]
+    assert torch.equal(jaccard_mask(cap, aug).cpu(), O.jaccard_mask(cap, aug, bsz))
+    assert build_mask(bsz, cap, aug, "simclr") is None
+    assert torch.equal(build_mask(bsz, cap, aug, "supcon").cpu(), O.jaccard_mask(cap, aug, bsz))
+    with pytest.raises(MMVQAError):
+        jaccard_mask(cap, aug, device="cpu")

@@ -189,3 +189,25 @@ def test_full_model(golden, name):
             gv = gv.clone()
             gv[0] = 0          # nn.Embedding(padding_idx=0): the reference never updates row 0
         close(gv, ref, 2e-3, 2e-5)
+
+
+def test_jaccard_mask(golden):
+    """oracle restatement == SimilarityCalculator.jaccard run from the reference source (supcon_utils.py:110-138),
+    bit for bit, including empty documents, repeated words, case folding and mixed whitespace."""
+    for name, case in golden("jaccard").items():
+        bsz = len(case["caption"])
+        got = O.jaccard_mask(case["caption"], case["aug"], bsz)
+        assert got.dtype == torch.float32 and torch.equal(got, case["mask"]), name
+    assert O.jaccard_similarity("", "") == 0.0
+    assert O.jaccard_similarity("a b", "B c") == 1.0 / 3.0
+
+
+def test_word_set_encoding_matches_python_sets():
+    """host half of mmvqa_b200.similarity: documents -> sorted unique word ids (no GPU needed)."""
+    from mmvqa_b200.similarity import encode_word_sets
+    vocab = {}
+    rows = encode_word_sets(["Lung  LUNG\tlung mass", "", "mass of the lung"], vocab)
+    assert [len(r) for r in rows] == [2, 0, 4]
+    assert all(r == sorted(set(r)) for r in rows)
+    inv = {v: k for k, v in vocab.items()}
+    assert {inv[i] for i in rows[0]} == {"lung", "mass"} and {inv[i] for i in rows[2]} == {"mass", "of", "the", "lung"}
