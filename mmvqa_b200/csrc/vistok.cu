@@ -23,13 +23,16 @@ template <int KB, int STAGES>
 struct VtCfg {
   static constexpr int A_BYTES = KB * 16384;
   static constexpr int B_STAGE = KB * 16384;
-  static constexpr int RAW = A_BYTES + STAGES * B_STAGE + 1024 + 256;
+  static constexpr int REP = KB == 1 ? 8 : 4;                        // SERF table replicas (see common.cuh)
+  static constexpr int TAB_BYTES = SERF_TAB_N * REP * 16;
+  static constexpr int RAW = A_BYTES + STAGES * B_STAGE + 1024 + 256 + TAB_BYTES;
   static constexpr int SMEM = RAW < 80 * 1024 ? 80 * 1024 : RAW;   // never more than 2 CTAs per SM (2 x 256 TMEM columns)
+  static_assert(SMEM <= 116224, "two projector CTAs must fit on one SM (227 KB)");
 };
 
-template <int MODE, int ACT>
+template <int MODE, int ACT, int REP>
 __device__ __forceinline__ void vt_epilogue_tile(const EpiParams& p, uint32_t tmem_row, int m, int n0, int bz, bool row_ok,
-                                                 int c_begin, float rscale, float& rowsum) {
+                                                 int c_begin, float rscale, float& rowsum, const float4* tab) {
 #pragma unroll 1
   for (int c = c_begin; c < c_begin + VT_BN / 2; c += 16) {
     uint32_t r[16];
@@ -45,20 +48,22 @@ __device__ __forceinline__ void vt_epilogue_tile(const EpiParams& p, uint32_t tm
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float a;
-            act_both_fast<ACT>(__uint_as_float(r[j]), a, v[j]);
+            if (ACT == MMVQA_ACT_SERF) serf_both_tab<REP>(tab, __uint_as_float(r[j]), a, v[j]);
+            else act_both_fast<ACT>(__uint_as_float(r[j]), a, v[j]);
             rowsum += (j < nvalid) ? a : 0.0f;
           }
           store16_bf16(reinterpret_cast<__nv_bfloat16*>(p.aux_out) + ((int64_t)bz * p.M + m) * p.ld_aux_out + nb, nvalid, v);
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float a = act_fast<ACT>(__uint_as_float(r[j]));
+            const float a = ACT == MMVQA_ACT_SERF ? serf_tab<REP>(tab, __uint_as_float(r[j])) : act_fast<ACT>(__uint_as_float(r[j]));
             rowsum += (j < nvalid) ? a : 0.0f;
           }
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = dact_fast<ACT>(__uint_as_float(r[j])) * rscale;
+        for (int j = 0; j < 16; ++j)
+          v[j] = (ACT == MMVQA_ACT_SERF ? dserf_tab<REP>(tab, __uint_as_float(r[j])) : dact_fast<ACT>(__uint_as_float(r[j]))) * rscale;
         store16_bf16(reinterpret_cast<__nv_bfloat16*>(p.C) + (int64_t)bz * p.c_batch_stride + (int64_t)m * p.ldc + nb, nvalid, v);
       }
     }
@@ -80,6 +85,8 @@ __global__ void __launch_bounds__(VT_THREADS) vistok_kernel(const __grid_constan
                  acc_empty = acc_full + 16, tmem_ptr_addr = acc_empty + 16;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_ptr_addr - smem_base));
+  float4* tab = reinterpret_cast<float4*>(smem_gen + (bar + 256 - smem_base));     // SERF interpolation table (32 KB)
+  if (p.act == MMVQA_ACT_SERF) serf_table_fill<Cfg::REP>(tab, threadIdx.x, VT_THREADS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int split = blockIdx.x, nsplit = gridDim.x;
@@ -166,10 +173,10 @@ __global__ void __launch_bounds__(VT_THREADS) vistok_kernel(const __grid_constan
       const uint32_t tmem_row = tmem_acc + ((uint32_t)(g * 32) << 16) + (uint32_t)(buf * VT_BN);
       const int n0 = (split + t * nsplit) * VT_BN;
       switch (p.act) {
-        case MMVQA_ACT_SERF: vt_epilogue_tile<MODE, MMVQA_ACT_SERF>(p, tmem_row, m, n0, bz, row_ok, c_begin, rscale, rowsum); break;
-        case MMVQA_ACT_GELU: vt_epilogue_tile<MODE, MMVQA_ACT_GELU>(p, tmem_row, m, n0, bz, row_ok, c_begin, rscale, rowsum); break;
-        case MMVQA_ACT_RELU: vt_epilogue_tile<MODE, MMVQA_ACT_RELU>(p, tmem_row, m, n0, bz, row_ok, c_begin, rscale, rowsum); break;
-        default: vt_epilogue_tile<MODE, MMVQA_ACT_NONE>(p, tmem_row, m, n0, bz, row_ok, c_begin, rscale, rowsum); break;
+        case MMVQA_ACT_SERF: vt_epilogue_tile<MODE, MMVQA_ACT_SERF, Cfg::REP>(p, tmem_row, m, n0, bz, row_ok, c_begin, rscale, rowsum, tab); break;
+        case MMVQA_ACT_GELU: vt_epilogue_tile<MODE, MMVQA_ACT_GELU, Cfg::REP>(p, tmem_row, m, n0, bz, row_ok, c_begin, rscale, rowsum, tab); break;
+        case MMVQA_ACT_RELU: vt_epilogue_tile<MODE, MMVQA_ACT_RELU, Cfg::REP>(p, tmem_row, m, n0, bz, row_ok, c_begin, rscale, rowsum, tab); break;
+        default: vt_epilogue_tile<MODE, MMVQA_ACT_NONE, Cfg::REP>(p, tmem_row, m, n0, bz, row_ok, c_begin, rscale, rowsum, tab); break;
       }
       // hand the accumulator back to the MMA warp
       tc_fence_before();
@@ -199,8 +206,9 @@ static int launch_vt(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t
   }
   const int n_tiles = (a->N + VT_BN - 1) / VT_BN;
   const int mt = (a->M + TC_BM - 1) / TC_BM;
-  // two CTAs per SM (TMEM: 2 x 256 columns): aim at one full wave of 2 * SMs CTAs, at least 2 pixel tiles per CTA
-  int nsplit = (2 * num_sms() + mt * a->batch - 1) / (mt * a->batch);
+  // two CTAs per SM (TMEM: 2 x 256 columns): ONE wave of at most 2 * SMs CTAs (rounding the split up gave 1.3 waves
+  // and a 36 % idle tail at the 112 x 112 level), at least 2 pixel tiles per CTA
+  int nsplit = (2 * num_sms()) / (mt * a->batch);
   if (nsplit > (n_tiles + 1) / 2) nsplit = (n_tiles + 1) / 2;
   if (nsplit < 1) nsplit = 1;
   dim3 grid(nsplit, mt, a->batch);

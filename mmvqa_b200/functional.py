@@ -62,6 +62,18 @@ class SideBranch:
             self.used = True
         return torch.cuda.stream(self.side)
 
+    def mark(self):
+        """remember this point of the main stream; `after_mark()` later forks from it (work enqueued on the main
+        stream in between is issued first but does not delay the branch)."""
+        self._mark = torch.cuda.Event()
+        self._mark.record(self.main)
+
+    def after_mark(self):
+        if self.side is not self.main:
+            self.side.wait_event(self._mark)
+            self.used = True
+        return torch.cuda.stream(self.side)
+
     def join(self):
         if self.used:
             ev = torch.cuda.Event()
@@ -503,12 +515,14 @@ class VisTokAllFn(torch.autograd.Function):
             saved[3 * n:3 * n + 3] = [fb, cw, actp]
             metas[n] = (Cc, Hh, Ww, ld, f.dtype)
             keep.append((fb, actp))
-        # fork BEFORE the big level is enqueued: the side branch only depends on what precedes this node
+        # the side branch only depends on what precedes this node, but the big level is ISSUED first so that its input
+        # cast and its kernel get the SMs before the small levels do (it is the critical path of the whole projector)
+        branch.mark()
+        run(order[0])
         if nlev > 1:
-            with branch.after_now():
+            with branch.after_mark():
                 for n in order[1:]:
                     run(n)
-        run(order[0])
         branch.join()
         ctx.save_for_backward(*saved)
         ctx.meta = (act, dtype, nlev, B, hidden, metas, order)
