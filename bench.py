@@ -293,7 +293,8 @@ def main_gpu(a):
     gs = GraphedTrainStep(loss_fn, dev[0], opt, warmup=3, post_backward=(buckets.pack if buckets else None),
                           eager_between=(buckets.allreduce if buckets else None),
                           step_kwargs=(step_kwargs if buckets else None),
-                          capture_error_mode=("thread_local" if world > 1 else "global"))
+                          capture_error_mode=("thread_local" if world > 1 else "global"),
+                          main_priority=a.main_priority)
     log("graph captured: %d launches per step" % gs.launches_per_step)
     launches = gs.launches_per_step
 
@@ -492,6 +493,7 @@ if __name__ == "__main__":
     ap.add_argument("--bf16-buckets", type=int, default=1, help="data parallel: all-reduce gradients as bf16 (bf16 path only)")
     ap.add_argument("--overlap-adam", type=int, default=1, help="1 GPU: update each layer under the rest of the backward pass")
     ap.add_argument("--nccl-channels", type=int, default=0, help="cap NCCL channels (CTAs) per collective; 0 = NCCL default")
+    ap.add_argument("--main-priority", type=int, default=-1, help="CUDA priority of the captured main stream (< 0 = above the side / optimizer streams)")
     ap.add_argument("--dp-mode", default="overlapped", choices=["overlapped", "twograph"])
     ap.add_argument("--pad-steps", type=int, default=100, help="untimed steps around the timed region (clock sampling)")
     a = ap.parse_args()

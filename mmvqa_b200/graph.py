@@ -25,7 +25,7 @@ class GraphedTrainStep:
 
     def __init__(self, loss_fn: Callable, example_inputs: Sequence[torch.Tensor], optimizer, warmup: int = 3,
                  post_backward: Callable = None, eager_between: Callable = None, step_kwargs: Callable = None,
-                 capture_error_mode: str = "global"):
+                 capture_error_mode: str = "global", main_priority: int = 0):
         self.loss_fn = loss_fn
         self.optimizer = optimizer
         self.post_backward = post_backward      # capturable, e.g. GradBuckets.pack
@@ -52,10 +52,13 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         self.graph_opt = None
         n0 = _lib.launch_count()
+        # main_priority < 0: the step is captured on a high-priority stream, so the kernels of the main chain win the
+        # SM slots over the work forked onto default-priority streams (weight-gradient branch, optimizer stream)
+        cap_stream = torch.cuda.Stream(priority=main_priority) if main_priority != 0 else None
         if self.eager_between is None:
             # capture_error_mode="thread_local": needed when collectives are captured (the NCCL watchdog thread
             # polls events of earlier eager collectives while this thread captures)
-            with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
+            with torch.cuda.graph(self.graph, stream=cap_stream, capture_error_mode=capture_error_mode):
                 self.static_loss = self._fwd_bwd(zero=False)
                 self._opt()
         else:

@@ -19,6 +19,7 @@ def main():
     ap.add_argument("--out", default="gpurun_out/timeline.csv")
     ap.add_argument("--dropout", type=int, default=1)
     ap.add_argument("--overlap", type=int, default=1)
+    ap.add_argument("--main-priority", type=int, default=-1)
     a = ap.parse_args()
     import mmvqa_b200
     from mmvqa_b200.graph import GraphedTrainStep
@@ -39,7 +40,7 @@ def main():
         logits, _, _ = model.forward_features([f0, f1, f2, f3, f4], ids, seg, mask)
         return crit(logits, target)
     dev = [t.cuda() for t in (lambda b: (*b[0], *b[1:]))(bench.synth_batch(a.batch, 0))]
-    gs = GraphedTrainStep(loss_fn, dev, opt, warmup=3)
+    gs = GraphedTrainStep(loss_fn, dev, opt, warmup=3, main_priority=a.main_priority)
     for _ in range(5):
         gs.replay(*dev)
     torch.cuda.synchronize()
