@@ -179,29 +179,31 @@ __global__ void __launch_bounds__(256) adam_kernel(const mmvqa_adam_desc* __rest
   if (vec) {
     const int64_t n4 = d.n / 4;
     for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
-      float4 p = reinterpret_cast<float4*>(d.p)[i], m = reinterpret_cast<float4*>(d.m)[i];
-      float4 v = reinterpret_cast<float4*>(d.v)[i];
+      // evict-first (streaming) accesses: 28 bytes per parameter pass through exactly once; keeping them out of the
+      // L2 working set matters when the update runs underneath the backward pass, whose saved activations live there
+      float4 p = __ldcs(reinterpret_cast<const float4*>(d.p) + i), m = __ldcs(reinterpret_cast<const float4*>(d.m) + i);
+      float4 v = __ldcs(reinterpret_cast<const float4*>(d.v) + i);
       float4 g;
       if (g16) {
-        const uint2 raw = reinterpret_cast<const uint2*>(gb)[i];
+        const uint2 raw = __ldcs(reinterpret_cast<const uint2*>(gb) + i);
         g.x = __uint_as_float(raw.x << 16); g.y = __uint_as_float(raw.x & 0xffff0000u);
         g.z = __uint_as_float(raw.y << 16); g.w = __uint_as_float(raw.y & 0xffff0000u);
       } else {
-        g = reinterpret_cast<const float4*>(g32)[i];
+        g = __ldcs(reinterpret_cast<const float4*>(g32) + i);
       }
       adam_one(p.x, m.x, v.x, g.x, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
       adam_one(p.y, m.y, v.y, g.y, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
       adam_one(p.z, m.z, v.z, g.z, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
       adam_one(p.w, m.w, v.w, g.w, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
-      reinterpret_cast<float4*>(d.p)[i] = p;
-      reinterpret_cast<float4*>(d.m)[i] = m;
-      reinterpret_cast<float4*>(d.v)[i] = v;
+      __stcs(reinterpret_cast<float4*>(d.p) + i, p);
+      __stcs(reinterpret_cast<float4*>(d.m) + i, m);
+      __stcs(reinterpret_cast<float4*>(d.v) + i, v);
       if (d.bf16_out) {
         __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
         uint2 o;
         o.x = *reinterpret_cast<uint32_t*>(&lo);
         o.y = *reinterpret_cast<uint32_t*>(&hi);
-        reinterpret_cast<uint2*>(d.bf16_out)[i] = o;
+        __stcs(reinterpret_cast<uint2*>(d.bf16_out) + i, o);
       }
     }
     done = n4 * 4;

@@ -46,11 +46,14 @@ class SideBranch:
     kept alive by the caller until join() (the caching allocator only tracks the allocating stream).
     `index` selects one of several side streams (independent branches that may all run at once)."""
 
-    def __init__(self, device, index: int = 0):
+    def __init__(self, device, index: int = 0, priority: int = 0):
         self.main = torch.cuda.current_stream(device)
-        key = (device.index if device.index is not None else torch.cuda.current_device(), self.main.cuda_stream, index)
+        key = (device.index if device.index is not None else torch.cuda.current_device(), self.main.cuda_stream, index,
+               priority)
         if key not in _SIDE:
-            _SIDE[key] = torch.cuda.Stream(device)
+            # priority -1: same class as a high-priority main stream (graph.GraphedTrainStep main_priority); the default
+            # 0 yields the SMs to the main chain (weight-gradient GEMMs, optimizer)
+            _SIDE[key] = torch.cuda.Stream(device, priority=priority)
         self.side = _SIDE[key] if _OVERLAP else self.main
         self.used = False
 
@@ -498,7 +501,7 @@ class VisTokAllFn(torch.autograd.Function):
         dev = feats[0].device
         vis = torch.zeros(nlev, B, hidden, device=dev, dtype=torch.float32)
         order = sorted(range(nlev), key=lambda n: -feats[n][0].numel())          # biggest level first, on main
-        branch = SideBranch(dev)
+        branch = SideBranch(dev, priority=-1)            # on the critical path like the main chain
         saved, metas = [None] * (3 * nlev), [None] * nlev
         keep = []
 
@@ -559,7 +562,7 @@ class VisTokAllFn(torch.autograd.Function):
                 dfeats[n] = df.view(B, Cc, Hh, Ww).to(fdt)
                 keep.append(wb)
         # every level is an independent pair of small GEMMs (atomics / latency bound): one branch per level
-        branches = [SideBranch(dev, index=1 + i) for i in range(max(nlev - 1, 0))]
+        branches = [SideBranch(dev, index=1 + i, priority=-1) for i in range(max(nlev - 1, 0))]
         for br, n in zip(branches, order[1:]):
             with br.after_now():
                 run(n)
