@@ -244,7 +244,10 @@ def main_gpu(a):
     if world > 1:
         if a.nccl_channels > 0:       # the exchange shares the SMs with the backward pass: fewer, fatter channels
             os.environ.setdefault("NCCL_MAX_NCHANNELS", str(a.nccl_channels))
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        opts = None
+        if a.nccl_high_priority:      # the exchange is on the critical path of the per-layer optimizer chain
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
     dt = torch.bfloat16 if a.dtype == "bf16" else torch.float32
     mmvqa_b200.set_compute_dtype(dt)
     B = a.batch
@@ -494,6 +497,7 @@ if __name__ == "__main__":
     ap.add_argument("--overlap-adam", type=int, default=1, help="1 GPU: update each layer under the rest of the backward pass")
     ap.add_argument("--nccl-channels", type=int, default=0, help="cap NCCL channels (CTAs) per collective; 0 = NCCL default")
     ap.add_argument("--main-priority", type=int, default=-1, help="CUDA priority of the captured main stream (< 0 = above the side / optimizer streams)")
+    ap.add_argument("--nccl-high-priority", type=int, default=0)
     ap.add_argument("--dp-mode", default="overlapped", choices=["overlapped", "twograph"])
     ap.add_argument("--pad-steps", type=int, default=100, help="untimed steps around the timed region (clock sampling)")
     a = ap.parse_args()

@@ -197,6 +197,11 @@ int mmvqa_mhsa_bwd(const void* qkv, const void* probs, const void* dout, void* d
  * arriving from the next layer through prev) and writes the total as dprev. */
 int mmvqa_rf_attn_fwd(const void* kqv, const float* prev, const float* mask, void* out, float* scores, int B, int T,
                       int heads, int d, int dtype, mmvqa_stream_t stream);
+/* Same forward with the shared-weight kqv projection (realformer.py:13,33) inside the kernel (bf16 path): x is the layer
+ * input [B*T, heads*d], wkqv the [3d, d] weight; kqv_out [B*T*heads, 3d] is WRITTEN (the backward pass reads it).
+ * Removes one GEMM launch per layer from the latency-bound small-batch chain. */
+int mmvqa_rf_attn_fwd_fused(const void* x, const void* wkqv, const float* prev, const float* mask, void* out, float* scores,
+                            void* kqv_out, int B, int T, int heads, int d, int dtype, mmvqa_stream_t stream);
 int mmvqa_rf_attn_bwd(const void* kqv, const float* scores, const void* dout, const float* dscores_in, void* dkqv,
                       float* dprev, int B, int T, int heads, int d, int dtype, mmvqa_stream_t stream);
 

@@ -365,7 +365,8 @@ static int launch_fwd(const void* qkv, const AttnLayout& L, const float* prev, c
     auto k = attn_tc_fwd_kernel<RF, TPV>;                                                                               \
     if (smem_tc > 48 * 1024) MMVQA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc)); \
     MMVQA_CUDA(launch_pdl(k, dim3(B * heads), dim3(nthr), smem_tc, st, (const bf16*)qkv, L, prev, mask, (bf16*)out, scores, \
-                          (bf16*)probs, Tn, heads, d, p, (unsigned long long)seed));                                    \
+                          (bf16*)probs, Tn, heads, d, p, (unsigned long long)seed, (const bf16*)nullptr,                \
+                          (const bf16*)nullptr));                                                                       \
   } while (0)
       if (Tp <= 32) TC_FWD(32); else if (Tp <= 64) TC_FWD(64); else if (Tp <= 96) TC_FWD(96); else TC_FWD(128);
 #undef TC_FWD
@@ -462,6 +463,34 @@ int mmvqa_rf_attn_fwd(const void* kqv, const float* prev, const float* mask, voi
   if (dtype == MMVQA_F32) return launch_fwd<float, true>(kqv, L, prev, mask, out, scores, nullptr, B, T, heads, d, 0.f, 0, as_stream(stream));
   if (dtype == MMVQA_BF16) return launch_fwd<__nv_bfloat16, true>(kqv, L, prev, mask, out, scores, nullptr, B, T, heads, d, 0.f, 0, as_stream(stream));
   return set_err(MMVQA_ERR_ARG, "rf_attn_fwd: bad dtype %d", dtype);
+}
+
+// RealFormer attention with the kqv projection inside (bf16 tensor-core path only): x [B*T, heads*d], wkqv [3d, d]
+int mmvqa_rf_attn_fwd_fused(const void* x, const void* wkqv, const float* prev, const float* mask, void* out, float* scores,
+                            void* kqv_out, int B, int T, int heads, int d, int dtype, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(x && wkqv && out && scores && kqv_out, "rf_attn_fwd_fused: null pointer");
+  int rc = check_shape("rf_attn_fwd_fused", B, T, heads, d);
+  if (rc) return rc;
+  MMVQA_REQUIRE(dtype == MMVQA_BF16, "rf_attn_fwd_fused: bf16 only (the fp32 path keeps the separate kqv GEMM)");
+  AttnLayout L = rf_layout(T, heads, d);
+  MMVQA_REQUIRE(tc_attention_ok(kqv_out, L, nullptr, T, heads, d) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wkqv)) & 15) == 0,
+                "rf_attn_fwd_fused: needs d %% 16 == 0, T <= 128 and 16-byte aligned operands");
+  const int Tp = (T + 15) & ~15, ldn = d + 8, ldt = Tp + 8;
+  const size_t smem = (size_t)(2 * Tp * ldn + d * ldt + Tp * ldn + 3 * d * ldn) * 2;
+  MMVQA_REQUIRE(smem <= 227 * 1024, "rf_attn_fwd_fused: T=%d d=%d needs %zu bytes of shared memory", T, d, smem);
+  const int nthr = 256;
+  cudaStream_t st = as_stream(stream);
+#define TC_FWDF(TPV)                                                                                                    \
+  do {                                                                                                                  \
+    auto k = attn_tc_fwd_kernel<true, TPV, true>;                                                                       \
+    if (smem > 48 * 1024) MMVQA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    MMVQA_CUDA(launch_pdl(k, dim3(B * heads), dim3(nthr), smem, st, (const bf16*)kqv_out, L, prev, mask, (bf16*)out, scores, \
+                          (bf16*)nullptr, T, heads, d, 0.0f, 0ull, (const bf16*)x, (const bf16*)wkqv));               \
+  } while (0)
+  if (Tp <= 32) TC_FWDF(32); else if (Tp <= 64) TC_FWDF(64); else if (Tp <= 96) TC_FWDF(96); else TC_FWDF(128);
+#undef TC_FWDF
+  MMVQA_LAUNCHED("rf_attn_fwd_fused");
+  return MMVQA_OK;
 }
 
 int mmvqa_rf_attn_bwd(const void* kqv, const float* scores, const void* dout, const float* dscores_in, void* dkqv,

@@ -87,15 +87,37 @@ __device__ __forceinline__ void zero_smem(void* base, int bytes) {
   for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) p[i] = z;
 }
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+// fire-and-forget copy of a global [rows, cols] bf16 tile (cols % 8 == 0) into a [rows][ld] smem tile: every thread
+// issues all of its 16-byte cp.async requests back to back, ONE memory latency for the whole tile
+__device__ __forceinline__ void stage_async(const bf16* __restrict__ src, int64_t row_stride, int rows, int cols, bf16* dst,
+                                            int ld) {
+  const int cpr = cols / 8, total = rows * cpr;
+  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
+    const int row = idx / cpr, ch = idx - row * cpr;
+    cp_async16(dst + row * ld + ch * 8, src + row * row_stride + ch * 8);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // forward.  TP = register-array bound on the padded sequence (32 / 64 / 96 / 128)
 // ---------------------------------------------------------------------------------------------------
-template <bool RF, int TP>
+// FUSED (RealFormer): the shared-weight kqv projection (realformer.py:13,33) runs inside this kernel --
+// kqv_bh = x[b, :, h d:(h+1) d] . Wkqv^T  ([T, d] x [d, 3d], mma.sync), written once to global memory for the backward
+// pass and straight into the Q / K / V^T shared-memory tiles; `qkv` is then the OUTPUT buffer and the separate
+// [M*heads, 3d] x [3d, d] GEMM launch disappears.  Wkqv (a weight) is requested before griddepcontrol.wait.
+template <bool RF, int TP, bool FUSED = false>
 __global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const bf16* __restrict__ qkv, AttnLayout L,
                                                           const float* __restrict__ prev, const float* __restrict__ mask,
                                                           bf16* __restrict__ out, float* __restrict__ scores,
                                                           bf16* __restrict__ probs, int Tn, int heads, int d, float drop_p,
-                                                          unsigned long long seed) {
+                                                          unsigned long long seed, const bf16* __restrict__ xin = nullptr,
+                                                          const bf16* __restrict__ wkqv = nullptr) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   constexpr int NT = TP / 8, KS = TP / 16;
   const int Tp = (Tn + 15) & ~15;            // rows / keys padded to the mma tile
@@ -107,14 +129,55 @@ __global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const bf16* __restrict
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const bf16* base = qkv + (int64_t)b * L.tok_batch + (int64_t)h * L.head_stride;
-  zero_smem(smem_attn, smem_bytes);
-  __syncthreads();
-  pdl_wait();
-  pdl_trigger();
-  stage_tile(base + L.q_off, L.row_stride, Tn, d, Qs, ldn, nullptr, 0);
-  stage_tile(base + L.k_off, L.row_stride, Tn, d, Ks, ldn, nullptr, 0);
-  stage_tile(base + L.v_off, L.row_stride, Tn, d, nullptr, 0, Vt, ldt);
-  __syncthreads();
+  if (FUSED) {
+    bf16* Xs = Vt + d * ldt;                         // [Tp][d+8]   this head's slice of the layer input
+    bf16* Ws = Xs + Tp * ldn;                        // [3d][d+8]   kqv weight, rows k | q | v
+    zero_smem(smem_attn, smem_bytes + Tp * ldn * 2);
+    __syncthreads();
+    stage_async(wkqv, d, 3 * d, d, Ws, ldn);         // weights do not depend on the previous kernel
+    pdl_wait();
+    pdl_trigger();
+    stage_async(xin + (int64_t)b * Tn * heads * d + (int64_t)h * d, (int64_t)heads * d, Tn, d, Xs, ldn);
+    cp_async_wait_all();
+    __syncthreads();
+    const int nwarps = blockDim.x >> 5, ntile_n = 3 * d / 8, npairs = (Tp / 16) * ntile_n;
+    bf16* kqv_out = const_cast<bf16*>(base);
+    for (int pi = warp; pi < npairs; pi += nwarps) {
+      const int sidx = pi / ntile_n, nt = pi - sidx * ntile_n;
+      float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      for (int kd = 0; kd < d / 16; ++kd) {
+        uint32_t a[4], bb[2];
+        load_a(a, Xs, ldn, sidx * 16, kd * 16, g, t);
+        load_b(bb, Ws, ldn, nt * 8, kd * 16, g, t);
+        mma_bf16_16816(c, a, bb);
+      }
+      const int rA = sidx * 16 + g, rB = rA + 8;
+      const int n = nt * 8 + 2 * t;                  // even: the pair (n, n+1) never straddles k | q | v (d % 8 == 0)
+      const int sec = n / d, cc = n - sec * d;
+      const uint32_t vA = pack2(c[0], c[1]), vB = pack2(c[2], c[3]);
+      if (sec == 2) {                                // V is consumed transposed
+        const __nv_bfloat162 pa = *reinterpret_cast<const __nv_bfloat162*>(&vA), pb = *reinterpret_cast<const __nv_bfloat162*>(&vB);
+        Vt[cc * ldt + rA] = pa.x; Vt[(cc + 1) * ldt + rA] = pa.y;
+        Vt[cc * ldt + rB] = pb.x; Vt[(cc + 1) * ldt + rB] = pb.y;
+      } else {
+        bf16* dst = (L.k_off == sec * d) ? Ks : Qs;  // section order in the packed row is given by the layout offsets
+        *reinterpret_cast<uint32_t*>(dst + rA * ldn + cc) = vA;
+        *reinterpret_cast<uint32_t*>(dst + rB * ldn + cc) = vB;
+      }
+      if (rA < Tn) *reinterpret_cast<uint32_t*>(kqv_out + (int64_t)rA * L.row_stride + n) = vA;
+      if (rB < Tn) *reinterpret_cast<uint32_t*>(kqv_out + (int64_t)rB * L.row_stride + n) = vB;
+    }
+    __syncthreads();
+  } else {
+    zero_smem(smem_attn, smem_bytes);
+    __syncthreads();
+    pdl_wait();
+    pdl_trigger();
+    stage_tile(base + L.q_off, L.row_stride, Tn, d, Qs, ldn, nullptr, 0);
+    stage_tile(base + L.k_off, L.row_stride, Tn, d, Ks, ldn, nullptr, 0);
+    stage_tile(base + L.v_off, L.row_stride, Tn, d, nullptr, 0, Vt, ldt);
+    __syncthreads();
+  }
   const int r0 = warp * 16;
   if (r0 >= Tp) return;
   const int nt_n = Tp / 8, ks_n = Tp / 16, kd_n = d / 16, nd_n = d / 8;

@@ -505,12 +505,16 @@ class VisTokAllFn(torch.autograd.Function):
         saved, metas = [None] * (3 * nlev), [None] * nlev
         keep = []
 
+        # operand casts of every level first, on the main stream: a cast issued next to another level's projector kernel
+        # waits for SM slots (67 us instead of 13 for the 112 x 112 level) and it heads the critical path
+        casted = [_pad_ld(f.detach().reshape(B * f.shape[1], f.shape[2] * f.shape[3]), dtype) for f in feats]
+
         def run(n):
             f, cw = feats[n], convs[n]
             _, Cc, Hh, Ww = f.shape
             HW = Hh * Ww
             w = weight_cache.get((cw,), dtype)
-            fb, ld = _pad_ld(f.detach().reshape(B * Cc, HW), dtype)
+            fb, ld = casted[n]
             need_bwd = ctx.needs_input_grad[3 + n] or ctx.needs_input_grad[3 + nlev + n]
             actp = torch.empty(B, hidden, ld, device=dev, dtype=dtype) if need_bwd else None
             ops.gemm(hidden, HW, Cc, w, Cc, False, fb, ld, True, None, 0, epilogue=EPI_ACT_ROWSUM, act=act, rowsum_out=vis[n],
@@ -733,15 +737,22 @@ class RealFormerEncoderFn(torch.autograd.Function):
         saved: List[Tensor] = []
         scores = prev
         parts = None
+        # the kqv projection rides inside the attention kernel on the tensor-core path (one launch less per layer)
+        fuse_kqv = (dt == torch.bfloat16 and d % 16 == 0 and T <= 128 and d <= 128 and
+                    (2 * ((T + 15) // 16 * 16) * (d + 8) + d * ((T + 15) // 16 * 16 + 8) + ((T + 15) // 16 * 16) * (d + 8)
+                     + 3 * d * (d + 8)) * 2 <= 200 * 1024 and _os.environ.get("MMVQA_NO_FUSED_KQV") is None)
         for l in range(n_layers):
             kqv_w, proj_w, g1, b1, w0, bb0, w2, bb2, g2, b2 = params[l * RF_PARAMS_PER_LAYER:(l + 1) * RF_PARAMS_PER_LAYER]
             wk = weight_cache.get((kqv_w,), dt)
             wp = weight_cache.get((proj_w,), dt)
             wf0 = weight_cache.get((w0,), dt)
             wf2 = weight_cache.get((w2,), dt)
-            kqv = torch.empty(M * heads, 3 * d, device=x.device, dtype=dt)
-            ops.gemm(M * heads, 3 * d, d, xin, d, False, wk, d, False, kqv, 3 * d, b_static=True)
-            attn, scores = ops.rf_attn_fwd(kqv, scores, maskf, B, T, heads, d)
+            if fuse_kqv:
+                attn, scores, kqv = ops.rf_attn_fwd_fused(xin, wk, scores, maskf, B, T, heads, d)
+            else:
+                kqv = torch.empty(M * heads, 3 * d, device=x.device, dtype=dt)
+                ops.gemm(M * heads, 3 * d, d, xin, d, False, wk, d, False, kqv, 3 * d, b_static=True)
+                attn, scores = ops.rf_attn_fwd(kqv, scores, maskf, B, T, heads, d)
             y1 = torch.empty(M, H, device=x.device, dtype=dt)
             ops.gemm(M, H, H, attn, H, False, wp, H, False, y1, H, epilogue=EPI_RESIDUAL, aux_in=xin, ld_aux_in=H,
                      dropout_p=p1, dropout_seed=seed + 2 * l, b_static=True)

@@ -229,6 +229,17 @@ def rf_attn_fwd(kqv: Tensor, prev: Optional[Tensor], mask: Optional[Tensor], B: 
     return out, scores
 
 
+def rf_attn_fwd_fused(x: Tensor, wkqv: Tensor, prev: Optional[Tensor], mask: Optional[Tensor], B: int, T: int, heads: int,
+                      d: int):
+    """kqv projection + residual attention in one launch (bf16): returns (out, scores, kqv)."""
+    out = torch.empty(B * T, heads * d, device=x.device, dtype=x.dtype)
+    scores = torch.empty(B, heads, T, T, device=x.device, dtype=torch.float32)
+    kqv = torch.empty(B * T * heads, 3 * d, device=x.device, dtype=x.dtype)
+    L.check(L.lib().mmvqa_rf_attn_fwd_fused(_p(x), _p(wkqv), _p(prev), _p(mask), _p(out), _p(scores), _p(kqv), B, T, heads, d,
+                                           dtype_code(x), _stream()), "rf_attn_fwd_fused")
+    return out, scores, kqv
+
+
 def rf_attn_bwd(kqv: Tensor, scores: Tensor, dout: Tensor, dscores_in: Optional[Tensor], want_dprev: bool, B: int, T: int,
                 heads: int, d: int):
     dkqv = torch.empty_like(kqv)

@@ -583,3 +583,34 @@ def test_jaccard_mask_against_golden_and_oracle(golden):
     assert torch.equal(build_mask(bsz, cap, aug, "supcon").cpu(), O.jaccard_mask(cap, aug, bsz))
     with pytest.raises(MMVQAError):
         jaccard_mask(cap, aug, device="cpu")
+
+
+# ------------------------------------------------------------------------------------------
+# RealFormer attention with the kqv projection inside the kernel == kqv GEMM + attention kernel
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,T,heads,d", [(3, 28, 8, 96), (2, 75, 8, 96), (2, 128, 2, 64), (2, 10, 8, 16)])
+def test_rf_attention_fused_kqv(B, T, heads, d):
+    bf = torch.bfloat16
+    H = heads * d
+    x = rnd(B * T, H, seed=70).to(bf).to(DEV)
+    w = (rnd(3 * d, d, seed=71) / math.sqrt(d)).to(bf).to(DEV)
+    prev = rnd(B, heads, T, T, seed=72).to(DEV)
+    mask = torch.ones(B, T, device=DEV)
+    mask[0, T - T // 3:] = 0
+    kqv_ref = torch.empty(B * T * heads, 3 * d, device=DEV, dtype=bf)
+    ops.gemm(B * T * heads, 3 * d, d, x, d, False, w, d, False, kqv_ref, 3 * d)
+    for pv in (prev, None):
+        out_ref, sc_ref = ops.rf_attn_fwd(kqv_ref, pv, mask, B, T, heads, d)
+        out, sc, kqv = ops.rf_attn_fwd_fused(x, w, pv, mask, B, T, heads, d)
+        close(kqv, kqv_ref, 2e-2, 2e-2, msg="kqv written by the fused kernel")      # bf16 rounding of two fp32 summation orders
+        close(sc, sc_ref, 2e-2, 6e-2, msg="scores")
+        close(out, out_ref, 3e-2, 3e-2, msg="attention output")
+        # against the fp64 reference arithmetic (realformer.py:33-44) on the bf16-rounded operands
+        kq = (x.double().view(B, T, heads, d) @ w.double().t()).view(B, T, heads, 3 * d)
+        k_, q_, v_ = kq[..., :d], kq[..., d:2 * d], kq[..., 2 * d:]
+        s_ = torch.einsum("bihd,bjhd->bhij", q_, k_) / math.sqrt(d)
+        if pv is not None:
+            s_ = s_ + pv.double()
+        s_ = s_ - 10000.0 * (1.0 - mask.double())[:, None, :, None]
+        o_ = torch.einsum("bhij,bjhd->bihd", torch.softmax(s_, -1), v_).reshape(B * T, H)
+        close(out, o_, 5e-2, 5e-2, msg="vs fp64")
