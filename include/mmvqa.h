@@ -204,6 +204,12 @@ int mmvqa_rf_attn_fwd_fused(const void* x, const void* wkqv, const float* prev, 
                             void* kqv_out, int B, int T, int heads, int d, int dtype, mmvqa_stream_t stream);
 int mmvqa_rf_attn_bwd(const void* kqv, const float* scores, const void* dout, const float* dscores_in, void* dkqv,
                       float* dprev, int B, int T, int heads, int d, int dtype, mmvqa_stream_t stream);
+/* Same backward with the input gradient of the kqv projection inside (bf16 path):
+ * dx [B*T, heads*d] = dkqv . wkqv + dres  (dres = gradient of the residual connection around the attention block, may be
+ * NULL).  dkqv is still written (the weight-gradient GEMM reads it).  Removes the dgrad GEMM launch from the chain. */
+int mmvqa_rf_attn_bwd_fused(const void* kqv, const float* scores, const void* dout, const float* dscores_in, void* dkqv,
+                            float* dprev, const void* wkqv, const void* dres, void* dx, int B, int T, int heads, int d,
+                            int dtype, mmvqa_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Input fusion and pooling

@@ -63,6 +63,7 @@ SIGNATURES = {
     "mmvqa_mhsa_bwd": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, f32, u64, i32, vp]),
     "mmvqa_rf_attn_fwd": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "mmvqa_rf_attn_fwd_fused": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "mmvqa_rf_attn_bwd_fused": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "mmvqa_rf_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "mmvqa_embed_ln_scatter_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32,
                                          f32, u64, i32, vp]),

@@ -403,7 +403,8 @@ static int launch_bwd(const void* qkv, const AttnLayout& L, const float* scores,
     auto k = attn_tc_bwd_kernel<RF, TPV>;                                                                               \
     if (smem_tc > 48 * 1024) MMVQA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc)); \
     MMVQA_CUDA(launch_pdl(k, dim3(B * heads), dim3(nthr), smem_tc, st, (const bf16*)qkv, L, scores, (const bf16*)probs,  \
-                          (const bf16*)dout, dscores_in, (bf16*)dqkv, dprev, Tn, heads, d, p, (unsigned long long)seed)); \
+                          (const bf16*)dout, dscores_in, (bf16*)dqkv, dprev, Tn, heads, d, p, (unsigned long long)seed, \
+                          (const bf16*)nullptr, (const bf16*)nullptr, (bf16*)nullptr));                                 \
   } while (0)
       if (Tp <= 32) TC_BWD(32); else if (Tp <= 64) TC_BWD(64); else if (Tp <= 96) TC_BWD(96); else TC_BWD(128);
 #undef TC_BWD
@@ -502,6 +503,36 @@ int mmvqa_rf_attn_bwd(const void* kqv, const float* scores, const void* dout, co
   if (dtype == MMVQA_F32) return launch_bwd<float, true>(kqv, L, scores, nullptr, dout, dscores_in, dkqv, dprev, B, T, heads, d, 0.f, 0, as_stream(stream));
   if (dtype == MMVQA_BF16) return launch_bwd<__nv_bfloat16, true>(kqv, L, scores, nullptr, dout, dscores_in, dkqv, dprev, B, T, heads, d, 0.f, 0, as_stream(stream));
   return set_err(MMVQA_ERR_ARG, "rf_attn_bwd: bad dtype %d", dtype);
+}
+
+// RealFormer attention backward with the kqv input gradient inside (bf16 tensor-core path only)
+int mmvqa_rf_attn_bwd_fused(const void* kqv, const float* scores, const void* dout, const float* dscores_in, void* dkqv,
+                            float* dprev, const void* wkqv, const void* dres, void* dx, int B, int T, int heads, int d,
+                            int dtype, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(kqv && scores && dout && dkqv && wkqv && dx, "rf_attn_bwd_fused: null pointer");
+  int rc = check_shape("rf_attn_bwd_fused", B, T, heads, d);
+  if (rc) return rc;
+  MMVQA_REQUIRE(dtype == MMVQA_BF16, "rf_attn_bwd_fused: bf16 only (the fp32 path keeps the separate dgrad GEMM)");
+  AttnLayout L = rf_layout(T, heads, d);
+  MMVQA_REQUIRE(tc_attention_ok(kqv, L, dout, T, heads, d) && (reinterpret_cast<uintptr_t>(dkqv) & 15) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(wkqv) | reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dres)) & 15) == 0,
+                "rf_attn_bwd_fused: needs d %% 16 == 0, T <= 128 and 16-byte aligned operands");
+  const int Tp = (T + 15) & ~15, ldn = d + 8, ldt = Tp + 8, ldg = 3 * d + 8;
+  const size_t smem = (size_t)(2 * Tp * ldn + 3 * d * ldt + 2 * Tp * ldt + Tp * ldg + 3 * d * ldn) * 2;
+  MMVQA_REQUIRE(smem <= 227 * 1024, "rf_attn_bwd_fused: T=%d d=%d needs %zu bytes of shared memory", T, d, smem);
+  cudaStream_t st = as_stream(stream);
+#define TC_BWDF(TPV)                                                                                                    \
+  do {                                                                                                                  \
+    auto k = attn_tc_bwd_kernel<true, TPV, true>;                                                                       \
+    if (smem > 48 * 1024) MMVQA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
+    MMVQA_CUDA(launch_pdl(k, dim3(B * heads), dim3(256), smem, st, (const bf16*)kqv, L, scores, (const bf16*)nullptr,    \
+                          (const bf16*)dout, dscores_in, (bf16*)dkqv, dprev, T, heads, d, 0.0f, 0ull, (const bf16*)wkqv, \
+                          (const bf16*)dres, (bf16*)dx));                                                               \
+  } while (0)
+  if (Tp <= 32) TC_BWDF(32); else if (Tp <= 64) TC_BWDF(64); else if (Tp <= 96) TC_BWDF(96); else TC_BWDF(128);
+#undef TC_BWDF
+  MMVQA_LAUNCHED("rf_attn_bwd_fused");
+  return MMVQA_OK;
 }
 
 int mmvqa_mhsa_fwd(const void* qkv, const float* mask, void* out, void* probs, int B, int T, int heads, int d,

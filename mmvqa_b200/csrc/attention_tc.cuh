@@ -87,6 +87,14 @@ __device__ __forceinline__ void zero_smem(void* base, int bytes) {
   for (int i = threadIdx.x; i < bytes / 16; i += blockDim.x) p[i] = z;
 }
 
+// B fragment (16 k x 8 n) of m16n8k16 from a ROW-MAJOR [k][n] bf16 tile (n contiguous): ldmatrix .trans hands every
+// thread (k = 2t, 2t+1 | n = g) of each 8x8 block -- exactly the col-major B layout, no transposed copy of the tile
+__device__ __forceinline__ void load_b_trans(uint32_t (&b)[2], const bf16* W, int ld, int k0, int n0, int lane) {
+  const bf16* row = W + (k0 + (lane & 15)) * ld + n0;        // lanes 0-7: rows k0..k0+7, lanes 8-15: rows k0+8..k0+15
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(row);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(b[0]), "=r"(b[1]) : "r"(addr));
+}
+
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
@@ -307,12 +315,18 @@ __global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const bf16* __restrict
 // ---------------------------------------------------------------------------------------------------
 // backward
 // ---------------------------------------------------------------------------------------------------
-template <bool RF, int TP>
+// FUSED (RealFormer): the input gradient of the shared-weight kqv projection is produced here as well --
+// dx[b, :, h d:(h+1) d] = dkqv_bh . Wkqv + dres  ([T, 3d] x [3d, d], mma.sync; dres = the residual gradient around the
+// attention block) -- so the [M*heads, 3d] x [3d, d] dgrad GEMM launch disappears from the backward chain.  dkqv is
+// still written to global memory: the weight-gradient GEMM on the side branch reads it.
+template <bool RF, int TP, bool FUSED = false>
 __global__ void __launch_bounds__(256) attn_tc_bwd_kernel(const bf16* __restrict__ qkv, AttnLayout L,
                                                           const float* __restrict__ scores, const bf16* __restrict__ probs,
                                                           const bf16* __restrict__ dout, const float* __restrict__ dscores_in,
                                                           bf16* __restrict__ dqkv, float* __restrict__ dprev, int Tn, int heads,
-                                                          int d, float drop_p, unsigned long long seed) {
+                                                          int d, float drop_p, unsigned long long seed,
+                                                          const bf16* __restrict__ wkqv = nullptr,
+                                                          const bf16* __restrict__ dres = nullptr, bf16* __restrict__ dx = nullptr) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   constexpr int NT = TP / 8, KS = TP / 16, ND = 16;
   const int Tp = (Tn + 15) & ~15;
@@ -324,7 +338,10 @@ __global__ void __launch_bounds__(256) attn_tc_bwd_kernel(const bf16* __restrict
   bf16* Qt = dOt + d * ldt;                          // [d][Tp+8]   B of dK = dS^T Q
   bf16* Pt = Qt + d * ldt;                           // [Tp][Tp+8]  P^T  (A of dV)
   bf16* dSt = Pt + Tp * ldt;                         // [Tp][Tp+8]  dS^T (A of dK)
-  const int smem_bytes = (2 * Tp * ldn + 3 * d * ldt + 2 * Tp * ldt) * 2;
+  const int ldg = 3 * d + 8;
+  bf16* Gs = dSt + Tp * ldt;                         // FUSED: [Tp][3d+8]  dkqv of this (batch, head), A of dx
+  bf16* Ws = Gs + Tp * ldg;                          // FUSED: [3d][d+8]   kqv weight, row-major [k][n]
+  const int smem_bytes = (2 * Tp * ldn + 3 * d * ldt + 2 * Tp * ldt + (FUSED ? Tp * ldg : 0)) * 2;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int H = heads * d;
@@ -333,6 +350,7 @@ __global__ void __launch_bounds__(256) attn_tc_bwd_kernel(const bf16* __restrict
   const int64_t sbase = ((int64_t)b * heads + h) * Tn * Tn;
   zero_smem(smem_attn, smem_bytes);
   __syncthreads();
+  if (FUSED) stage_async(wkqv, d, 3 * d, d, Ws, ldn);   // weights: in flight before the dependency wait, needed last
   pdl_wait();
   pdl_trigger();
   stage_tile(base + L.v_off, L.row_stride, Tn, d, Vs, ldn, nullptr, 0);
@@ -475,15 +493,20 @@ __global__ void __launch_bounds__(256) attn_tc_bwd_kernel(const bf16* __restrict
     for (int nd = 0; nd < ND; ++nd) {
       if (nd < nd_n) {
         const int sc = nd * 8 + 2 * t;
-        if (iA < Tn) *reinterpret_cast<uint32_t*>(dbase + L.q_off + (int64_t)iA * L.row_stride + sc) = pack2(dq[nd][0] * inv_sqrt_d, dq[nd][1] * inv_sqrt_d);
-        if (iB < Tn) *reinterpret_cast<uint32_t*>(dbase + L.q_off + (int64_t)iB * L.row_stride + sc) = pack2(dq[nd][2] * inv_sqrt_d, dq[nd][3] * inv_sqrt_d);
+        const uint32_t qa = pack2(dq[nd][0] * inv_sqrt_d, dq[nd][1] * inv_sqrt_d), qb = pack2(dq[nd][2] * inv_sqrt_d, dq[nd][3] * inv_sqrt_d);
+        if (iA < Tn) *reinterpret_cast<uint32_t*>(dbase + L.q_off + (int64_t)iA * L.row_stride + sc) = qa;
+        if (iB < Tn) *reinterpret_cast<uint32_t*>(dbase + L.q_off + (int64_t)iB * L.row_stride + sc) = qb;
+        if (FUSED) {   // rows >= Tn hold zeros (dS is zero there)
+          *reinterpret_cast<uint32_t*>(Gs + iA * ldg + L.q_off + sc) = qa;
+          *reinterpret_cast<uint32_t*>(Gs + iB * ldg + L.q_off + sc) = qb;
+        }
       }
     }
   }
   __syncthreads();
-  if (r0 >= Tp) return;
+  if (!FUSED && r0 >= Tp) return;
   // ---- phase 2: this warp now owns KEY rows j in [r0, r0+16): dV = P^T dO, dK = dS^T Q / sqrt(d)
-  {
+  if (r0 < Tp) {
     const int jA = r0 + g, jB = r0 + g + 8;
     float dv[ND][4], dk[ND][4];
 #pragma unroll
@@ -510,14 +533,52 @@ __global__ void __launch_bounds__(256) attn_tc_bwd_kernel(const bf16* __restrict
     for (int nd = 0; nd < ND; ++nd) {
       if (nd < nd_n) {
         const int sc = nd * 8 + 2 * t;
+        const uint32_t va = pack2(dv[nd][0], dv[nd][1]), vb = pack2(dv[nd][2], dv[nd][3]);
+        const uint32_t ka = pack2(dk[nd][0] * inv_sqrt_d, dk[nd][1] * inv_sqrt_d), kb = pack2(dk[nd][2] * inv_sqrt_d, dk[nd][3] * inv_sqrt_d);
         if (jA < Tn) {
-          *reinterpret_cast<uint32_t*>(dbase + L.v_off + (int64_t)jA * L.row_stride + sc) = pack2(dv[nd][0], dv[nd][1]);
-          *reinterpret_cast<uint32_t*>(dbase + L.k_off + (int64_t)jA * L.row_stride + sc) = pack2(dk[nd][0] * inv_sqrt_d, dk[nd][1] * inv_sqrt_d);
+          *reinterpret_cast<uint32_t*>(dbase + L.v_off + (int64_t)jA * L.row_stride + sc) = va;
+          *reinterpret_cast<uint32_t*>(dbase + L.k_off + (int64_t)jA * L.row_stride + sc) = ka;
         }
         if (jB < Tn) {
-          *reinterpret_cast<uint32_t*>(dbase + L.v_off + (int64_t)jB * L.row_stride + sc) = pack2(dv[nd][2], dv[nd][3]);
-          *reinterpret_cast<uint32_t*>(dbase + L.k_off + (int64_t)jB * L.row_stride + sc) = pack2(dk[nd][2] * inv_sqrt_d, dk[nd][3] * inv_sqrt_d);
+          *reinterpret_cast<uint32_t*>(dbase + L.v_off + (int64_t)jB * L.row_stride + sc) = vb;
+          *reinterpret_cast<uint32_t*>(dbase + L.k_off + (int64_t)jB * L.row_stride + sc) = kb;
         }
+        if (FUSED) {   // padded key rows: P^T / dS^T rows are zero there, so these are zeros
+          *reinterpret_cast<uint32_t*>(Gs + jA * ldg + L.v_off + sc) = va;
+          *reinterpret_cast<uint32_t*>(Gs + jB * ldg + L.v_off + sc) = vb;
+          *reinterpret_cast<uint32_t*>(Gs + jA * ldg + L.k_off + sc) = ka;
+          *reinterpret_cast<uint32_t*>(Gs + jB * ldg + L.k_off + sc) = kb;
+        }
+      }
+    }
+  }
+  if (FUSED) {
+    // ---- phase 3: dx = dkqv . Wkqv + dres over all warps; (16-row strip, 8-column tile) pairs round-robin
+    cp_async_wait_all();
+    __syncthreads();
+    const int nwarps = blockDim.x >> 5, ntile_n = d / 8, npairs = (Tp / 16) * ntile_n, kk_n = 3 * d / 16;
+    const int64_t xoff = (int64_t)b * Tn * H + (int64_t)h * d;
+    for (int pi = warp; pi < npairs; pi += nwarps) {
+      const int sidx = pi / ntile_n, nt = pi - sidx * ntile_n;
+      float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      for (int kk = 0; kk < kk_n; ++kk) {
+        uint32_t a[4], bb[2];
+        load_a(a, Gs, ldg, sidx * 16, kk * 16, g, t);
+        load_b_trans(bb, Ws, ldn, kk * 16, nt * 8, lane);
+        mma_bf16_16816(c, a, bb);
+      }
+      const int rA = sidx * 16 + g, rB = rA + 8, n = nt * 8 + 2 * t;
+      if (rA < Tn) {
+        const int64_t o = xoff + (int64_t)rA * H + n;
+        float r0_ = 0.0f, r1_ = 0.0f;
+        if (dres) { const __nv_bfloat162 rr = *reinterpret_cast<const __nv_bfloat162*>(dres + o); r0_ = __bfloat162float(rr.x); r1_ = __bfloat162float(rr.y); }
+        *reinterpret_cast<uint32_t*>(dx + o) = pack2(c[0] + r0_, c[1] + r1_);
+      }
+      if (rB < Tn) {
+        const int64_t o = xoff + (int64_t)rB * H + n;
+        float r0_ = 0.0f, r1_ = 0.0f;
+        if (dres) { const __nv_bfloat162 rr = *reinterpret_cast<const __nv_bfloat162*>(dres + o); r0_ = __bfloat162float(rr.x); r1_ = __bfloat162float(rr.y); }
+        *reinterpret_cast<uint32_t*>(dx + o) = pack2(c[2] + r0_, c[3] + r1_);
       }
     }
   }

@@ -806,6 +806,13 @@ class RealFormerEncoderFn(torch.autograd.Function):
         branch = SideBranch(saved[0].device)
         keep = []
         parts = None
+        Tp_ = (T + 15) // 16 * 16
+        fuse_kqv = (dt == torch.bfloat16 and d % 16 == 0 and T <= 128 and d <= 128 and
+                    (2 * Tp_ * (d + 8) + 3 * d * (Tp_ + 8) + 2 * Tp_ * (Tp_ + 8) + Tp_ * (3 * d + 8) + 3 * d * (d + 8)) * 2
+                    <= 200 * 1024 and _os.environ.get("MMVQA_FUSED_KQV_BWD") is not None)
+        # (opt-in: measured at B = 16, T = 28 the fused backward is 4 us per layer SLOWER than attention backward + the
+        # PDL-overlapped dgrad GEMM -- 120 KB of shared memory and a third serial phase on 128 CTAs; the forward fusion
+        # is the one that pays)
         sink = _GRAD_SINK
         for l in reversed(range(n_layers)):
             xin, kqv, scores, attn, y1, mean1, rstd1, x1, hpre, hact, y2, mean2, rstd2 = saved[l * nsave:(l + 1) * nsave]
@@ -854,14 +861,19 @@ class RealFormerEncoderFn(torch.autograd.Function):
                 dwp = gemm_wgrad(dpr, H, M, H, attn, H, H)
             dattn = gemm_dgrad(dpr, H, M, H, wp, H)
             want_dprev = (l > 0) or (has_prev and ctx.needs_input_grad[2])
-            dkqv, dprev = ops.rf_attn_bwd(kqv, scores, dattn, ds, want_dprev, B, T, heads, d)
+            if fuse_kqv:
+                # dx_in = dkqv . Wkqv (per head) + dy1 comes out of the attention backward kernel itself
+                dkqv, dprev, dxin = ops.rf_attn_bwd_fused(kqv, scores, dattn, ds, want_dprev, wk, dy1, B, T, heads, d)
+            else:
+                dkqv, dprev = ops.rf_attn_bwd(kqv, scores, dattn, ds, want_dprev, B, T, heads, d)
             with branch.after_now():
                 dwk = gemm_wgrad(dkqv, 3 * d, M * heads, 3 * d, xin, d, d, zeroed=zl[5 * H + F4:].view(3 * d, d))
             keep.append((dff, dhpre, dpr, dkqv, dy2, dy1))
-            # dx_in = dkqv . Wkqv (per head) + dy1 (residual around the attention block)
-            dxin = torch.empty(M, H, device=dx.device, dtype=dt)
-            ops.gemm(M * heads, d, 3 * d, dkqv, 3 * d, False, wk, d, True, dxin, d, epilogue=EPI_RESIDUAL, aux_in=dy1,
-                     ld_aux_in=d, b_static=True)
+            if not fuse_kqv:
+                # dx_in = dkqv . Wkqv (per head) + dy1 (residual around the attention block)
+                dxin = torch.empty(M, H, device=dx.device, dtype=dt)
+                ops.gemm(M * heads, d, 3 * d, dkqv, 3 * d, False, wk, d, True, dxin, d, epilogue=EPI_RESIDUAL, aux_in=dy1,
+                         ld_aux_in=d, b_static=True)
             base = l * RF_PARAMS_PER_LAYER
             gl = [dwk.view(kqv_w.shape), dwp.view(proj_w.shape), dg1, db1, dw0.view(w0.shape), dbb0, dw2.view(w2.shape), dbb2,
                   dg2, db2]

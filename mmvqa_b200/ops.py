@@ -249,6 +249,18 @@ def rf_attn_bwd(kqv: Tensor, scores: Tensor, dout: Tensor, dscores_in: Optional[
     return dkqv, dprev
 
 
+def rf_attn_bwd_fused(kqv: Tensor, scores: Tensor, dout: Tensor, dscores_in: Optional[Tensor], want_dprev: bool,
+                      wkqv: Tensor, dres: Optional[Tensor], B: int, T: int, heads: int, d: int):
+    """attention backward + input gradient of the kqv projection (bf16): returns (dkqv, dprev, dx) with
+    dx [B*T, heads*d] = dkqv . wkqv + dres."""
+    dkqv = torch.empty_like(kqv)
+    dprev = torch.empty_like(scores) if want_dprev else None
+    dx = torch.empty(B * T, heads * d, device=kqv.device, dtype=kqv.dtype)
+    L.check(L.lib().mmvqa_rf_attn_bwd_fused(_p(kqv), _p(scores), _p(dout), _p(dscores_in), _p(dkqv), _p(dprev), _p(wkqv),
+                                           _p(dres), _p(dx), B, T, heads, d, dtype_code(kqv), _stream()), "rf_attn_bwd_fused")
+    return dkqv, dprev, dx
+
+
 def mhsa_fwd(qkv: Tensor, mask: Optional[Tensor], B: int, T: int, heads: int, d: int, p: float, seed: int):
     out = torch.empty(B * T, heads * d, device=qkv.device, dtype=qkv.dtype)
     probs = torch.empty(B, heads, T, T, device=qkv.device, dtype=qkv.dtype)

@@ -614,3 +614,33 @@ def test_rf_attention_fused_kqv(B, T, heads, d):
         s_ = s_ - 10000.0 * (1.0 - mask.double())[:, None, :, None]
         o_ = torch.einsum("bhij,bjhd->bihd", torch.softmax(s_, -1), v_).reshape(B * T, H)
         close(out, o_, 5e-2, 5e-2, msg="vs fp64")
+
+
+@pytest.mark.parametrize("B,T,heads,d", [(3, 28, 8, 96), (2, 75, 8, 96), (2, 64, 4, 64), (2, 10, 8, 16)])
+def test_rf_attention_backward_fused_kqv_dgrad(B, T, heads, d):
+    """attention backward with dx = dkqv . Wkqv + dres inside == attention backward + the separate dgrad GEMM."""
+    bf = torch.bfloat16
+    H = heads * d
+    kqv = rnd(B * T * heads, 3 * d, seed=80).to(bf).to(DEV)
+    w = (rnd(3 * d, d, seed=81) / math.sqrt(d)).to(bf).to(DEV)
+    prev = rnd(B, heads, T, T, seed=82).to(DEV)
+    mask = torch.ones(B, T, device=DEV)
+    mask[0, T - T // 3:] = 0
+    dout = rnd(B * T, H, seed=83).to(bf).to(DEV)
+    dsc = (0.1 * rnd(B, heads, T, T, seed=84)).to(DEV)
+    dres = rnd(B * T, H, seed=85).to(bf).to(DEV)
+    _, scores = ops.rf_attn_fwd(kqv, prev, mask, B, T, heads, d)
+    for ds_in, res in ((dsc, dres), (None, None)):
+        dkqv_ref, dprev_ref = ops.rf_attn_bwd(kqv, scores, dout, ds_in, True, B, T, heads, d)
+        dx_ref = torch.empty(B * T, H, device=DEV, dtype=bf)
+        if res is not None:
+            ops.gemm(B * T * heads, d, 3 * d, dkqv_ref, 3 * d, False, w, d, True, dx_ref, d, epilogue=EPI_RESIDUAL, aux_in=res,
+                     ld_aux_in=d)
+        else:
+            ops.gemm(B * T * heads, d, 3 * d, dkqv_ref, 3 * d, False, w, d, True, dx_ref, d)
+        dkqv, dprev, dx = ops.rf_attn_bwd_fused(kqv, scores, dout, ds_in, True, w, res, B, T, heads, d)
+        assert torch.equal(dkqv, dkqv_ref) and torch.equal(dprev, dprev_ref)           # same code path for these two
+        scale = dx_ref.float().abs().max().item()
+        close(dx, dx_ref, 2e-2, 2e-2 * scale, msg="dx from the fused kernel")
+        dx64 = (dkqv_ref.double() @ w.double()).view(B * T, H) + (res.double() if res is not None else 0.0)
+        close(dx, dx64, 2e-2, 2e-2 * scale, msg="dx vs fp64")
