@@ -14,6 +14,7 @@ if torch.cuda.is_available():
     from mmvqa_b200.graph import GraphedTrainStep
     from mmvqa_b200.models.realformer import ResEncoderBlock, run_blocks
     from mmvqa_b200.optim import FusedAdam
+    from mmvqa_b200.parallel import LayerwiseReducer
 
 DEV = "cuda"
 
@@ -143,7 +144,10 @@ def test_overlapped_adam_equals_plain(graph):
             late = nn.Parameter(torch.ones(8, device=DEV))       # a parameter that is left to the ordinary step()
             params = list(blocks.parameters()) + list(head.parameters()) + [late]
             # `head` also goes early, through the post-accumulate hooks (early_groups) instead of the sink
-            opt = FusedAdam(params, lr=1e-3, overlap_backward=overlap, early_groups=[list(head.parameters())])
+            # overlapped run: also through the data-parallel reducer (world size 1: pack into the persistent bf16
+            # layer buckets on the communication stream, no collective) -- Adam then reads bf16 gradients
+            red = LayerwiseReducer(torch.bfloat16) if overlap else None
+            opt = FusedAdam(params, lr=1e-3, overlap_backward=overlap, early_groups=[list(head.parameters())], reduce_fn=red)
 
             def loss_fn(x):
                 h, _ = run_blocks(list(blocks), x, None, mask, False)
@@ -164,6 +168,8 @@ def test_overlapped_adam_equals_plain(graph):
                 torch.cuda.synchronize()
                 sd = opt.state_dict()
                 assert float(sd["state"][0]["step"]) == 3.0
+                if red is not None:
+                    assert len(red._buckets) == 3 + 1 + 1          # three layers, the hooked head, the rest
             finally:
                 opt.close()
             return [p.detach().clone() for p in params]
