@@ -269,7 +269,9 @@ def main_gpu(a):
     overlapped_dp = world > 1 and a.dp_mode == "overlapped"
     reducer = LayerwiseReducer(bucket_dt) if overlapped_dp else None
     opt = FusedAdam(params, lr=1e-5, overlap_backward=((world == 1 or overlapped_dp) and bool(a.overlap_adam)),
-                    reduce_fn=reducer, early_groups=[list(model.transformer.bert_embedding.parameters())])
+                    reduce_fn=reducer,
+                    early_groups=[list(model.transformer.bert_embedding.parameters()),
+                                  list(model.fc1.parameters()) + list(model.classifier.parameters())])
     crit = ASLSingleLabel()
     buckets = GradBuckets(params, dtype=bucket_dt) if (world > 1 and not overlapped_dp) else None
     if buckets is not None:
@@ -287,7 +289,7 @@ def main_gpu(a):
         feats, ids, seg, mask, target = synth_batch(B, 1000 * rank + i)
         host.append([t.pin_memory() for t in (*feats, ids, seg, mask, target)])
     dev = [[t.cuda() for t in hb] for hb in host]
-    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host[0])      # payload; the packed buffer adds < 2 KB of padding
 
     def step_kwargs():
         plist = [p for p in params if p.grad is not None]
@@ -306,26 +308,29 @@ def main_gpu(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # every batch in the graph's packed input layout: one copy per step refreshes all nine input tensors
+    dev_flat = [gs.pack_like(db, device=db[0].device)[0] for db in dev]
+    host_flat = [gs.pack_like(hb, pin_memory=True)[0] for hb in host]
     log("timing value")
     # ---- value: inputs resident in HBM ----
     for i in range(max(a.warmup, 3)):
-        gs.replay(*dev[i % NB])
+        gs.replay_packed(dev_flat[i % NB])
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         # pad the sampled window so nvidia-smi sees the load (untimed replays; the SAME count on every rank, the
         # step contains a collective), then the timed region
         for _ in range(a.pad_steps):
-            gs.replay(*dev[0])
+            gs.replay_packed(dev_flat[0])
         barrier()
         e0.record()
         for i in range(a.steps):
-            gs.replay(*dev[i % NB])
+            gs.replay_packed(dev_flat[i % NB])
         e1.record()
         barrier()
         ms_total = e0.elapsed_time(e1)
         for _ in range(a.pad_steps // 2):
-            gs.replay(*dev[0])
+            gs.replay_packed(dev_flat[0])
         torch.cuda.synchronize()
     loss_val = float(gs.static_loss)
     if world > 1:
@@ -342,15 +347,14 @@ def main_gpu(a):
     # D2H loss read of every step are inside the timed region.
     loss_host = torch.empty((), dtype=torch.float32).pin_memory()
     copy_stream = torch.cuda.Stream()
-    staging = [t.clone() for t in dev[0]]
+    staging = torch.empty_like(gs.static_flat)
     main = torch.cuda.current_stream()
     staged, consumed = torch.cuda.Event(), torch.cuda.Event()
 
     def prefetch(i):
         copy_stream.wait_event(consumed)                  # staging buffer free again
         with torch.cuda.stream(copy_stream):
-            for dst, src in zip(staging, host[i % NB]):
-                dst.copy_(src, non_blocking=True)
+            staging.copy_(host_flat[i % NB], non_blocking=True)      # ONE pinned-host -> device copy per step
             staged.record(copy_stream)
 
     def e2e_steps(n):
@@ -358,12 +362,11 @@ def main_gpu(a):
         prefetch(0)
         for i in range(n):
             main.wait_event(staged)
-            for dst, src in zip(gs.static_inputs, staging):
-                dst.copy_(src, non_blocking=True)
+            gs.static_flat.copy_(staging, non_blocking=True)
             consumed.record(main)
             if i + 1 < n:
                 prefetch(i + 1)
-            gs.replay(*gs.static_inputs)
+            gs.replay_packed(gs.static_flat)
             loss_host.copy_(gs.static_loss, non_blocking=True)
             main.synchronize()                            # the loss is read on the host every step
     e2e_steps(3)
