@@ -81,16 +81,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// same, and ties the 16 destination registers of an earlier tcgen05.ld to the wait: nothing that reads them can be
-// scheduled above it (needed when other work sits between the load and the wait)
-__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t* r) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-               :
-               : "memory");
-}
-
 // UMMA shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, version 1):
 //  [0,14) start >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 |
 //  [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)

@@ -65,18 +65,6 @@ class SideBranch:
             self.used = True
         return torch.cuda.stream(self.side)
 
-    def mark(self):
-        """remember this point of the main stream; `after_mark()` later forks from it (work enqueued on the main
-        stream in between is issued first but does not delay the branch)."""
-        self._mark = torch.cuda.Event()
-        self._mark.record(self.main)
-
-    def after_mark(self):
-        if self.side is not self.main:
-            self.side.wait_event(self._mark)
-            self.used = True
-        return torch.cuda.stream(self.side)
-
     def join(self):
         if self.used:
             ev = torch.cuda.Event()
@@ -541,7 +529,6 @@ class VisTokAllFn(torch.autograd.Function):
         dev = dvis.device
         dvs = dvis.contiguous().float()
         dfeats, dws = [None] * nlev, [None] * nlev
-        branch = SideBranch(dev)
         keep = []
 
         def run(n):
