@@ -23,7 +23,7 @@ class FusedAdam(torch.optim.Optimizer):
     The step counter lives on the device, so a captured CUDA graph of ``step()`` can be replayed."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, overlap_backward=False,
-                 reduce_fn=None, early_groups=None):
+                 reduce_fn=None, early_groups=None, sink_group: int = 1):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.grad_scale = 1.0
         self._tables = {}
@@ -46,6 +46,10 @@ class FusedAdam(torch.optim.Optimizer):
         self._group_of = {id(p): gi for gi, g in enumerate(self.param_groups) for p in g["params"]}
         self._comm_stream = None
         self._hook_groups = []
+        # sink_group: how many consecutive gradient-sink calls (layers) share one exchange + one update launch.  With a
+        # reduce_fn, fewer and larger all-reduces use the links better and occupy the SMs for less time in total.
+        self.sink_group = max(1, int(sink_group))
+        self._pending = []         # [(params, grads)] handed in by the sink, not launched yet
         if overlap_backward:
             Fn.set_grad_sink(self._sink)
             # early_groups: lists of ordinary parameters (e.g. the BertEmbeddings tables, whose gradients appear before
@@ -148,6 +152,31 @@ class FusedAdam(torch.optim.Optimizer):
                 (not from_hook and any(p.grad is not None for p in params)):
             return False            # unknown / shared / accumulating parameters: leave them to autograd + step()
         gi = gis.pop()
+        gs = [g.contiguous() for g in grads]
+        for p, g in zip(params, gs):
+            if not from_hook:
+                p.grad = g          # visible to hooks / loggers exactly as after a normal backward
+            self._early_ids.add(id(p))
+        if from_hook or self.sink_group == 1:
+            self._flush_early(gi, list(params), gs, side_stream)
+        else:
+            self._pending.append((gi, list(params), gs))
+            if len(self._pending) >= self.sink_group:
+                self._flush_pending(side_stream)
+        return True
+
+    def _flush_pending(self, side_stream) -> None:
+        if not self._pending:
+            return
+        gi = self._pending[0][0]
+        params = [p for _, ps, _ in self._pending for p in ps]
+        grads = [g for _, _, gs in self._pending for g in gs]
+        self._pending = []
+        self._flush_early(gi, params, grads, side_stream)
+
+    def _flush_early(self, gi, params, gs, side_stream) -> None:
+        """exchange (reduce_fn, communication stream) + update (optimizer stream) of `params`, ordered after everything
+        enqueued so far on the current stream and on `side_stream`."""
         dev = params[0].device
         main = torch.cuda.current_stream(dev)
         if self._opt_stream is None:
@@ -162,7 +191,6 @@ class FusedAdam(torch.optim.Optimizer):
             ev2 = torch.cuda.Event()
             ev2.record(side_stream)
             first.wait_event(ev2)
-        gs = [g.contiguous() for g in grads]
         gr = gs
         if self.reduce_fn is not None:
             with torch.cuda.stream(self._comm_stream):
@@ -171,13 +199,8 @@ class FusedAdam(torch.optim.Optimizer):
             ev3.record(self._comm_stream)
             self._opt_stream.wait_event(ev3)
         with torch.cuda.stream(self._opt_stream):
-            self._launch(gi, ("early", id(params[0])), list(params), gr, self.early_ctas)
-        for p, g in zip(params, gs):
-            if not from_hook:
-                p.grad = g          # visible to hooks / loggers exactly as after a normal backward
-            self._early_ids.add(id(p))
+            self._launch(gi, ("early", id(params[0]), len(params)), list(params), gr, self.early_ctas)
         self._early_keep.append(gs)
-        return True
 
     @torch.no_grad()
     def step(self, closure=None, grads=None):
@@ -189,6 +212,9 @@ class FusedAdam(torch.optim.Optimizer):
                 loss = closure()
         if grads is not None and self._early_ids:
             raise RuntimeError("FusedAdam: step(grads=...) cannot be combined with overlap_backward")
+        # layers still waiting for a full sink group (the backward node joined its side branch before returning, so
+        # the current stream already orders their weight gradients)
+        self._flush_pending(None)
         for gi, group in enumerate(self.param_groups):
             plist = [p for p in group["params"] if p.grad is not None and id(p) not in self._early_ids]
             if not plist:

@@ -128,8 +128,9 @@ def test_graph_replay_equals_eager(dt):
         Fn.invalidate_weight_cache()
 
 
+@pytest.mark.parametrize("group", [1, 2], ids=["per-layer", "two-layer-groups"])
 @pytest.mark.parametrize("graph", [False, True], ids=["eager", "graph"])
-def test_overlapped_adam_equals_plain(graph):
+def test_overlapped_adam_equals_plain(graph, group):
     """overlap_backward: every encoder layer is updated on the optimizer stream from inside the backward node; the
     result must be the update a plain step() after backward makes (same kernel, same gradients)."""
     with mmvqa_b200.compute_dtype_scope(torch.bfloat16):
@@ -147,7 +148,8 @@ def test_overlapped_adam_equals_plain(graph):
             # overlapped run: also through the data-parallel reducer (world size 1: pack into the persistent bf16
             # layer buckets on the communication stream, no collective) -- Adam then reads bf16 gradients
             red = LayerwiseReducer(torch.bfloat16) if overlap else None
-            opt = FusedAdam(params, lr=1e-3, overlap_backward=overlap, early_groups=[list(head.parameters())], reduce_fn=red)
+            opt = FusedAdam(params, lr=1e-3, overlap_backward=overlap, early_groups=[list(head.parameters())], reduce_fn=red,
+                            sink_group=group)
 
             def loss_fn(x):
                 h, _ = run_blocks(list(blocks), x, None, mask, False)
@@ -169,7 +171,8 @@ def test_overlapped_adam_equals_plain(graph):
                 sd = opt.state_dict()
                 assert float(sd["state"][0]["step"]) == 3.0
                 if red is not None:
-                    assert len(red._buckets) == 3 + 1 + 1          # three layers, the hooked head, the rest
+                    # three layers (or a two-layer group + one layer flushed by step()), the hooked head, the rest
+                    assert len(red._buckets) == (3 if group == 1 else 2) + 1 + 1
             finally:
                 opt.close()
             return [p.detach().clone() for p in params]
