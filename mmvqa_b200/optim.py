@@ -28,6 +28,7 @@ class FusedAdam(torch.optim.Optimizer):
         self.grad_scale = 1.0
         self._tables = {}
         self._keepalive = []       # pinned host tables referenced by memcpy nodes of captured graphs
+        self._eager_tables = {}    # last eagerly built table per key (kept until it is rebuilt)
         self._refreshed = {}       # group index -> ids of parameters whose bf16 cache copy the kernel rewrites
         self._step_dev = None
         # overlap_backward: layers whose backward node offers its gradients early (functional.set_grad_sink) are
@@ -124,7 +125,13 @@ class FusedAdam(torch.optim.Optimizer):
         dev.copy_(host, non_blocking=True)
         self._tables[gi] = (key, dev, len(rows))
         self._refreshed[gi] = refreshed
-        self._keepalive.append((host, dev))
+        # a table uploaded inside a CUDA-graph capture is referenced by the graph's memcpy node for as long as the graph
+        # lives; an eager rebuild (new gradient buffers) only has to outlive the launch that follows, so it replaces the
+        # previous eager table of the same key instead of accumulating
+        if torch.cuda.is_current_stream_capturing():
+            self._keepalive.append((host, dev))
+        else:
+            self._eager_tables[gi] = (host, dev)
         return dev, len(rows)
 
     def _advance(self, device):
