@@ -269,7 +269,7 @@ def main_gpu(a):
     overlapped_dp = world > 1 and a.dp_mode == "overlapped"
     reducer = LayerwiseReducer(bucket_dt) if overlapped_dp else None
     opt = FusedAdam(params, lr=1e-5, overlap_backward=((world == 1 or overlapped_dp) and bool(a.overlap_adam)),
-                    reduce_fn=reducer, sink_group=(a.sink_group if overlapped_dp else 1),
+                    reduce_fn=reducer, sink_group=(a.sink_group if overlapped_dp else a.sink_group_1gpu),
                     early_groups=[list(model.transformer.bert_embedding.parameters()),
                                   list(model.fc1.parameters()) + list(model.classifier.parameters())])
     crit = ASLSingleLabel()
@@ -502,6 +502,7 @@ if __name__ == "__main__":
     ap.add_argument("--main-priority", type=int, default=-1, help="CUDA priority of the captured main stream (< 0 = above the side / optimizer streams)")
     ap.add_argument("--nccl-high-priority", type=int, default=0)
     ap.add_argument("--sink-group", type=int, default=4, help="data parallel: encoder layers per all-reduce + Adam launch")
+    ap.add_argument("--sink-group-1gpu", type=int, default=1, help="single GPU: encoder layers per Adam launch")
     ap.add_argument("--dp-mode", default="overlapped", choices=["overlapped", "twograph"])
     ap.add_argument("--pad-steps", type=int, default=100, help="untimed steps around the timed region (clock sampling)")
     a = ap.parse_args()
