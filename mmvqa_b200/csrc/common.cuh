@@ -264,7 +264,9 @@ template <int ACT> __device__ __forceinline__ float dact_fast(float x) {
 // x = 6 to fp32 precision), so a cubic Hermite interpolant over 256 intervals of width 3/32 reproduces g to ~1e-6
 // and g' to ~1e-5 with ONE 128-bit shared-memory load and ~20 FMA-pipe instructions per element, no MUFU:
 //   serf(x) = x g(x),   serf'(x) = g(x) + x g'(x).
-// Entry i holds (g_i, h g'_i, g_{i+1}, h g'_{i+1}); the nodes are evaluated with the accurate libdevice functions by
+// Entry i holds the cubic of interval i in the local variable t = (x - x_i) / h:  g = c0 + t (c1 + t (c2 + t c3)) with
+// c0 = g_i, c1 = h g'_i, c2 = 3 (g_{i+1} - g_i) - 2 h g'_i - h g'_{i+1}, c3 = h g'_i + h g'_{i+1} - 2 (g_{i+1} - g_i)
+// (the Hermite interpolant, expanded once at fill time so the lookup is three FMAs); the nodes are evaluated with the accurate libdevice functions by
 // the CTA itself in its prologue (no host-side state, valid inside CUDA-graph capture).
 // The table is stored 8 times, replica k in the k-th 16-byte bank group: entry (i, k) sits at float4 index 8 i + k and
 // lane l reads replica l & 7, so the 8 lanes of every quarter-warp phase of the 128-bit load hit 8 different bank
@@ -292,7 +294,8 @@ __device__ __forceinline__ void serf_table_fill(float4* tab, int tid, int nthrea
     float g0, m0, g1, m1;
     serf_node(i, g0, m0);
     serf_node(i + 1, g1, m1);
-    const float4 e = make_float4(g0, m0, g1, m1);
+    const float dl = g1 - g0;
+    const float4 e = make_float4(g0, m0, 3.0f * dl - 2.0f * m0 - m1, m0 + m1 - 2.0f * dl);
 #pragma unroll
     for (int k = 0; k < REP; ++k) tab[i * REP + k] = e;
   }
@@ -304,11 +307,8 @@ __device__ __forceinline__ void serf_both_tab(const float4* tab, float x, float&
   const int i = (int)u;
   const float t = u - (float)i;
   const float4 e = tab[i * REP + (threadIdx.x & (REP - 1))];
-  const float dl = e.z - e.x;
-  const float c2 = fmaf(3.0f, dl, fmaf(-2.0f, e.y, -e.w));
-  const float c3 = fmaf(-2.0f, dl, e.y + e.w);
-  const float g = fmaf(t, fmaf(t, fmaf(t, c3, c2), e.y), e.x);
-  const float gp = fmaf(t, fmaf(3.0f * t, c3, 2.0f * c2), e.y) * SERF_TAB_INV_H;
+  const float g = fmaf(t, fmaf(t, fmaf(t, e.w, e.z), e.y), e.x);
+  const float gp = fmaf(t, fmaf(3.0f * t, e.w, e.z + e.z), e.y) * SERF_TAB_INV_H;
   a = x * g;
   d = fmaf(x, gp, g);
 }
@@ -318,10 +318,7 @@ __device__ __forceinline__ float serf_tab(const float4* tab, float x) {
   const int i = (int)u;
   const float t = u - (float)i;
   const float4 e = tab[i * REP + (threadIdx.x & (REP - 1))];
-  const float dl = e.z - e.x;
-  const float c2 = fmaf(3.0f, dl, fmaf(-2.0f, e.y, -e.w));
-  const float c3 = fmaf(-2.0f, dl, e.y + e.w);
-  return x * fmaf(t, fmaf(t, fmaf(t, c3, c2), e.y), e.x);
+  return x * fmaf(t, fmaf(t, fmaf(t, e.w, e.z), e.y), e.x);
 }
 template <int REP>
 __device__ __forceinline__ float dserf_tab(const float4* tab, float x) {
