@@ -151,3 +151,51 @@ def test_shim_aliases_reference_import_paths():
     finally:
         shim.uninstall()
         sys.modules.update(saved)
+
+
+def test_serf_hermite_table_accuracy():
+    """The projector kernel evaluates SERF / SERF' from a cubic table of g(x) = erf(softplus(x)) (csrc/common.cuh).
+    This replays the table construction and the lookup in numpy float32 -- same constants (parsed from the header), same
+    formulas -- and checks them against the reference definition models/serf.py:23-24 in float64, including the
+    saturated tails (x < -18: 0, x > 6: slope exactly 1, as the reference's clamp gives for x > 50)."""
+    import math
+    import re
+
+    import numpy as np
+    src = open(os.path.join(ROOT, "mmvqa_b200", "csrc", "common.cuh")).read()
+    N = int(re.search(r"SERF_TAB_N = (\d+);", src).group(1))
+    X0 = np.float32(re.search(r"SERF_TAB_X0 = (-?[\d.]+)f;", src).group(1))
+    H = np.float32(re.search(r"SERF_TAB_H = ([\d.]+)f;", src).group(1))
+    assert abs(float(X0) + N * float(H) - 6.0) < 1e-6
+
+    def erf64(v):
+        return np.vectorize(math.erf)(v)
+
+    def node(i):
+        if i <= 0:
+            return np.float32(0), np.float32(0)
+        if i >= N:
+            return np.float32(1), np.float32(0)
+        x = np.float64(X0 + H * np.float32(i))
+        sp = np.log1p(np.exp(x))
+        return np.float32(math.erf(sp)), np.float32(float(H) * 1.1283791670955126 * np.exp(-sp * sp) / (1.0 + np.exp(-x)))
+    tab = np.zeros((N, 4), np.float32)
+    for i in range(N):
+        (g0, m0), (g1, m1) = node(i), node(i + 1)
+        dl = np.float32(g1 - g0)
+        tab[i] = [g0, m0, np.float32(3) * dl - np.float32(2) * m0 - m1, m0 + m1 - np.float32(2) * dl]
+    x = np.concatenate([np.linspace(-40, 70, 400001), [-18.0, 6.0, 0.0, 50.0, 50.5]]).astype(np.float32)
+    u = np.clip((x - X0) * np.float32(1.0 / H), 0, N - 0.001).astype(np.float32)
+    i = u.astype(np.int32)
+    t = (u - i).astype(np.float32)
+    e = tab[i]
+    g = e[:, 0] + t * (e[:, 1] + t * (e[:, 2] + t * e[:, 3]))
+    gp = (e[:, 1] + t * (2 * e[:, 2] + 3 * t * e[:, 3])) / H
+    a, d = x * g, g + x * gp
+    xd = x.astype(np.float64)
+    sp = np.log1p(np.exp(np.minimum(xd, 50.0)))
+    a_ref = xd * erf64(sp)
+    d_ref = np.where(xd > 50.0, erf64(sp), erf64(sp) + xd * 1.1283791670955126 * np.exp(-sp * sp) / (1.0 + np.exp(-xd)))
+    assert np.abs(a - a_ref).max() < 2e-6, np.abs(a - a_ref).max()
+    assert np.abs(d - d_ref).max() < 1e-5, np.abs(d - d_ref).max()
+    assert np.all(a[x > 6.0] == x[x > 6.0]) and np.all(d[x > 6.5] == 1.0)      # SERF(x) = x, SERF'(x) = 1 in the saturated tail
