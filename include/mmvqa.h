@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MMVQA_ABI_VERSION 2
+#define MMVQA_ABI_VERSION 3
 
 enum { MMVQA_F32 = 0, MMVQA_BF16 = 1 };
 enum { MMVQA_ACT_NONE = 0, MMVQA_ACT_SERF = 1, MMVQA_ACT_GELU = 2, MMVQA_ACT_RELU = 3 };
@@ -51,6 +51,12 @@ const char* mmvqa_last_error(void);
 int mmvqa_device_sm(void);
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t mmvqa_launch_count(void);
+/* Dropout under CUDA-graph replay.  nn.Dropout (models/realformer.py:22-26,44, transformer.py:26,45,58, BertEmbeddings)
+ * draws a new mask on every call; a captured graph would freeze the by-value seeds.  When `counter` (a DEVICE uint64,
+ * NULL = off) is registered, every kernel launched afterwards that draws a dropout mask uses
+ * seed + *counter * 0x9E3779B97F4A7C15 instead of seed, read on the device at run time; the graph itself increments
+ * the counter once per replay, so forward and backward of one replay agree and consecutive replays differ. */
+int mmvqa_set_dropout_counter(const uint64_t* counter);
 
 /* ------------------------------------------------------------------------------------
  * Caption-similarity mask.  replaces SimilarityCalculator.jaccard /
@@ -275,6 +281,12 @@ typedef struct mmvqa_adam_desc {
 int mmvqa_adam_step(const mmvqa_adam_desc* table, int n_chunks, float lr, float beta1, float beta2, float eps,
                     float weight_decay, int step, const int* step_dev, float grad_scale, int max_ctas,
                     mmvqa_stream_t stream);
+/* Same update with the two values a training loop changes between steps read from DEVICE memory:
+ * hyper_dev[0] = lr (ReduceLROnPlateau, vqamed2019/train.py:161,233; pretrain/roco_train.py:91,162),
+ * hyper_dev[1] = grad_scale.  A captured graph of this launch follows scheduler.step() as long as the caller refreshes
+ * the two floats before the replay. */
+int mmvqa_adam_step_dev(const mmvqa_adam_desc* table, int n_chunks, const float* hyper_dev, float beta1, float beta2,
+                        float eps, float weight_decay, const int* step_dev, int max_ctas, mmvqa_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libmmvqa_sm100.so")
 F32, BF16 = 0, 1
 ACT_NONE, ACT_SERF, ACT_GELU, ACT_RELU = 0, 1, 2, 3
 EPI_STORE, EPI_ACT, EPI_RESIDUAL, EPI_DACT, EPI_ACT_ROWSUM, EPI_DACT_SCALE = range(6)
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 vp, i64, i32, f32, u64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64
 
@@ -47,6 +47,7 @@ SIGNATURES = {
     "mmvqa_last_error": (C.c_char_p, []),
     "mmvqa_device_sm": (i32, []),
     "mmvqa_launch_count": (i64, []),
+    "mmvqa_set_dropout_counter": (i32, [vp]),
     "mmvqa_gemm": (i32, [C.POINTER(GemmArgs), vp]),
     "mmvqa_bias_act_fwd": (i32, [vp, vp, vp, i64, i32, i32, i32, vp]),
     "mmvqa_bias_act_bwd": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, vp]),
@@ -78,6 +79,7 @@ SIGNATURES = {
     "mmvqa_supcon_rows": (i32, [vp, vp, vp, vp, i32, i32, i32, i32, f32, f32, vp]),
     "mmvqa_jaccard_mask": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "mmvqa_adam_step": (i32, [C.POINTER(AdamDesc), i32, f32, f32, f32, f32, f32, i32, vp, f32, i32, vp]),
+    "mmvqa_adam_step_dev": (i32, [C.POINTER(AdamDesc), i32, vp, f32, f32, f32, f32, vp, i32, vp]),
 }
 
 _LIB = None
@@ -115,3 +117,9 @@ def check(rc: int, what: str = "") -> None:
 
 def launch_count() -> int:
     return int(lib().mmvqa_launch_count())
+
+
+def set_dropout_counter(counter) -> None:
+    """register (tensor) / clear (None) the device uint64 step counter mixed into every dropout seed of the kernels
+    launched from now on (CUDA-graph replay: mmvqa_b200.graph.GraphedTrainStep)."""
+    check(lib().mmvqa_set_dropout_counter(None if counter is None else counter.data_ptr()), "set_dropout_counter")

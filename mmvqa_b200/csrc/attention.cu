@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(1024) attn_fwd_kernel(const T* __restrict__ qk
                                                        const float* __restrict__ prev, const float* __restrict__ mask,
                                                        T* __restrict__ out, float* __restrict__ scores,
                                                        T* __restrict__ probs, int Tn, int heads, int d, float drop_p,
-                                                       unsigned long long seed, int vec) {
+                                                       unsigned long long seed, const unsigned long long* seed_ctr, int vec) {
   extern __shared__ float sm[];
   const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* Ks = sm;                       // [Tn][d+1]
@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(1024) attn_fwd_kernel(const T* __restrict__ qk
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const T* base = qkv + (int64_t)b * L.tok_batch + (int64_t)h * L.head_stride;
   pdl_wait();
+  if (drop_p > 0.0f) seed = seed_eff(seed, seed_ctr);
   pdl_trigger();
   {
     const TileSrc tiles[3] = {{base + L.k_off, L.row_stride, Ks, d + 1}, {base + L.q_off, L.row_stride, Qs, d},
@@ -199,7 +200,8 @@ __global__ void __launch_bounds__(1024) attn_bwd_kernel(const T* __restrict__ qk
                                                        const float* __restrict__ scores, const T* __restrict__ probs,
                                                        const T* __restrict__ dout, const float* __restrict__ dscores_in,
                                                        T* __restrict__ dqkv, float* __restrict__ dprev, int Tn, int heads,
-                                                       int d, float drop_p, unsigned long long seed, int vec, int resident) {
+                                                       int d, float drop_p, unsigned long long seed, const unsigned long long* seed_ctr, int vec,
+                                                       int resident) {
   extern __shared__ float sm[];
   const int nwarp = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float* X = sm;                        // [Tn][d+1]  V (then K, then Q when the tiles do not all fit)
@@ -214,6 +216,7 @@ __global__ void __launch_bounds__(1024) attn_bwd_kernel(const T* __restrict__ qk
   T* dbase = dqkv + (int64_t)b * L.tok_batch + (int64_t)h * L.head_stride;
   const int64_t sbase = ((int64_t)b * heads + h) * Tn * Tn;
   pdl_wait();
+  if (drop_p > 0.0f) seed = seed_eff(seed, seed_ctr);
   pdl_trigger();
   if (resident) {
     const TileSrc tiles[4] = {{base + L.v_off, L.row_stride, X, d + 1}, {dout + (int64_t)b * Tn * H + h * d, (int64_t)H, dO, d},
@@ -365,7 +368,7 @@ static int launch_fwd(const void* qkv, const AttnLayout& L, const float* prev, c
     auto k = attn_tc_fwd_kernel<RF, TPV>;                                                                               \
     if (smem_tc > 48 * 1024) MMVQA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc)); \
     MMVQA_CUDA(launch_pdl(k, dim3(B * heads), dim3(nthr), smem_tc, st, (const bf16*)qkv, L, prev, mask, (bf16*)out, scores, \
-                          (bf16*)probs, Tn, heads, d, p, (unsigned long long)seed, (const bf16*)nullptr,                \
+                          (bf16*)probs, Tn, heads, d, p, (unsigned long long)seed, g_seed_ctr, (const bf16*)nullptr,    \
                           (const bf16*)nullptr));                                                                       \
   } while (0)
       if (Tp <= 32) TC_FWD(32); else if (Tp <= 64) TC_FWD(64); else if (Tp <= 96) TC_FWD(96); else TC_FWD(128);
@@ -383,7 +386,7 @@ static int launch_fwd(const void* qkv, const AttnLayout& L, const float* prev, c
   const int vec = (d % vn == 0 && L.row_stride % vn == 0 && L.head_stride % vn == 0 && L.q_off % vn == 0 && L.k_off % vn == 0 &&
                    L.v_off % vn == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0) ? 1 : 0;
   MMVQA_CUDA(launch_pdl(kern, dim3(B * heads), dim3(nthreads), smem, st, (const T*)qkv, L, prev, mask, (T*)out, scores, (T*)probs, Tn, heads, d, p,
-                        (unsigned long long)seed, vec));
+                        (unsigned long long)seed, g_seed_ctr, vec));
   MMVQA_LAUNCHED("attn_fwd");
   return MMVQA_OK;
 }
@@ -404,7 +407,7 @@ static int launch_bwd(const void* qkv, const AttnLayout& L, const float* scores,
     if (smem_tc > 48 * 1024) MMVQA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc)); \
     MMVQA_CUDA(launch_pdl(k, dim3(B * heads), dim3(nthr), smem_tc, st, (const bf16*)qkv, L, scores, (const bf16*)probs,  \
                           (const bf16*)dout, dscores_in, (bf16*)dqkv, dprev, Tn, heads, d, p, (unsigned long long)seed, \
-                          (const bf16*)nullptr, (const bf16*)nullptr, (bf16*)nullptr));                                 \
+                          g_seed_ctr, (const bf16*)nullptr, (const bf16*)nullptr, (bf16*)nullptr));                     \
   } while (0)
       if (Tp <= 32) TC_BWD(32); else if (Tp <= 64) TC_BWD(64); else if (Tp <= 96) TC_BWD(96); else TC_BWD(128);
 #undef TC_BWD
@@ -426,7 +429,7 @@ static int launch_bwd(const void* qkv, const AttnLayout& L, const float* scores,
                    (reinterpret_cast<uintptr_t>(dout) & 15) == 0) ? 1 : 0;
   const int nthreads = 32 * (Tn < 8 ? 8 : (Tn > 32 ? 32 : Tn));
   MMVQA_CUDA(launch_pdl(kern, dim3(B * heads), dim3(nthreads), smem, st, (const T*)qkv, L, scores, (const T*)probs, (const T*)dout,
-                        dscores_in, (T*)dqkv, dprev, Tn, heads, d, p, (unsigned long long)seed, vec, resident));
+                        dscores_in, (T*)dqkv, dprev, Tn, heads, d, p, (unsigned long long)seed, g_seed_ctr, vec, resident));
   MMVQA_LAUNCHED("attn_bwd");
   return MMVQA_OK;
 }
@@ -486,7 +489,7 @@ int mmvqa_rf_attn_fwd_fused(const void* x, const void* wkqv, const float* prev, 
     auto k = attn_tc_fwd_kernel<true, TPV, true>;                                                                       \
     if (smem > 48 * 1024) MMVQA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
     MMVQA_CUDA(launch_pdl(k, dim3(B * heads), dim3(nthr), smem, st, (const bf16*)kqv_out, L, prev, mask, (bf16*)out, scores, \
-                          (bf16*)nullptr, T, heads, d, 0.0f, 0ull, (const bf16*)x, (const bf16*)wkqv));               \
+                          (bf16*)nullptr, T, heads, d, 0.0f, 0ull, g_seed_ctr, (const bf16*)x, (const bf16*)wkqv));   \
   } while (0)
   if (Tp <= 32) TC_FWDF(32); else if (Tp <= 64) TC_FWDF(64); else if (Tp <= 96) TC_FWDF(96); else TC_FWDF(128);
 #undef TC_FWDF
@@ -526,8 +529,8 @@ int mmvqa_rf_attn_bwd_fused(const void* kqv, const float* scores, const void* do
     auto k = attn_tc_bwd_kernel<true, TPV, true>;                                                                       \
     if (smem > 48 * 1024) MMVQA_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   \
     MMVQA_CUDA(launch_pdl(k, dim3(B * heads), dim3(256), smem, st, (const bf16*)kqv, L, scores, (const bf16*)nullptr,    \
-                          (const bf16*)dout, dscores_in, (bf16*)dkqv, dprev, T, heads, d, 0.0f, 0ull, (const bf16*)wkqv, \
-                          (const bf16*)dres, (bf16*)dx));                                                               \
+                          (const bf16*)dout, dscores_in, (bf16*)dkqv, dprev, T, heads, d, 0.0f, 0ull, g_seed_ctr,       \
+                          (const bf16*)wkqv, (const bf16*)dres, (bf16*)dx));                                            \
   } while (0)
   if (Tp <= 32) TC_BWDF(32); else if (Tp <= 64) TC_BWDF(64); else if (Tp <= 96) TC_BWDF(96); else TC_BWDF(128);
 #undef TC_BWDF

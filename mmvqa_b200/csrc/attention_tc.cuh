@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const bf16* __restrict
                                                           const float* __restrict__ prev, const float* __restrict__ mask,
                                                           bf16* __restrict__ out, float* __restrict__ scores,
                                                           bf16* __restrict__ probs, int Tn, int heads, int d, float drop_p,
-                                                          unsigned long long seed, const bf16* __restrict__ xin = nullptr,
+                                                          unsigned long long seed, const unsigned long long* seed_ctr,
+                                                          const bf16* __restrict__ xin = nullptr,
                                                           const bf16* __restrict__ wkqv = nullptr) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
   constexpr int NT = TP / 8, KS = TP / 16;
@@ -263,6 +264,7 @@ __global__ void __launch_bounds__(256) attn_tc_fwd_kernel(const bf16* __restrict
   const float invA = sumA > 0.0f ? 1.0f / sumA : 0.0f, invB = sumB > 0.0f ? 1.0f / sumB : 0.0f;
   const uint32_t thr = (uint32_t)(drop_p * 4294967296.0);
   const float inv_keep = drop_p > 0.0f ? 1.0f / (1.0f - drop_p) : 1.0f;
+  if (!RF && drop_p > 0.0f) seed = seed_eff(seed, seed_ctr);
 #pragma unroll
   for (int nt = 0; nt < NT; ++nt) {
     if (nt < nt_n) {
@@ -325,6 +327,7 @@ __global__ void __launch_bounds__(256) attn_tc_bwd_kernel(const bf16* __restrict
                                                           const bf16* __restrict__ dout, const float* __restrict__ dscores_in,
                                                           bf16* __restrict__ dqkv, float* __restrict__ dprev, int Tn, int heads,
                                                           int d, float drop_p, unsigned long long seed,
+                                                          const unsigned long long* seed_ctr,
                                                           const bf16* __restrict__ wkqv = nullptr,
                                                           const bf16* __restrict__ dres = nullptr, bf16* __restrict__ dx = nullptr) {
   extern __shared__ __align__(16) uint8_t smem_attn[];
@@ -353,6 +356,7 @@ __global__ void __launch_bounds__(256) attn_tc_bwd_kernel(const bf16* __restrict
   if (FUSED) stage_async(wkqv, d, 3 * d, d, Ws, ldn);   // weights: in flight before the dependency wait, needed last
   pdl_wait();
   pdl_trigger();
+  if (!RF && drop_p > 0.0f) seed = seed_eff(seed, seed_ctr);
   stage_tile(base + L.v_off, L.row_stride, Tn, d, Vs, ldn, nullptr, 0);
   stage_tile(dout + (int64_t)b * Tn * H + h * d, (int64_t)H, Tn, d, dOs, ldn, dOt, ldt);
   stage_tile(base + L.k_off, L.row_stride, Tn, d, nullptr, 0, Kt, ldt);

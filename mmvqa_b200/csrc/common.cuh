@@ -11,6 +11,9 @@ namespace mmvqa {
 
 extern thread_local char g_err[512];
 extern std::atomic<int64_t> g_launches;
+// device-resident dropout step counter (mmvqa_set_dropout_counter): every kernel that draws a dropout mask mixes
+// *g_seed_ctr into its seed, so a CUDA graph that increments the counter gets fresh masks on every replay
+extern const unsigned long long* g_seed_ctr;
 
 int set_err(int code, const char* fmt, ...);
 
@@ -362,6 +365,10 @@ __device__ __forceinline__ float block_max(float v, float* red) {
   return t;
 }
 
+// effective dropout seed: host seed + device step counter (NULL = eager mode, the host draws a new seed per call)
+__device__ __forceinline__ unsigned long long seed_eff(unsigned long long seed, const unsigned long long* ctr) {
+  return ctr ? seed + (*ctr) * 0x9E3779B97F4A7C15ull : seed;
+}
 // counter-based dropout keep decision (one 32-bit hash per element); identical in fwd and bwd
 __device__ __forceinline__ uint32_t hash32(uint64_t seed, uint64_t idx) {
   uint64_t z = idx + seed * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull;

@@ -9,6 +9,7 @@ namespace mmvqa {
 
 thread_local char g_err[512] = {0};
 std::atomic<int64_t> g_launches{0};
+const unsigned long long* g_seed_ctr = nullptr;
 
 int set_err(int code, const char* fmt, ...) {
   va_list ap;
@@ -166,7 +167,8 @@ __global__ void __launch_bounds__(256) scale_kernel(T* __restrict__ x, const flo
 // y = x * keep / (1-p), keep from the counter hash of (seed, element index)
 template <typename T>
 __global__ void __launch_bounds__(256) dropout_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, float p,
-                                                      uint64_t seed) {
+                                                      uint64_t seed, const unsigned long long* seed_ctr) {
+  seed = seed_eff(seed, seed_ctr);
   uint32_t thr = (uint32_t)(p * 4294967296.0);
   float inv = 1.0f / (1.0f - p);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -363,7 +365,8 @@ __global__ void __launch_bounds__(256) add_ln_fwd_parts(const float* __restrict_
                                                         const float* __restrict__ beta, T* __restrict__ y,
                                                         T* __restrict__ sum_out, float* __restrict__ mean_out,
                                                         float* __restrict__ rstd_out, int64_t rows, int cols, float eps,
-                                                        float p, unsigned long long seed) {
+                                                        float p, unsigned long long seed,
+                                                        const unsigned long long* seed_ctr) {
   constexpr int N = Vec16<T>::N;
   constexpr int ITER = LN_CACHE / N;
   const int lane = threadIdx.x & 31;
@@ -372,6 +375,7 @@ __global__ void __launch_bounds__(256) add_ln_fwd_parts(const float* __restrict_
   pdl_trigger();
   if (row >= rows) return;
   const bool drop = p > 0.0f;
+  if (drop) seed = seed_eff(seed, seed_ctr);
   const uint32_t thr = (uint32_t)(p * 4294967296.0);
   const float inv_keep = drop ? 1.0f / (1.0f - p) : 1.0f;
   const T* rr = res ? res + row * cols : nullptr;
@@ -491,6 +495,7 @@ struct LnBwdExtra {
   float* dxsum;             // optional: += column sums of dx_drop (or of dx when dx_drop == NULL)
   float p;
   unsigned long long seed;
+  const unsigned long long* seed_ctr;
   // optional (packed kernel only): the incoming gradient is sum_i dy_parts[i] (fp32 split-K slabs of the dgrad GEMM)
   // + dy (the residual branch, may be NULL), rounded to T -- exactly what a dgrad GEMM with a residual epilogue stores
   const float* dy_parts;
@@ -518,6 +523,7 @@ __global__ void __launch_bounds__(128) ln_bwd_packed(const T* __restrict__ dy, c
   T* dxd = reinterpret_cast<T*>(ex.dx_drop);
   const bool want_sum = ex.dxsum != nullptr;
   const bool drop = ex.p > 0.0f;
+  if (drop) ex.seed = seed_eff(ex.seed, ex.seed_ctr);
   const uint32_t thr = (uint32_t)(ex.p * 4294967296.0);
   const float inv_keep = drop ? 1.0f / (1.0f - ex.p) : 1.0f;
   for (int64_t row = blockIdx.x * (int64_t)nwarp + warp; row < rows; row += (int64_t)gridDim.x * nwarp) {
@@ -659,6 +665,7 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const T* __restrict__ dy, c
   T* dxd = reinterpret_cast<T*>(ex.dx_drop);
   const bool want_sum = ex.dxsum != nullptr;
   const bool drop = ex.p > 0.0f;
+  if (drop) ex.seed = seed_eff(ex.seed, ex.seed_ctr);
   const uint32_t thr = (uint32_t)(ex.p * 4294967296.0);
   const float inv_keep = drop ? 1.0f / (1.0f - ex.p) : 1.0f;
   for (int64_t row = blockIdx.x * (int64_t)nwarp + warp; row < rows; row += (int64_t)gridDim.x * nwarp) {
@@ -826,6 +833,10 @@ extern "C" {
 int mmvqa_abi_version(void) { return MMVQA_ABI_VERSION; }
 const char* mmvqa_last_error(void) { return g_err; }
 int64_t mmvqa_launch_count(void) { return g_launches.load(); }
+int mmvqa_set_dropout_counter(const uint64_t* counter) {
+  g_seed_ctr = reinterpret_cast<const unsigned long long*>(counter);
+  return MMVQA_OK;
+}
 
 int mmvqa_device_sm(void) {
   int dev = 0, major = 0, minor = 0;
@@ -953,9 +964,9 @@ int mmvqa_dropout(const void* x, void* y, int64_t n, float p, uint64_t seed, int
   int64_t maxg = (int64_t)num_sms() * 16;
   int grid = (int)((n + 255) / 256 < maxg ? (n + 255) / 256 : maxg);
   if (dtype == MMVQA_F32)
-    dropout_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)x, (float*)y, n, p, seed);
+    dropout_kernel<float><<<grid, 256, 0, as_stream(stream)>>>((const float*)x, (float*)y, n, p, seed, g_seed_ctr);
   else if (dtype == MMVQA_BF16)
-    dropout_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, p, seed);
+    dropout_kernel<__nv_bfloat16><<<grid, 256, 0, as_stream(stream)>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, p, seed, g_seed_ctr);
   else
     return set_err(MMVQA_ERR_ARG, "dropout: bad dtype %d", dtype);
   MMVQA_LAUNCHED("dropout");
@@ -1018,7 +1029,7 @@ static int layernorm_bwd_impl(const void* dy, const float* dy_parts, int nparts,
   size_t smem = sizeof(float) * 3 * (size_t)cols * (vec ? 4 : 1);     // vec path: one slab per warp
   MMVQA_REQUIRE(smem <= 48 * 1024, "layernorm_bwd: cols %d too large", cols);
   LnBwdExtra ex;
-  ex.dx_drop = dx_drop; ex.dxsum = dxsum; ex.p = dx_drop ? dropout_p : 0.0f; ex.seed = dropout_seed;
+  ex.dx_drop = dx_drop; ex.dxsum = dxsum; ex.p = dx_drop ? dropout_p : 0.0f; ex.seed = dropout_seed; ex.seed_ctr = g_seed_ctr;
   ex.dy_parts = dy_parts; ex.nparts = nparts; ex.part_stride = part_stride;
   // packed kernel: 4-warp CTAs (one row per warp) when the problem is small, 8-warp CTAs with a row loop otherwise
   if (vec && aligned16(gamma)) {
@@ -1098,11 +1109,11 @@ int mmvqa_add_layernorm_fwd_parts(const float* parts, int nparts, int64_t part_s
   if (dtype == MMVQA_F32)
     MMVQA_CUDA(launch_pdl(add_ln_fwd_parts<float>, grid, dim3(256), 0, st, parts, nparts, part_stride, (const float*)res, gamma,
                           beta, (float*)y, (float*)sum_out, mean, rstd, rows, cols, eps, dropout_p,
-                          (unsigned long long)dropout_seed));
+                          (unsigned long long)dropout_seed, g_seed_ctr));
   else
     MMVQA_CUDA(launch_pdl(add_ln_fwd_parts<__nv_bfloat16>, grid, dim3(256), 0, st, parts, nparts, part_stride,
                           (const __nv_bfloat16*)res, gamma, beta, (__nv_bfloat16*)y, (__nv_bfloat16*)sum_out, mean, rstd, rows,
-                          cols, eps, dropout_p, (unsigned long long)dropout_seed));
+                          cols, eps, dropout_p, (unsigned long long)dropout_seed, g_seed_ctr));
   MMVQA_LAUNCHED("add_layernorm_fwd_parts");
   return MMVQA_OK;
 }

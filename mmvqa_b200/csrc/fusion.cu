@@ -15,7 +15,9 @@ __global__ void __launch_bounds__(128) embed_fwd_kernel(const int64_t* __restric
                                                         const float* __restrict__ beta, const float* __restrict__ vis,
                                                         T* __restrict__ h, float* __restrict__ mean_out,
                                                         float* __restrict__ rstd_out, int B, int Tn, int H, int nvis,
-                                                        float eps, float drop_p, unsigned long long seed) {
+                                                        float eps, float drop_p, unsigned long long seed,
+                                                        const unsigned long long* seed_ctr) {
+  if (drop_p > 0.0f) seed = seed_eff(seed, seed_ctr);
   const int lane = threadIdx.x & 31;
   const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= (int64_t)B * Tn) return;
@@ -64,7 +66,9 @@ __global__ void __launch_bounds__(128) embed_bwd_kernel(const T* __restrict__ dh
                                                         float* __restrict__ dpos, float* __restrict__ dtyp,
                                                         float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                         float* __restrict__ dvis, int B, int Tn, int H, int nvis,
-                                                        int padding_idx, float drop_p, unsigned long long seed) {
+                                                        int padding_idx, float drop_p, unsigned long long seed,
+                                                        const unsigned long long* seed_ctr) {
+  if (drop_p > 0.0f) seed = seed_eff(seed, seed_ctr);
   extern __shared__ float sm[];  // [2][H] dgamma / dbeta block partials
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   for (int c = threadIdx.x; c < 2 * H; c += blockDim.x) sm[c] = 0.0f;
@@ -190,9 +194,9 @@ int mmvqa_embed_ln_scatter_fwd(const int64_t* ids, const int64_t* seg, const flo
   const int64_t rows = (int64_t)B * T;
   const int grid = (int)((rows + 3) / 4);
   if (dtype == MMVQA_F32)
-    embed_fwd_kernel<float><<<grid, 128, 0, as_stream(stream)>>>(ids, seg, word, pos, typ, gamma, beta, vis, (float*)h, mean, rstd, B, T, H, nvis, eps, dropout_p, dropout_seed);
+    embed_fwd_kernel<float><<<grid, 128, 0, as_stream(stream)>>>(ids, seg, word, pos, typ, gamma, beta, vis, (float*)h, mean, rstd, B, T, H, nvis, eps, dropout_p, dropout_seed, g_seed_ctr);
   else if (dtype == MMVQA_BF16)
-    embed_fwd_kernel<__nv_bfloat16><<<grid, 128, 0, as_stream(stream)>>>(ids, seg, word, pos, typ, gamma, beta, vis, (__nv_bfloat16*)h, mean, rstd, B, T, H, nvis, eps, dropout_p, dropout_seed);
+    embed_fwd_kernel<__nv_bfloat16><<<grid, 128, 0, as_stream(stream)>>>(ids, seg, word, pos, typ, gamma, beta, vis, (__nv_bfloat16*)h, mean, rstd, B, T, H, nvis, eps, dropout_p, dropout_seed, g_seed_ctr);
   else
     return set_err(MMVQA_ERR_ARG, "embed_fwd: bad dtype %d", dtype);
   MMVQA_LAUNCHED("embed_ln_scatter_fwd");
@@ -212,9 +216,9 @@ int mmvqa_embed_ln_scatter_bwd(const void* dh, const int64_t* ids, const int64_t
   const size_t smem = sizeof(float) * 2 * (size_t)H;
   MMVQA_REQUIRE(smem <= 48 * 1024, "embed_bwd: H %d too large", H);
   if (dtype == MMVQA_F32)
-    embed_bwd_kernel<float><<<grid, 128, smem, as_stream(stream)>>>((const float*)dh, ids, seg, word, pos, typ, gamma, mean, rstd, dword, dpos, dtyp, dgamma, dbeta, dvis, B, T, H, nvis, padding_idx, dropout_p, dropout_seed);
+    embed_bwd_kernel<float><<<grid, 128, smem, as_stream(stream)>>>((const float*)dh, ids, seg, word, pos, typ, gamma, mean, rstd, dword, dpos, dtyp, dgamma, dbeta, dvis, B, T, H, nvis, padding_idx, dropout_p, dropout_seed, g_seed_ctr);
   else if (dtype == MMVQA_BF16)
-    embed_bwd_kernel<__nv_bfloat16><<<grid, 128, smem, as_stream(stream)>>>((const __nv_bfloat16*)dh, ids, seg, word, pos, typ, gamma, mean, rstd, dword, dpos, dtyp, dgamma, dbeta, dvis, B, T, H, nvis, padding_idx, dropout_p, dropout_seed);
+    embed_bwd_kernel<__nv_bfloat16><<<grid, 128, smem, as_stream(stream)>>>((const __nv_bfloat16*)dh, ids, seg, word, pos, typ, gamma, mean, rstd, dword, dpos, dtyp, dgamma, dbeta, dvis, B, T, H, nvis, padding_idx, dropout_p, dropout_seed, g_seed_ctr);
   else
     return set_err(MMVQA_ERR_ARG, "embed_bwd: bad dtype %d", dtype);
   MMVQA_LAUNCHED("embed_ln_scatter_bwd");

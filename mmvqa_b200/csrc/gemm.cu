@@ -55,7 +55,7 @@ extern "C" int mmvqa_gemm(const mmvqa_gemm_args* a, mmvqa_stream_t stream) {
   ep.accumulate = a->accumulate; ep.split_k = split_k; ep.batch = batch;
   ep.c_batch_stride = a->c_batch_stride;
   ep.c_split_stride = (!a->accumulate && split_k > 1) ? a->c_split_stride : 0;
-  ep.dropout_p = a->dropout_p; ep.dropout_seed = a->dropout_seed;
+  ep.dropout_p = a->dropout_p; ep.dropout_seed = a->dropout_seed; ep.seed_ctr = g_seed_ctr;
   ep.trace = reinterpret_cast<unsigned long long*>(a->trace);
   if (a->dtype == MMVQA_F32) return gemm_simt_f32(&v, ep, as_stream(stream));
   int sm = mmvqa_device_sm();

@@ -15,7 +15,7 @@ struct EpiParams {
   int accumulate, split_k, batch;
   int64_t c_batch_stride;
   int64_t c_split_stride;
-  float dropout_p; unsigned long long dropout_seed;
+  float dropout_p; unsigned long long dropout_seed; const unsigned long long* seed_ctr;
   unsigned long long* trace;
 };
 
@@ -34,7 +34,7 @@ __device__ __forceinline__ float epi_element(const EpiParams& p, int bz, int m, 
     case MMVQA_EPI_RESIDUAL: {
       if (p.dropout_p > 0.0f) {
         uint32_t thr = (uint32_t)(p.dropout_p * 4294967296.0);
-        v = hash32(p.dropout_seed, (uint64_t)m * (uint64_t)p.N + (uint64_t)n) >= thr ? v / (1.0f - p.dropout_p) : 0.0f;
+        v = hash32(seed_eff(p.dropout_seed, p.seed_ctr), (uint64_t)m * (uint64_t)p.N + (uint64_t)n) >= thr ? v / (1.0f - p.dropout_p) : 0.0f;
       }
       out = v + to_f(reinterpret_cast<const AUX*>(p.aux_in)[(int64_t)m * p.ld_aux_in + n]);
       break;

@@ -210,6 +210,7 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_ro
   mbar_wait(tmem_full_bar, 0);
   tc_fence_after();
   if (threadIdx.x == 64) TC_TRACE(6);
+  const unsigned long long dseed = (EPI == MMVQA_EPI_RESIDUAL && p.dropout_p > 0.0f) ? seed_eff(p.dropout_seed, p.seed_ctr) : 0ull;
 #pragma unroll 1
   for (int ci = 0; ci < NCH; ++ci) {
     const int c = c_begin + ci * 16;
@@ -263,7 +264,7 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_ro
         if (p.dropout_p > 0.0f) {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            v[j] = hash32(p.dropout_seed, (uint64_t)m * (uint64_t)p.N + (uint64_t)(nb + j)) >= thr ? v[j] * inv_keep : 0.0f;
+            v[j] = hash32(dseed, (uint64_t)m * (uint64_t)p.N + (uint64_t)(nb + j)) >= thr ? v[j] * inv_keep : 0.0f;
         }
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] += a[j];

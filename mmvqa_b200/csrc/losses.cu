@@ -156,9 +156,15 @@ __device__ __forceinline__ void adam_one(float& p, float& m, float& v, float g, 
 
 __global__ void __launch_bounds__(256) adam_kernel(const mmvqa_adam_desc* __restrict__ table, float lr, float beta1,
                                                    float beta2, float eps, float wd, float bc1, float bc2_sqrt,
-                                                   float grad_scale, const int* __restrict__ step_dev, int n_chunks) {
+                                                   float grad_scale, const int* __restrict__ step_dev, int n_chunks,
+                                                   const float* __restrict__ hyper_dev) {
   pdl_wait();
-  pdl_trigger();
+  // (no early launch_dependents: this kernel rewrites the bf16 weight copies that a dependent GEMM launched with
+  // b_static = 1 would prefetch before its own griddepcontrol.wait; the implicit trigger at completion is the safe one)
+  if (hyper_dev) {   // lr / grad_scale refreshed by the host between graph replays
+    lr = hyper_dev[0];
+    grad_scale = hyper_dev[1];
+  }
   if (step_dev) {  // step counter lives on the device (CUDA-graph replay safe)
     const float t = (float)(*step_dev);
     bc1 = 1.0f - powf(beta1, t);
@@ -276,7 +282,18 @@ int mmvqa_adam_step(const mmvqa_adam_desc* table, int n_chunks, float lr, float 
   const float bc2 = 1.0f - powf(beta2, (float)step);
   const int grid = (max_ctas > 0 && max_ctas < n_chunks) ? max_ctas : n_chunks;
   MMVQA_CUDA(launch_pdl(adam_kernel, dim3(grid), dim3(256), 0, as_stream(stream), table, lr, beta1, beta2, eps, weight_decay, bc1,
-                        sqrtf(bc2), grad_scale, step_dev, n_chunks));
+                        sqrtf(bc2), grad_scale, step_dev, n_chunks, (const float*)nullptr));
+  MMVQA_LAUNCHED("adam_step");
+  return MMVQA_OK;
+}
+
+int mmvqa_adam_step_dev(const mmvqa_adam_desc* table, int n_chunks, const float* hyper_dev, float beta1, float beta2,
+                        float eps, float weight_decay, const int* step_dev, int max_ctas, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(table && n_chunks >= 0 && hyper_dev && step_dev, "adam_dev: bad args");
+  if (n_chunks == 0) return MMVQA_OK;
+  const int grid = (max_ctas > 0 && max_ctas < n_chunks) ? max_ctas : n_chunks;
+  MMVQA_CUDA(launch_pdl(adam_kernel, dim3(grid), dim3(256), 0, as_stream(stream), table, 0.0f, beta1, beta2, eps, weight_decay,
+                        1.0f, 1.0f, 1.0f, step_dev, n_chunks, hyper_dev));
   MMVQA_LAUNCHED("adam_step");
   return MMVQA_OK;
 }

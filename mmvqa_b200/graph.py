@@ -21,7 +21,14 @@ class GraphedTrainStep:
     the step is two graphs -- forward/backward/bucket-packing and the optimizer -- with the collective launched
     eagerly between the two replays, so no NCCL kernel is ever recorded into a graph.
     ``replay(*inputs)`` copies new inputs into the static buffers (device or pinned-host sources, non-blocking),
-    replays and returns the static loss tensor."""
+    replays and returns the static loss tensor.
+
+    What a replay must NOT freeze: (1) dropout masks -- the graph increments a device step counter that every dropout
+    kernel mixes into its seed (``mmvqa_set_dropout_counter``), so each replay draws new masks and forward / backward of
+    one replay agree; (2) ``lr`` / ``grad_scale`` -- ``FusedAdam`` reads them from device memory that
+    ``replay`` refreshes from ``param_groups`` first, so ``ReduceLROnPlateau.step()`` between replays takes effect
+    (vqamed2019/train.py:160-161).  ``close()`` drops the graphs (needed before an NCCL communicator they captured is
+    destroyed)."""
 
     def __init__(self, loss_fn: Callable, example_inputs: Sequence[torch.Tensor], optimizer, warmup: int = 3,
                  post_backward: Callable = None, eager_between: Callable = None, step_kwargs: Callable = None,
@@ -45,6 +52,19 @@ class GraphedTrainStep:
             dst.copy_(src)
         if hasattr(optimizer, "init_state"):
             optimizer.init_state()              # optimizer state must not be born inside the capture
+        if hasattr(optimizer, "refresh_hyper"):
+            optimizer.refresh_hyper()
+        # device step counter of the dropout masks: registered for the warm-up and the capture only, so the pointer is
+        # baked into this graph's kernels and eager calls made later keep drawing host seeds
+        self._drop_ctr = torch.zeros(1, dtype=torch.int64, device=example_inputs[0].device)
+        _lib.set_dropout_counter(self._drop_ctr)
+        try:
+            self._capture(warmup, capture_error_mode, main_priority)
+        finally:
+            _lib.set_dropout_counter(None)
+
+    def _capture(self, warmup, capture_error_mode, main_priority):
+        optimizer = self.optimizer
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -86,6 +106,7 @@ class GraphedTrainStep:
     def _fwd_bwd(self, zero: bool = True):
         if zero:
             self.optimizer.zero_grad(set_to_none=True)
+        self._drop_ctr.add_(1)                  # captured: every replay draws new dropout masks
         loss = self.loss_fn(*self.static_inputs)
         loss.backward()
         if self.post_backward is not None:
@@ -114,6 +135,7 @@ class GraphedTrainStep:
         """replay with a batch stored in the packed layout (device or pinned host): ONE copy refreshes every input."""
         if flat is not self.static_flat:
             self.static_flat.copy_(flat, non_blocking=True)
+        self._pre_replay()
         self.graph.replay()
         if self.graph_opt is not None:
             self.eager_between()
@@ -124,8 +146,21 @@ class GraphedTrainStep:
         for dst, src in zip(self.static_inputs, inputs):
             if src is not dst:
                 dst.copy_(src, non_blocking=True)
+        self._pre_replay()
         self.graph.replay()
         if self.graph_opt is not None:
             self.eager_between()
             self.graph_opt.replay()
         return self.static_loss
+
+    def _pre_replay(self):
+        if self.graph is None:
+            raise RuntimeError("GraphedTrainStep.replay() after close()")
+        if hasattr(self.optimizer, "refresh_hyper"):
+            self.optimizer.refresh_hyper()      # lr / grad_scale changed by a scheduler since the last replay
+
+    def close(self) -> None:
+        """drop the captured graphs (and the NCCL work they hold) after the device has drained."""
+        torch.cuda.synchronize()
+        self.graph = None
+        self.graph_opt = None

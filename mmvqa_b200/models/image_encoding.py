@@ -19,9 +19,19 @@ except Exception:  # pragma: no cover - depends on the environment
     _timm = None
 
     def _timm_create(name, features_only=True, pretrained=True, **kw):
-        """Shape-identical stand-in for timm's features_only tf_efficientnetv2_m when timm is absent:
-        torchvision efficientnet_v2_m taps features[1,2,3,5,7] = 24/48/80/176/512 channels at
-        strides 2/4/8/16/32."""
+        """timm is absent.  A randomly initialised torchvision efficientnet_v2_m (taps features[1,2,3,5,7] = 24/48/80/
+        176/512 channels at strides 2/4/8/16/32) has the right SHAPES but neither the pretrained
+        weights nor timm's state-dict keys, so it is only handed out when the caller opted in
+        (MMVQA_ALLOW_TORCHVISION_EFFNET=1: tests, synthetic benchmarks); otherwise this raises like the reference's
+        `import timm` would."""
+        import os
+        if os.environ.get("MMVQA_ALLOW_TORCHVISION_EFFNET") != "1":
+            raise ImportError("timm is not installed: get_image_encoder('%s') cannot build the pretrained backbone. "
+                              "Set MMVQA_ALLOW_TORCHVISION_EFFNET=1 to get a randomly initialised, shape-identical "
+                              "torchvision stand-in (tests / synthetic benchmarks only)." % name)
+        import warnings
+        warnings.warn("timm missing: using a RANDOMLY INITIALISED torchvision efficientnet_v2_m stand-in "
+                      "(state-dict keys differ from timm's; reference checkpoints will not load into the backbone)")
         return TorchvisionEffNetV2Features()
 
 

@@ -364,6 +364,13 @@ def adam_step(table: Tensor, n_chunks: int, lr: float, beta1: float, beta2: floa
                                    weight_decay, step, _p(step_dev), grad_scale, max_ctas, _stream()), "adam_step")
 
 
+def adam_step_dev(table: Tensor, n_chunks: int, hyper_dev: Tensor, beta1: float, beta2: float, eps: float,
+                  weight_decay: float, step_dev: Tensor, max_ctas: int = 0) -> None:
+    """Adam with lr = hyper_dev[0], grad_scale = hyper_dev[1] read on the device (graph replay follows lr schedulers)."""
+    L.check(L.lib().mmvqa_adam_step_dev(C.cast(table.data_ptr(), C.POINTER(L.AdamDesc)), n_chunks, _p(hyper_dev), beta1, beta2,
+                                       eps, weight_decay, _p(step_dev), max_ctas, _stream()), "adam_step_dev")
+
+
 # ------------------------------------------------------------------------------- caption similarity
 def jaccard_mask(ids_a: Tensor, len_a: Tensor, ids_b: Tensor, len_b: Tensor) -> Tensor:
     """ids_* [n, lmax] int32 sorted unique word ids per document, len_* [n] int32 -> [na, nb] fp32 Jaccard mask with

@@ -20,7 +20,11 @@ class FusedAdam(torch.optim.Optimizer):
     """Drop-in for ``torch.optim.Adam(params, lr)`` (no amsgrad / maximize / capturable flags).
 
     ``grad_scale`` multiplies every gradient inside the kernel (1/world_size after an all-reduce SUM).
-    The step counter lives on the device, so a captured CUDA graph of ``step()`` can be replayed."""
+    The step counter, every group's ``lr`` and ``grad_scale`` live on the device, so a captured CUDA graph of
+    ``step()`` can be replayed and still follows ``ReduceLROnPlateau`` / manual ``param_groups[i]['lr']`` changes
+    (vqamed2019/train.py:161,233): ``refresh_hyper()`` re-uploads them when they changed -- eager ``step()`` calls it
+    itself, ``GraphedTrainStep.replay`` calls it before every replay.  betas / eps / weight_decay are kernel
+    arguments: changing them after a capture needs a re-capture."""
 
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, overlap_backward=False,
                  reduce_fn=None, early_groups=None, sink_group: int = 1):
@@ -31,6 +35,8 @@ class FusedAdam(torch.optim.Optimizer):
         self._eager_tables = {}    # last eagerly built table per key (kept until it is rebuilt)
         self._refreshed = {}       # group index -> ids of parameters whose bf16 cache copy the kernel rewrites
         self._step_dev = None
+        self._hyper_dev = None     # [n_groups, 2] fp32 on the device: lr, grad_scale
+        self._hyper_host = None    # pinned mirror
         # overlap_backward: layers whose backward node offers its gradients early (functional.set_grad_sink) are
         # updated on a separate stream while the rest of the backward pass runs -- Adam is pure HBM traffic, the
         # small-batch backward is latency bound, so the two overlap almost for free.  step() updates what is left.
@@ -77,7 +83,38 @@ class FusedAdam(torch.optim.Optimizer):
         if p0.is_cuda:
             st = self.state.get(p0, {})
             s0 = int(st["step"].item()) if "step" in st else 0
-            self._step_dev = torch.full((1,), s0, dtype=torch.int32, device=p0.device)
+            if self._step_dev is None:
+                self._step_dev = torch.full((1,), s0, dtype=torch.int32, device=p0.device)
+            else:                               # keep the tensor a captured graph already references
+                self._step_dev.fill_(s0)
+            if self._hyper_dev is None:
+                ng = len(self.param_groups)
+                self._hyper_host = torch.full((ng, 2), float("nan"), dtype=torch.float32).pin_memory()
+                self._hyper_dev = torch.zeros(ng, 2, dtype=torch.float32, device=p0.device)
+                self.refresh_hyper()
+
+    def refresh_hyper(self) -> None:
+        """upload lr / grad_scale of every group if they changed since the last upload (stream-ordered copy on the
+        current stream).  Never called while capturing: a graph reads the values its caller uploaded before replay."""
+        if self._hyper_dev is None:
+            return
+        if self._hyper_dev.shape[0] != len(self.param_groups):      # add_param_group after construction
+            ng = len(self.param_groups)
+            self._hyper_host = torch.full((ng, 2), float("nan"), dtype=torch.float32).pin_memory()
+            self._hyper_dev = torch.zeros(ng, 2, dtype=torch.float32, device=self._hyper_dev.device)
+        changed = False
+        for gi, group in enumerate(self.param_groups):
+            lr, gs = float(group["lr"]), float(self.grad_scale)
+            if self._hyper_host[gi, 0].item() != lr or self._hyper_host[gi, 1].item() != gs:
+                changed = True
+        if changed:
+            # a fresh pinned buffer per change: an earlier asynchronous copy may not have read the old one yet
+            host = torch.empty_like(self._hyper_host).pin_memory()
+            for gi, group in enumerate(self.param_groups):
+                host[gi, 0] = float(group["lr"])
+                host[gi, 1] = float(self.grad_scale)
+            self._hyper_host = host
+            self._hyper_dev.copy_(host, non_blocking=True)
 
     def _state_of(self, p):
         st = self.state[p]
@@ -135,10 +172,11 @@ class FusedAdam(torch.optim.Optimizer):
         return dev, len(rows)
 
     def _advance(self, device):
-        if self._step_dev is None:
-            st0 = self._state_of(self.param_groups[0]["params"][0])
-            self._step_dev = torch.full((1,), int(st0["step"].item()), dtype=torch.int32, device=device)
+        if self._step_dev is None or self._hyper_dev is None:
+            self._init_step_counter()
         if not self._stepped:
+            if not torch.cuda.is_current_stream_capturing():
+                self.refresh_hyper()
             self._step_dev += 1
             self._stepped = True
 
@@ -146,8 +184,8 @@ class FusedAdam(torch.optim.Optimizer):
         group = self.param_groups[gi]
         table, n = self._table(key, plist, grads)
         b1, b2 = group["betas"]
-        ops.adam_step(table, n, group["lr"], b1, b2, group["eps"], group["weight_decay"], 0, self._step_dev,
-                      self.grad_scale, max_ctas)
+        ops.adam_step_dev(table, n, self._hyper_dev[gi], b1, b2, group["eps"], group["weight_decay"], self._step_dev,
+                          max_ctas)
 
     @torch.no_grad()
     def _sink(self, params, grads, side_stream, from_hook: bool = False) -> bool:
@@ -275,5 +313,5 @@ class FusedAdam(torch.optim.Optimizer):
     def load_state_dict(self, sd):
         super().load_state_dict(sd)
         self._tables.clear()
-        self._step_dev = None
-        self._init_step_counter()
+        self._init_step_counter()      # in place: a captured graph keeps reading the same device counter
+        self.refresh_hyper()

@@ -20,6 +20,10 @@ def broadcast_parameters(module: torch.nn.Module, src: int = 0) -> None:
         return
     for t in list(module.parameters()) + list(module.buffers()):
         dist.broadcast(t.data, src)
+    # writes through .data do not bump Parameter._version: the cached bf16 operand copies of the non-source ranks
+    # would silently keep the pre-broadcast weights
+    from .functional import invalidate_weight_cache
+    invalidate_weight_cache()
 
 
 class GradBuckets:
