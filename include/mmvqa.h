@@ -264,6 +264,42 @@ int mmvqa_supcon_rows(const float* logits, const float* mask, float* loss_rows, 
                       int row_offset, float temperature, float base_temperature, mmvqa_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * Whole RealFormer encoder forward in ONE launch (small batches; bf16 only).
+ * replaces: RealFormer.forward, models/mmbert.py:103-108 = n_layers x ResEncoderBlock.forward,
+ * models/realformer.py:30-51 (resmha + proj + dropout + ln1 + ff + dropout + ln2), i.e. the same arithmetic as the
+ * per-operator chain mmvqa_rf_attn_fwd_fused / mmvqa_gemm / mmvqa_add_layernorm_fwd*, kept on chip by one 8-CTA
+ * cluster per group of samples (mmvqa_b200/csrc/rf_encoder.cu).  Every intermediate the backward pass needs is
+ * written to the stacked [n_layers, ...] buffers below, in the layouts of the per-operator entry points.
+ * Per-layer parameter pointers are HOST arrays of DEVICE pointers (weights bf16 row-major as nn.Linear stores them,
+ * biases / LayerNorm parameters fp32).  mmvqa_rf_encoder_fwd_supported() tells whether a shape can take this path (hidden 768,
+ * 8 heads, ff 3072, T <= 32, <= 16 layers, few enough sample groups to be co-resident); other shapes use the
+ * per-operator entry points. */
+typedef struct mmvqa_rf_encoder_args {
+  int B, T, hidden, heads, ff, n_layers;
+  const void* const* wkqv;      /* [n_layers] -> bf16 [3*d, d]      realformer.py:13 */
+  const void* const* wproj;     /* [n_layers] -> bf16 [hidden, hidden]  :14 */
+  const void* const* w1;        /* [n_layers] -> bf16 [ff, hidden]  ff.0  :22 */
+  const void* const* w2;        /* [n_layers] -> bf16 [hidden, ff]  ff.2  :25 */
+  const float* const* b1; const float* const* b2;
+  const float* const* ln1_w; const float* const* ln1_b; const float* const* ln2_w; const float* const* ln2_b;
+  const void* x0;               /* bf16 [M, hidden]: encoder input (M = B*T) */
+  void* xout;                   /* bf16 [n_layers, M, hidden]: output of layer l = input of layer l+1 */
+  void* kqv;                    /* bf16 [n_layers, M*heads, 3*d] */
+  float* scores;                /* fp32 [n_layers, B, heads, T, T] */
+  void* att; void* y1; void* x1;        /* bf16 [n_layers, M, hidden] */
+  void* hpre; void* hact;               /* bf16 [n_layers, M, ff] */
+  void* y2;                             /* bf16 [n_layers, M, hidden] */
+  float* mean1; float* rstd1; float* mean2; float* rstd2;   /* fp32 [n_layers, M] */
+  const float* prev;            /* optional fp32 [B, heads, T, T]: scores entering layer 0 */
+  const float* mask;            /* optional fp32 [B, T] */
+  float dropout_p1, dropout_p2, eps;
+  uint64_t dropout_seed;        /* layer l uses seed + 2l (proj branch) and seed + 2l + 1 (ff branch) */
+  void* trace;                  /* optional int64 [4, 16, 16]: clock64 stamps of CTA 0 per role / layer / phase (tuning) */
+} mmvqa_rf_encoder_args;
+int mmvqa_rf_encoder_fwd_supported(int B, int T, int hidden, int heads, int ff, int n_layers);
+int mmvqa_rf_encoder_fwd(const mmvqa_rf_encoder_args* args, mmvqa_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * Optimiser: multi-tensor Adam, torch.optim.Adam semantics
  * (vqamed2019/train.py:160, no amsgrad, L2 weight decay).  `table` is a DEVICE array of n_chunks
  * descriptors, each a contiguous chunk (<= 32768 elements is a good size) of one parameter

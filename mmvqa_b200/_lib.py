@@ -37,6 +37,20 @@ class GemmArgs(C.Structure):
     ]
 
 
+class RfEncoderArgs(C.Structure):
+    _fields_ = [
+        ("B", i32), ("T", i32), ("hidden", i32), ("heads", i32), ("ff", i32), ("n_layers", i32),
+        ("wkqv", C.POINTER(vp)), ("wproj", C.POINTER(vp)), ("w1", C.POINTER(vp)), ("w2", C.POINTER(vp)),
+        ("b1", C.POINTER(vp)), ("b2", C.POINTER(vp)),
+        ("ln1_w", C.POINTER(vp)), ("ln1_b", C.POINTER(vp)), ("ln2_w", C.POINTER(vp)), ("ln2_b", C.POINTER(vp)),
+        ("x0", vp), ("xout", vp), ("kqv", vp), ("scores", vp), ("att", vp), ("y1", vp), ("x1", vp),
+        ("hpre", vp), ("hact", vp), ("y2", vp),
+        ("mean1", vp), ("rstd1", vp), ("mean2", vp), ("rstd2", vp),
+        ("prev", vp), ("mask", vp),
+        ("dropout_p1", f32), ("dropout_p2", f32), ("eps", f32), ("dropout_seed", u64), ("trace", vp),
+    ]
+
+
 class AdamDesc(C.Structure):
     _fields_ = [("p", vp), ("m", vp), ("v", vp), ("g", vp), ("bf16_out", vp), ("n", i64), ("flags", i64)]
 
@@ -66,6 +80,8 @@ SIGNATURES = {
     "mmvqa_rf_attn_fwd_fused": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "mmvqa_rf_attn_bwd_fused": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "mmvqa_rf_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "mmvqa_rf_encoder_fwd_supported": (i32, [i32, i32, i32, i32, i32, i32]),
+    "mmvqa_rf_encoder_fwd": (i32, [C.POINTER(RfEncoderArgs), vp]),
     "mmvqa_embed_ln_scatter_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32,
                                          f32, u64, i32, vp]),
     "mmvqa_embed_ln_scatter_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32,

@@ -728,6 +728,25 @@ class RealFormerEncoderFn(torch.autograd.Function):
         fuse_kqv = (dt == torch.bfloat16 and d % 16 == 0 and T <= 128 and d <= 128 and
                     (2 * ((T + 15) // 16 * 16) * (d + 8) + d * ((T + 15) // 16 * 16 + 8) + ((T + 15) // 16 * 16) * (d + 8)
                      + 3 * d * (d + 8)) * 2 <= 200 * 1024 and _os.environ.get("MMVQA_NO_FUSED_KQV") is None)
+        # small batches: the whole encoder forward is ONE launch of the sample-stationary cluster kernel
+        # (csrc/rf_encoder.cu); it writes the same intermediates the per-operator chain below saves
+        F4_ = params[4].shape[0]
+        if dt == torch.bfloat16 and _os.environ.get("MMVQA_NO_RF_ENCODER") is None and \
+                ops.rf_encoder_supported(B, T, H, heads, F4_, n_layers):
+            layers = []
+            for l in range(n_layers):
+                kqv_w, proj_w, g1, b1, w0, bb0, w2, bb2, g2, b2 = params[l * RF_PARAMS_PER_LAYER:(l + 1) * RF_PARAMS_PER_LAYER]
+                layers.append((weight_cache.get((kqv_w,), dt), weight_cache.get((proj_w,), dt), weight_cache.get((w0,), dt),
+                               weight_cache.get((w2,), dt), bb0.detach(), bb2.detach(), g1.detach(), b1.detach(), g2.detach(),
+                               b2.detach()))
+            o = ops.rf_encoder_fwd(xin, layers, prev, maskf, B, T, heads, p1, p2, 1e-5, seed)
+            for l in range(n_layers):
+                saved += [xin if l == 0 else o["xout"][l - 1], o["kqv"][l], o["scores"][l], o["att"][l], o["y1"][l],
+                          o["mean1"][l], o["rstd1"][l], o["x1"][l], o["hpre"][l], o["hact"][l], o["y2"][l], o["mean2"][l],
+                          o["rstd2"][l]]
+            ctx.save_for_backward(*saved, *params)
+            ctx.meta = (B, T, H, heads, d, n_layers, p1, p2, seed, dt, prev is not None)
+            return o["xout"][n_layers - 1].view(B, T, H), o["scores"][n_layers - 1]
         for l in range(n_layers):
             kqv_w, proj_w, g1, b1, w0, bb0, w2, bb2, g2, b2 = params[l * RF_PARAMS_PER_LAYER:(l + 1) * RF_PARAMS_PER_LAYER]
             wk = weight_cache.get((kqv_w,), dt)

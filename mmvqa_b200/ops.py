@@ -240,6 +240,54 @@ def rf_attn_fwd_fused(x: Tensor, wkqv: Tensor, prev: Optional[Tensor], mask: Opt
     return out, scores, kqv
 
 
+RF_TRACE_BUFFER: Optional[Tensor] = None      # int64 [4, 16, 16] CUDA tensor: phase stamps of CTA 0 (tools/rf_encoder_check.py)
+
+
+def rf_encoder_supported(B: int, T: int, hidden: int, heads: int, ff: int, n_layers: int) -> bool:
+    return bool(L.lib().mmvqa_rf_encoder_fwd_supported(B, T, hidden, heads, ff, n_layers))
+
+
+def rf_encoder_fwd(x0: Tensor, layers, prev: Optional[Tensor], mask: Optional[Tensor], B: int, T: int, heads: int, p1: float,
+                   p2: float, eps: float, seed: int):
+    """whole RealFormer encoder forward in one launch (bf16).  `layers` = per layer (wkqv, wproj, w1, w2 [bf16 operand
+    copies], b1, b2, ln1_w, ln1_b, ln2_w, ln2_b [fp32]).  Returns the dict of stacked [n_layers, ...] buffers the backward
+    pass reads (same layouts as the per-operator path)."""
+    n = len(layers)
+    M, H = x0.shape
+    F4 = layers[0][2].shape[0]
+    d = H // heads
+    dev, bf = x0.device, torch.bfloat16
+    out = dict(
+        xout=torch.empty(n, M, H, device=dev, dtype=bf), kqv=torch.empty(n, M * heads, 3 * d, device=dev, dtype=bf),
+        scores=torch.empty(n, B, heads, T, T, device=dev, dtype=torch.float32),
+        att=torch.empty(n, M, H, device=dev, dtype=bf), y1=torch.empty(n, M, H, device=dev, dtype=bf),
+        x1=torch.empty(n, M, H, device=dev, dtype=bf), hpre=torch.empty(n, M, F4, device=dev, dtype=bf),
+        hact=torch.empty(n, M, F4, device=dev, dtype=bf), y2=torch.empty(n, M, H, device=dev, dtype=bf),
+        mean1=torch.empty(n, M, device=dev, dtype=torch.float32), rstd1=torch.empty(n, M, device=dev, dtype=torch.float32),
+        mean2=torch.empty(n, M, device=dev, dtype=torch.float32), rstd2=torch.empty(n, M, device=dev, dtype=torch.float32))
+    a = L.RfEncoderArgs()
+    a.B, a.T, a.hidden, a.heads, a.ff, a.n_layers = B, T, H, heads, F4, n
+    arrs = []
+    for k, name in enumerate(("wkqv", "wproj", "w1", "w2", "b1", "b2", "ln1_w", "ln1_b", "ln2_w", "ln2_b")):
+        for lay in layers:
+            t = lay[k]
+            want = bf if k < 4 else torch.float32
+            if t.dtype != want or not t.is_contiguous() or not t.is_cuda:
+                raise L.MMVQAError("rf_encoder_fwd: parameter %s must be a contiguous CUDA %s tensor" % (name, want))
+        arr = (L.vp * n)(*[lay[k].data_ptr() for lay in layers])
+        arrs.append(arr)
+        setattr(a, name, C.cast(arr, C.POINTER(L.vp)))
+    a.x0 = _p(_cont(x0, "x0"))
+    for name in ("xout", "kqv", "scores", "att", "y1", "x1", "hpre", "hact", "y2", "mean1", "rstd1", "mean2", "rstd2"):
+        setattr(a, name, out[name].data_ptr())
+    a.prev = _p(prev)
+    a.mask = _p(mask)
+    a.dropout_p1, a.dropout_p2, a.eps, a.dropout_seed = p1, p2, eps, seed & 0xFFFFFFFFFFFFFFFF
+    a.trace = _p(RF_TRACE_BUFFER)
+    L.check(L.lib().mmvqa_rf_encoder_fwd(C.byref(a), _stream()), "rf_encoder_fwd")
+    return out
+
+
 def rf_attn_bwd(kqv: Tensor, scores: Tensor, dout: Tensor, dscores_in: Optional[Tensor], want_dprev: bool, B: int, T: int,
                 heads: int, d: int):
     dkqv = torch.empty_like(kqv)
