@@ -41,10 +41,11 @@ constexpr int RF_B_BYTES = RF_N * RF_H * 2;                // 98304
 constexpr int RF_WK_BYTES = 3 * RF_D * RF_D * 2;           // 55296: Wkqv [288][96]
 constexpr int RF_LDN = RF_D + 8, RF_LDT = RF_TP + 8;       // padded rows of the mma.sync tiles
 constexpr int RF_QKV_BYTES = (2 * RF_TP * RF_LDN + RF_D * RF_LDT) * 2;   // Q, K, V^T of one sample: 20992
+constexpr int RF_YS_OFF = RF_B_OFF + RF_WK_BYTES;           // [64][104] bf16 LayerNorm input rows (aliases the Q/K/V^T scratch)
 constexpr int RF_XS_OFF = RF_B_OFF + RF_B_BYTES;           // [64][104] bf16: this head's slice of the layer input
 constexpr int RF_XS_BYTES = RF_N * RF_LDN * 2;
-constexpr int RF_RED_OFF = RF_XS_OFF + RF_XS_BYTES;        // [2][4][32] floats
-constexpr int RF_STAT_OFF = RF_RED_OFF + 1024;             // [2 (ln)][8 (src)][64][2] floats
+constexpr int RF_X1S_OFF = RF_XS_OFF + RF_XS_BYTES;        // [64][104] bf16: this head's slice of x1 (residual of the FF block)
+constexpr int RF_STAT_OFF = RF_X1S_OFF + RF_XS_BYTES;      // [2 (ln)][8 (src)][64][2] floats
 constexpr int RF_BAR_OFF = RF_STAT_OFF + 8192;
 constexpr int RF_SMEM = RF_BAR_OFF + 256;
 static_assert(RF_WK_BYTES + 2 * RF_QKV_BYTES <= RF_B_BYTES, "attention scratch must fit the B region");
@@ -56,6 +57,9 @@ struct RfEncParams {
   CUtensorMap wp[RF_MAXL], w1[RF_MAXL], w2[RF_MAXL];   // weights: 3-D {64, rows, k-chunks}
   CUtensorMap tm_att, tm_x1, tm_hact;                  // gathers: 4-D {64, M, k-chunks, layer}
   const bf16* wkqv[RF_MAXL];
+  const void* wp_raw[RF_MAXL];
+  const void* w1_raw[RF_MAXL];
+  const void* w2_raw[RF_MAXL];
   const float* b1[RF_MAXL];
   const float* b2[RF_MAXL];
   const float* g1[RF_MAXL];
@@ -147,75 +151,115 @@ __device__ __forceinline__ void st_cluster_f32x2(uint32_t remote, float a, float
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void compute_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// column sums over the 32 lanes of a warp for 32 register values: afterwards lane l holds sum over lanes of v[l]
-// (transposing butterfly, 31 shuffles).  v is destroyed.
-__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int half = 16; half >= 1; half >>= 1) {
-    const bool hi = (lane & half) != 0;
-#pragma unroll
-    for (int k = 0; k < half; ++k) {
-      const float send = hi ? v[k] : v[k + half];
-      const float recv = __shfl_xor_sync(0xffffffffu, send, half);
-      v[k] = (hi ? v[k + half] : v[k]) + recv;
-    }
+__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+// after a bar.sync of the 256 compute threads: 8 lanes publish "this CTA reached the sync point" to the 8 CTAs of the
+// cluster.  One release fence per arriving lane (cumulative over what the other threads wrote before the bar.sync),
+// then a relaxed remote arrival.
+__device__ __forceinline__ void cluster_publish(uint32_t local_bar, int ctid) {
+  if (ctid < RF_HEADS) {
+    asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    const uint32_t remote = map_to_cta(local_bar, (uint32_t)ctid);
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
   }
-  return v[0];
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
 }
 
-__device__ __forceinline__ float bf16_round(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
-
 // ---------------------------------------------------------------------------------------------------------------
-// LayerNorm over the 768 features of each token, features spread over the 8 CTAs of the cluster (96 each) and, inside
-// the CTA, over TMEM-lane threads: thread (q = quadrant, lane) holds feature 32 q + lane (q < 3) of the 32 tokens
-// 32 ch ... 32 ch + 31 in v[].  Two-pass statistics per CTA, merged across CTAs with Chan's formula.
-// On return lane j of every warp holds mean / rstd of token 32 ch + j.
+// LayerNorm over the 768 features of each of the 64 token columns; this CTA holds 96 of them per token in
+// Ys[token][96] (bf16, already rounded: the statistics are those of the stored tensor, as in add_ln_fwd_*).
+// Thread (token c = ctid / 4, part = ctid % 4) owns 24 features: two-pass statistics inside the CTA, (sum, M2) of the
+// 8 CTAs exchanged through distributed shared memory and merged with Chan's formula, then y_out = (y - mean) * rstd *
+// gamma + beta goes to shared memory (next operand / residual) and, with the LayerNorm input itself, to global memory
+// with 128-bit stores.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cluster_ln_stats(const float (&v)[32], bool feat_ok, int q, int ch, int lane, uint32_t rank,
-                                                 uint8_t* smem, int ln_which, uint32_t cl_bar, uint32_t parity, float eps,
-                                                 float& mean_out, float& rstd_out) {
-  float* red = reinterpret_cast<float*>(smem + RF_RED_OFF);                  // [2][4][32]
+__device__ __forceinline__ void cluster_layernorm(uint8_t* smem, int ctid, uint32_t rank, int ln_which, uint32_t cl_bar,
+                                                  uint32_t parity, float eps, const float* __restrict__ gamma,
+                                                  const float* __restrict__ beta, int nrows, int64_t row0,
+                                                  bf16* __restrict__ ysum_out, bf16* __restrict__ y_out,
+                                                  bf16* out_smem, float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  const bf16* Ys = reinterpret_cast<const bf16*>(smem + RF_YS_OFF);
   float* stat = reinterpret_cast<float*>(smem + RF_STAT_OFF) + ln_which * (RF_HEADS * RF_N * 2);   // [8][64][2]
-  float t[32];
+  const int c = ctid >> 2, part = ctid & 3;
+  const int f0 = 24 * part;
+  compute_sync();                                       // Ys complete
+  float v[24];
+  uint4 raw[3];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) t[j] = feat_ok ? v[j] : 0.0f;
-  const float s_w = warp_colsum32(t, lane);
-  compute_sync();                                       // previous readers of red[] are done
-  red[(ch * 4 + q) * 32 + lane] = s_w;
-  compute_sync();
-  const float lsum = red[(ch * 4 + 0) * 32 + lane] + red[(ch * 4 + 1) * 32 + lane] + red[(ch * 4 + 2) * 32 + lane];
-  const float lmean = lsum * (1.0f / (float)RF_D);
-#pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const float d = v[j] - __shfl_sync(0xffffffffu, lmean, j);
-    t[j] = feat_ok ? d * d : 0.0f;
+  for (int i = 0; i < 3; ++i) {
+    raw[i] = *reinterpret_cast<const uint4*>(Ys + c * RF_LDN + f0 + 8 * i);
+    unpack8(raw[i], v + 8 * i);
   }
-  const float m2_w = warp_colsum32(t, lane);
-  compute_sync();
-  red[(ch * 4 + q) * 32 + lane] = m2_w;
-  compute_sync();
-  const float lm2 = red[(ch * 4 + 0) * 32 + lane] + red[(ch * 4 + 1) * 32 + lane] + red[(ch * 4 + 2) * 32 + lane];
-  if (q == 0) {   // one warp per column half publishes (sum, M2) of its 32 tokens to every CTA of the cluster
-    const uint32_t local = smem_u32(stat + ((int)rank * RF_N + ch * 32 + lane) * 2);
+  float lsum = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) lsum += v[i];
+  lsum += __shfl_xor_sync(0xffffffffu, lsum, 1);
+  lsum += __shfl_xor_sync(0xffffffffu, lsum, 2);
+  const float lmean = lsum * (1.0f / (float)RF_D);
+  float lm2 = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 24; ++i) {
+    const float d = v[i] - lmean;
+    lm2 += d * d;
+  }
+  lm2 += __shfl_xor_sync(0xffffffffu, lm2, 1);
+  lm2 += __shfl_xor_sync(0xffffffffu, lm2, 2);
+  if (part == 0) {
+    const uint32_t local = smem_u32(stat + ((int)rank * RF_N + c) * 2);
 #pragma unroll
     for (uint32_t r = 0; r < RF_HEADS; ++r) st_cluster_f32x2(map_to_cta(local, r), lsum, lm2);
   }
-  compute_sync();                                       // both publishing warps have issued their remote stores
-  if (threadIdx.x == 4 * 32) cluster_arrive_all(cl_bar);
+  const int64_t goff = (row0 + c) * RF_H + RF_D * (int)rank + f0;
+  if (c < nrows) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) *reinterpret_cast<uint4*>(ysum_out + goff + 8 * i) = raw[i];
+  }
+  compute_sync();                                       // every publishing thread has issued its remote stores
+  cluster_publish(cl_bar, ctid);
   mbar_wait_cluster(cl_bar, parity);
-  const int tok = ch * 32 + lane;
   float tot = 0.0f;
 #pragma unroll
-  for (int s = 0; s < RF_HEADS; ++s) tot += stat[(s * RF_N + tok) * 2];
+  for (int s = 0; s < RF_HEADS; ++s) tot += stat[(s * RF_N + c) * 2];
   const float mean = tot * (1.0f / (float)RF_H);
   float m2 = 0.0f;
 #pragma unroll
   for (int s = 0; s < RF_HEADS; ++s) {
-    const float ds = stat[(s * RF_N + tok) * 2] * (1.0f / (float)RF_D) - mean;
-    m2 += stat[(s * RF_N + tok) * 2 + 1] + (float)RF_D * ds * ds;
+    const float ds = stat[(s * RF_N + c) * 2] * (1.0f / (float)RF_D) - mean;
+    m2 += stat[(s * RF_N + c) * 2 + 1] + (float)RF_D * ds * ds;
   }
-  mean_out = mean;
-  rstd_out = rsqrtf(m2 * (1.0f / (float)RF_H) + eps);
+  const float rstd = rsqrtf(m2 * (1.0f / (float)RF_H) + eps);
+  const float* gm = gamma + RF_D * (int)rank + f0;
+  const float* bt = beta + RF_D * (int)rank + f0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    uint4 o;
+    uint32_t* ow = &o.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int e = 8 * i + 2 * k;
+      const float a0 = (v[e] - mean) * rstd * __ldg(gm + e) + __ldg(bt + e);
+      const float a1 = (v[e + 1] - mean) * rstd * __ldg(gm + e + 1) + __ldg(bt + e + 1);
+      ow[k] = c < nrows ? pack2(a0, a1) : 0u;
+    }
+    *reinterpret_cast<uint4*>(out_smem + c * RF_LDN + f0 + 8 * i) = o;
+    if (c < nrows) *reinterpret_cast<uint4*>(y_out + goff + 8 * i) = o;
+  }
+  if (rank == 0 && part == 0 && c < nrows) {
+    mean_out[row0 + c] = mean;
+    rstd_out[row0 + c] = rstd;
+  }
 }
 
 #define RF_TRACE(role, slot)                                                                  \
@@ -246,9 +290,11 @@ __global__ void __cluster_dims__(RF_HEADS, 1, 1) __launch_bounds__(RF_THREADS, 1
   const uint32_t cl_s1 = bars + 128, cl_e1 = bars + 136, cl_s2 = bars + 144, cl_s3 = bars + 152, cl_e2 = bars + 160;
   const uint32_t tmem_ptr_addr = bars + 192;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem + RF_BAR_OFF + 192);
+  volatile int* cur_layer = reinterpret_cast<volatile int*>(smem + RF_BAR_OFF + 200);
 
   if ((sbase & 1023u) != 0) __trap();                   // swizzled tiles need a 1024-byte aligned base
   if (threadIdx.x == 0) {
+    *cur_layer = -1;
     for (int i = 0; i < 2; ++i) {
       mbar_init(a_full + 8 * i, 1);
       mbar_init(a_empty + 8 * i, 1);
@@ -287,20 +333,25 @@ __global__ void __cluster_dims__(RF_HEADS, 1, 1) __launch_bounds__(RF_THREADS, 1
         mbar_expect_tx(full, RF_A_STAGE);
         ++it;
       };
+#pragma unroll 1
       for (int l = 0; l < L; ++l) {
         uint32_t full, dst;
         RF_TRACE(0, 0);
+#pragma unroll 1
         for (int c = 0; c < 3; ++c) {                   // proj: rows [96h, 96h+96), 4 k-chunks per box
           slot(full, dst);
           tma_load_3d(dst, &p.wp[l], full, 0, 96 * (int)h, 4 * c);
         }
         RF_TRACE(0, 1);
+#pragma unroll 1
         for (int m = 0; m < 3; ++m)                     // FF1: rows [384h + 128m, +128), 3 k-chunks per box
+#pragma unroll 1
           for (int c = 0; c < 4; ++c) {
             slot(full, dst);
             tma_load_3d(dst, &p.w1[l], full, 0, RF_FS * (int)h + 128 * m, 3 * c);
           }
         RF_TRACE(0, 2);
+#pragma unroll 1
         for (int c = 0; c < 12; ++c) {                  // FF2: rows [96h, 96h+96), K = 3072
           slot(full, dst);
           tma_load_3d(dst, &p.w2[l], full, 0, 96 * (int)h, 4 * c);
@@ -313,6 +364,7 @@ __global__ void __cluster_dims__(RF_HEADS, 1, 1) __launch_bounds__(RF_THREADS, 1
     if (lane == 0) {
       uint32_t nfree = 0;                               // completed phases of bres_free consumed so far
       uint32_t nchunk = 0;
+#pragma unroll 1
       for (int l = 0; l < L; ++l) {
         const uint32_t lp = (uint32_t)l & 1u;
         // Wkqv of this layer: the B region is free once the FF2 MMAs of the previous layer have retired
@@ -341,6 +393,7 @@ __global__ void __cluster_dims__(RF_HEADS, 1, 1) __launch_bounds__(RF_THREADS, 1
         mbar_wait(bres_free, nfree & 1u); ++nfree;
         RF_TRACE(1, 6);
         fence_proxy_async();
+#pragma unroll 1
         for (int c = 0; c < 8; ++c, ++nchunk) {
           const uint32_t s = nchunk & 1u, ph = (nchunk >> 1) & 1u;
           mbar_wait(b_empty + 8 * s, ph ^ 1u);
@@ -374,14 +427,17 @@ __global__ void __cluster_dims__(RF_HEADS, 1, 1) __launch_bounds__(RF_THREADS, 1
                     (first && j == 0) ? 0u : 1u);
       };
       const uint32_t bres = sbase + RF_B_OFF;
+#pragma unroll 1
       for (int l = 0; l < L; ++l) {
         // ---- proj: K = 768, A boxes of 96 rows x 4 k-chunks (12288 B per chunk), B resident (8192 B per chunk)
         RF_TRACE(2, 0);
         mbar_wait(bres_full, nres & 1u); ++nres;
         tc_fence_after();
         RF_TRACE(2, 1);
+#pragma unroll 1
         for (int c = 0; c < 3; ++c) {
           a_acquire();
+#pragma unroll 1
           for (int k = 0; k < 4; ++k) mma_kc(a_base + k * 12288, bres + (4 * c + k) * 8192, tmem + RF_TM_PROJ, c == 0 && k == 0);
           a_release();
         }
@@ -392,9 +448,12 @@ __global__ void __cluster_dims__(RF_HEADS, 1, 1) __launch_bounds__(RF_THREADS, 1
         mbar_wait(bres_full, nres & 1u); ++nres;
         tc_fence_after();
         RF_TRACE(2, 3);
+#pragma unroll 1
         for (int m = 0; m < 3; ++m) {
+#pragma unroll 1
           for (int c = 0; c < 4; ++c) {
             a_acquire();
+#pragma unroll 1
             for (int k = 0; k < 3; ++k)
               mma_kc(a_base + k * 16384, bres + (3 * c + k) * 8192, tmem + RF_TM_FF1 + m * RF_N, c == 0 && k == 0);
             a_release();
@@ -405,6 +464,7 @@ __global__ void __cluster_dims__(RF_HEADS, 1, 1) __launch_bounds__(RF_THREADS, 1
         umma_commit(bres_free);
         // ---- FF2: K = 3072; A boxes of 96 rows x 4 k-chunks, B chunks of 6 k-chunks in two slots
         uint32_t b_base = 0;
+#pragma unroll 1
         for (int kc = 0; kc < RF_KC_F; ++kc) {
           if (kc % 6 == 0) {
             const uint32_t s = nchunk & 1u, ph = (nchunk >> 1) & 1u;
@@ -425,6 +485,29 @@ __global__ void __cluster_dims__(RF_HEADS, 1, 1) __launch_bounds__(RF_THREADS, 1
         umma_commit(bres_free);
         RF_TRACE(2, 8);
       }
+    }
+  } else if (warp == 3) {
+    // =========================== L2 prefetcher ===========================
+    // The weight boxes are first touches of HBM (the fp32 masters and Adam state stream 1.5 GB through L2 every step), and
+    // the ring holds only 96 KB in flight: with HBM latency under every TMA op the ring is latency bound.  This warp
+    // touches the NEXT layer's weight slices of this CTA with prefetch.global.L2 while the current layer computes (the
+    // clusters share the lines: cluster g takes lines g, g + nclusters, ...), so the TMA boxes find them in L2.
+    const int ncl = (int)gridDim.x / RF_HEADS;
+#pragma unroll 1
+    for (int l = 0; l + 1 < L; ++l) {
+      while (*cur_layer < l) __nanosleep(200);          // layer l has started (counter written by the compute warps)
+      const char* base[3] = {reinterpret_cast<const char*>(p.wp_raw[l + 1]) + (size_t)RF_D * h * RF_H * 2,
+                             reinterpret_cast<const char*>(p.w1_raw[l + 1]) + (size_t)RF_FS * h * RF_H * 2,
+                             reinterpret_cast<const char*>(p.w2_raw[l + 1]) + (size_t)RF_D * h * RF_F * 2};
+      const int nline[3] = {RF_D * RF_H * 2 / 128, RF_FS * RF_H * 2 / 128, RF_D * RF_F * 2 / 128};
+#pragma unroll 1
+      for (int w = 0; w < 3; ++w)
+#pragma unroll 1
+        for (int i = grp + ncl * lane; i < nline[w]; i += ncl * 32)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(base[w] + (size_t)i * 128));
+      if (grp == 0 && h == 0)
+        for (int i = lane; i < RF_WK_BYTES / 128; i += 32)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(p.wkqv[l + 1]) + (size_t)i * 128));
     }
   } else if (warp >= 4) {
     // =========================== attention + epilogues (256 threads) ===========================
@@ -454,10 +537,10 @@ __global__ void __cluster_dims__(RF_HEADS, 1, 1) __launch_bounds__(RF_THREADS, 1
       *reinterpret_cast<uint4*>(Xs + r * RF_LDN + c8 * 8) = v;
     }
     compute_sync();
-    float x1r[32];                                      // x1 (rounded) of this thread's feature: residual of the FF block
-#pragma unroll
-    for (int j = 0; j < 32; ++j) x1r[j] = 0.0f;
+    bf16* X1s = reinterpret_cast<bf16*>(smem + RF_X1S_OFF);                     // [64][104]
+    bf16* Ys = reinterpret_cast<bf16*>(smem + RF_YS_OFF);                       // [64][104]
 
+#pragma unroll 1
     for (int l = 0; l < L; ++l) {
       const uint32_t lp = (uint32_t)l & 1u;
       // ------------------------------------------------------------------ kqv + attention (mma.sync)
@@ -468,6 +551,7 @@ __global__ void __cluster_dims__(RF_HEADS, 1, 1) __launch_bounds__(RF_THREADS, 1
         for (int i = ctid; i < 2 * RF_QKV_BYTES / 16; i += 256) z[i] = make_uint4(0, 0, 0, 0);
       }
       if (ctid == 0) RF_TRACE(3, 0);
+      if (ctid == 0) *cur_layer = l;
       mbar_wait(wkqv_full, lp);
       compute_sync();
       if (ctid == 0) RF_TRACE(3, 1);
@@ -495,7 +579,7 @@ __global__ void __cluster_dims__(RF_HEADS, 1, 1) __launch_bounds__(RF_THREADS, 1
               const int r = strip * 16 + g + 8 * half;
               if (r >= nrows) continue;
               const uint32_t val = pack2(c[2 * half], c[2 * half + 1]);
-              const int s = r / T, tq = r - s * T;
+              const int s = r >= T ? 1 : 0, tq = r - s * T;      // at most two samples per cluster
               bf16* Qs = reinterpret_cast<bf16*>(qkv_base + s * RF_QKV_BYTES);
               bf16* Ks = Qs + RF_TP * RF_LDN;
               bf16* Vt = Ks + RF_TP * RF_LDN;
@@ -614,60 +698,39 @@ __global__ void __cluster_dims__(RF_HEADS, 1, 1) __launch_bounds__(RF_THREADS, 1
       }
       // publish: the attention rows of this head are in global memory, the B region may be overwritten by the gather
       fence_proxy_async();
-      __threadfence();
       compute_sync();
-      if (ctid == 0) cluster_arrive_all(cl_s1);
+      cluster_publish(cl_s1, ctid);
       if (ctid == 0) RF_TRACE(3, 3);
 
-      // ------------------------------------------------------------------ proj epilogue: + residual, LN1
-      float v[32];
+      // ------------------------------------------------------------------ proj epilogue: dropout, + residual -> Ys; LN1
       mbar_wait(tmem_full + 0, lp);
       tc_fence_after();
       if (ctid == 0) RF_TRACE(3, 4);
-      {
-        uint32_t r[32];
-        __syncwarp();
-        tmem_ld16(tmem_lane + RF_TM_PROJ + ch * 32, r);
-        tmem_ld16(tmem_lane + RF_TM_PROJ + ch * 32 + 16, r + 16);
-        tmem_ld_wait();
+      if (feat_ok) {
         const unsigned long long sd = seed0 + 2ull * (unsigned long long)l;
-        bf16* y1o = p.y1 + (int64_t)l * MH;
+#pragma unroll 1
+        for (int cb = 0; cb < 32; cb += 8) {
+          uint32_t r[8];
+          __syncwarp();
+          tmem_ld8(tmem_lane + RF_TM_PROJ + ch * 32 + cb, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int c = ch * 32 + j;
-          float a = __uint_as_float(r[j]);
-          const int64_t row = row0 + c;
-          if (p.p1 > 0.0f) a = hash32(sd, (uint64_t)row * RF_H + (uint64_t)f_glob) >= thr1 ? a * keep1 : 0.0f;
-          a += feat_ok ? __bfloat162float(Xs[c * RF_LDN + f_loc]) : 0.0f;
-          a = bf16_round(a);
-          v[j] = a;
-          if (feat_ok && c < nrows) y1o[row * RF_H + f_glob] = __float2bfloat16_rn(a);
+          for (int k = 0; k < 8; ++k) {
+            const int c = ch * 32 + cb + k;
+            float a = __uint_as_float(r[k]);
+            if (p.p1 > 0.0f) a = hash32(sd, (uint64_t)(row0 + c) * RF_H + (uint64_t)f_glob) >= thr1 ? a * keep1 : 0.0f;
+            a += __bfloat162float(Xs[c * RF_LDN + f_loc]);
+            Ys[c * RF_LDN + f_loc] = __float2bfloat16_rn(a);
+          }
         }
       }
-      float mean, rstd;
       if (ctid == 0) RF_TRACE(3, 5);
-      cluster_ln_stats(v, feat_ok, q, ch, lane, h, smem, 0, cl_e1, lp, p.eps, mean, rstd);
+      cluster_layernorm(smem, ctid, h, 0, cl_e1, lp, p.eps, p.g1[l], p.be1[l], nrows, row0, p.y1 + (int64_t)l * MH,
+                        p.x1 + (int64_t)l * MH, X1s, p.mean1 + (int64_t)l * M, p.rstd1 + (int64_t)l * M);
       if (ctid == 0) RF_TRACE(3, 6);
-      {
-        const float gm = feat_ok ? __ldg(p.g1[l] + f_glob) : 0.0f, bt = feat_ok ? __ldg(p.be1[l] + f_glob) : 0.0f;
-        bf16* x1o = p.x1 + (int64_t)l * MH;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int c = ch * 32 + j;
-          const float mj = __shfl_sync(0xffffffffu, mean, j), rj = __shfl_sync(0xffffffffu, rstd, j);
-          const float o = bf16_round((v[j] - mj) * rj * gm + bt);
-          x1r[j] = o;
-          if (feat_ok && c < nrows) x1o[(int64_t)(row0 + c) * RF_H + f_glob] = __float2bfloat16_rn(o);
-        }
-        if (h == 0 && q == 0 && ch * 32 + lane < nrows) {
-          p.mean1[(int64_t)l * M + row0 + ch * 32 + lane] = mean;
-          p.rstd1[(int64_t)l * M + row0 + ch * 32 + lane] = rstd;
-        }
-      }
       fence_proxy_async();
-      __threadfence();
       compute_sync();
-      if (ctid == 0) cluster_arrive_all(cl_s2);
+      cluster_publish(cl_s2, ctid);
       if (ctid == 0) RF_TRACE(3, 7);
 
       // ------------------------------------------------------------------ FF1 epilogue: + bias, SERF
@@ -681,16 +744,16 @@ __global__ void __cluster_dims__(RF_HEADS, 1, 1) __launch_bounds__(RF_THREADS, 1
           if (ctid == 0) RF_TRACE(3, 8 + m);
           const int fh = RF_FS * (int)h + 128 * m + 32 * q + lane;
           const float bias = __ldg(p.b1[l] + fh);
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            uint32_t r[16];
+#pragma unroll 1
+          for (int cb = 0; cb < 32 && ch * 32 + cb < nrows; cb += 8) {
+            uint32_t r[8];
             __syncwarp();
-            tmem_ld16(tmem_lane + RF_TM_FF1 + m * RF_N + ch * 32 + half * 16, r);
+            tmem_ld8(tmem_lane + RF_TM_FF1 + m * RF_N + ch * 32 + cb, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int c = ch * 32 + half * 16 + j;
-              const float a = __uint_as_float(r[j]) + bias;
+            for (int k = 0; k < 8; ++k) {
+              const int c = ch * 32 + cb + k;
+              const float a = __uint_as_float(r[k]) + bias;
               if (c < nrows) {
                 const int64_t off = (int64_t)(row0 + c) * RF_F + fh;
                 hpo[off] = __float2bfloat16_rn(a);
@@ -701,56 +764,37 @@ __global__ void __cluster_dims__(RF_HEADS, 1, 1) __launch_bounds__(RF_THREADS, 1
         }
       }
       fence_proxy_async();
-      __threadfence();
       compute_sync();
-      if (ctid == 0) cluster_arrive_all(cl_s3);
+      cluster_publish(cl_s3, ctid);
       if (ctid == 0) RF_TRACE(3, 11);
 
-      // ------------------------------------------------------------------ FF2 epilogue: + bias, dropout, residual, LN2
+      // ------------------------------------------------------------------ FF2 epilogue: + bias, dropout, + x1 -> Ys; LN2
       mbar_wait(tmem_full + 8 * 4, lp);
       tc_fence_after();
       if (ctid == 0) RF_TRACE(3, 12);
-      {
-        uint32_t r[32];
-        __syncwarp();
-        tmem_ld16(tmem_lane + RF_TM_FF2 + ch * 32, r);
-        tmem_ld16(tmem_lane + RF_TM_FF2 + ch * 32 + 16, r + 16);
-        tmem_ld_wait();
+      if (feat_ok) {
         const unsigned long long sd = seed0 + 2ull * (unsigned long long)l + 1ull;
-        const float bias = feat_ok ? __ldg(p.b2[l] + f_glob) : 0.0f;
-        bf16* y2o = p.y2 + (int64_t)l * MH;
+        const float bias = __ldg(p.b2[l] + f_glob);
+#pragma unroll 1
+        for (int cb = 0; cb < 32; cb += 8) {
+          uint32_t r[8];
+          __syncwarp();
+          tmem_ld8(tmem_lane + RF_TM_FF2 + ch * 32 + cb, r);
+          tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int c = ch * 32 + j;
-          float a = __uint_as_float(r[j]) + bias;
-          const int64_t row = row0 + c;
-          if (p.p2 > 0.0f) a = hash32(sd, (uint64_t)row * RF_H + (uint64_t)f_glob) >= thr2 ? a * keep2 : 0.0f;
-          a = bf16_round(a + x1r[j]);
-          v[j] = a;
-          if (feat_ok && c < nrows) y2o[row * RF_H + f_glob] = __float2bfloat16_rn(a);
+          for (int k = 0; k < 8; ++k) {
+            const int c = ch * 32 + cb + k;
+            float a = __uint_as_float(r[k]) + bias;
+            if (p.p2 > 0.0f) a = hash32(sd, (uint64_t)(row0 + c) * RF_H + (uint64_t)f_glob) >= thr2 ? a * keep2 : 0.0f;
+            a += __bfloat162float(X1s[c * RF_LDN + f_loc]);
+            Ys[c * RF_LDN + f_loc] = __float2bfloat16_rn(a);
+          }
         }
       }
       if (ctid == 0) RF_TRACE(3, 13);
-      cluster_ln_stats(v, feat_ok, q, ch, lane, h, smem, 1, cl_e2, lp, p.eps, mean, rstd);
+      cluster_layernorm(smem, ctid, h, 1, cl_e2, lp, p.eps, p.g2[l], p.be2[l], nrows, row0, p.y2 + (int64_t)l * MH,
+                        p.xout + (int64_t)l * MH, Xs, p.mean2 + (int64_t)l * M, p.rstd2 + (int64_t)l * M);
       if (ctid == 0) RF_TRACE(3, 14);
-      {
-        const float gm = feat_ok ? __ldg(p.g2[l] + f_glob) : 0.0f, bt = feat_ok ? __ldg(p.be2[l] + f_glob) : 0.0f;
-        bf16* xo = p.xout + (int64_t)l * MH;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int c = ch * 32 + j;
-          const float mj = __shfl_sync(0xffffffffu, mean, j), rj = __shfl_sync(0xffffffffu, rstd, j);
-          const bf16 o = __float2bfloat16_rn((v[j] - mj) * rj * gm + bt);
-          if (feat_ok) {
-            Xs[c * RF_LDN + f_loc] = c < nrows ? o : __float2bfloat16_rn(0.0f);   // next layer's kqv operand and residual
-            if (c < nrows) xo[(int64_t)(row0 + c) * RF_H + f_glob] = o;
-          }
-        }
-        if (h == 0 && q == 0 && ch * 32 + lane < nrows) {
-          p.mean2[(int64_t)l * M + row0 + ch * 32 + lane] = mean;
-          p.rstd2[(int64_t)l * M + row0 + ch * 32 + lane] = rstd;
-        }
-      }
       compute_sync();                                   // Xs complete before the next layer's kqv reads it
       if (ctid == 0) RF_TRACE(3, 15);
     }
@@ -846,6 +890,7 @@ int mmvqa_rf_encoder_fwd(const mmvqa_rf_encoder_args* a, mmvqa_stream_t stream) 
     if ((rc = rf_weight_map(&prm.w1[l], a->w1[l], RF_F, RF_H, 128, 3, "ff.0.weight"))) return rc;
     if ((rc = rf_weight_map(&prm.w2[l], a->w2[l], RF_H, RF_F, RF_D, 4, "ff.2.weight"))) return rc;
     prm.wkqv[l] = reinterpret_cast<const bf16*>(a->wkqv[l]);
+    prm.wp_raw[l] = a->wproj[l]; prm.w1_raw[l] = a->w1[l]; prm.w2_raw[l] = a->w2[l];
     prm.b1[l] = a->b1[l]; prm.b2[l] = a->b2[l];
     prm.g1[l] = a->ln1_w[l]; prm.be1[l] = a->ln1_b[l]; prm.g2[l] = a->ln2_w[l]; prm.be2[l] = a->ln2_b[l];
   }

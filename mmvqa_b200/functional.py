@@ -728,10 +728,13 @@ class RealFormerEncoderFn(torch.autograd.Function):
         fuse_kqv = (dt == torch.bfloat16 and d % 16 == 0 and T <= 128 and d <= 128 and
                     (2 * ((T + 15) // 16 * 16) * (d + 8) + d * ((T + 15) // 16 * 16 + 8) + ((T + 15) // 16 * 16) * (d + 8)
                      + 3 * d * (d + 8)) * 2 <= 200 * 1024 and _os.environ.get("MMVQA_NO_FUSED_KQV") is None)
-        # small batches: the whole encoder forward is ONE launch of the sample-stationary cluster kernel
-        # (csrc/rf_encoder.cu); it writes the same intermediates the per-operator chain below saves
+        # opt-in (MMVQA_RF_ENCODER=1): the whole encoder forward as ONE launch of the sample-stationary cluster kernel
+        # (csrc/rf_encoder.cu); it writes the same intermediates the per-operator chain below saves.  Measured at the
+        # flagship shape (B = 16, T = 28, 12 layers): 717 us against 634 us for the chain below -- one 8-CTA cluster per
+        # sample pair keeps 64 of the 148 SMs busy and each of them is bound by its own TMA ingest (~0.7 us per 48 KB box
+        # with two boxes in flight), so the chain, which spreads every GEMM over the whole chip, stays the default.
         F4_ = params[4].shape[0]
-        if dt == torch.bfloat16 and _os.environ.get("MMVQA_NO_RF_ENCODER") is None and \
+        if dt == torch.bfloat16 and _os.environ.get("MMVQA_RF_ENCODER") == "1" and \
                 ops.rf_encoder_supported(B, T, H, heads, F4_, n_layers):
             layers = []
             for l in range(n_layers):

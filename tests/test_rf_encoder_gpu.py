@@ -31,10 +31,7 @@ def _blocks(n_layers, seed=0, drop=0.0):
 
 
 def _run(native, x, mask, prev, params, drop=0.0, seed=1234):
-    if native:
-        os.environ.pop("MMVQA_NO_RF_ENCODER", None)
-    else:
-        os.environ["MMVQA_NO_RF_ENCODER"] = "1"
+    os.environ["MMVQA_RF_ENCODER"] = "1" if native else "0"
     seen = {}
     orig = torch.autograd.function.FunctionCtx.save_for_backward
 
@@ -46,7 +43,7 @@ def _run(native, x, mask, prev, params, drop=0.0, seed=1234):
         y, sc = Fn.RealFormerEncoderFn.apply(x, mask, prev, 8, drop, drop, seed, *params)
     finally:
         torch.autograd.function.FunctionCtx.save_for_backward = orig
-        os.environ.pop("MMVQA_NO_RF_ENCODER", None)
+        os.environ.pop("MMVQA_RF_ENCODER", None)
     return y, sc, seen["saved"]
 
 
@@ -102,7 +99,13 @@ def test_cluster_kernel_matches_the_oracle():
         x = torch.randn(B, T, 768, device="cuda")
         mask = torch.ones(B, T, device="cuda", dtype=torch.long)
         mask[2, 20:] = 0
-        y, prev = run_blocks(list(blocks), x, None, mask, False)
+        os.environ["MMVQA_RF_ENCODER"] = "1"
+        n0 = mmvqa_b200._lib.launch_count()
+        try:
+            y, prev = run_blocks(list(blocks), x, None, mask, False)
+        finally:
+            os.environ.pop("MMVQA_RF_ENCODER", None)
+        assert mmvqa_b200._lib.launch_count() - n0 <= 6, "the encoder did not take the one-launch path"
         sd = {k: v.detach().cpu().float() for k, v in blocks.state_dict().items()}
         xo, po = x.cpu(), None
         for l in range(L):

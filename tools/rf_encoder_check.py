@@ -43,10 +43,7 @@ def main():
     prev0 = None
 
     def run(native: bool, xin):
-        if native:
-            os.environ.pop("MMVQA_NO_RF_ENCODER", None)
-        else:
-            os.environ["MMVQA_NO_RF_ENCODER"] = "1"
+        os.environ["MMVQA_RF_ENCODER"] = "1" if native else "0"
         seen = {}
         orig = torch.autograd.function.FunctionCtx.save_for_backward
 
@@ -130,7 +127,7 @@ def main():
     t_ops = timeit(False)
     t_one = timeit(True)
     print("forward, B=%d T=%d L=%d: per-operator chain %.1f us, cluster kernel %.1f us (%.2fx)" % (B, T, a.L, t_ops, t_one, t_ops / t_one))
-    os.environ.pop("MMVQA_NO_RF_ENCODER", None)
+    os.environ.pop("MMVQA_RF_ENCODER", None)
     if a.trace:
         from mmvqa_b200 import ops
         buf = torch.zeros(4, 16, 16, dtype=torch.int64, device="cuda")
