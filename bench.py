@@ -188,6 +188,63 @@ def config_dict(B, n):
             "l2": "4 rotating input batches (147 MB) and 1.3 GB of weights + Adam state are streamed every step (> 126 MB L2)"}
 
 
+def gpu_eager_bar(model_state, B, steps=10):
+    """The GPU-side bar of SURVEY.md section 8d: the reference arithmetic as plain eager PyTorch on the same B200 (cuBLAS /
+    cuDNN / ATen kernels, ~30 launches per layer), fp32 and bf16 autocast, eager and CUDA-graphed, same batch, same
+    torch.optim.Adam.  /root/reference does not exist on the GPU box, so this runs the oracle port (oracle/mmbert_oracle.py:
+    the line-by-line torch restatement of models/*.py that tests/test_oracle_golden.py pins bit-exactly to vectors
+    generated from the unmodified reference) -- a reported bar, never the product path."""
+    from oracle import mmbert_oracle as O
+    out = {}
+    feats, ids, seg, mask, target = [t.cuda() if torch.is_tensor(t) else [u.cuda() for u in t] for t in synth_batch(B, 1234)]
+    for name, autocast, graphed in (("fp32_eager", False, False), ("bf16_autocast_eager", True, False),
+                                    ("fp32_cuda_graph", False, True), ("bf16_autocast_cuda_graph", True, True)):
+        try:
+            p = {k: v.detach().clone().float().cuda().requires_grad_(v.is_floating_point()) for k, v in model_state.items()}
+            params = [v for v in p.values() if v.requires_grad]
+            opt = torch.optim.Adam(params, lr=1e-5, capturable=graphed)
+
+            def step():
+                opt.zero_grad(set_to_none=True)
+                with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    logits = O.model_forward(feats, ids, seg, mask, p, encoder="realformer", n_layers=LAYERS, dataset="VQA-Med")
+                    loss = O.asl_single_label(logits.float(), target)
+                loss.backward()
+                opt.step()
+                return loss
+            run = step
+            if graphed:
+                s_ = torch.cuda.Stream()
+                s_.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s_):
+                    for _ in range(3):
+                        step()
+                torch.cuda.current_stream().wait_stream(s_)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    step()
+                run = g.replay
+            for _ in range(3):
+                run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                run()
+            e1.record()
+            e1.synchronize()
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"samples_per_s": B / (ms * 1e-3), "ms_per_step": ms}
+            del p, params, opt
+        except Exception as ex:      # e.g. an op that cannot be captured: report, do not fail the bench
+            out[name] = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
+        torch.cuda.synchronize()
+        torch.cuda.empty_cache()
+    out["what"] = ("oracle port of models/*.py as eager PyTorch on this GPU (ATen/cuBLAS), same batch, torch.optim.Adam; "
+                   "dropout off (the port has none)")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
@@ -389,13 +446,23 @@ def main_gpu(a):
         nonlocal gs
         if world > 1:
             dist.barrier()
+            if gs is not None:
+                gs.close()               # drops the graph (and the NCCL work it captured) after the device has drained
+                gs = None
             torch.cuda.synchronize()
-            if overlapped_dp:
+            th = threading.Thread(target=dist.destroy_process_group, daemon=True)
+            th.start()
+            th.join(timeout=30)
+            if th.is_alive():            # communicator teardown stuck on captured work: leave without it
                 sys.stdout.flush()
                 sys.stderr.flush()
                 os._exit(0)
-            dist.destroy_process_group()
     if rank != 0:
+        finish()
+        return
+    if a.quick:          # tuning runs: the two timed regions only
+        print(json.dumps({"quick": True, "value": value, "ms_per_step": ms_step, "e2e": e2e_value, "ms_e2e": ms_e2e / a.steps,
+                          "gpu_launches_per_step": launches, "n_gpus": world, "clocks": clocks.summary()}), flush=True)
         finish()
         return
     hbm, tf_burst, tf_sus, which = peaks()
@@ -467,6 +534,41 @@ def main_gpu(a):
                            "bound": "hbm", "achieved": adam_gbs, "peak": hbm, "unit": "GB/s", "frac": adam_gbs / hbm,
                            "ms_per_launch": ms_adam, "share_of_step": ms_adam / ms_step},
             "step_tensor_frac": value / world * STEP_GFLOP_PER_SAMPLE * 1e9 / (tf_burst * 1e12)}
+    # ---- hot path only: feature maps -> loss -> all gradients, no optimizer ----
+    log("hot path only")
+    hot = None
+    try:
+        class _NoOptimizer:
+            """zero_grad only: the captured step is forward + loss + backward, nothing else"""
+            def zero_grad(self, set_to_none=True):
+                for p_ in params:
+                    p_.grad = None
+
+            def step(self):
+                pass
+        gh = GraphedTrainStep(loss_fn, dev[0], _NoOptimizer(), warmup=2, main_priority=a.main_priority)
+        for i in range(5):
+            gh.replay_packed(dev_flat[i % NB])
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(a.steps):
+            gh.replay_packed(dev_flat[i % NB])
+        e1.record()
+        e1.synchronize()
+        ms_hot = e0.elapsed_time(e1) / a.steps
+        hot = {"ms_per_step": ms_hot, "samples_per_s": B / (ms_hot * 1e-3), "launches_per_step": gh.launches_per_step,
+               "tensor_frac": B / (ms_hot * 1e-3) * STEP_GFLOP_PER_SAMPLE * 1e9 / (tf_burst * 1e12),
+               "what": "projector -> encoder -> heads -> ASL, forward + backward (every gradient), CUDA-graph replay, no Adam"}
+        gh.close()
+        del gh
+    except Exception as ex:
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        hot = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
+    eager = None
+    if world == 1 and not a.no_eager_bar:
+        log("eager PyTorch bar")
+        eager = gpu_eager_bar({k: v.detach() for k, v in model.state_dict().items()}, B)
     cpu = None
     if world == 1 and not a.no_cpu:
         state = {k: v.detach().cpu() for k, v in model.state_dict().items()}
@@ -480,7 +582,8 @@ def main_gpu(a):
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / a.steps},
             "gpu_launches": launches * a.steps, "gpu_launches_per_step": launches, "clocks": clocks.summary(),
-            "roofline": roof, "cpu_baseline": cpu, "loss": loss_val, "dropout": bool(a.dropout), "params": nparams}
+            "roofline": roof, "cpu_baseline": cpu, "hot_path_only": hot, "gpu_eager_reference": eager,
+            "loss": loss_val, "dropout": bool(a.dropout), "params": nparams}
     print(json.dumps(line), flush=True)
     finish()
 
@@ -495,6 +598,7 @@ if __name__ == "__main__":
     ap.add_argument("--batch", type=int, default=16, help="samples per GPU (weak scaling)")
     ap.add_argument("--dropout", type=int, default=1, help="1: training-mode dropout on (throughput runs), 0: off")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-eager-bar", action="store_true", help="skip the eager-PyTorch-on-GPU bar")
     ap.add_argument("--verbose", action="store_true", help="progress lines on stderr")
     ap.add_argument("--bf16-buckets", type=int, default=1, help="data parallel: all-reduce gradients as bf16 (bf16 path only)")
     ap.add_argument("--overlap-adam", type=int, default=1, help="1 GPU: update each layer under the rest of the backward pass")
@@ -504,6 +608,7 @@ if __name__ == "__main__":
     ap.add_argument("--sink-group", type=int, default=4, help="data parallel: encoder layers per all-reduce + Adam launch")
     ap.add_argument("--sink-group-1gpu", type=int, default=1, help="single GPU: encoder layers per Adam launch")
     ap.add_argument("--dp-mode", default="overlapped", choices=["overlapped", "twograph"])
+    ap.add_argument("--quick", action="store_true", help="tuning: print value / e2e only (no roofline, no CPU leg)")
     ap.add_argument("--pad-steps", type=int, default=100, help="untimed steps around the timed region (clock sampling)")
     a = ap.parse_args()
     if os.environ.get("MMVQA_BENCH_WATCHDOG"):      # debugging aid: dump every thread's stack and exit if the run hangs

@@ -956,25 +956,27 @@ class SupConFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, Fm: Tensor, mask: Optional[Tensor], bsz: int, n_anchor_rows: int, temperature: float,
-                base_temperature: float, dtype: torch.dtype):
+                base_temperature: float, dtype: torch.dtype, row_offset: int = 0):
+        """anchors = rows [row_offset, row_offset + n_anchor_rows) of the contrast matrix (row_offset > 0: the
+        local-anchor slice of a data-parallel rank, mmvqa_b200.parallel.supcon_loss_sharded)."""
         N, D = Fm.shape
         Fc, ld = _pad_ld(Fm.detach(), dtype)
         raw = torch.empty(n_anchor_rows, N, device=Fm.device, dtype=torch.float32)
-        ops.gemm(n_anchor_rows, N, D, Fc, ld, False, Fc, ld, False, raw, N)
-        loss_rows, G = ops.supcon_rows(raw, None if mask is None else mask.contiguous().float(), bsz, 0, temperature,
+        ops.gemm(n_anchor_rows, N, D, Fc[row_offset:], ld, False, Fc, ld, False, raw, N)
+        loss_rows, G = ops.supcon_rows(raw, None if mask is None else mask.contiguous().float(), bsz, row_offset, temperature,
                                        base_temperature, True)
         ctx.save_for_backward(Fc, G)
-        ctx.meta = (N, D, ld, n_anchor_rows, dtype, Fm.dtype)
+        ctx.meta = (N, D, ld, n_anchor_rows, dtype, Fm.dtype, row_offset)
         return loss_rows
 
     @staticmethod
     def backward(ctx, dloss_rows):
         Fc, G = ctx.saved_tensors
-        N, D, ld, R, dtype, in_dtype = ctx.meta
+        N, D, ld, R, dtype, in_dtype, off = ctx.meta
         Gs = G * dloss_rows.reshape(-1, 1).float()
         Gc, ldg = _pad_ld(Gs, dtype)
         dF = torch.zeros(N, D, device=Fc.device, dtype=torch.float32)
-        # anchor role: dF[:R] += G . F ;  contrast role: dF += G^T . F[:R]
-        ops.gemm(R, D, N, Gc, ldg, False, Fc, ld, True, dF, D, accumulate=True)
-        ops.gemm(N, D, R, Gc, ldg, True, Fc, ld, True, dF, D, accumulate=True)
-        return dF.to(in_dtype), None, None, None, None, None, None
+        # anchor role: dF[off:off+R] += G . F ;  contrast role: dF += G^T . F[off:off+R]
+        ops.gemm(R, D, N, Gc, ldg, False, Fc, ld, True, dF[off:], D, accumulate=True)
+        ops.gemm(N, D, R, Gc, ldg, True, Fc[off:], ld, True, dF, D, accumulate=True)
+        return dF.to(in_dtype), None, None, None, None, None, None, None

@@ -166,3 +166,70 @@ def gather_mask_rows(mask_local_rows: torch.Tensor) -> torch.Tensor:
     outs = [torch.empty_like(mask_local_rows) for _ in range(dist.get_world_size())]
     dist.all_gather(outs, mask_local_rows.contiguous())
     return torch.cat(outs, dim=0)
+
+
+class _GatherFeaturesRS(torch.autograd.Function):
+    """all-gather of [n_local, n_views, D] embeddings (rank-major) whose backward is a REDUCE-SCATTER (sum): with
+    local-anchor rows every rank holds a different gradient of the gathered tensor -- the anchor-role rows of its own
+    samples and the contrast-role contributions to everybody else's -- and each rank needs only the sum over ranks of
+    its own slice (collective 2)."""
+
+    @staticmethod
+    def forward(ctx, feat):
+        world = dist.get_world_size()
+        feat = feat.contiguous()
+        out = torch.empty((world * feat.shape[0],) + tuple(feat.shape[1:]), device=feat.device, dtype=feat.dtype)
+        if dist.get_backend() == "nccl":
+            dist.all_gather_into_tensor(out, feat)
+        else:
+            dist.all_gather(list(out.chunk(world, dim=0)), feat)
+        ctx.n = feat.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, dgathered):
+        n, rank = ctx.n, dist.get_rank()
+        g = dgathered.contiguous()
+        if dist.get_backend() == "nccl":
+            out = torch.empty((n,) + tuple(g.shape[1:]), device=g.device, dtype=g.dtype)
+            dist.reduce_scatter_tensor(out, g, op=dist.ReduceOp.SUM)
+            return out
+        dist.all_reduce(g, op=dist.ReduceOp.SUM)          # gloo has no reduce-scatter: all-reduce + slice
+        return g[rank * n:(rank + 1) * n]
+
+
+def supcon_loss_sharded(feat_local: torch.Tensor, mask: Optional[torch.Tensor] = None, temperature: float = 0.07,
+                        base_temperature: float = 0.07) -> torch.Tensor:
+    """SupConLoss (models/SupConLoss/loss.py:21-98, contrast_mode 'all') of the GLOBAL batch with the anchor rows
+    partitioned over the ranks: every rank all-gathers the embeddings, computes the similarity rows of ITS samples'
+    anchors against all world * n_local * n_views contrasts (1 / world of the N x N problem) and returns
+
+        loss_r = world * sum_{local anchors} row_loss / (n_views * bsz_global),
+
+    so that mean_r loss_r is the reference's loss of the global batch (loss.py:96) and, with the usual data-parallel
+    gradient averaging, every replica receives the global-batch gradient: the backward of the gather is a reduce-scatter
+    of the contrast-role gradients.  `mask`: optional FULL [bsz_global, bsz_global] float mask (gather_mask_rows).
+    Single process: identical to SupConLoss()(feat_local, mask=mask)."""
+    from . import functional as Fn
+    from .config import compute_dtype
+    if feat_local.dim() < 3:
+        raise ValueError('`features` needs to be [bsz, n_views, ...],at least 3 dimensions are required')
+    feat_local = feat_local.reshape(feat_local.shape[0], feat_local.shape[1], -1)
+    world = dist.get_world_size() if is_dist() else 1
+    rank = dist.get_rank() if is_dist() else 0
+    n, nv = feat_local.shape[0], feat_local.shape[1]
+    gathered = _GatherFeaturesRS.apply(feat_local) if world > 1 else feat_local
+    bsz = world * n
+    if mask is not None and tuple(mask.shape) != (bsz, bsz):
+        raise ValueError("supcon_loss_sharded: mask must be the full [bsz_global, bsz_global] matrix")
+    Fm = gathered.transpose(0, 1).reshape(nv * bsz, -1)                 # view-major contrast matrix (loss.py:58)
+    if Fm.dtype not in (torch.float32, torch.bfloat16):
+        Fm = Fm.float()
+    Fm = Fm.contiguous()
+    m = None if mask is None else mask.float().to(Fm.device)
+    total = None
+    for v in range(nv):
+        rows = Fn.SupConFn.apply(Fm, m, bsz, n, float(temperature), float(base_temperature), compute_dtype(),
+                                 v * bsz + rank * n)
+        total = rows.sum() if total is None else total + rows.sum()
+    return total * (float(world) / float(nv * bsz))

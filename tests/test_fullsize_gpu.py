@@ -179,3 +179,100 @@ def test_supcon_global_batch_2048():
             assert abs(loss.item() - ref.item()) < tol * abs(ref.item()), (dt, loss.item(), ref.item())
             e = (fd.grad.cpu() - gref).abs().max() / gref.abs().max()
             assert e < (1e-3 if dt == torch.float32 else 0.15), (dt, float(e))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs[0] and configs[2] at their real sizes (only hidden-64 goldens covered them)
+# ------------------------------------------------------------------------------------------------------------------
+RESNET_MAPS = [(2048, 7), (1024, 14), (512, 28), (256, 56), (64, 112)]      # token order deep -> shallow (image_encoding.py:13,87)
+
+
+def _full_model(transformer_model, cnn_encoder, heads, n_layers, dataset, task, supcon=False, seed=7):
+    import types
+    import torch.nn as nn
+    from transformers import BertConfig, BertModel
+    from mmvqa_b200.models import image_encoding as IE
+    from mmvqa_b200.models import mmbert as MM
+    args = types.SimpleNamespace(task=task, clinicalbert="", transformer_model=transformer_model, cnn_encoder=cnn_encoder,
+                                 num_vis=5, hidden_size=768, use_relu=False, heads=heads, hidden_dropout_prob=0.1,
+                                 n_layers=n_layers, vocab_size=30522, dataset=dataset, supcon=supcon)
+    old = MM.AutoModel.from_pretrained
+    MM.AutoModel.from_pretrained = staticmethod(lambda name, *a, **k: BertModel(BertConfig(num_hidden_layers=1)))
+    IE.models_dict[5]["tf_efficientnetv2_m"][0] = lambda *a, **k: nn.Identity()
+    IE.models_dict[5]["resnet152"][0] = lambda *a, **k: nn.Identity()
+    try:
+        torch.manual_seed(seed)
+        return MM.Model(args).eval()
+    finally:
+        MM.AutoModel.from_pretrained = old
+
+
+def test_c1_resnet152_transformer12_forward_fullsize():
+    """configs[0]: ResNet152 map shapes (2048@7^2 ... 64@112^2, deep -> shallow token order), Transformer-12 (12 heads x
+    64, shared pre-norm), hidden 768, num_vis 5, B = 16, T = 28, un-swapped vocab head -> logits [16, 30522], forward.
+    fp32 path: 1e-4 of the logit range and bit-exact argmax; bf16 path: 5e-2 of the range."""
+    B = 16
+    model = _full_model("transformer", "resnet152", 12, 12, "VQA-Med", "VQA")
+    g = torch.Generator().manual_seed(21)
+    feats = [torch.randn(B, c, s, s, generator=g).abs() for c, s in RESNET_MAPS]
+    _, ids, seg, mask, _ = bench.synth_batch(B, 5)
+    p = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    with torch.no_grad():
+        ref = O.model_forward(feats, ids, seg, mask, p, encoder="transformer", n_layers=12, heads=12, dataset="VQA-Med")
+    assert ref.shape == (B, 30522)
+    model = model.to(DEV)
+    for dt, tol in ((torch.float32, 1e-4), (torch.bfloat16, 5e-2)):
+        with mmvqa_b200.compute_dtype_scope(dt), torch.no_grad():
+            logits, z1, z2 = model.forward_features([f.to(DEV) for f in feats], ids.to(DEV), seg.to(DEV), mask.to(DEV))
+        assert z1 == 0 and z2 == 0 and logits.shape == (B, 30522)
+        err = ((logits.float().cpu() - ref).abs().max() / ref.abs().max()).item()
+        assert err < tol, (dt, err)
+        if dt == torch.float32:
+            assert torch.equal(logits.argmax(-1).cpu(), ref.argmax(-1)), "fp32 argmax must equal the reference's"
+    model.cpu()
+
+
+def test_c3_mlm_step_at_the_per_gpu_shape():
+    """configs[2] on one of its 8 GPUs: RealFormer-12 MLM step, B = 32 (256 / 8), T = 75, V = 30522, EffNetV2-M maps,
+    forward + NLL over every position (roco_utils.py:235-236, target 0 is a class) + backward, against the oracle."""
+    from mmvqa_b200 import functional as Fn
+    B, Tn, V = 32, 75, 30522
+    model = _full_model("realformer", "tf_efficientnetv2_m", 8, 12, "roco", "MLM")
+    g = torch.Generator().manual_seed(31)
+    feats = [torch.randn(B, c, s, s, generator=g).abs() for c, s in bench.EFFNET_MAPS]
+    ids = torch.randint(1000, V, (B, Tn), generator=g)
+    ids[:, :5] = 0
+    seg = torch.zeros(B, Tn, dtype=torch.long)
+    mask = torch.ones(B, Tn, dtype=torch.long)
+    for b in range(B):
+        mask[b, 40 + b:] = 0
+    target = torch.where(torch.rand(B, Tn, generator=g) < 0.15, ids, torch.zeros_like(ids))
+    names = ["transformer.mains.0.kqv.weight", "transformer.mains.11.ff.0.weight", "transformer.mains.6.ln2.bias",
+             "classifier.2.weight", "fc1.bias", "transformer.trans.conv5.weight"]
+    p = {k: v.detach().clone().requires_grad_(k in names) for k, v in model.state_dict().items()}
+    ref_logits = O.model_forward(feats, ids, seg, mask, p, encoder="realformer", n_layers=12, dataset="roco")
+    ref_loss = O.mlm_nll(ref_logits, target)
+    ref_grads = dict(zip(names, torch.autograd.grad(ref_loss, [p[n] for n in names])))
+    ref_logits = ref_logits.detach()
+    model = model.to(DEV)
+    params = dict(model.named_parameters())
+    for dt, tol, gtol in ((torch.float32, 2e-4, 3e-3), (torch.bfloat16, 6e-2, 0.15)):
+        with mmvqa_b200.compute_dtype_scope(dt):
+            model.zero_grad(set_to_none=True)
+            logits = model.forward_features([f.to(DEV) for f in feats], ids.to(DEV), seg.to(DEV), mask.to(DEV))
+            assert logits.shape == (B, Tn, V)
+            loss = Fn.CrossEntropyRowsFn.apply(logits.view(B * Tn, V), target.view(-1).to(DEV)).mean()
+            loss.backward()
+        err = ((logits.float().cpu() - ref_logits).abs().max() / ref_logits.abs().max()).item()
+        assert err < tol, (dt, err)
+        assert abs(loss.item() - ref_loss.item()) < (1e-4 if dt == torch.float32 else 3e-2) * ref_loss.item()
+        if dt == torch.float32:
+            # 2400 rows x 30522 classes of a random-init head: near-ties between the two largest logits exist at the
+            # 1e-6 level, so the token-level argmax is checked as a rate (the VQA answer argmax above is bit-exact)
+            same = (logits.argmax(-1).cpu() == ref_logits.argmax(-1)).float().mean().item()
+            assert same >= 0.995, same
+        for n, gr in ref_grads.items():
+            e = ((params[n].grad.cpu() - gr).abs().max() / gr.abs().max().clamp_min(1e-12)).item()
+            assert e < gtol, (dt, n, e)
+        del logits, loss
+    model.cpu()

@@ -20,6 +20,20 @@ def _free_port():
     return p
 
 
+def _supcon_rows_torch(features, mask, temperature=0.07, base_temperature=0.07):
+    """per-anchor SupCon losses (loss.py:58-96 before the final mean), contrast_mode 'all'."""
+    bsz, nv, _ = features.shape
+    cf = features.transpose(0, 1).reshape(nv * bsz, -1)
+    logits = cf @ cf.t() / temperature
+    logits = logits - logits.max(dim=1, keepdim=True)[0].detach()
+    m = mask.float().repeat(nv, nv)
+    lm = 1.0 - torch.eye(nv * bsz)
+    m = m * lm
+    exp_logits = torch.exp(logits) * lm
+    log_prob = logits - torch.log(exp_logits.sum(1, keepdim=True))
+    return -(temperature / base_temperature) * (m * log_prob).sum(1) / m.sum(1)
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -55,6 +69,16 @@ def _worker(rank, world, port, q):
     full_mask = gather_mask_rows(soft[rank * 3:(rank + 1) * 3])
     sl = O.supcon_loss(gathered, mask=full_mask)
     sl.backward()
+    # local-anchor rows: the same gather with a reduce-scatter backward; each rank evaluates only the
+    # loss rows of its own samples' anchors (here with plain torch ops restating loss.py:72-96 per anchor row)
+    from mmvqa_b200.parallel import _GatherFeaturesRS
+    f2 = F[rank * 3:(rank + 1) * 3].clone().requires_grad_(True)
+    g2 = _GatherFeaturesRS.apply(f2)
+    rows = _supcon_rows_torch(g2, full_mask)                              # [2 * 6] per-anchor losses, view-major
+    mine = torch.cat([rows[v * 6 + rank * 3: v * 6 + rank * 3 + 3] for v in range(2)])
+    loss_r = mine.sum() * (2.0 / 12.0)                                   # world * sum(local rows) / (n_views * bsz_global)
+    loss_r.backward()
+    q.put({"rank2": rank, "df2": f2.grad.clone(), "loss_r": loss_r.detach().clone()})
     if rank == 0:
         q.put({"state": {k: v.clone() for k, v in model.state_dict().items()}, "avg": [a.clone() for a in avg],
                "lay": lay,
@@ -71,7 +95,7 @@ def test_dp_world2_gloo():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=120) for _ in range(3)]
+    got = [q.get(timeout=120) for _ in range(5)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -100,3 +124,9 @@ def test_dp_world2_gloo():
     # ranks, so each local slice receives world x the single-process gradient (DP averaging divides it back)
     for r in range(2):
         torch.testing.assert_close(dfs[r] / 2, F.grad[r * 3:(r + 1) * 3], rtol=1e-5, atol=1e-6)
+    # local-anchor partition: mean over ranks of the per-rank losses == the global loss, and the reduce-scatter hands
+    # every rank the same world x gradient of its slice as the redundant formulation above
+    sh = {x["rank2"]: x for x in got if "rank2" in x}
+    torch.testing.assert_close(0.5 * (sh[0]["loss_r"] + sh[1]["loss_r"]), ref.detach(), rtol=1e-5, atol=1e-6)
+    for r in range(2):
+        torch.testing.assert_close(sh[r]["df2"] / 2, F.grad[r * 3:(r + 1) * 3], rtol=1e-5, atol=1e-6)

@@ -105,7 +105,8 @@ def test_cluster_kernel_matches_the_oracle():
             y, prev = run_blocks(list(blocks), x, None, mask, False)
         finally:
             os.environ.pop("MMVQA_RF_ENCODER", None)
-        assert mmvqa_b200._lib.launch_count() - n0 <= 6, "the encoder did not take the one-launch path"
+        # the input cast + one bf16 cast per weight (the cache was invalidated above) + ONE encoder launch
+        assert mmvqa_b200._lib.launch_count() - n0 <= 4 * L + 3, "the encoder did not take the one-launch path"
         sd = {k: v.detach().cpu().float() for k, v in blocks.state_dict().items()}
         xo, po = x.cpu(), None
         for l in range(L):

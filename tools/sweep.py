@@ -75,6 +75,46 @@ def bench(kind, B, T, iters=5):
     return ms, sps, frac
 
 
+EFFNET_MAPS = [(24, 112), (48, 56), (80, 28), (176, 14), (512, 7)]
+
+
+def bench_projector(B, num_vis, act, iters=5):
+    """visual-token projector forward + backward (image_encoding.py:100-115) over the first `num_vis` pyramid levels
+    (num_vis < 5 = "first k tokens of the 5"); act = projector activation (SERF default, ReLU with
+    --use_relu, image_encoding.py:68,94)."""
+    from mmvqa_b200 import functional as Fn
+    from mmvqa_b200._lib import ACT_RELU, ACT_SERF
+    torch.manual_seed(0)
+    feats = [torch.randn(B, c, s, s, device="cuda").abs_().requires_grad_(True) for c, s in EFFNET_MAPS[:num_vis]]
+    ws = [torch.randn(H, c, 1, 1, device="cuda").mul_(c ** -0.5).requires_grad_(True) for c, _ in EFFNET_MAPS[:num_vis]]
+    go = torch.randn(num_vis, B, H, device="cuda")
+    code = ACT_SERF if act == "serf" else ACT_RELU
+
+    def one():
+        for t in feats + ws:
+            t.grad = None
+        Fn.vistok_project_all(feats, ws, code).backward(go)
+    for _ in range(2):
+        one()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        one()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        g.replay()
+    e1.record()
+    e1.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    flops = 3 * sum(2 * s * s * c * H for c, s in EFFNET_MAPS[:num_vis])
+    sps = B / (ms * 1e-3)
+    del g
+    return ms, sps, sps * flops / (peak * 1e12)
+
+
 if __name__ == "__main__":
     quick = "--quick" in sys.argv
     mmvqa_b200.set_compute_dtype("bf16")
@@ -90,4 +130,15 @@ if __name__ == "__main__":
                           flush=True)
                 except Exception as e:   # noqa: BLE001
                     print(f"{kind:11s} T={T:4d} B={B:5d}  FAILED {type(e).__name__}: {str(e)[:120]}", flush=True)
+                torch.cuda.empty_cache()
+    print("visual-token projector fwd+bwd (EfficientNetV2-M map shapes), bf16")
+    for act in ("serf", "relu"):
+        for nv in ([1, 5] if quick else [1, 2, 3, 4, 5]):
+            for B in ([16] if quick else [16, 64]):
+                try:
+                    ms, sps, frac = bench_projector(B, nv, act)
+                    print(f"projector {act:4s} num_vis={nv} B={B:4d}  {ms:9.3f} ms/step  {sps:10.0f} samples/s  {100 * frac:5.1f}% of bf16 peak",
+                          flush=True)
+                except Exception as e:   # noqa: BLE001
+                    print(f"projector {act:4s} num_vis={nv} B={B:4d}  FAILED {type(e).__name__}: {str(e)[:120]}", flush=True)
                 torch.cuda.empty_cache()
