@@ -256,6 +256,17 @@ int mmvqa_asl_fwd_bwd(const void* logits, int64_t ld, const int64_t* target, flo
  * = (softmax - onehot) * scale, written in place of / next to the logits */
 int mmvqa_ce_fwd_bwd(const void* logits, int64_t ld, const int64_t* target, float* loss_rows, void* dlogits,
                      int64_t ld_d, int64_t rows, int C, float scale, int dtype, mmvqa_stream_t stream);
+/* Chunked vocabulary cross entropy: the [rows, V] logits of the MLM head
+ * (classifier[2], models/mmbert.py:137,154-155) and their log-softmax / gradient (pretrain/roco_utils.py:235-236) are
+ * never materialised.  The caller produces the fp32 logits of columns [col0, col0 + Vc) with mmvqa_gemm into a
+ * [rows, ld] scratch chunk; _stats folds the chunk into a running (row max, row sum-exp) and picks up the target logit
+ * (loss_row = rowmax + log(rowsum) - tgt_logit after the last chunk); in the backward pass the chunk is recomputed and
+ * _grad turns it into dlogits = (softmax - onehot) * row_scale[row] (storage type dl_dtype) for the dgrad / wgrad GEMMs. */
+int mmvqa_ce_chunk_stats(const float* logits, int64_t ld, const int64_t* target, int64_t rows, int col0, int Vc,
+                         float* rowmax, float* rowsum, float* tgt_logit, int first, mmvqa_stream_t stream);
+int mmvqa_ce_chunk_grad(const float* logits, int64_t ld, const int64_t* target, int64_t rows, int col0, int Vc,
+                        const float* rowmax, const float* rowsum, const float* row_scale, void* dlogits, int64_t ld_d,
+                        int dl_dtype, mmvqa_stream_t stream);
 /* SupCon row pass, models/SupConLoss/loss.py:72-96, over logits = anchor.contrast^T (NOT yet divided
  * by temperature) [R, N] fp32 for anchors row_offset..row_offset+R of the global N.  mask is the
  * un-tiled [bsz, bsz] float mask (NULL = SimCLR identity).  Writes per-anchor loss terms

@@ -15,10 +15,15 @@ namespace mmvqa {
 
 constexpr int TC_BM = 128, TC_BK = 64;
 
-int launch_tc_bn32(int stages, const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st);
-int launch_tc_bn64(int stages, const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st);
-int launch_tc_bn128(int stages, const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st);
-int launch_tc_bn256(int stages, const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st);
+int launch_tc_bn32(int stages, int kps, const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st);
+int launch_tc_bn64(int stages, int kps, const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st);
+int launch_tc_bn128(int stages, int kps, const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st);
+int launch_tc_bn256(int stages, int kps, const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st);
+static bool chunkable(const mmvqa_gemm_args* a) {
+  const bool a_ok = a->a_trans ? (a->M % 64 == 0) : (a->K % 64 == 0);
+  const bool b_ok = a->b_trans ? (a->N % 64 == 0) : (a->K % 64 == 0);
+  return a_ok && b_ok;
+}
 
 // ---------------------------------------------------------------------------------
 // host: tensor maps + dispatch
@@ -56,6 +61,27 @@ int tc_make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t rows,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_err(MMVQA_ERR_CUDA, "gemm(bf16): cuTensorMapEncodeTiled(%s) failed with %d (inner=%lld rows=%lld ld=%lld)", what, (int)r, (long long)inner, (long long)rows, (long long)ld);
+  return MMVQA_OK;
+}
+
+int tc_make_map_chunked(CUtensorMap* map, const void* base, int64_t inner, int64_t rows, int64_t ld, int nbatch,
+                        int64_t batch_rows, int box_rows, int box_chunks, const char* what) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return set_err(MMVQA_ERR_CUDA, "gemm(bf16): cuTensorMapEncodeTiled unavailable");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0 || inner % 64 != 0 || box_rows > 256 || box_chunks > 256 ||
+      box_chunks < 1)
+    return set_err(MMVQA_ERR_ARG, "gemm(bf16): operand %s cannot use the chunked map (ld=%lld inner=%lld)", what, (long long)ld,
+                   (long long)inner);
+  const bool batched = nbatch > 1 && batch_rows > 0;
+  cuuint64_t dims[4] = {64, (cuuint64_t)rows, (cuuint64_t)(inner / 64), (cuuint64_t)(batched ? nbatch : 1)};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, 128, (cuuint64_t)(batched ? batch_rows * ld * 2 : rows * ld * 2)};
+  if (strides[2] % 16 != 0) strides[2] = (strides[2] + 15) / 16 * 16;
+  cuuint32_t box[4] = {64, (cuuint32_t)box_rows, (cuuint32_t)box_chunks, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(MMVQA_ERR_CUDA, "gemm(bf16): cuTensorMapEncodeTiled(%s, chunked) failed with %d (inner=%lld rows=%lld ld=%lld box %d x %d)", what, (int)r, (long long)inner, (long long)rows, (long long)ld, box_rows, box_chunks);
   return MMVQA_OK;
 }
 
@@ -108,11 +134,28 @@ int gemm_tc_bf16(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st)
     const int cap = bn == 128 ? 3 : (bn == 256 ? 2 : 4);
     if (stages > cap) stages = cap;
   }
+  // k-blocks per ring stage.  A stage costs a CTA ~0.3-0.4 us whatever it carries (profiles/r02_tma_dsmem_ubench.txt,
+  // profiles/r01_gemm_phase_trace.txt), so short-K problems -- the whole fine-tune step: K = 448 ... 3072 / split --
+  // take two fat stages: 4 k-blocks per stage when one CTA per SM covers the grid, 2 when two CTAs must share an SM
+  // (<= 96 KB rings).  Long-K multi-wave problems keep the thin ring with 2-3 CTAs per SM (epilogue under main loop).
+  int kps = 1;
+  static const int env_kps = env_int("MMVQA_TC_KPS");
+  const int per_kb = TC_BM * TC_BK * 2 + bn * TC_BK * 2;
+  const bool fits4 = 2 * 4 * per_kb <= 200 * 1024, fits2 = 2 * 2 * per_kb <= 200 * 1024;
+  const bool fits2_pair = 2 * 2 * per_kb <= 100 * 1024;                  // two such CTAs on one SM
+  if (chunkable(a) && kblocks >= 2 && kblocks <= 24) {
+    if (ctas <= sms) kps = (fits4 && kblocks >= 4) ? 4 : (fits2 ? 2 : 1);
+    else if (ctas <= 2 * (int64_t)sms) kps = fits2_pair ? 2 : 1;         // one wave only with two CTAs per SM
+    else kps = fits2 ? 2 : 1;
+  }
+  if (env_kps == 1) kps = 1;
+  if ((env_kps == 2 || env_kps == 4) && chunkable(a) && kblocks >= 2) kps = (env_kps == 4 && fits4) ? 4 : (fits2 ? 2 : 1);
+  if (kps > 1) stages = 2;
   switch (bn) {
-    case 256: return launch_tc_bn256(stages, a, ep, st);
-    case 128: return launch_tc_bn128(stages, a, ep, st);
-    case 64: return launch_tc_bn64(stages, a, ep, st);
-    default: return launch_tc_bn32(stages, a, ep, st);
+    case 256: return launch_tc_bn256(stages, kps, a, ep, st);
+    case 128: return launch_tc_bn128(stages, kps, a, ep, st);
+    case 64: return launch_tc_bn64(stages, kps, a, ep, st);
+    default: return launch_tc_bn32(stages, kps, a, ep, st);
   }
 }
 

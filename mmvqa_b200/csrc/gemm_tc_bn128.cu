@@ -2,7 +2,9 @@
 
 namespace mmvqa {
 
-int launch_tc_bn128(int stages, const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st) {
+int launch_tc_bn128(int stages, int kps, const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st) {
+  if (kps == 2) return launch_tc_major<128, 2, 2>(a, ep, st);
+  if (kps != 1) return set_err(MMVQA_ERR_ARG, "gemm(bf16): no %d-k-block stage for this tile", kps);
   switch (stages) {
     case 2: return launch_tc_major<128, 2>(a, ep, st);
     case 3: return launch_tc_major<128, 3>(a, ep, st);

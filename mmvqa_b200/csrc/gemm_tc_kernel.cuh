@@ -9,6 +9,11 @@ namespace mmvqa {
 
 int tc_make_map(CUtensorMap* map, const void* base, int64_t inner, int64_t rows, int64_t ld, int nbatch,
                 int64_t batch_rows, int box_inner, int box_rows, const char* what);
+// 4-D map {64, rows, inner / 64, batch} over a stored [rows, inner] matrix: dimension 2 walks the 64-element chunks of
+// the contiguous dimension, so ONE box {64, box_rows, box_chunks} brings several chunks (K-major operand: several
+// k-blocks; MN-major operand: the 64-wide groups of a tile).  Needs inner % 64 == 0.
+int tc_make_map_chunked(CUtensorMap* map, const void* base, int64_t inner, int64_t rows, int64_t ld, int nbatch,
+                        int64_t batch_rows, int box_rows, int box_chunks, const char* what);
 
 
 constexpr int TC_BM = 128;      // UMMA M (cta_group::1)
@@ -50,6 +55,12 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_g(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
@@ -104,12 +115,16 @@ __device__ __forceinline__ unsigned long long gtime() {
     if (p.trace) p.trace[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + (slot)] = gtime(); \
   } while (0)
 
-template <int BN, int STAGES_>
+// KPS = 64-wide k-blocks per ring stage.  Measured (tools/ubench/stream_bench*.cu, the phase tracer): a ring stage costs
+// a CTA ~0.3-0.4 us whatever its size up to 64 KB and whatever the ring depth, so small-K problems take FEWER, FATTER
+// stages: one TMA box per operand brings KPS k-blocks (4-D tensor map, tc_make_map_chunked).
+template <int BN, int STAGES_, int KPS_ = 1>
 struct TcCfg {
   static constexpr int STAGES = STAGES_;
-  static constexpr int A_BYTES = TC_BM * TC_BK * 2;   // 16 KB
+  static constexpr int KPS = KPS_;
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;   // 16 KB per k-block
   static constexpr int B_BYTES = BN * TC_BK * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGE_BYTES = KPS * (A_BYTES + B_BYTES);
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
 };
@@ -364,11 +379,11 @@ __device__ __forceinline__ void tc_epilogue_act(const EpiParams& p, uint32_t tme
 // ---------------------------------------------------------------------------------
 // kernel: one 128 x BN output tile (of one batch entry / one K split) per CTA
 // ---------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, int STAGES>
+template <int BN, bool A_MN, bool B_MN, int STAGES, int KPS = 1>
 __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                              const __grid_constant__ CUtensorMap tmB, EpiParams p,
                                                              int a_batched, int b_batched, int b_static) {
-  using Cfg = TcCfg<BN, STAGES>;
+  using Cfg = TcCfg<BN, STAGES, KPS>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bar_base = smem_base + Cfg::STAGES * Cfg::STAGE_BYTES;
@@ -386,6 +401,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
   const int kb0 = ks * kb_per;
   const int kb1 = min(kblocks, kb0 + kb_per);
   const int nkb = max(0, kb1 - kb0);
+  const int nst = (nkb + KPS - 1) / KPS;          // ring stages of this CTA (KPS k-blocks each)
   if (threadIdx.x == 0) TC_TRACE(0);
 
   if (warp == 0) {
@@ -402,6 +418,40 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = *tmem_ptr_gen;
+  // operand loads of ring stage i (k-blocks kb0 + i*KPS ...) into the slot at `sa` / `sb`.
+  // KPS == 1: the 3-D maps {inner, rows, batch}; KPS > 1: the 4-D chunked maps {64, rows, chunk, batch} -- one box per
+  // operand carries KPS k-blocks (K-major: box {64, rows, KPS}; MN-major: box {64, 64 KPS k-rows, tile / 64 groups},
+  // so the 64-wide MN groups are 8 KB * KPS apart).  Out-of-range chunks / rows are zero-filled by the TMA unit.
+  auto load_a = [&](uint32_t sa, uint32_t full, int i) {
+    const int kb = kb0 + i * KPS;
+    const int zb = a_batched ? bz : 0;
+    if (KPS == 1) {
+      if (A_MN) {  // stored [K, M]: two boxes of 64 (m) x 64 (k)
+        tma_load_3d(sa, &tmA, full, m0, kb * TC_BK, zb);
+        tma_load_3d(sa + 8192, &tmA, full, m0 + 64, kb * TC_BK, zb);
+      } else {     // stored [M, K]: one box of 64 (k) x 128 (m)
+        tma_load_3d(sa, &tmA, full, kb * TC_BK, m0, zb);
+      }
+    } else {
+      if (A_MN) tma_load_4d_g(sa, &tmA, full, 0, kb * TC_BK, m0 / 64, zb);
+      else tma_load_4d_g(sa, &tmA, full, 0, m0, kb, zb);
+    }
+  };
+  auto load_b = [&](uint32_t sb, uint32_t full, int i) {
+    const int kb = kb0 + i * KPS;
+    const int zb = b_batched ? bz : 0;
+    if (KPS == 1) {
+      if (B_MN) {  // stored [K, N]: BN/64 boxes of 64 (n) x 64 (k)
+#pragma unroll
+        for (int j = 0; j < BN / 64; ++j) tma_load_3d(sb + j * 8192, &tmB, full, n0 + j * 64, kb * TC_BK, zb);
+      } else {     // stored [N, K]: one box of 64 (k) x BN (n)
+        tma_load_3d(sb, &tmB, full, kb * TC_BK, n0, zb);
+      }
+    } else {
+      if (B_MN) tma_load_4d_g(sb, &tmB, full, 0, kb * TC_BK, n0 / 64, zb);
+      else tma_load_4d_g(sb, &tmB, full, 0, n0, kb, zb);
+    }
+  };
   // Programmatic dependent launch: this CTA may be resident while the previous kernel on the stream is still running.
   // The weight operand (b_static) does not depend on that kernel, so its first ring slots are requested now; the
   // activation operand, the epilogue inputs and every store wait for griddepcontrol.wait below.
@@ -411,18 +461,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     if (b_static) {
-      b_ahead = nkb < Cfg::STAGES ? nkb : Cfg::STAGES;
+      b_ahead = nst < Cfg::STAGES ? nst : Cfg::STAGES;
       for (int i = 0; i < b_ahead; ++i) {
         const uint32_t full = bar_base + 8 * i;
         mbar_expect_tx(full, Cfg::STAGE_BYTES);
-        const uint32_t sb = smem_base + i * Cfg::STAGE_BYTES + Cfg::A_BYTES;
-        const int k0 = (kb0 + i) * TC_BK;
-        if (B_MN) {
-#pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_3d(sb + j * 8192, &tmB, full, n0 + j * 64, k0, b_batched ? bz : 0);
-        } else {
-          tma_load_3d(sb, &tmB, full, k0, n0, b_batched ? bz : 0);
-        }
+        load_b(smem_base + i * Cfg::STAGE_BYTES + KPS * Cfg::A_BYTES, full, i);
       }
     }
   }
@@ -433,35 +476,19 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int i = 0; i < nkb; ++i) {
+      for (int i = 0; i < nst; ++i) {
         const int s = i % Cfg::STAGES;
         const uint32_t ph = (uint32_t)(i / Cfg::STAGES) & 1u;
         const uint32_t full = bar_base + 8 * s;
-        const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
-        const int k0 = (kb0 + i) * TC_BK;
+        const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES, sb = sa + KPS * Cfg::A_BYTES;
         if (i < b_ahead) {   // slot armed and its B tile already in flight: only A is missing
-          if (A_MN) {
-            tma_load_3d(sa, &tmA, full, m0, k0, a_batched ? bz : 0);
-            tma_load_3d(sa + 8192, &tmA, full, m0 + 64, k0, a_batched ? bz : 0);
-          } else {
-            tma_load_3d(sa, &tmA, full, k0, m0, a_batched ? bz : 0);
-          }
+          load_a(sa, full, i);
           continue;
         }
         mbar_wait(bar_base + 8 * (Cfg::STAGES + s), ph ^ 1u);
         mbar_expect_tx(full, Cfg::STAGE_BYTES);
-        if (A_MN) {  // stored [K, M]: two boxes of 64 (m) x 64 (k)
-          tma_load_3d(sa, &tmA, full, m0, k0, a_batched ? bz : 0);
-          tma_load_3d(sa + 8192, &tmA, full, m0 + 64, k0, a_batched ? bz : 0);
-        } else {     // stored [M, K]: one box of 64 (k) x 128 (m)
-          tma_load_3d(sa, &tmA, full, k0, m0, a_batched ? bz : 0);
-        }
-        if (B_MN) {  // stored [K, N]: BN/64 boxes of 64 (n) x 64 (k)
-#pragma unroll
-          for (int j = 0; j < BN / 64; ++j) tma_load_3d(sb + j * 8192, &tmB, full, n0 + j * 64, k0, b_batched ? bz : 0);
-        } else {     // stored [N, K]: one box of 64 (k) x BN (n)
-          tma_load_3d(sb, &tmB, full, k0, n0, b_batched ? bz : 0);
-        }
+        load_a(sa, full, i);
+        load_b(sb, full, i);
       }
       TC_TRACE(3);
     }
@@ -471,20 +498,29 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, majors, N>>3, M>>4
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      for (int i = 0; i < nkb; ++i) {
+      for (int i = 0; i < nst; ++i) {
         const int s = i % Cfg::STAGES;
         const uint32_t ph = (uint32_t)(i / Cfg::STAGES) & 1u;
         mbar_wait(bar_base + 8 * s, ph);
         tc_fence_after();
         if (i == 0) TC_TRACE(4);
-        const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES, sb = sa + Cfg::A_BYTES;
+        const uint32_t sa = smem_base + s * Cfg::STAGE_BYTES, sb = sa + KPS * Cfg::A_BYTES;
 #pragma unroll
-        for (int j = 0; j < TC_BK / TC_UK; ++j) {
-          // K-major: 16 bf16 = 32 bytes inside the swizzled 128-byte row; SBO = 8 rows * 128 B.
-          // MN-major: 16 k-rows = 2 groups of 8 rows (1024 B each); LBO = next 64-wide MN group.
-          const uint64_t ad = A_MN ? make_sdesc(sa + j * 2048, 8192, 1024) : make_sdesc(sa + j * 32, 16, 1024);
-          const uint64_t bd = B_MN ? make_sdesc(sb + j * 2048, 8192, 1024) : make_sdesc(sb + j * 32, 16, 1024);
-          umma_bf16(tmem_acc, ad, bd, idesc, (i > 0 || j > 0) ? 1u : 0u);
+        for (int c = 0; c < KPS; ++c) {
+          if (i * KPS + c < nkb) {   // k-blocks beyond this CTA's range (K tail / next split) were loaded but are not used
+#pragma unroll
+            for (int j = 0; j < TC_BK / TC_UK; ++j) {
+              // K-major: 16 bf16 = 32 bytes inside the swizzled 128-byte row; SBO = 8 rows * 128 B; k-block c is one
+              //   [rows][128 B] tile further.
+              // MN-major: 16 k-rows = 2 groups of 8 rows (1024 B each); LBO = next 64-wide MN group (8 KB * KPS away);
+              //   k-block c is 64 k-rows = 8 KB further inside every group.
+              const uint64_t ad = A_MN ? make_sdesc(sa + c * 8192 + j * 2048, 8192 * KPS, 1024)
+                                       : make_sdesc(sa + c * Cfg::A_BYTES + j * 32, 16, 1024);
+              const uint64_t bd = B_MN ? make_sdesc(sb + c * 8192 + j * 2048, 8192 * KPS, 1024)
+                                       : make_sdesc(sb + c * Cfg::B_BYTES + j * 32, 16, 1024);
+              umma_bf16(tmem_acc, ad, bd, idesc, (i > 0 || c > 0 || j > 0) ? 1u : 0u);
+            }
+          }
         }
         umma_commit(bar_base + 8 * (Cfg::STAGES + s));  // frees the smem slot when these MMAs retire
       }
@@ -518,19 +554,37 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
   if (warp == 0) tmem_dealloc(tmem_acc, Cfg::TMEM_COLS);
 }
 
-template <int BN, bool A_MN, bool B_MN, int STAGES>
+// can this operand be addressed through the chunked map?  (the 64-element chunks must tile its contiguous dimension)
+static inline bool tc_chunkable(const mmvqa_gemm_args* a) {
+  const bool a_ok = a->a_trans ? (a->M % 64 == 0) : (a->K % 64 == 0);
+  const bool b_ok = a->b_trans ? (a->N % 64 == 0) : (a->K % 64 == 0);
+  return a_ok && b_ok;
+}
+
+template <int BN, bool A_MN, bool B_MN, int STAGES, int KPS = 1>
 static int launch_tc(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st) {
-  using Cfg = TcCfg<BN, STAGES>;
+  using Cfg = TcCfg<BN, STAGES, KPS>;
   CUtensorMap tmA, tmB;
   int rc;
-  // A: K-major stored [M, K] -> inner K, box 64 x 128;  MN-major stored [K, M] -> inner M, box 64 x 64
-  if (A_MN) rc = tc_make_map(&tmA, a->A, a->M, a->K, a->lda, a->batch, a->a_batch_rows, 64, 64, "A");
-  else rc = tc_make_map(&tmA, a->A, a->K, a->M, a->lda, a->batch, a->a_batch_rows, 64, TC_BM, "A");
-  if (rc) return rc;
-  if (B_MN) rc = tc_make_map(&tmB, a->B, a->N, a->K, a->ldb, a->batch, a->b_batch_rows, 64, 64, "B");
-  else rc = tc_make_map(&tmB, a->B, a->K, a->N, a->ldb, a->batch, a->b_batch_rows, 64, BN, "B");
-  if (rc) return rc;
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES>;
+  if (KPS == 1) {
+    // A: K-major stored [M, K] -> inner K, box 64 x 128;  MN-major stored [K, M] -> inner M, box 64 x 64
+    if (A_MN) rc = tc_make_map(&tmA, a->A, a->M, a->K, a->lda, a->batch, a->a_batch_rows, 64, 64, "A");
+    else rc = tc_make_map(&tmA, a->A, a->K, a->M, a->lda, a->batch, a->a_batch_rows, 64, TC_BM, "A");
+    if (rc) return rc;
+    if (B_MN) rc = tc_make_map(&tmB, a->B, a->N, a->K, a->ldb, a->batch, a->b_batch_rows, 64, 64, "B");
+    else rc = tc_make_map(&tmB, a->B, a->K, a->N, a->ldb, a->batch, a->b_batch_rows, 64, BN, "B");
+    if (rc) return rc;
+  } else {
+    MMVQA_REQUIRE(tc_chunkable(a), "gemm(bf16): multi-k-block stages need contiguous dimensions that are multiples of 64");
+    // K-major stored [rows, K]: box {64, tile rows, KPS chunks};  MN-major stored [K, MN]: box {64, 64 KPS k-rows, tile / 64}
+    if (A_MN) rc = tc_make_map_chunked(&tmA, a->A, a->M, a->K, a->lda, a->batch, a->a_batch_rows, 64 * KPS, TC_BM / 64, "A");
+    else rc = tc_make_map_chunked(&tmA, a->A, a->K, a->M, a->lda, a->batch, a->a_batch_rows, TC_BM, KPS, "A");
+    if (rc) return rc;
+    if (B_MN) rc = tc_make_map_chunked(&tmB, a->B, a->N, a->K, a->ldb, a->batch, a->b_batch_rows, 64 * KPS, BN / 64, "B");
+    else rc = tc_make_map_chunked(&tmB, a->B, a->K, a->N, a->ldb, a->batch, a->b_batch_rows, BN, KPS, "B");
+    if (rc) return rc;
+  }
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES, KPS>;
   static bool attr_set = false;
   if (!attr_set) {
     MMVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
@@ -545,12 +599,12 @@ static int launch_tc(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t
   return MMVQA_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int KPS = 1>
 static int launch_tc_major(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st) {
-  if (a->a_trans && a->b_trans) return launch_tc<BN, true, true, STAGES>(a, ep, st);
-  if (a->a_trans) return launch_tc<BN, true, false, STAGES>(a, ep, st);
-  if (a->b_trans) return launch_tc<BN, false, true, STAGES>(a, ep, st);
-  return launch_tc<BN, false, false, STAGES>(a, ep, st);
+  if (a->a_trans && a->b_trans) return launch_tc<BN, true, true, STAGES, KPS>(a, ep, st);
+  if (a->a_trans) return launch_tc<BN, true, false, STAGES, KPS>(a, ep, st);
+  if (a->b_trans) return launch_tc<BN, false, true, STAGES, KPS>(a, ep, st);
+  return launch_tc<BN, false, false, STAGES, KPS>(a, ep, st);
 }
 
 

@@ -97,6 +97,53 @@ __global__ void __launch_bounds__(256) ce_kernel(const T* __restrict__ logits, i
 }
 
 // ---------------------------------------------------------------------------------
+// cross entropy over a vocabulary that is never materialised: the [M, V] logits are produced in column chunks
+// (vocab GEMM per chunk), pass 1 keeps a running (max, sum-exp, target logit) per row, pass 2 recomputes each chunk and
+// turns it into the gradient chunk (models/mmbert.py:154-155 + pretrain/roco_utils.py:235-236)
+// ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ce_chunk_stats_kernel(const float* __restrict__ logits, int64_t ld,
+                                                             const int64_t* __restrict__ target, int col0, int Vc,
+                                                             float* __restrict__ rowmax, float* __restrict__ rowsum,
+                                                             float* __restrict__ tgt_logit, int first) {
+  __shared__ float red[32];
+  const int64_t r = blockIdx.x;
+  const float* x = logits + r * ld;
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < Vc; c += blockDim.x) mx = fmaxf(mx, x[c]);
+  mx = block_max(mx, red);
+  float se = 0.0f;
+  for (int c = threadIdx.x; c < Vc; c += blockDim.x) se += expf(x[c] - mx);
+  se = block_sum(se, red);
+  if (threadIdx.x == 0) {
+    if (first) {
+      rowmax[r] = mx;
+      rowsum[r] = se;
+    } else {
+      const float m0 = rowmax[r], s0 = rowsum[r];
+      const float m1 = fmaxf(m0, mx);
+      rowmax[r] = m1;
+      rowsum[r] = s0 * expf(m0 - m1) + se * expf(mx - m1);
+    }
+    const int y = (int)target[r] - col0;
+    if (y >= 0 && y < Vc) tgt_logit[r] = x[y];
+  }
+}
+template <typename O>
+__global__ void __launch_bounds__(256) ce_chunk_grad_kernel(const float* __restrict__ logits, int64_t ld,
+                                                            const int64_t* __restrict__ target, int col0, int Vc,
+                                                            const float* __restrict__ rowmax, const float* __restrict__ rowsum,
+                                                            const float* __restrict__ row_scale, O* __restrict__ dl,
+                                                            int64_t ld_d) {
+  const int64_t r = blockIdx.x;
+  const float* x = logits + r * ld;
+  O* d = dl + r * ld_d;
+  const float lse = rowmax[r] + logf(rowsum[r]);
+  const float sc = row_scale[r];
+  const int y = (int)target[r] - col0;
+  for (int c = threadIdx.x; c < Vc; c += blockDim.x) d[c] = from_f<O>((expf(x[c] - lse) - (c == y ? 1.0f : 0.0f)) * sc);
+}
+
+// ---------------------------------------------------------------------------------
 // SupCon: one block per anchor row of raw = anchor . contrast^T (not yet divided by temperature)
 // ---------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) supcon_rows_kernel(const float* __restrict__ raw, const float* __restrict__ mask,
@@ -259,6 +306,34 @@ int mmvqa_ce_fwd_bwd(const void* logits, int64_t ld, const int64_t* target, floa
   else
     return set_err(MMVQA_ERR_ARG, "ce: bad dtype %d", dtype);
   MMVQA_LAUNCHED("ce_fwd_bwd");
+  return MMVQA_OK;
+}
+
+int mmvqa_ce_chunk_stats(const float* logits, int64_t ld, const int64_t* target, int64_t rows, int col0, int Vc,
+                         float* rowmax, float* rowsum, float* tgt_logit, int first, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(logits && target && rowmax && rowsum && tgt_logit && rows >= 0 && Vc > 0 && ld >= Vc && col0 >= 0,
+                "ce_chunk_stats: bad args");
+  MMVQA_REQUIRE(rows <= 2147483647LL, "ce_chunk_stats: too many rows");
+  if (rows == 0) return MMVQA_OK;
+  ce_chunk_stats_kernel<<<(int)rows, 256, 0, as_stream(stream)>>>(logits, ld, target, col0, Vc, rowmax, rowsum, tgt_logit, first);
+  MMVQA_LAUNCHED("ce_chunk_stats");
+  return MMVQA_OK;
+}
+
+int mmvqa_ce_chunk_grad(const float* logits, int64_t ld, const int64_t* target, int64_t rows, int col0, int Vc,
+                        const float* rowmax, const float* rowsum, const float* row_scale, void* dlogits, int64_t ld_d,
+                        int dl_dtype, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(logits && target && rowmax && rowsum && row_scale && dlogits && rows >= 0 && Vc > 0 && ld >= Vc && ld_d >= Vc,
+                "ce_chunk_grad: bad args");
+  MMVQA_REQUIRE(rows <= 2147483647LL, "ce_chunk_grad: too many rows");
+  if (rows == 0) return MMVQA_OK;
+  if (dl_dtype == MMVQA_F32)
+    ce_chunk_grad_kernel<float><<<(int)rows, 256, 0, as_stream(stream)>>>(logits, ld, target, col0, Vc, rowmax, rowsum, row_scale, (float*)dlogits, ld_d);
+  else if (dl_dtype == MMVQA_BF16)
+    ce_chunk_grad_kernel<__nv_bfloat16><<<(int)rows, 256, 0, as_stream(stream)>>>(logits, ld, target, col0, Vc, rowmax, rowsum, row_scale, (__nv_bfloat16*)dlogits, ld_d);
+  else
+    return set_err(MMVQA_ERR_ARG, "ce_chunk_grad: bad dtype %d", dl_dtype);
+  MMVQA_LAUNCHED("ce_chunk_grad");
   return MMVQA_OK;
 }
 

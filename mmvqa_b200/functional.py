@@ -949,6 +949,64 @@ class CrossEntropyRowsFn(torch.autograd.Function):
         return g, None
 
 
+class ChunkedVocabCEFn(torch.autograd.Function):
+    """Per-row NLL of log_softmax(h W^T + b) (mmbert.py:154-155 + pretrain/roco_utils.py:235-236) WITHOUT the [M, V] logits:
+    the vocabulary is walked in column chunks -- vocab GEMM into an [M, chunk] fp32 scratch, online log-sum-exp
+    (mmvqa_ce_chunk_stats); the backward pass recomputes each chunk, turns it into dlogits (mmvqa_ce_chunk_grad) and
+    feeds it straight to the dgrad (dh += dl W_c) and wgrad (dW_c = dl^T h, db_c = colsum dl) GEMMs.  Memory is
+    M * chunk * 6 bytes instead of two [M, V] fp32 tensors (2 x 293 MB at M = 2400); the price is one extra vocab GEMM."""
+
+    @staticmethod
+    def forward(ctx, h: Tensor, weight: Tensor, bias: Tensor, target: Tensor, chunk: int):
+        dt = h.dtype
+        M, H = h.shape
+        V = weight.shape[0]
+        hc = h if h.is_contiguous() else h.contiguous()
+        w = weight_cache.get((weight,), dt)
+        tgt = target.contiguous().long()
+        scratch = torch.empty(M, chunk, device=h.device, dtype=torch.float32)
+        rowmax = torch.empty(M, device=h.device, dtype=torch.float32)
+        rowsum = torch.empty(M, device=h.device, dtype=torch.float32)
+        tl = torch.zeros(M, device=h.device, dtype=torch.float32)
+        b32 = bias.detach().float()
+        for c0 in range(0, V, chunk):
+            vc = min(chunk, V - c0)
+            ops.gemm(M, vc, H, hc, H, False, w[c0:c0 + vc], H, False, scratch, chunk, bias=b32[c0:c0 + vc], b_static=True)
+            ops.ce_chunk_stats(scratch, chunk, tgt, M, c0, vc, rowmax, rowsum, tl, c0 == 0)
+        ctx.save_for_backward(hc, weight, bias, tgt, rowmax, rowsum)
+        ctx.meta = (chunk, dt)
+        return rowmax + torch.log(rowsum) - tl
+
+    @staticmethod
+    def backward(ctx, dloss_rows):
+        hc, weight, bias, tgt, rowmax, rowsum = ctx.saved_tensors
+        chunk, dt = ctx.meta
+        M, H = hc.shape
+        V = weight.shape[0]
+        w = weight_cache.get((weight,), dt)
+        b32 = bias.detach().float()
+        rs = dloss_rows.reshape(-1).contiguous().float()
+        scratch = torch.empty(M, chunk, device=hc.device, dtype=torch.float32)
+        dl = torch.empty(M, chunk, device=hc.device, dtype=dt)
+        dh = torch.zeros(M, H, device=hc.device, dtype=torch.float32)
+        dW = torch.empty(V, H, device=hc.device, dtype=torch.float32)
+        db = torch.empty(V, device=hc.device, dtype=torch.float32)
+        for c0 in range(0, V, chunk):
+            vc = min(chunk, V - c0)
+            ops.gemm(M, vc, H, hc, H, False, w[c0:c0 + vc], H, False, scratch, chunk, bias=b32[c0:c0 + vc], b_static=True)
+            ops.ce_chunk_grad(scratch, chunk, tgt, M, c0, vc, rowmax, rowsum, rs, dl, chunk)
+            ops.gemm(M, H, vc, dl, chunk, False, w[c0:c0 + vc], H, True, dh, H, accumulate=True, b_static=True)
+            ops.gemm(vc, H, M, dl, chunk, True, hc, H, True, dW[c0:c0 + vc], H)
+            db[c0:c0 + vc] = ops.colsum(dl, M, vc, chunk)
+        return dh.to(dt), dW, db, None, None
+
+
+def chunked_vocab_ce(h: Tensor, weight: Tensor, bias: Tensor, target: Tensor, chunk: int = 4096) -> Tensor:
+    """per-row MLM losses [M] for hidden states h [M, H] (compute dtype) and the vocabulary projection (weight [V, H],
+    bias [V]); see ChunkedVocabCEFn."""
+    return ChunkedVocabCEFn.apply(to_compute(h), weight, bias, target, int(chunk))
+
+
 class SupConFn(torch.autograd.Function):
     """SupConLoss core (models/SupConLoss/loss.py:58-96) on the view-major contrast matrix F [N, D]:
     raw = anchors . F^T on the tensor cores, then one fused row pass (max, masked exp-sum, positives

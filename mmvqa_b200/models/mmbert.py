@@ -132,6 +132,25 @@ class Model(nn.Module):
         z = Fn.add_layer_norm(z, None, ln.weight, ln.bias, ln.eps)
         return Fn.linear(z, c2.weight, c2.bias, out_fp32=True)
 
+    def mlm_loss(self, h, target, chunk=4096):
+        """mean over ALL B*T positions of NLL(log_softmax(classifier(SERF(fc1(h))))) -- the MLM objective of
+        pretrain/roco_utils.py:235-236 on top of mmbert.py:154-155 -- with the vocabulary projection fused into a chunked
+        cross entropy (Fn.chunked_vocab_ce): same value and gradients as
+        ``NLLLoss()(log_softmax(self._classify(h), -1).permute(0, 2, 1), target)`` without the [B, T, V] logits.
+        h = encoder output [B, T, hidden] (``model.encode_features`` / ``model.transformer``)."""
+        z = Fn.linear(h, self.fc1.weight, self.fc1.bias, act=ACT_SERF)
+        c0, ln, c2 = self.classifier[0], self.classifier[1], self.classifier[2]
+        z = Fn.linear(z, c0.weight, c0.bias)
+        z = Fn.add_layer_norm(z, None, ln.weight, ln.bias, ln.eps)
+        rows = Fn.chunked_vocab_ce(z.reshape(-1, z.shape[-1]), c2.weight, c2.bias, target.reshape(-1), chunk)
+        return rows.mean()
+
+    def encode_features(self, feats, input_ids, segment_ids, input_mask):
+        """feature maps -> encoder output [B, T, hidden] (the input of heads() / mlm_loss())."""
+        tr = self.transformer
+        h = tr.fuse(tr.trans.project_stacked(feats), input_ids, segment_ids)
+        return tr.encode(h, input_mask)
+
     def _project(self, z):
         z = Fn.linear(z, self.head[0].weight, self.head[0].bias, act=ACT_SERF)
         z = Fn.linear(z, self.head[2].weight, self.head[2].bias, out_fp32=True)

@@ -396,6 +396,18 @@ def ce_fwd_bwd(logits: Tensor, ld: int, target: Tensor, rows: int, C_: int, scal
     return loss_rows
 
 
+def ce_chunk_stats(chunk: Tensor, ld: int, target: Tensor, rows: int, col0: int, Vc: int, rowmax: Tensor, rowsum: Tensor,
+                   tgt_logit: Tensor, first: bool) -> None:
+    L.check(L.lib().mmvqa_ce_chunk_stats(_p(chunk), ld, _p(target), rows, col0, Vc, _p(rowmax), _p(rowsum), _p(tgt_logit),
+                                        int(first), _stream()), "ce_chunk_stats")
+
+
+def ce_chunk_grad(chunk: Tensor, ld: int, target: Tensor, rows: int, col0: int, Vc: int, rowmax: Tensor, rowsum: Tensor,
+                  row_scale: Tensor, dl: Tensor, ld_d: int) -> None:
+    L.check(L.lib().mmvqa_ce_chunk_grad(_p(chunk), ld, _p(target), rows, col0, Vc, _p(rowmax), _p(rowsum), _p(row_scale),
+                                       _p(dl), ld_d, dtype_code(dl), _stream()), "ce_chunk_grad")
+
+
 def supcon_rows(raw: Tensor, mask: Optional[Tensor], bsz: int, row_offset: int, temperature: float, base_temperature: float,
                 want_grad: bool):
     R, N = raw.shape

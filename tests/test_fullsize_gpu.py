@@ -276,3 +276,83 @@ def test_c3_mlm_step_at_the_per_gpu_shape():
             assert e < gtol, (dt, n, e)
         del logits, loss
     model.cpu()
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_chunked_vocab_ce_at_the_c3_shape(dt):
+    """SURVEY section 8f-1 at M = 2400 (B = 32, T = 75), V = 30522, hidden 768: the chunked vocab GEMM + cross entropy
+    (never allocates [M, V]) against O.mlm_nll on CPU -- loss, dh, dW, db -- and against the two-tensor path of the same
+    library for peak memory."""
+    from mmvqa_b200 import functional as Fn
+    M, H, V = 2400, 768, 30522
+    g = torch.Generator().manual_seed(41)
+    h = torch.randn(M, H, generator=g)
+    W = torch.randn(V, H, generator=g) * 0.05
+    b = torch.randn(V, generator=g) * 0.1
+    target = torch.where(torch.rand(M, generator=g) < 0.15, torch.randint(1000, V, (M,), generator=g), torch.zeros(M, dtype=torch.long))
+    hr, Wr, br = h.clone().requires_grad_(True), W.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = O.mlm_nll((hr @ Wr.t() + br).view(1, M, V), target.view(1, M))
+    ref.backward()
+    with mmvqa_b200.compute_dtype_scope(dt):
+        Fn.invalidate_weight_cache()
+        hd = h.to(DEV).requires_grad_(True)
+        Wd = torch.nn.Parameter(W.to(DEV))
+        bd = torch.nn.Parameter(b.to(DEV))
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        loss = Fn.chunked_vocab_ce(hd, Wd, bd, target.to(DEV), 4096).mean()
+        loss.backward()
+        torch.cuda.synchronize()
+        peak_chunked = torch.cuda.max_memory_allocated() - base
+        tol, gtol = (1e-5, 2e-3) if dt == torch.float32 else (2e-3, 6e-2)
+        assert abs(loss.item() - ref.item()) < tol * ref.item(), (loss.item(), ref.item())
+        for got, want, nm in ((hd.grad, hr.grad, "dh"), (Wd.grad, Wr.grad, "dW"), (bd.grad, br.grad, "db")):
+            e = ((got.float().cpu() - want).abs().max() / want.abs().max()).item()
+            assert e < gtol, (nm, e)
+        # the two-tensor path: fp32 logits [M, V] + their gradient
+        hd2 = h.to(DEV).requires_grad_(True)
+        Wd.grad = None
+        bd.grad = None
+        torch.cuda.synchronize()
+        torch.cuda.reset_peak_memory_stats()
+        base = torch.cuda.memory_allocated()
+        logits = Fn.linear(hd2, Wd, bd, out_fp32=True)
+        loss2 = Fn.CrossEntropyRowsFn.apply(logits, target.to(DEV)).mean()
+        loss2.backward()
+        torch.cuda.synchronize()
+        peak_full = torch.cuda.max_memory_allocated() - base
+        assert abs(loss2.item() - loss.item()) < (1e-5 if dt == torch.float32 else 2e-3) * abs(loss.item())
+        assert peak_chunked < 0.6 * peak_full, (peak_chunked, peak_full)      # 2 x 293 MB of logits are gone
+        Fn.invalidate_weight_cache()
+
+
+def test_model_mlm_loss_equals_logits_path():
+    """Model.mlm_loss (chunked) == NLL(log_softmax(Model logits)) on a 2-layer full-width model."""
+    from mmvqa_b200 import functional as Fn
+    B, Tn, V = 4, 75, 30522
+    model = _mlm_model(False).to(DEV)
+    g = torch.Generator().manual_seed(17)
+    feats = [torch.randn(B, c, s, s, generator=g).abs().to(DEV) for c, s in bench.EFFNET_MAPS]
+    ids = torch.randint(1000, V, (B, Tn), generator=g).to(DEV)
+    seg = torch.zeros(B, Tn, dtype=torch.long, device=DEV)
+    mask = torch.ones(B, Tn, dtype=torch.long, device=DEV)
+    target = torch.where(torch.rand(B, Tn, generator=g) < 0.15, ids.cpu(), torch.zeros(B, Tn, dtype=torch.long)).to(DEV)
+    for dt, tol in ((torch.float32, 1e-5), (torch.bfloat16, 3e-3)):
+        with mmvqa_b200.compute_dtype_scope(dt):
+            Fn.invalidate_weight_cache()
+            model.zero_grad(set_to_none=True)
+            logits = model.forward_features(feats, ids, seg, mask)
+            l_ref = Fn.CrossEntropyRowsFn.apply(logits.view(B * Tn, V), target.view(-1)).mean()
+            l_ref.backward()
+            g_ref = {n: p.grad.clone() for n, p in model.named_parameters() if p.grad is not None}
+            model.zero_grad(set_to_none=True)
+            l_new = model.mlm_loss(model.encode_features(feats, ids, seg, mask), target)
+            l_new.backward()
+            assert abs(l_new.item() - l_ref.item()) < tol * abs(l_ref.item())
+            for n in ("classifier.2.weight", "classifier.2.bias", "fc1.weight", "transformer.mains.0.kqv.weight"):
+                p = dict(model.named_parameters())[n]
+                e = ((p.grad - g_ref[n]).abs().max() / g_ref[n].abs().max().clamp_min(1e-12)).item()
+                assert e < (2e-3 if dt == torch.float32 else 8e-2), (dt, n, e)
+    Fn.invalidate_weight_cache()
+    model.cpu()
