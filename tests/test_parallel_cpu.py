@@ -69,6 +69,19 @@ def _worker(rank, world, port, q):
     full_mask = gather_mask_rows(soft[rank * 3:(rank + 1) * 3])
     sl = O.supcon_loss(gathered, mask=full_mask)
     sl.backward()
+    # row-sparse exchange of an embedding-table gradient: all-gather of the touched rows == dense all-reduce(SUM)
+    emb = nn.Parameter(torch.zeros(20, 4))
+    other = nn.Parameter(torch.zeros(3))
+    ids = torch.tensor([[1, 5, 5, 7], [0, 5, 19, 1]][rank])              # duplicates inside a rank and across ranks
+    contrib = torch.randn(4, 4, generator=torch.Generator().manual_seed(50 + rank))
+    g_emb = torch.zeros(20, 4).index_add_(0, ids, contrib)
+    g_other = torch.full((3,), float(rank + 1))
+    red2 = LayerwiseReducer(torch.float32)
+    red2.register_row_sparse(emb, lambda: ids)
+    out2 = red2([emb, other], [g_emb, g_other])
+    dense_sum = g_emb.clone()
+    dist.all_reduce(dense_sum)
+    q.put({"rank3": rank, "sparse": out2[0].clone(), "dense": dense_sum, "other": out2[1].clone()})
     # local-anchor rows: the same gather with a reduce-scatter backward; each rank evaluates only the
     # loss rows of its own samples' anchors (here with plain torch ops restating loss.py:72-96 per anchor row)
     from mmvqa_b200.parallel import _GatherFeaturesRS
@@ -95,7 +108,7 @@ def test_dp_world2_gloo():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=120) for _ in range(5)]
+    got = [q.get(timeout=120) for _ in range(7)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -124,6 +137,10 @@ def test_dp_world2_gloo():
     # ranks, so each local slice receives world x the single-process gradient (DP averaging divides it back)
     for r in range(2):
         torch.testing.assert_close(dfs[r] / 2, F.grad[r * 3:(r + 1) * 3], rtol=1e-5, atol=1e-6)
+    for x in got:
+        if "rank3" in x:
+            torch.testing.assert_close(x["sparse"], x["dense"])
+            torch.testing.assert_close(x["other"], torch.full((3,), 3.0))
     # local-anchor partition: mean over ranks of the per-rank losses == the global loss, and the reduce-scatter hands
     # every rank the same world x gradient of its slice as the redundant formulation above
     sh = {x["rank2"]: x for x in got if "rank2" in x}
