@@ -328,7 +328,10 @@ def main_gpu(a):
     from mmvqa_b200.parallel import LayerwiseReducer
     bucket_dt = torch.bfloat16 if (dt == torch.bfloat16 and a.bf16_buckets) else torch.float32
     overlapped_dp = world > 1 and a.dp_mode == "overlapped"
-    reducer = LayerwiseReducer(bucket_dt) if overlapped_dp else None
+    # in-switch all-reduce of the library (csrc/comm.cu) from 4 GPUs on: measured 3.14 ms/step against 3.37 ms for NCCL's
+    # ring kernels at 8 GPUs (profiles/r02_scaling_notes.txt); at 2 GPUs a ring moves the same bytes and NCCL is 2 % faster
+    use_mm = (a.multimem == 1) or (a.multimem < 0 and world >= 4)
+    reducer = LayerwiseReducer(bucket_dt, multimem=use_mm, multimem_ctas=a.multimem_ctas) if overlapped_dp else None
     opt = FusedAdam(params, lr=1e-5, overlap_backward=((world == 1 or overlapped_dp) and bool(a.overlap_adam)),
                     reduce_fn=reducer, sink_group=(a.sink_group if overlapped_dp else a.sink_group_1gpu),
                     early_groups=[list(model.transformer.bert_embedding.parameters()),
@@ -620,6 +623,8 @@ if __name__ == "__main__":
     ap.add_argument("--sink-group", type=int, default=4, help="data parallel: encoder layers per all-reduce + Adam launch")
     ap.add_argument("--sink-group-1gpu", type=int, default=1, help="single GPU: encoder layers per Adam launch")
     ap.add_argument("--dp-mode", default="overlapped", choices=["overlapped", "twograph"])
+    ap.add_argument("--multimem", type=int, default=-1, help="data parallel: in-switch all-reduce kernel of the library (symmetric memory) instead of NCCL; -1 = from 4 GPUs on")
+    ap.add_argument("--multimem-ctas", type=int, default=16)
     ap.add_argument("--sparse-embed", type=int, default=1, help="data parallel: exchange the touched embedding rows, not the dense table gradient")
     ap.add_argument("--feat-dtype", default="fp32", choices=["fp32", "bf16"], help="dtype of the feature maps handed to the path (fp32 = as the reference's backbone emits them)")
     ap.add_argument("--quick", action="store_true", help="tuning: print value / e2e only (no roofline, no CPU leg)")

@@ -335,6 +335,17 @@ int mmvqa_adam_step(const mmvqa_adam_desc* table, int n_chunks, float lr, float 
 int mmvqa_adam_step_dev(const mmvqa_adam_desc* table, int n_chunks, const float* hyper_dev, float beta1, float beta2,
                         float eps, float weight_decay, const int* step_dev, int max_ctas, mmvqa_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Data-parallel gradient exchange (collective 1; the reference has no distributed code -- this is
+ * what DDP's all-reduce would do around vqamed2019/train.py:173-174).  In-place SUM all-reduce of a bucket that lives in
+ * symmetric memory bound to an NVLink multicast object: multimem.ld_reduce / multimem.st through the NVSwitch, two
+ * shots, a few CTAs.  multicast_ptr = multicast address of the bucket (same offset on every rank), signal_pads_dev =
+ * DEVICE array of `world` pointers to the ranks' signal pads (uint32 words, zero when idle; ctas * world words used).
+ * Every rank must launch it with the same arguments in the same order (a collective).  dtype F32 or BF16 (fp32
+ * accumulation in the switch). */
+int mmvqa_multimem_allreduce(void* multicast_ptr, const void* signal_pads_dev, int rank, int world, int64_t nbytes, int dtype,
+                             int max_ctas, mmvqa_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

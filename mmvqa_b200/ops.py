@@ -431,6 +431,14 @@ def adam_step_dev(table: Tensor, n_chunks: int, hyper_dev: Tensor, beta1: float,
                                        eps, weight_decay, _p(step_dev), max_ctas, _stream()), "adam_step_dev")
 
 
+def multimem_allreduce(multicast_ptr: int, signal_pads_dev: int, rank: int, world: int, nbytes: int, dtype: torch.dtype,
+                       max_ctas: int = 16) -> None:
+    """in-switch SUM all-reduce of a symmetric-memory bucket (csrc/comm.cu); a collective: same call on every rank."""
+    L.check(L.lib().mmvqa_multimem_allreduce(multicast_ptr, signal_pads_dev, rank, world, nbytes,
+                                            L.BF16 if dtype == torch.bfloat16 else L.F32, max_ctas, _stream()),
+            "multimem_allreduce")
+
+
 # ------------------------------------------------------------------------------- caption similarity
 def jaccard_mask(ids_a: Tensor, len_a: Tensor, ids_b: Tensor, len_b: Tensor) -> Tensor:
     """ids_* [n, lmax] int32 sorted unique word ids per document, len_* [n] int32 -> [na, nb] fp32 Jaccard mask with

@@ -101,10 +101,15 @@ class LayerwiseReducer:
     update runs on, so with ``overlap_backward`` the all-reduce of layer l travels over NVLink while layers
     l-1 ... 0 are still in backward; the whole data-parallel step (NCCL kernels included) is one CUDA graph."""
 
-    def __init__(self, dtype: torch.dtype = torch.float32):
+    def __init__(self, dtype: torch.dtype = torch.float32, multimem: bool = False, multimem_ctas: int = 16):
         self.dtype = dtype
         self._buckets = {}
         self.bytes_per_step = 0
+        # multimem: buckets in symmetric memory, all-reduced in the NVSwitch by the library's own kernel
+        # (mmvqa_multimem_allreduce) instead of NCCL ring kernels
+        self.multimem = bool(multimem) and is_dist() and dist.get_backend() == "nccl"
+        self.multimem_ctas = multimem_ctas
+        self._handles = {}
         self._row_sparse = {}      # id(param) -> callable returning the int64 row ids this rank touched in the step
         self._dense = {}           # id(param) -> persistent dense gradient buffer of a row-sparse parameter
 
@@ -166,14 +171,31 @@ class LayerwiseReducer:
             for g in grads:
                 offs.append(total)
                 total += (g.numel() + 7) // 8 * 8          # 16-byte aligned views for fp32 and bf16
-            flat = torch.zeros(total, device=grads[0].device, dtype=self.dtype)
+            flat = None
+            if self.multimem:
+                import torch.distributed._symmetric_memory as symm_mem
+                flat = symm_mem.empty(total, dtype=self.dtype, device=grads[0].device)
+                hdl = symm_mem.rendezvous(flat, dist.group.WORLD)          # collective: same bucket order on every rank
+                if getattr(hdl, "multicast_ptr", 0):
+                    flat.zero_()
+                    self._handles[key] = hdl
+                else:
+                    flat = None                                            # no multicast support: NCCL
+            if flat is None:
+                flat = torch.zeros(total, device=grads[0].device, dtype=self.dtype)
             views = [flat[o:o + g.numel()].view_as(g) for o, g in zip(offs, grads)]
             ent = self._buckets[key] = (flat, views)
             self.bytes_per_step += flat.numel() * flat.element_size()
         flat, views = ent
         torch._foreach_copy_(views, list(grads))
         if is_dist():
-            dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+            hdl = self._handles.get(key)
+            if hdl is not None:
+                from . import ops
+                ops.multimem_allreduce(hdl.multicast_ptr, hdl.signal_pad_ptrs_dev, hdl.rank, hdl.world_size,
+                                       flat.numel() * flat.element_size(), self.dtype, self.multimem_ctas)
+            else:
+                dist.all_reduce(flat, op=dist.ReduceOp.SUM)
         return views
 
     @property

@@ -56,6 +56,24 @@ def _worker(rank, world, port, q):
     params = [torch.nn.Parameter(torch.zeros(1000, device="cuda")), torch.nn.Parameter(torch.zeros(7, device="cuda"))]
     views = red(params, gr)
     out["reduced"] = [v.float().cpu() * red.grad_scale for v in views]
+    # the library's in-switch all-reduce (multimem.ld_reduce / multimem.st over symmetric memory), bf16 and fp32 buckets,
+    # called repeatedly (the signal pads must return to their idle state) and with an odd element count
+    for dt, key in ((torch.bfloat16, "mm_bf16"), (torch.float32, "mm_fp32")):
+        redm = LayerwiseReducer(dt, multimem=True, multimem_ctas=8)
+        gen = torch.Generator(device="cuda").manual_seed(3 + rank)
+        res = []
+        for it in range(3):
+            gm = [torch.randn(300001, device="cuda", generator=gen), torch.randn(77, device="cuda", generator=gen)]
+            pm = params if it else [torch.nn.Parameter(torch.zeros(300001, device="cuda")), torch.nn.Parameter(torch.zeros(77, device="cuda"))]
+            if it == 0:
+                params = pm
+            vm = redm(params, gm)
+            torch.cuda.synchronize()
+            exp = [g.to(dt).float() for g in gm]
+            for e in exp:
+                dist.all_reduce(e)
+            res.append([(v.float() - e).abs().max().item() / e.abs().max().item() for v, e in zip(vm, exp)])
+        out[key] = {"err": res, "used_multimem": len(redm._handles) > 0}
     q.put(out)
     dist.barrier()
     dist.destroy_process_group()
@@ -97,5 +115,9 @@ def test_supcon_exchanges_over_nccl():
                 e = ((df - want).abs().max() / want.abs().max()).item()
                 assert e < gtol, (key, r, e)
     for r in range(world):
+        for key, tol in (("mm_bf16", 1e-2), ("mm_fp32", 1e-6)):
+            assert got[r][key]["used_multimem"], "B200 / NVSwitch boxes support NVLink multicast: the NCCL fallback was taken"
+            for errs in got[r][key]["err"]:
+                assert max(errs) < tol, (key, errs)
         torch.testing.assert_close(got[r]["reduced"][0], torch.full((1000,), 1.5))
         torch.testing.assert_close(got[r]["reduced"][1], torch.full((7,), 3.0))
