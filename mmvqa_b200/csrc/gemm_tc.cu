@@ -143,7 +143,9 @@ int gemm_tc_bf16(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t st)
   const int per_kb = TC_BM * TC_BK * 2 + bn * TC_BK * 2;
   const bool fits4 = 2 * 4 * per_kb <= 200 * 1024, fits2 = 2 * 2 * per_kb <= 200 * 1024;
   const bool fits2_pair = 2 * 2 * per_kb <= 100 * 1024;                  // two such CTAs on one SM
-  if (chunkable(a) && kblocks >= 2 && kblocks <= 24) {
+  // (wide tiles with few k-blocks -- the K = 448 weight-gradient GEMMs of the side branch -- keep the thin 96 KB ring: a
+  // 128 KB ring takes the whole SM and, inside the step, delays the main-chain kernels that share it: 26.7 -> 36.2 us)
+  if (chunkable(a) && kblocks >= 2 && kblocks <= 24 && (bn < 128 || kblocks >= 12)) {
     if (ctas <= sms) kps = (fits4 && kblocks >= 4) ? 4 : (fits2 ? 2 : 1);
     else if (ctas <= 2 * (int64_t)sms) kps = fits2_pair ? 2 : 1;         // one wave only with two CTAs per SM
     else kps = fits2 ? 2 : 1;
