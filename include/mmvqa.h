@@ -311,6 +311,30 @@ int mmvqa_rf_encoder_fwd_supported(int B, int T, int hidden, int heads, int ff, 
 int mmvqa_rf_encoder_fwd(const mmvqa_rf_encoder_args* args, mmvqa_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
+ * Backward of the attention block of ONE RealFormer layer in one cluster launch (small batches; bf16 only):
+ * the backward of  x1 = ln1(x + dropout(proj(resmha(x))))  (models/realformer.py:30-45,49) = LN1 backward, proj dgrad,
+ * residual-attention backward and kqv dgrad (+ residual), i.e. mmvqa_layernorm_bwd_parts | mmvqa_gemm | mmvqa_rf_attn_bwd |
+ * mmvqa_gemm of the per-operator chain (mmvqa_b200/csrc/rf_attn_block.cu).
+ *   in : dy_parts [nparts, M, hidden] fp32 (+ dy_res [M, hidden], optional) = gradient w.r.t. x1; y1, mean1, rstd1, ln1_w of
+ *        the forward LN1; wproj [hidden, hidden], wkqv [3d, d] (bf16 operand copies); kqv [M*heads, 3d], scores
+ *        [B, heads, T, T] saved by the forward pass; dscores_in = score gradient arriving from layer l + 1 (optional).
+ *   out: dpr [M, hidden] = dropout(d y1) (operand of the proj weight-gradient GEMM), dkqv [M*heads, 3d] (operand of the kqv
+ *        weight-gradient GEMM), dprev (score gradient for layer l - 1, optional), dxin [M, hidden] = gradient w.r.t. the
+ *        layer input (before the FF block of layer l - 1), dln1_w / dln1_b ACCUMULATED into zero-filled fp32 buffers. */
+typedef struct mmvqa_rf_attn_block_bwd_args {
+  int B, T, hidden, heads;
+  const float* dy_parts; int nparts; int64_t part_stride;
+  const void* dy_res;
+  const void* y1; const float* mean1; const float* rstd1; const float* ln1_w;
+  const void* wproj; const void* wkqv;
+  const void* kqv; const float* scores; const float* dscores_in;
+  void* dpr; void* dkqv; float* dprev; void* dxin; float* dln1_w; float* dln1_b;
+  float dropout_p; uint64_t dropout_seed;      /* the forward's proj-branch dropout (seed + 2l) */
+} mmvqa_rf_attn_block_bwd_args;
+int mmvqa_rf_attn_block_bwd_supported(int B, int T, int hidden, int heads);
+int mmvqa_rf_attn_block_bwd(const mmvqa_rf_attn_block_bwd_args* args, mmvqa_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
  * Optimiser: multi-tensor Adam, torch.optim.Adam semantics
  * (vqamed2019/train.py:160, no amsgrad, L2 weight decay).  `table` is a DEVICE array of n_chunks
  * descriptors, each a contiguous chunk (<= 32768 elements is a good size) of one parameter

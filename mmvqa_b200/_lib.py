@@ -51,6 +51,19 @@ class RfEncoderArgs(C.Structure):
     ]
 
 
+class RfAttnBlockBwdArgs(C.Structure):
+    _fields_ = [
+        ("B", i32), ("T", i32), ("hidden", i32), ("heads", i32),
+        ("dy_parts", vp), ("nparts", i32), ("part_stride", i64),
+        ("dy_res", vp),
+        ("y1", vp), ("mean1", vp), ("rstd1", vp), ("ln1_w", vp),
+        ("wproj", vp), ("wkqv", vp),
+        ("kqv", vp), ("scores", vp), ("dscores_in", vp),
+        ("dpr", vp), ("dkqv", vp), ("dprev", vp), ("dxin", vp), ("dln1_w", vp), ("dln1_b", vp),
+        ("dropout_p", f32), ("dropout_seed", u64),
+    ]
+
+
 class AdamDesc(C.Structure):
     _fields_ = [("p", vp), ("m", vp), ("v", vp), ("g", vp), ("bf16_out", vp), ("n", i64), ("flags", i64)]
 
@@ -80,6 +93,8 @@ SIGNATURES = {
     "mmvqa_rf_attn_fwd_fused": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "mmvqa_rf_attn_bwd_fused": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "mmvqa_rf_attn_bwd": (i32, [vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "mmvqa_rf_attn_block_bwd_supported": (i32, [i32, i32, i32, i32]),
+    "mmvqa_rf_attn_block_bwd": (i32, [C.POINTER(RfAttnBlockBwdArgs), vp]),
     "mmvqa_rf_encoder_fwd_supported": (i32, [i32, i32, i32, i32, i32, i32]),
     "mmvqa_rf_encoder_fwd": (i32, [C.POINTER(RfEncoderArgs), vp]),
     "mmvqa_embed_ln_scatter_fwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, f32,

@@ -823,6 +823,12 @@ class RealFormerEncoderFn(torch.autograd.Function):
         # PDL-overlapped dgrad GEMM -- 120 KB of shared memory and a third serial phase on 128 CTAs; the forward fusion
         # is the one that pays)
         sink = _GRAD_SINK
+        # opt-in (MMVQA_RF_ATTN_BWD=1): the attention block of every layer as one cluster kernel (csrc/rf_attn_block.cu).
+        # Measured at B = 16, T = 28: it takes the same ~47 us as the four launches it replaces (one 8-CTA cluster per
+        # sample pair = 64 SMs with 4 of 8 warps busy in the attention phases), 2.76 vs 2.71 ms/step -- parity-tested,
+        # not the default.
+        attn_block = (dt == torch.bfloat16 and _os.environ.get("MMVQA_RF_ATTN_BWD", "0") == "1" and
+                      ops.rf_attn_block_bwd_supported(B, T, H, heads))
         for l in reversed(range(n_layers)):
             xin, kqv, scores, attn, y1, mean1, rstd1, x1, hpre, hact, y2, mean2, rstd2 = saved[l * nsave:(l + 1) * nsave]
             kqv_w, proj_w, g1, b1, w0, bb0, w2, bb2, g2, b2 = params[l * RF_PARAMS_PER_LAYER:(l + 1) * RF_PARAMS_PER_LAYER]
@@ -847,6 +853,32 @@ class RealFormerEncoderFn(torch.autograd.Function):
             with branch.after_now():
                 dw0 = gemm_wgrad(dhpre, F4, M, F4, x1, H, H)
             ns = split_k_slabs(M, H, F4, dx.device, dt)
+            if attn_block:
+                # LN1 backward + proj dgrad + attention backward + kqv dgrad in ONE cluster launch (csrc/rf_attn_block.cu):
+                # it consumes the fp32 split-K slabs of the FF1 dgrad and dy2 directly
+                if parts is None:
+                    parts = torch.empty(max(ns, 1), M, H, device=dx.device, dtype=torch.float32)
+                ops.gemm(M, H, F4, dhpre, F4, False, wf0, H, True, parts, H, split_k=max(ns, 1), c_split_stride=M * H,
+                         b_static=True)
+                want_dprev = (l > 0) or (has_prev and ctx.needs_input_grad[2])
+                dpr, dkqv, dprev, dxin = ops.rf_attn_block_bwd(parts, dy2, y1, mean1, rstd1, g1.detach(), wp, wk, kqv, scores, ds,
+                                                               want_dprev, dg1, db1, B, T, heads, p1, seed + 2 * l)
+                with branch.after_now():
+                    dwp = gemm_wgrad(dpr, H, M, H, attn, H, H)
+                    dwk = gemm_wgrad(dkqv, 3 * d, M * heads, 3 * d, xin, d, d, zeroed=zl[5 * H + F4:].view(3 * d, d))
+                keep.append((dff, dhpre, dpr, dkqv, dy2))
+                base = l * RF_PARAMS_PER_LAYER
+                gl = [dwk.view(kqv_w.shape), dwp.view(proj_w.shape), dg1, db1, dw0.view(w0.shape), dbb0, dw2.view(w2.shape), dbb2,
+                      dg2, db2]
+                pl = params[base:base + RF_PARAMS_PER_LAYER]
+                if sink is not None and all(ctx.needs_input_grad[7 + base + i] for i in range(RF_PARAMS_PER_LAYER)) and \
+                        sink(pl, gl, branch.side):
+                    keep.append(gl)
+                else:
+                    grads[base:base + RF_PARAMS_PER_LAYER] = gl
+                dx = dxin
+                ds = dprev
+                continue
             if ns > 1:
                 # dgrad through FF1 as split-K slabs; LN1 backward sums them and adds the residual gradient dy2
                 if parts is None:

@@ -288,6 +288,34 @@ def rf_encoder_fwd(x0: Tensor, layers, prev: Optional[Tensor], mask: Optional[Te
     return out
 
 
+def rf_attn_block_bwd_supported(B: int, T: int, hidden: int, heads: int) -> bool:
+    return bool(L.lib().mmvqa_rf_attn_block_bwd_supported(B, T, hidden, heads))
+
+
+def rf_attn_block_bwd(dy_parts: Tensor, dy_res: Optional[Tensor], y1: Tensor, mean1: Tensor, rstd1: Tensor, ln1_w: Tensor,
+                      wproj: Tensor, wkqv: Tensor, kqv: Tensor, scores: Tensor, dscores_in: Optional[Tensor], want_dprev: bool,
+                      dln1_w: Tensor, dln1_b: Tensor, B: int, T: int, heads: int, p: float, seed: int):
+    """LN1 backward + proj dgrad + residual-attention backward + kqv dgrad of one layer in one cluster launch (bf16).
+    dy_parts [nparts, M, H] fp32.  Returns (dpr, dkqv, dprev, dxin); dln1_w / dln1_b are accumulated in place."""
+    nparts, M, H = dy_parts.shape
+    dpr = torch.empty(M, H, device=y1.device, dtype=y1.dtype)
+    dkqv = torch.empty_like(kqv)
+    dxin = torch.empty(M, H, device=y1.device, dtype=y1.dtype)
+    dprev = torch.empty_like(scores) if want_dprev else None
+    a = L.RfAttnBlockBwdArgs()
+    a.B, a.T, a.hidden, a.heads = B, T, H, heads
+    a.dy_parts, a.nparts, a.part_stride = _p(_cont(dy_parts, "dy_parts")), nparts, M * H
+    a.dy_res = _p(dy_res)
+    a.y1, a.mean1, a.rstd1, a.ln1_w = _p(_cont(y1, "y1")), _p(mean1), _p(rstd1), _p(ln1_w)
+    a.wproj, a.wkqv = _p(_cont(wproj, "wproj")), _p(_cont(wkqv, "wkqv"))
+    a.kqv, a.scores, a.dscores_in = _p(_cont(kqv, "kqv")), _p(_cont(scores, "scores")), _p(dscores_in)
+    a.dpr, a.dkqv, a.dprev, a.dxin = _p(dpr), _p(dkqv), _p(dprev), _p(dxin)
+    a.dln1_w, a.dln1_b = _p(dln1_w), _p(dln1_b)
+    a.dropout_p, a.dropout_seed = p, seed & 0xFFFFFFFFFFFFFFFF
+    L.check(L.lib().mmvqa_rf_attn_block_bwd(C.byref(a), _stream()), "rf_attn_block_bwd")
+    return dpr, dkqv, dprev, dxin
+
+
 def rf_attn_bwd(kqv: Tensor, scores: Tensor, dout: Tensor, dscores_in: Optional[Tensor], want_dprev: bool, B: int, T: int,
                 heads: int, d: int):
     dkqv = torch.empty_like(kqv)

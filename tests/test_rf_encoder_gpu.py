@@ -144,3 +144,49 @@ def test_unsupported_shapes_take_the_operator_chain():
     assert not ops.rf_encoder_supported(16, 75, 768, 8, 3072, 12)     # T > 32
     assert not ops.rf_encoder_supported(64, 28, 768, 8, 3072, 12)     # too many sample groups to be co-resident
     assert not ops.rf_encoder_supported(16, 28, 128, 8, 512, 2)       # other widths
+
+
+@pytest.mark.parametrize("B,T,L,with_prev,drop", [(16, 28, 3, False, 0.0), (3, 28, 2, True, 0.0), (1, 9, 1, False, 0.0),
+                                                  (5, 32, 2, False, 0.0), (4, 28, 2, False, 0.3)])
+def test_attention_block_backward_cluster_kernel(B, T, L, with_prev, drop):
+    """csrc/rf_attn_block.cu (LN1 backward + proj dgrad + attention backward + kqv dgrad in one cluster launch) against
+    the four per-operator launches it replaces: every parameter gradient, the input gradient and the gradient of the
+    incoming scores.  Same bf16 arithmetic, different reduction orders: 5e-2 of each tensor's max (dropout on: the same
+    counter-hash masks are regenerated on both sides)."""
+    assert ops.rf_attn_block_bwd_supported(B, T, 768, 8)
+    with mmvqa_b200.compute_dtype_scope(torch.bfloat16):
+        Fn.invalidate_weight_cache()
+        blocks = _blocks(L, seed=5, drop=drop)
+        params = []
+        for b in blocks:
+            params.extend(block_params(b))
+        x = torch.randn(B, T, 768, device="cuda").bfloat16()
+        mask = torch.ones(B, T, device="cuda")
+        for i in range(B):
+            mask[i, T - (i % min(T, 5)):] = 0.0
+        prev = torch.randn(B, 8, T, T, device="cuda") if with_prev else None
+        g = torch.randn(B, T, 768, device="cuda").bfloat16()
+        gs = torch.randn(B, 8, T, T, device="cuda") * 0.1
+        res = {}
+        for mode in ("0", "1"):
+            os.environ["MMVQA_RF_ATTN_BWD"] = mode
+            try:
+                xin = x.clone().requires_grad_(True)
+                pv = None if prev is None else prev.clone().requires_grad_(True)
+                for p in params:
+                    p.grad = None
+                n0 = mmvqa_b200._lib.launch_count()
+                y, sc, _ = _run(False, xin, mask, pv, params, drop=drop, seed=4321)
+                n1 = mmvqa_b200._lib.launch_count()
+                torch.autograd.backward([y, sc], [g, gs])
+                n2 = mmvqa_b200._lib.launch_count()
+                res[mode] = ([p.grad.clone() for p in params] + [xin.grad.clone()] + ([pv.grad.clone()] if pv is not None else []),
+                             n2 - n1)
+            finally:
+                os.environ.pop("MMVQA_RF_ATTN_BWD", None)
+        assert res["1"][1] <= res["0"][1] - 3 * L, "the cluster kernel must replace four launches per layer with one"
+        for i, (u, v) in enumerate(zip(res["0"][0], res["1"][0])):
+            assert torch.isfinite(v.float()).all(), i
+            e = ((u.float() - v.float()).abs().max() / u.float().abs().max().clamp_min(1e-6)).item()
+            assert e < 5e-2, (i, e)
+        Fn.invalidate_weight_cache()
