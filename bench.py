@@ -490,6 +490,40 @@ def main_gpu(a):
     opt.close()                    # rank 0 works alone from here on: no gradient sink, no collective
     opt.reduce_fn = None
     opt.zero_grad(set_to_none=True)
+    # (captured BEFORE any eager backward on the default stream: AccumulateGrad nodes born there would tie the legacy
+    # stream to the capture)
+    # ---- hot path only (SURVEY.md section 8d (i)): feature maps -> loss -> all gradients, no optimizer ----
+    log("hot path only")
+    hot = None
+    try:
+        class _NoOptimizer:
+            """zero_grad only: the captured step is forward + loss + backward, nothing else"""
+            def zero_grad(self, set_to_none=True):
+                for p_ in params:
+                    p_.grad = None
+
+            def step(self):
+                pass
+        gh = GraphedTrainStep(loss_fn, dev[0], _NoOptimizer(), warmup=2, main_priority=a.main_priority)
+        for i in range(5):
+            gh.replay_packed(dev_flat[i % NB])
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(a.steps):
+            gh.replay_packed(dev_flat[i % NB])
+        e1.record()
+        e1.synchronize()
+        ms_hot = e0.elapsed_time(e1) / a.steps
+        hot = {"ms_per_step": ms_hot, "samples_per_s": B / (ms_hot * 1e-3), "launches_per_step": gh.launches_per_step,
+               "tensor_frac": B / (ms_hot * 1e-3) * STEP_GFLOP_PER_SAMPLE * 1e9 / (tf_burst * 1e12),
+               "what": "projector -> encoder -> heads -> ASL, forward + backward (every gradient), CUDA-graph replay, no Adam"}
+        gh.close()
+        del gh
+    except Exception as ex:
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        hot = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
+    opt.zero_grad(set_to_none=True)
     _ops.gemm_record(True)
     loss_fn(*dev[0]).backward()
     rec = _ops.gemm_record(False)
@@ -549,37 +583,6 @@ def main_gpu(a):
                            "bound": "hbm", "achieved": adam_gbs, "peak": hbm, "unit": "GB/s", "frac": adam_gbs / hbm,
                            "ms_per_launch": ms_adam, "share_of_step": ms_adam / ms_step},
             "step_tensor_frac": value / world * STEP_GFLOP_PER_SAMPLE * 1e9 / (tf_burst * 1e12)}
-    # ---- hot path only (SURVEY.md section 8d (i)): feature maps -> loss -> all gradients, no optimizer ----
-    log("hot path only")
-    hot = None
-    try:
-        class _NoOptimizer:
-            """zero_grad only: the captured step is forward + loss + backward, nothing else"""
-            def zero_grad(self, set_to_none=True):
-                for p_ in params:
-                    p_.grad = None
-
-            def step(self):
-                pass
-        gh = GraphedTrainStep(loss_fn, dev[0], _NoOptimizer(), warmup=2, main_priority=a.main_priority)
-        for i in range(5):
-            gh.replay_packed(dev_flat[i % NB])
-        torch.cuda.synchronize()
-        e0.record()
-        for i in range(a.steps):
-            gh.replay_packed(dev_flat[i % NB])
-        e1.record()
-        e1.synchronize()
-        ms_hot = e0.elapsed_time(e1) / a.steps
-        hot = {"ms_per_step": ms_hot, "samples_per_s": B / (ms_hot * 1e-3), "launches_per_step": gh.launches_per_step,
-               "tensor_frac": B / (ms_hot * 1e-3) * STEP_GFLOP_PER_SAMPLE * 1e9 / (tf_burst * 1e12),
-               "what": "projector -> encoder -> heads -> ASL, forward + backward (every gradient), CUDA-graph replay, no Adam"}
-        gh.close()
-        del gh
-    except Exception as ex:
-        import traceback
-        traceback.print_exc(file=sys.stderr)
-        hot = {"error": "%s: %s" % (type(ex).__name__, str(ex)[:200])}
     eager = None
     if world == 1 and not a.no_eager_bar:
         log("eager PyTorch bar")

@@ -57,6 +57,8 @@ extern "C" int mmvqa_gemm(const mmvqa_gemm_args* a, mmvqa_stream_t stream) {
   ep.c_split_stride = (!a->accumulate && split_k > 1) ? a->c_split_stride : 0;
   ep.dropout_p = a->dropout_p; ep.dropout_seed = a->dropout_seed; ep.seed_ctr = g_seed_ctr;
   ep.trace = reinterpret_cast<unsigned long long*>(a->trace);
+  static const int no_stage_env = getenv("MMVQA_TC_NO_STAGE") != nullptr ? atoi(getenv("MMVQA_TC_NO_STAGE")) : 0;
+  ep.no_stage = no_stage_env;
   if (a->dtype == MMVQA_F32) return gemm_simt_f32(&v, ep, as_stream(stream));
   int sm = mmvqa_device_sm();
   if (sm < 0) return sm;

@@ -92,6 +92,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait for an EARLIER tcgen05.ld into r[]: the registers are in/out operands, so no use of them can move above the wait
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
 // UMMA shared-memory matrix descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, version 1):
 //  [0,14) start >> 4 | [16,30) leading byte offset >> 4 | [32,46) stride byte offset >> 4 |
 //  [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
@@ -147,13 +155,14 @@ __device__ __forceinline__ void load16_bf16(const __nv_bfloat16* src, int nvalid
     for (int j = 0; j < 16; ++j) out[j] = j < nvalid ? __bfloat162float(src[j]) : 0.0f;
   }
 }
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
 __device__ __forceinline__ void store16_bf16(__nv_bfloat16* dst, int nvalid, const float* v) {
   if (nvalid == 16 && al16(dst, 0, 2)) {
-    Vec16<__nv_bfloat16> a, b;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { a.set(j, v[j]); b.set(j, v[8 + j]); }
-    a.store(dst);
-    b.store(dst + 8);
+    reinterpret_cast<uint4*>(dst)[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    reinterpret_cast<uint4*>(dst)[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
   } else {
 #pragma unroll
     for (int j = 0; j < 16; ++j)
@@ -188,12 +197,45 @@ __device__ __forceinline__ void unpack_pre(const uint4* pre, int ci, float* out)
   }
 }
 
+// ---------------------------------------------------------------------------------
+// Coalesced output: "thread = accumulator row" means a direct store touches 32 different rows per instruction (32-byte
+// pieces of 32 lines; measured: 7.9 us to write one 128 x 256 bf16 tile, more than its 4.5 us main loop).  Instead every
+// epilogue warp parks 128-byte row pieces of its 32 rows in the ring's shared memory (free once the accumulator is
+// complete; pitch 144 B -> conflict-free 128-bit accesses both ways) and writes them back 4 rows x 128 B per instruction.
+// The pieces of a warp are written and read by that warp only: __syncwarp is the only synchronisation.
+// ---------------------------------------------------------------------------------
+constexpr int STG_PITCH = 144;                     // bytes per staged row piece (128 + 16 padding)
+constexpr int STG_WARP_BYTES = 32 * STG_PITCH;     // 4608
+constexpr int STG_BYTES = 8 * STG_WARP_BYTES;      // 36864 for the 8 epilogue warps (x2 with a second output)
+
+__device__ __forceinline__ void stg_put16(uint8_t* stg, int lane, int unit, const float* v, bool as_bf16) {
+  uint8_t* dst = stg + lane * STG_PITCH + unit * 16;
+  if (as_bf16) {
+    *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    *reinterpret_cast<uint4*>(dst + 16) = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(dst + 16 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+}
+// rows [0, rows_valid) x `units` 16-byte units of the warp's staged pieces -> global rows base + r * row_bytes
+__device__ __forceinline__ void stg_flush(const uint8_t* stg, uint8_t* base, int64_t row_bytes, int rows_valid, int units, int lane) {
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int idx = it * 32 + lane, r = idx >> 3, u = idx & 7;
+    if (r < rows_valid && u < units)
+      *reinterpret_cast<uint4*>(base + (int64_t)r * row_bytes + u * 16) = *reinterpret_cast<const uint4*>(stg + r * STG_PITCH + u * 16);
+  }
+  __syncwarp();
+}
+
 template <int EPI, int ACT, int BN>
 __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_row, int m, int n0, int bz, bool first,
                                             bool row_ok, bool has_acc, int c_begin, int64_t c_split_off,
-                                            uint32_t tmem_full_bar) {
+                                            uint32_t tmem_full_bar, uint8_t* stg = nullptr, uint8_t* stg_aux = nullptr,
+                                            int rows_valid = 0) {
   constexpr int NCH = BN / 2 / 16;                 // 16-column chunks this warp owns
-  constexpr int NBQ = (BN / 2 + 31) / 32;
   constexpr bool PRE = (EPI == MMVQA_EPI_RESIDUAL || EPI == MMVQA_EPI_DACT) && BN <= 128;
   const int lane = threadIdx.x & 31;
   float rowsum = 0.0f;
@@ -216,33 +258,43 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_ro
       for (int i = 0; i < NCH * 2; ++i) pre[i] = __ldg(reinterpret_cast<const uint4*>(ax) + i);
     }
   }
-  float bias_l[NBQ];
-#pragma unroll
-  for (int q = 0; q < NBQ; ++q) {
-    const int col = n0 + c_begin + q * 32 + lane;
-    bias_l[q] = (use_bias && q * 32 + lane < BN / 2 && col < p.N) ? __ldg(p.bias + col) : 0.0f;
-  }
+  // (the bias is read per chunk with warp-uniform 128-bit loads: the ncu capture of the 4096 x 3072 x 768 GEMM showed the
+  // epilogue at ~550 instructions per 16-column chunk, the kernel bound by issue slots and instruction fetch)
+  const bool bias_vec = use_bias && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0;
   mbar_wait(tmem_full_bar, 0);
   tc_fence_after();
   if (threadIdx.x == 64) TC_TRACE(6);
   const unsigned long long dseed = (EPI == MMVQA_EPI_RESIDUAL && p.dropout_p > 0.0f) ? seed_eff(p.dropout_seed, p.seed_ctr) : 0ull;
+  // the TMEM read of chunk ci + 1 is in flight while chunk ci is processed (a tcgen05.ld round trip is ~0.2 us)
+  uint32_t rn[16];
+  __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
+  tmem_ld16(tmem_row + (uint32_t)c_begin, rn);
 #pragma unroll 1
   for (int ci = 0; ci < NCH; ++ci) {
     const int c = c_begin + ci * 16;
     uint32_t r[16];
-    __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
-    tmem_ld16(tmem_row + (uint32_t)c, r);
-    tmem_ld_wait();
+    __syncwarp();
+    tmem_ld_wait16(rn);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[j] = rn[j];
+    if (ci + 1 < NCH) tmem_ld16(tmem_row + (uint32_t)(c + 16), rn);
     if (threadIdx.x == 64 && ci == 0) TC_TRACE(9);
     const int nb = n0 + c;
     float v[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {   // accumulator + bias; warp-uniform shuffles, outside the per-row predicate below
-      const int o = ci * 16 + j;
-      float src = bias_l[0];
+    for (int j = 0; j < 16; ++j) v[j] = has_acc ? __uint_as_float(r[j]) : 0.0f;
+    if (use_bias) {
+      if (bias_vec && nb + 16 <= p.N) {
 #pragma unroll
-      for (int q = 1; q < NBQ; ++q) src = (o >> 5) == q ? bias_l[q] : src;
-      v[j] = (has_acc ? __uint_as_float(r[j]) : 0.0f) + __shfl_sync(0xffffffffu, src, o & 31);
+        for (int j = 0; j < 4; ++j) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j);
+          v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (nb + j < p.N) v[j] += __ldg(p.bias + nb + j);
+      }
     }
     if (row_ok && nb < p.N) {
       const int nvalid = min(16, p.N - nb);
@@ -269,7 +321,10 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_ro
         for (int j = 0; j < 16; ++j) v[j] *= rscale;
       }
       if (EPI == MMVQA_EPI_ACT) {
-        if (p.aux_out) store16_bf16(reinterpret_cast<__nv_bfloat16*>(p.aux_out) + (int64_t)m * p.ld_aux_out + nb, nvalid, v);
+        if (p.aux_out) {
+          if (stg_aux) stg_put16(stg_aux, lane, (ci & 3) * 2, v, true);
+          else store16_bf16(reinterpret_cast<__nv_bfloat16*>(p.aux_out) + (int64_t)m * p.ld_aux_out + nb, nvalid, v);
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = act_fast<ACT>(v[j]);
       } else if (EPI == MMVQA_EPI_RESIDUAL) {
@@ -304,14 +359,18 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_ro
           for (int j = 0; j < 16; ++j)
             if (j < nvalid) atomicAdd(c32 + j, v[j]);
         }
+      } else if (stg) {
+        stg_put16(stg, lane, p.c_bf16 ? (ci & 3) * 2 : (ci & 1) * 4, v, p.c_bf16 != 0);
       } else if (p.c_bf16) {
         store16_bf16(reinterpret_cast<__nv_bfloat16*>(p.C) + coff, nvalid, v);
       } else {
         store16_f32(reinterpret_cast<float*>(p.C) + coff, nvalid, v);
       }
+      if (nvalid < 16) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j)
-        if (j >= nvalid) v[j] = 0.0f;
+        for (int j = 0; j < 16; ++j)
+          if (j >= nvalid) v[j] = 0.0f;
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) v[j] = 0.0f;   // rows / columns outside the problem add nothing to the column sums
@@ -321,7 +380,6 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_ro
       // column sums over the warp's 32 rows: transposing butterfly, 16 shuffles; lane l ends with column
       // 8*b4 + 4*b3 + 2*b2 + b1 of the chunk (b_k = bit k of l), duplicated on the lane pair (l, l^1)
       __syncwarp();
-      const int lane = threadIdx.x & 31;
       {
         const bool hi = lane & 16;
 #pragma unroll
@@ -360,19 +418,169 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_ro
       if ((lane & 1) == 0 && nb + col < p.N) atomicAdd(p.colsum_out + nb + col, v[0]);
     }
   next_chunk:;
+    if (EPI != MMVQA_EPI_ACT_ROWSUM && stg != nullptr) {   // warp-uniform: write the staged pass back, 4 rows x 128 B per instruction
+      const int per_pass = p.c_bf16 ? 4 : 2;
+      if ((ci % per_pass) == per_pass - 1 || ci == NCH - 1) {
+        const int ci0 = ci - (ci % per_pass);
+        const int col0 = n0 + c_begin + ci0 * 16;
+        if (col0 < p.N) {
+          const int ncols = min(p.N - col0, (ci - ci0 + 1) * 16);
+          const int elem = p.c_bf16 ? 2 : 4;
+          uint8_t* base = reinterpret_cast<uint8_t*>(p.C) +
+                          ((int64_t)bz * p.c_batch_stride + c_split_off + (int64_t)(m - lane) * p.ldc + col0) * elem;
+          stg_flush(stg, base, p.ldc * elem, rows_valid, ncols * elem / 16, lane);
+          if (EPI == MMVQA_EPI_ACT && stg_aux != nullptr) {
+            uint8_t* abase = reinterpret_cast<uint8_t*>(p.aux_out) + ((int64_t)(m - lane) * p.ld_aux_out + col0) * 2;
+            stg_flush(stg_aux, abase, p.ld_aux_out * 2, rows_valid, ncols * 2 / 16, lane);
+          }
+        }
+      }
+    }
   }
   if (EPI == MMVQA_EPI_ACT_ROWSUM && row_ok) atomicAdd(p.rowsum_out + (int64_t)bz * p.M + m, rowsum * p.scale);
 }
 
+// ---------------------------------------------------------------------------------
+// Lean epilogue for the common case: the warp's 32 rows x BN/2 columns lie inside the problem, the output is staged
+// through shared memory, no column sums / row scales / atomics.  The general tc_epilogue above pays ~190 instructions and
+// a dozen taken branches per 16-column chunk for its guards (ncu source page, profiles/r02_gemm_epilogue.txt: the
+// 4096 x 3072 x 768 GEMM spent 4.2 us per tile in it against a 4.9 us main loop); here a chunk is one TMEM read, the
+// epilogue arithmetic, two 128-bit shared-memory stores, and every 128 bytes of row a write-back of 4 rows x 128 B per
+// instruction.  The TMEM read and the residual / pre-activation row of chunk i + 1 are in flight while chunk i is
+// processed.  Same arithmetic, same dropout index, same rounding as tc_epilogue.
+// ---------------------------------------------------------------------------------
+template <int EPI, int ACT, int BN>
+__device__ __forceinline__ void tc_epilogue_fast(const EpiParams& p, uint32_t tmem_row, int m, int n0, int bz, bool first,
+                                                 int c_begin, int64_t c_split_off, uint32_t tmem_full_bar, uint8_t* stg,
+                                                 uint8_t* stg_aux) {
+  constexpr int NCH = BN / 2 / 16;
+  constexpr bool AUXIN = (EPI == MMVQA_EPI_RESIDUAL || EPI == MMVQA_EPI_DACT);
+  const int lane = threadIdx.x & 31;
+  const int col0 = n0 + c_begin;
+  const bool use_bias = p.bias != nullptr && first;
+  const uint4* ax = nullptr;
+  uint4 a_lo = make_uint4(0, 0, 0, 0), a_hi = a_lo;
+  if (AUXIN) {   // first chunk of the residual / pre-activation row: fetched while the main loop is still running
+    ax = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.aux_in) + (int64_t)m * p.ld_aux_in + col0);
+    a_lo = __ldg(ax);
+    a_hi = __ldg(ax + 1);
+  }
+  const uint32_t thr = (uint32_t)(p.dropout_p * 4294967296.0);
+  const float inv_keep = p.dropout_p > 0.0f ? 1.0f / (1.0f - p.dropout_p) : 1.0f;
+  const bool c_bf16 = p.c_bf16 != 0;
+  const int elem = c_bf16 ? 2 : 4;
+  const int per_pass = c_bf16 ? 4 : 2;                       // chunks per 128 bytes of output row
+  const int units = (NCH < per_pass ? NCH : per_pass) * (c_bf16 ? 2 : 4);
+  // write-back geometry: lane -> row (lane >> 3) + 4 it of the warp's 32, 16-byte unit lane & 7
+  const int64_t row_bytes = p.ldc * elem;
+  uint8_t* cbase = reinterpret_cast<uint8_t*>(p.C) +
+                   ((int64_t)bz * p.c_batch_stride + c_split_off + (int64_t)(m - lane + (lane >> 3)) * p.ldc + col0) * elem + (lane & 7) * 16;
+  const uint32_t soff = (lane >> 3) * STG_PITCH + (lane & 7) * 16;
+  uint8_t* abase = nullptr;
+  int64_t arow_bytes = 0;
+  if (EPI == MMVQA_EPI_ACT && stg_aux != nullptr) {
+    arow_bytes = p.ld_aux_out * 2;
+    abase = reinterpret_cast<uint8_t*>(p.aux_out) + ((int64_t)(m - lane + (lane >> 3)) * p.ld_aux_out + col0) * 2 + (lane & 7) * 16;
+  }
+  mbar_wait(tmem_full_bar, 0);
+  tc_fence_after();
+  if (threadIdx.x == 64) TC_TRACE(6);
+  const unsigned long long dseed = (EPI == MMVQA_EPI_RESIDUAL && p.dropout_p > 0.0f) ? seed_eff(p.dropout_seed, p.seed_ctr) : 0ull;
+  uint32_t rn[16];
+  __syncwarp();  // tcgen05.ld is .sync.aligned: the warp must be converged
+  tmem_ld16(tmem_row + (uint32_t)c_begin, rn);
+#pragma unroll 1
+  for (int ci = 0; ci < NCH; ++ci) {
+    uint32_t r[16];
+    tmem_ld_wait16(rn);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[j] = rn[j];
+    const uint4 q_lo = a_lo, q_hi = a_hi;
+    if (ci + 1 < NCH) {
+      tmem_ld16(tmem_row + (uint32_t)(c_begin + (ci + 1) * 16), rn);
+      if (AUXIN) {
+        a_lo = __ldg(ax + 2 * (ci + 1));
+        a_hi = __ldg(ax + 2 * (ci + 1) + 1);
+      }
+    }
+    const int nb = col0 + ci * 16;
+    float v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]);
+    if (use_bias) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + nb) + j);
+        v[4 * j] += b4.x; v[4 * j + 1] += b4.y; v[4 * j + 2] += b4.z; v[4 * j + 3] += b4.w;
+      }
+    }
+    if (EPI == MMVQA_EPI_ACT) {
+      if (stg_aux != nullptr) stg_put16(stg_aux, lane, (ci & 3) * 2, v, true);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = act_fast<ACT>(v[j]);
+    } else if (AUXIN) {
+      const uint32_t w[8] = {q_lo.x, q_lo.y, q_lo.z, q_lo.w, q_hi.x, q_hi.y, q_hi.z, q_hi.w};
+      if (EPI == MMVQA_EPI_RESIDUAL) {
+        if (p.dropout_p > 0.0f) {
+          const uint64_t i0 = (uint64_t)m * (uint64_t)p.N + (uint64_t)nb;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = hash32(dseed, i0 + (uint64_t)j) >= thr ? v[j] * inv_keep : 0.0f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[2 * j] += __uint_as_float(w[j] << 16);
+          v[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[2 * j] *= dact_fast<ACT>(__uint_as_float(w[j] << 16));
+          v[2 * j + 1] *= dact_fast<ACT>(__uint_as_float(w[j] & 0xffff0000u));
+        }
+      }
+    }
+    stg_put16(stg, lane, c_bf16 ? (ci & 3) * 2 : (ci & 1) * 4, v, c_bf16);
+    if (((ci + 1) & (per_pass - 1)) == 0 || ci == NCH - 1) {   // warp-uniform: 128 bytes of every row are staged
+      const int ci0 = ci & ~(per_pass - 1);
+      __syncwarp();
+      if ((lane & 7) < units) {
+        uint8_t* g = cbase + (int64_t)ci0 * 16 * elem;
+#pragma unroll
+        for (int it = 0; it < 8; ++it)
+          *reinterpret_cast<uint4*>(g + it * 4 * row_bytes) = *reinterpret_cast<const uint4*>(stg + soff + it * 4 * STG_PITCH);
+        if (EPI == MMVQA_EPI_ACT && stg_aux != nullptr) {
+          uint8_t* ga = abase + (int64_t)ci0 * 32;
+#pragma unroll
+          for (int it = 0; it < 8; ++it)
+            *reinterpret_cast<uint4*>(ga + it * 4 * arow_bytes) = *reinterpret_cast<const uint4*>(stg_aux + soff + it * 4 * STG_PITCH);
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <int EPI, int BN>
+__device__ __forceinline__ void tc_epilogue_fast_act(const EpiParams& p, uint32_t tmem_row, int m, int n0, int bz, bool first,
+                                                     int c_begin, uint32_t tmem_full_bar, uint8_t* stg, uint8_t* stg_aux) {
+  switch (p.act) {
+    case MMVQA_ACT_SERF: tc_epilogue_fast<EPI, MMVQA_ACT_SERF, BN>(p, tmem_row, m, n0, bz, first, c_begin, 0, tmem_full_bar, stg, stg_aux); break;
+    case MMVQA_ACT_GELU: tc_epilogue_fast<EPI, MMVQA_ACT_GELU, BN>(p, tmem_row, m, n0, bz, first, c_begin, 0, tmem_full_bar, stg, stg_aux); break;
+    case MMVQA_ACT_RELU: tc_epilogue_fast<EPI, MMVQA_ACT_RELU, BN>(p, tmem_row, m, n0, bz, first, c_begin, 0, tmem_full_bar, stg, stg_aux); break;
+    default: tc_epilogue_fast<EPI, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, c_begin, 0, tmem_full_bar, stg, stg_aux); break;
+  }
+}
+
 template <int EPI, int BN>
 __device__ __forceinline__ void tc_epilogue_act(const EpiParams& p, uint32_t tmem_row, int m, int n0, int bz, bool first,
-                                                bool row_ok, bool has_acc, int c_begin, uint32_t tmem_full_bar) {
+                                                bool row_ok, bool has_acc, int c_begin, uint32_t tmem_full_bar,
+                                                uint8_t* stg = nullptr, uint8_t* stg_aux = nullptr, int rows_valid = 0) {
   const int64_t c_split_off = 0;   // activation epilogues never run split-K
   switch (p.act) {
-    case MMVQA_ACT_SERF: tc_epilogue<EPI, MMVQA_ACT_SERF, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, c_split_off, tmem_full_bar); break;
-    case MMVQA_ACT_GELU: tc_epilogue<EPI, MMVQA_ACT_GELU, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, c_split_off, tmem_full_bar); break;
-    case MMVQA_ACT_RELU: tc_epilogue<EPI, MMVQA_ACT_RELU, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, c_split_off, tmem_full_bar); break;
-    default: tc_epilogue<EPI, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, c_split_off, tmem_full_bar); break;
+    case MMVQA_ACT_SERF: tc_epilogue<EPI, MMVQA_ACT_SERF, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, c_split_off, tmem_full_bar, stg, stg_aux, rows_valid); break;
+    case MMVQA_ACT_GELU: tc_epilogue<EPI, MMVQA_ACT_GELU, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, c_split_off, tmem_full_bar, stg, stg_aux, rows_valid); break;
+    case MMVQA_ACT_RELU: tc_epilogue<EPI, MMVQA_ACT_RELU, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, c_split_off, tmem_full_bar, stg, stg_aux, rows_valid); break;
+    default: tc_epilogue<EPI, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, c_split_off, tmem_full_bar, stg, stg_aux, rows_valid); break;
   }
 }
 
@@ -538,13 +746,44 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
     const int64_t c_split_off = (int64_t)ks * p.c_split_stride;
     const uint32_t tmem_row = tmem_acc + ((uint32_t)(g * 32) << 16);
     const bool has_acc = nkb > 0;
+    // staged, coalesced output through the ring's shared memory (free once the accumulator barrier has completed)
+    const int elem = p.c_bf16 ? 2 : 4;
+    const bool stage_ok = p.C != nullptr && !p.accumulate && p.epilogue != MMVQA_EPI_ACT_ROWSUM && !p.no_stage &&
+                          (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (p.ldc * elem) % 16 == 0 && ((int64_t)p.N * elem) % 16 == 0 &&
+                          (p.c_batch_stride * elem) % 16 == 0 && (p.c_split_stride * elem) % 16 == 0;
+    const bool aux_ok = stage_ok && p.epilogue == MMVQA_EPI_ACT && p.aux_out != nullptr &&
+                        Cfg::STAGES * Cfg::STAGE_BYTES >= 2 * STG_BYTES && (reinterpret_cast<uintptr_t>(p.aux_out) & 15) == 0 &&
+                        (p.ld_aux_out * 2) % 16 == 0;
+    uint8_t* stg = stage_ok ? smem_gen + (warp - 2) * STG_WARP_BYTES : nullptr;
+    uint8_t* stg_aux = aux_ok ? smem_gen + STG_BYTES + (warp - 2) * STG_WARP_BYTES : nullptr;
+    const bool cta_ok = !(nkb == 0 && ks != 0 && p.c_split_stride == 0);
+    const int rows_valid = cta_ok ? max(0, min(32, p.M - (m0 + g * 32))) : 0;
+    // lean path: every row and column of this warp's 32 x BN/2 block is inside the problem and nothing needs a guard
+    const bool aux_in_al = (reinterpret_cast<uintptr_t>(p.aux_in) & 15) == 0 && (p.ld_aux_in * 2) % 16 == 0;
+    bool fast_ok = stage_ok && has_acc && rows_valid == 32 && n0 + c_begin + BN / 2 <= p.N && p.colsum_out == nullptr &&
+                   (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
     switch (p.epilogue) {
-      case MMVQA_EPI_ACT: tc_epilogue_act<MMVQA_EPI_ACT, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, tmem_full_bar); break;
-      case MMVQA_EPI_RESIDUAL: tc_epilogue<MMVQA_EPI_RESIDUAL, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, c_split_off, tmem_full_bar); break;
-      case MMVQA_EPI_DACT: tc_epilogue_act<MMVQA_EPI_DACT, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, tmem_full_bar); break;
+      case MMVQA_EPI_STORE: fast_ok = fast_ok && p.rowscale == nullptr; break;
+      case MMVQA_EPI_ACT: fast_ok = fast_ok && (p.aux_out == nullptr || (aux_ok && p.c_bf16)); break;
+      case MMVQA_EPI_RESIDUAL:
+      case MMVQA_EPI_DACT: fast_ok = fast_ok && aux_in_al; break;
+      default: fast_ok = false;
+    }
+    if (fast_ok) {
+      switch (p.epilogue) {
+        case MMVQA_EPI_ACT: tc_epilogue_fast_act<MMVQA_EPI_ACT, BN>(p, tmem_row, m, n0, bz, first, c_begin, tmem_full_bar, stg, stg_aux); break;
+        case MMVQA_EPI_RESIDUAL: tc_epilogue_fast<MMVQA_EPI_RESIDUAL, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, c_begin, c_split_off, tmem_full_bar, stg, nullptr); break;
+        case MMVQA_EPI_DACT: tc_epilogue_fast_act<MMVQA_EPI_DACT, BN>(p, tmem_row, m, n0, bz, first, c_begin, tmem_full_bar, stg, nullptr); break;
+        default: tc_epilogue_fast<MMVQA_EPI_STORE, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, c_begin, c_split_off, tmem_full_bar, stg, nullptr); break;
+      }
+    } else
+    switch (p.epilogue) {
+      case MMVQA_EPI_ACT: tc_epilogue_act<MMVQA_EPI_ACT, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, tmem_full_bar, stg, stg_aux, rows_valid); break;
+      case MMVQA_EPI_RESIDUAL: tc_epilogue<MMVQA_EPI_RESIDUAL, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, c_split_off, tmem_full_bar, stg, nullptr, rows_valid); break;
+      case MMVQA_EPI_DACT: tc_epilogue_act<MMVQA_EPI_DACT, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, tmem_full_bar, stg, nullptr, rows_valid); break;
       case MMVQA_EPI_ACT_ROWSUM: tc_epilogue_act<MMVQA_EPI_ACT_ROWSUM, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, tmem_full_bar); break;
-      case MMVQA_EPI_DACT_SCALE: tc_epilogue_act<MMVQA_EPI_DACT_SCALE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, tmem_full_bar); break;
-      default: tc_epilogue<MMVQA_EPI_STORE, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, c_split_off, tmem_full_bar); break;
+      case MMVQA_EPI_DACT_SCALE: tc_epilogue_act<MMVQA_EPI_DACT_SCALE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, tmem_full_bar, stg, nullptr, rows_valid); break;
+      default: tc_epilogue<MMVQA_EPI_STORE, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, row_ok, has_acc, c_begin, c_split_off, tmem_full_bar, stg, nullptr, rows_valid); break;
     }
     if (threadIdx.x == 64) TC_TRACE(7);
   }

@@ -62,3 +62,9 @@ if "--more" in sys.argv:
     run("ff2 split4 slabs", M, H, F4, bias=bias_h, split_k=4, c_split_stride=M * H, cdt=torch.float32)
     run("ff2 split6 slabs", M, H, F4, bias=bias_h, split_k=6, c_split_stride=M * H, cdt=torch.float32)
     run("ff2 split8 slabs", M, H, F4, bias=bias_h, split_k=8, c_split_stride=M * H, cdt=torch.float32)
+if "--big" in sys.argv:
+    run("mid 4096x3072x768 plain", 4096, F4, H)
+    run("mid 4096x3072x768 +bias+SERF", 4096, F4, H, bias=bias_f, epilogue=EPI_ACT, act=ACT_SERF,
+        aux_out=torch.empty(4096, F4, device="cuda", dtype=bf), ld_aux_out=F4)
+    run("mid 4096x768x3072 +bias+residual", 4096, H, F4, bias=bias_h, epilogue=EPI_RESIDUAL, aux_in=r(4096, H), ld_aux_in=H)
+    run("wgrad-like 3072x768x4096 fp32 out", F4, H, 4096, cdt=torch.float32)
