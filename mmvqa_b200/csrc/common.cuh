@@ -303,28 +303,46 @@ __device__ __forceinline__ void serf_table_fill(float4* tab, int tid, int nthrea
     for (int k = 0; k < REP; ++k) tab[i * REP + k] = e;
   }
 }
-// a = serf(x), d = serf'(x)
+// table entry of x and the local variable t in [0, 1).  The interval index is taken from the mantissa of
+// u + 1.5 * 2^23 added with round-down (floor(u) sits in the low bits, u - floor(u) follows with two FADDs): no F2I / I2F,
+// which issue on the quarter-rate XU pipe, and a single FFMA + two FMNMX for the clamped coordinate.  The projector
+// evaluates ~205 M activations per step and is bound by instruction issue (profiles/r01_ncu_vistok_extract.txt).
+// `tab` here is this lane's handle from serf_tab_handle(): the shared-memory address of its replica minus the bias of
+// the magic constant, so that the entry address is ONE multiply-add of the raw bits of u + 1.5 * 2^23.
 template <int REP>
-__device__ __forceinline__ void serf_both_tab(const float4* tab, float x, float& a, float& d) {
-  const float u = fminf(fmaxf((x - SERF_TAB_X0) * SERF_TAB_INV_H, 0.0f), (float)SERF_TAB_N - 0.001f);
-  const int i = (int)u;
-  const float t = u - (float)i;
-  const float4 e = tab[i * REP + (threadIdx.x & (REP - 1))];
-  const float g = fmaf(t, fmaf(t, fmaf(t, e.w, e.z), e.y), e.x);
-  const float gp = fmaf(t, fmaf(3.0f * t, e.w, e.z + e.z), e.y) * SERF_TAB_INV_H;
-  a = x * g;
-  d = fmaf(x, gp, g);
+__device__ __forceinline__ uint32_t serf_tab_handle(const float4* tab) {
+  return (uint32_t)__cvta_generic_to_shared(tab) + (threadIdx.x & (REP - 1)) * 16u - 0x4B400000u * (16u * REP);
 }
 template <int REP>
-__device__ __forceinline__ float serf_tab(const float4* tab, float x) {
-  const float u = fminf(fmaxf((x - SERF_TAB_X0) * SERF_TAB_INV_H, 0.0f), (float)SERF_TAB_N - 0.001f);
-  const int i = (int)u;
-  const float t = u - (float)i;
-  const float4 e = tab[i * REP + (threadIdx.x & (REP - 1))];
+__device__ __forceinline__ float4 serf_tab_entry(uint32_t tab, float x, float& t) {
+  const float u = fminf(fmaxf(fmaf(x, SERF_TAB_INV_H, -SERF_TAB_X0 * SERF_TAB_INV_H), 0.0f), (float)SERF_TAB_N - 0.001f);
+  const float um = __fadd_rd(u, 12582912.0f);
+  t = u - (um - 12582912.0f);
+  float4 e;
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+      : "=f"(e.x), "=f"(e.y), "=f"(e.z), "=f"(e.w)
+      : "r"((uint32_t)__float_as_int(um) * (16u * REP) + tab));
+  return e;
+}
+// a = serf(x), d = serf'(x)
+template <int REP>
+__device__ __forceinline__ void serf_both_tab(uint32_t tab, float x, float& a, float& d) {
+  float t;
+  const float4 e = serf_tab_entry<REP>(tab, x, t);
+  const float q = fmaf(t, e.w, e.z);                 // c2 + t c3
+  const float g = fmaf(t, fmaf(t, q, e.y), e.x);
+  const float gp = fmaf(t, q + fmaf(t, e.w, q), e.y);   // c1 + t (2 c2 + 3 t c3)
+  a = x * g;
+  d = fmaf(x * SERF_TAB_INV_H, gp, g);
+}
+template <int REP>
+__device__ __forceinline__ float serf_tab(uint32_t tab, float x) {
+  float t;
+  const float4 e = serf_tab_entry<REP>(tab, x, t);
   return x * fmaf(t, fmaf(t, fmaf(t, e.w, e.z), e.y), e.x);
 }
 template <int REP>
-__device__ __forceinline__ float dserf_tab(const float4* tab, float x) {
+__device__ __forceinline__ float dserf_tab(uint32_t tab, float x) {
   float a, d;
   serf_both_tab<REP>(tab, x, a, d);
   return d;

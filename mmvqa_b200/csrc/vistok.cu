@@ -32,7 +32,7 @@ struct VtCfg {
 
 template <int MODE, int ACT, int REP>
 __device__ __forceinline__ void vt_epilogue_tile(const EpiParams& p, uint32_t tmem_row, int m, int n0, int bz, bool row_ok,
-                                                 int c_begin, float rscale, float& rowsum, const float4* tab) {
+                                                 int c_begin, float rscale, float& rowsum, uint32_t tab) {
 #pragma unroll 1
   for (int c = c_begin; c < c_begin + VT_BN / 2; c += 16) {
     uint32_t r[16];
@@ -44,22 +44,27 @@ __device__ __forceinline__ void vt_epilogue_tile(const EpiParams& p, uint32_t tm
       const int nvalid = min(16, p.N - nb);
       float v[16];
       if (MODE == 0) {
+        float part = 0.0f;
+        if (nvalid < 16) {   // ragged last chunk of a row of pixels: columns past N hold act(0) = 0 for SERF / ReLU / GELU, but mask anyway
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (j >= nvalid) r[j] = 0u;
+        }
         if (p.aux_out) {   // forward that keeps act'(.) (bf16) for the backward pass
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             float a;
             if (ACT == MMVQA_ACT_SERF) serf_both_tab<REP>(tab, __uint_as_float(r[j]), a, v[j]);
             else act_both_fast<ACT>(__uint_as_float(r[j]), a, v[j]);
-            rowsum += (j < nvalid) ? a : 0.0f;
+            part += a;
           }
           store16_bf16(reinterpret_cast<__nv_bfloat16*>(p.aux_out) + ((int64_t)bz * p.M + m) * p.ld_aux_out + nb, nvalid, v);
         } else {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float a = ACT == MMVQA_ACT_SERF ? serf_tab<REP>(tab, __uint_as_float(r[j])) : act_fast<ACT>(__uint_as_float(r[j]));
-            rowsum += (j < nvalid) ? a : 0.0f;
-          }
+          for (int j = 0; j < 16; ++j)
+            part += ACT == MMVQA_ACT_SERF ? serf_tab<REP>(tab, __uint_as_float(r[j])) : act_fast<ACT>(__uint_as_float(r[j]));
         }
+        rowsum += part;
       } else {
 #pragma unroll
         for (int j = 0; j < 16; ++j)
@@ -165,6 +170,7 @@ __global__ void __launch_bounds__(VT_THREADS) vistok_kernel(const __grid_constan
     const int m = m0 + g * 32 + lane;
     const bool row_ok = m < p.M;
     float rscale = 0.0f, rowsum = 0.0f;
+    const uint32_t tabh = serf_tab_handle<Cfg::REP>(tab);
     if (MODE == 1 && row_ok) rscale = __ldg(p.rowscale + (int64_t)bz * p.M + m) * p.scale;
     for (int t = 0; t < my_tiles; ++t) {
       const int buf = t & 1;
@@ -173,10 +179,10 @@ __global__ void __launch_bounds__(VT_THREADS) vistok_kernel(const __grid_constan
       const uint32_t tmem_row = tmem_acc + ((uint32_t)(g * 32) << 16) + (uint32_t)(buf * VT_BN);
       const int n0 = (split + t * nsplit) * VT_BN;
       switch (p.act) {
-        case MMVQA_ACT_SERF: vt_epilogue_tile<MODE, MMVQA_ACT_SERF, Cfg::REP>(p, tmem_row, m, n0, bz, row_ok, c_begin, rscale, rowsum, tab); break;
-        case MMVQA_ACT_GELU: vt_epilogue_tile<MODE, MMVQA_ACT_GELU, Cfg::REP>(p, tmem_row, m, n0, bz, row_ok, c_begin, rscale, rowsum, tab); break;
-        case MMVQA_ACT_RELU: vt_epilogue_tile<MODE, MMVQA_ACT_RELU, Cfg::REP>(p, tmem_row, m, n0, bz, row_ok, c_begin, rscale, rowsum, tab); break;
-        default: vt_epilogue_tile<MODE, MMVQA_ACT_NONE, Cfg::REP>(p, tmem_row, m, n0, bz, row_ok, c_begin, rscale, rowsum, tab); break;
+        case MMVQA_ACT_SERF: vt_epilogue_tile<MODE, MMVQA_ACT_SERF, Cfg::REP>(p, tmem_row, m, n0, bz, row_ok, c_begin, rscale, rowsum, tabh); break;
+        case MMVQA_ACT_GELU: vt_epilogue_tile<MODE, MMVQA_ACT_GELU, Cfg::REP>(p, tmem_row, m, n0, bz, row_ok, c_begin, rscale, rowsum, tabh); break;
+        case MMVQA_ACT_RELU: vt_epilogue_tile<MODE, MMVQA_ACT_RELU, Cfg::REP>(p, tmem_row, m, n0, bz, row_ok, c_begin, rscale, rowsum, tabh); break;
+        default: vt_epilogue_tile<MODE, MMVQA_ACT_NONE, Cfg::REP>(p, tmem_row, m, n0, bz, row_ok, c_begin, rscale, rowsum, tabh); break;
       }
       // hand the accumulator back to the MMA warp
       tc_fence_before();

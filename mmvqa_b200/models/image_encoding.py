@@ -115,8 +115,12 @@ class ResNetTransfer(Transfer):
     same tensors, so the backbone runs ONCE here and the five maps are tapped on the way (deep->shallow
     token order is preserved)."""
 
-    def forward(self, img):
-        ch = list(self.model.children())
+    @staticmethod
+    def tap_feature_maps(backbone, img):
+        """One pass over `backbone.children()[:-2]`, returning the outputs of the prefixes [:-2], [:-3], [:-4], [:-5],
+        [:-7] in that (deep -> shallow) order -- the five tensors image_encoding.py:72-85 obtains by re-running each
+        prefix from the image (tests/test_host_cpu.py::test_resnet_single_pass_taps_equal_the_five_prefix_runs)."""
+        ch = list(backbone.children())
         n = len(ch)
         taps = {n - 2: 0, n - 3: 1, n - 4: 2, n - 5: 3, n - 7: 4}     # prefix length -> token index
         feats = [None] * 5
@@ -125,7 +129,10 @@ class ResNetTransfer(Transfer):
             x = m(x)
             if (i + 1) in taps:
                 feats[taps[i + 1]] = x
-        return self.project(feats)
+        return feats
+
+    def forward(self, img):
+        return self.project(self.tap_feature_maps(self.model, img))
 
 
 class Timm_EFfNetV2(Transfer):

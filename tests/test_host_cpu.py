@@ -199,3 +199,23 @@ def test_serf_hermite_table_accuracy():
     assert np.abs(a - a_ref).max() < 2e-6, np.abs(a - a_ref).max()
     assert np.abs(d - d_ref).max() < 1e-5, np.abs(d - d_ref).max()
     assert np.all(a[x > 6.0] == x[x > 6.0]) and np.all(d[x > 6.5] == 1.0)      # SERF(x) = x, SERF'(x) = 1 in the saturated tail
+
+
+def test_resnet_single_pass_taps_equal_the_five_prefix_runs():
+    """SURVEY.md section 8 row f4 (backbone hand-off): the reference re-runs five prefixes of the ResNet from the image
+    (image_encoding.py:72-85: children()[:-2], [:-3], [:-4], [:-5], [:-7]); ResNetTransfer here runs the backbone once
+    and taps the same five tensors.  Bit-exact in eval mode (same modules, same inputs, same order of operations)."""
+    from torchvision import models
+    torch.manual_seed(0)
+    backbone = models.resnet18(weights=None).eval()          # same children() layout as resnet152, CPU-sized
+    img = torch.randn(2, 3, 64, 64)
+    with torch.no_grad():
+        taps = IE.ResNetTransfer.tap_feature_maps(backbone, img)
+        ch = list(backbone.children())
+        for tok, cut in enumerate((2, 3, 4, 5, 7)):
+            want = nn.Sequential(*ch[:-cut])(img)
+            assert taps[tok].shape == want.shape
+            assert torch.equal(taps[tok], want), "token %d (prefix [:-%d]) differs" % (tok, cut)
+    # deep -> shallow token order, the channel counts of models_dict scale with the architecture (resnet18: /4)
+    assert [t.shape[1] for t in taps] == [512, 256, 128, 64, 64]
+    assert [t.shape[-1] for t in taps] == [2, 4, 8, 16, 32]

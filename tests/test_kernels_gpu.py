@@ -509,6 +509,43 @@ def test_persistent_projector_kernel(Cc, HW, hidden, Bn, act):
         close(got, G_ref, 2e-2, 2e-3 * float(G_ref.abs().max()), msg="recompute backward")
 
 
+def test_projector_takes_bf16_feature_maps_in_place():
+    """SURVEY.md section 8 row f4 (backbone hand-off): a backbone running under bf16 autocast hands the projector bf16
+    NCHW maps; they are the TMA operand as they are (no cast launch).  Same tokens and the same weight gradients as the
+    fp32 maps holding the same (bf16-representable) values, and close to the oracle (image_encoding.py:100-115)."""
+    import mmvqa_b200
+    from mmvqa_b200 import functional as Fn
+    mmvqa_b200.set_compute_dtype("bf16")
+    try:
+        B, hidden = 2, 256
+        shapes = [(24, 40), (48, 20), (80, 12), (176, 6), (512, 3)]       # odd pixel counts too: 36 and 9 need the padded ld
+        feats32 = [rnd(B, c, s, s, seed=300 + i).abs().bfloat16().float().to(DEV) for i, (c, s) in enumerate(shapes)]
+        ws = [(rnd(hidden, c, 1, 1, seed=310 + i) * c ** -0.5).to(DEV).requires_grad_(True) for i, (c, _) in enumerate(shapes)]
+        go = rnd(len(shapes), B, hidden, seed=320).to(DEV)
+        outs, grads = [], []
+        Fn.vistok_project_all(feats32, ws, ACTS["serf"])          # warm the bf16 weight-operand cache: count map casts only
+        for feats in (feats32, [f.bfloat16() for f in feats32]):
+            for w in ws:
+                w.grad = None
+            n0 = mmvqa_b200.launch_count()
+            v = Fn.vistok_project_all(feats, ws, ACTS["serf"])
+            launches = mmvqa_b200.launch_count() - n0
+            v.backward(go)
+            outs.append((v.detach().clone(), launches))
+            grads.append([w.grad.detach().clone() for w in ws])
+        (v32, l32), (v16, l16) = outs
+        # same operand bytes; the pooled sums are combined with one fp32 atomic per (row, pixel split): order only
+        close(v16, v32, 1e-5, 1e-6, msg="tokens from bf16 maps vs fp32 maps")
+        for g32, g16 in zip(*grads):
+            close(g16, g32, 1e-5, 1e-6 * float(g32.abs().max()), msg="dW")     # split-K atomics: order only
+        assert l16 < l32, "bf16 maps should skip the cast launches (%d vs %d)" % (l16, l32)
+        for n, (f, w) in enumerate(zip(feats32, ws)):
+            Y = torch.einsum("mc,bcn->bmn", w.detach().reshape(hidden, -1).bfloat16().float().cpu(), f.flatten(2).cpu())
+            close(v16[n], O.activation("serf", Y).mean(-1), 1e-2, 2e-3, msg="level %d vs oracle" % n)
+    finally:
+        mmvqa_b200.set_compute_dtype("bf16")
+
+
 # ------------------------------------------------------------------------------------------
 # split-K slabs: GEMM partial tiles reduced by the LayerNorm pass that follows (realformer.py:49-50 at M = 448)
 # ------------------------------------------------------------------------------------------
