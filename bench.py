@@ -349,9 +349,13 @@ def main_gpu(a):
         step_ids["ids"] = ids                      # the graph's static input_ids tensor (row-sparse embedding exchange)
         logits, _, _ = model.forward_features([f0, f1, f2, f3, f4], ids, seg, mask)
         return crit(logits, target)
+    word_w = model.transformer.bert_embedding.word_embeddings.weight
     if reducer is not None and a.sparse_embed:
         # the word-embedding gradient has at most B*T non-zero rows: exchange those instead of the dense 47 MB table
-        reducer.register_row_sparse(model.transformer.bert_embedding.word_embeddings.weight, lambda: step_ids["ids"])
+        reducer.register_row_sparse(word_w, lambda: step_ids["ids"])
+    if a.sparse_embed and (world == 1 or reducer is not None):
+        # ... and Adam skips the table rows that have never received gradient (their update is exactly the identity)
+        opt.register_row_sparse(word_w, (lambda: step_ids["ids"]) if reducer is None else (lambda: reducer.gathered_ids(word_w)))
 
     NB = 4
     host = []
@@ -367,7 +371,18 @@ def main_gpu(a):
         plist = [p for p in params if p.grad is not None]
         return dict(grads=buckets.grads(plist))
     log("building the graphed step")
-    gs = GraphedTrainStep(loss_fn, dev[0], opt, warmup=3, post_backward=(buckets.pack if buckets else None),
+
+    class _HotOnly:
+        """--hot-only (tuning): zero_grad only, the captured step is forward + loss + backward"""
+        def zero_grad(self, set_to_none=True):
+            for p_ in params:
+                p_.grad = None
+
+        def step(self):
+            pass
+    if a.hot_only:
+        opt.close()
+    gs = GraphedTrainStep(loss_fn, dev[0], (_HotOnly() if a.hot_only else opt), warmup=3, post_backward=(buckets.pack if buckets else None),
                           eager_between=(buckets.allreduce if buckets else None),
                           step_kwargs=(step_kwargs if buckets else None),
                           capture_error_mode=("thread_local" if world > 1 else "global"),
@@ -628,9 +643,10 @@ if __name__ == "__main__":
     ap.add_argument("--dp-mode", default="overlapped", choices=["overlapped", "twograph"])
     ap.add_argument("--multimem", type=int, default=-1, help="data parallel: in-switch all-reduce kernel of the library (symmetric memory) instead of NCCL; -1 = from 4 GPUs on")
     ap.add_argument("--multimem-ctas", type=int, default=16)
-    ap.add_argument("--sparse-embed", type=int, default=1, help="data parallel: exchange the touched embedding rows, not the dense table gradient")
+    ap.add_argument("--sparse-embed", type=int, default=1, help="exchange (data parallel) and update (Adam row gate) only the touched word-embedding rows; exact")
     ap.add_argument("--feat-dtype", default="fp32", choices=["fp32", "bf16"], help="dtype of the feature maps handed to the path (fp32 = as the reference's backbone emits them)")
     ap.add_argument("--quick", action="store_true", help="tuning: print value / e2e only (no roofline, no CPU leg)")
+    ap.add_argument("--hot-only", action="store_true", help="tuning (with --quick): no optimizer in the captured step")
     ap.add_argument("--pad-steps", type=int, default=100, help="untimed steps around the timed region (clock sampling)")
     a = ap.parse_args()
     if os.environ.get("MMVQA_BENCH_WATCHDOG"):      # debugging aid: dump every thread's stack and exit if the run hangs

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define MMVQA_ABI_VERSION 3
+#define MMVQA_ABI_VERSION 4
 
 enum { MMVQA_F32 = 0, MMVQA_BF16 = 1 };
 enum { MMVQA_ACT_NONE = 0, MMVQA_ACT_SERF = 1, MMVQA_ACT_GELU = 2, MMVQA_ACT_RELU = 3 };
@@ -144,6 +144,17 @@ int mmvqa_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int cols,
 int mmvqa_cast(const void* src, int src_dtype, void* dst, int dst_dtype, int64_t n, mmvqa_stream_t stream);
 int mmvqa_cast_pad(const void* src, int src_dtype, int64_t ld_src, void* dst, int dst_dtype, int64_t ld_dst,
                    int64_t rows, int cols, mmvqa_stream_t stream);
+/* Hint: pull up to MMVQA_PREFETCH_MAX address ranges into L2 (prefetch.global.L2, one request per 128-byte line, a
+ * few CTAs).  No result, no dependency: launched on a side stream one encoder layer ahead of the main chain so the next
+ * layer's bf16 weights (forward: models/realformer.py:47-51 walks 12 layers x 14 MB, more than L2 keeps) and saved
+ * activations (backward) are L2 hits when the latency-bound M = B*T kernels ask for them. */
+#define MMVQA_PREFETCH_MAX 16
+typedef struct mmvqa_prefetch_list {
+  const void* ptr[MMVQA_PREFETCH_MAX];
+  int64_t bytes[MMVQA_PREFETCH_MAX];
+  int n;
+} mmvqa_prefetch_list;
+int mmvqa_l2_prefetch(const mmvqa_prefetch_list* list, int ctas, mmvqa_stream_t stream);
 /* x *= *scalar (device scalar); used to apply the incoming loss gradient without a host sync */
 int mmvqa_scale_by_device_scalar(void* x, int dtype, const float* scalar, float host_factor, int64_t n,
                                  mmvqa_stream_t stream);
@@ -344,7 +355,15 @@ int mmvqa_rf_attn_block_bwd(const mmvqa_rf_attn_block_bwd_args* args, mmvqa_stre
 typedef struct mmvqa_adam_desc {
   float* p; float* m; float* v; const void* g; void* bf16_out; int64_t n;
   int64_t flags;             /* bit 0: g is bf16 (all-reduced bf16 gradient bucket) instead of fp32 */
+  const unsigned char* row_live;   /* optional row gate (embedding tables, weight_decay == 0 only): the chunk is n / row_len
+                                whole rows and row r is skipped while row_live[r] == 0.  A row whose gradient has been zero
+                                in every step so far has m = v = 0, so its Adam update is exactly the identity: skipping it
+                                changes no bit of the result and saves 28 B/parameter of HBM traffic on the 23.4 M-parameter
+                                word-embedding table, of which a step touches <= B*T rows (models/mmbert.py:52-63) */
+  int64_t row_len;           /* elements per row when row_live != NULL (multiple of 4, rows 16-byte aligned) */
 } mmvqa_adam_desc;
+/* row_live[ids[i]] = 1 for i < n (ids outside [0, rows) are ignored): the rows that receive gradient in this step */
+int mmvqa_mark_rows(unsigned char* row_live, const int64_t* ids, int64_t n, int64_t rows, mmvqa_stream_t stream);
 /* `step` (1-based) sets the bias corrections; if step_dev != NULL the kernel reads the step from
  * that device int instead, so a captured CUDA graph can be replayed while the host bumps it.
  * max_ctas > 0 caps the grid (the CTAs stride over the table): an update that runs underneath the backward pass

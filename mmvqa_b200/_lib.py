@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libmmvqa_sm100.so")
 F32, BF16 = 0, 1
 ACT_NONE, ACT_SERF, ACT_GELU, ACT_RELU = 0, 1, 2, 3
 EPI_STORE, EPI_ACT, EPI_RESIDUAL, EPI_DACT, EPI_ACT_ROWSUM, EPI_DACT_SCALE = range(6)
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 vp, i64, i32, f32, u64 = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64
 
@@ -35,6 +35,13 @@ class GemmArgs(C.Structure):
         ("dropout_p", f32), ("dropout_seed", u64),
         ("c_split_stride", i64), ("b_static", i32), ("trace", vp),
     ]
+
+
+PREFETCH_MAX = 16
+
+
+class PrefetchList(C.Structure):
+    _fields_ = [("ptr", vp * PREFETCH_MAX), ("bytes", i64 * PREFETCH_MAX), ("n", i32)]
 
 
 class RfEncoderArgs(C.Structure):
@@ -65,7 +72,8 @@ class RfAttnBlockBwdArgs(C.Structure):
 
 
 class AdamDesc(C.Structure):
-    _fields_ = [("p", vp), ("m", vp), ("v", vp), ("g", vp), ("bf16_out", vp), ("n", i64), ("flags", i64)]
+    _fields_ = [("p", vp), ("m", vp), ("v", vp), ("g", vp), ("bf16_out", vp), ("n", i64), ("flags", i64),
+                ("row_live", vp), ("row_len", i64)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/mmvqa.h
@@ -79,6 +87,7 @@ SIGNATURES = {
     "mmvqa_bias_act_fwd": (i32, [vp, vp, vp, i64, i32, i32, i32, vp]),
     "mmvqa_bias_act_bwd": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, vp]),
     "mmvqa_colsum": (i32, [vp, i64, vp, i64, i32, i32, vp]),
+    "mmvqa_l2_prefetch": (i32, [C.POINTER(PrefetchList), i32, vp]),
     "mmvqa_cast": (i32, [vp, i32, vp, i32, i64, vp]),
     "mmvqa_cast_pad": (i32, [vp, i32, i64, vp, i32, i64, i64, i32, vp]),
     "mmvqa_scale_by_device_scalar": (i32, [vp, i32, vp, f32, i64, vp]),
@@ -113,6 +122,7 @@ SIGNATURES = {
     "mmvqa_jaccard_mask": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
     "mmvqa_adam_step": (i32, [C.POINTER(AdamDesc), i32, f32, f32, f32, f32, f32, i32, vp, f32, i32, vp]),
     "mmvqa_multimem_allreduce": (i32, [vp, vp, i32, i32, i64, i32, i32, vp]),
+    "mmvqa_mark_rows": (i32, [vp, vp, i64, i64, vp]),
     "mmvqa_adam_step_dev": (i32, [C.POINTER(AdamDesc), i32, vp, f32, f32, f32, f32, vp, i32, vp]),
 }
 

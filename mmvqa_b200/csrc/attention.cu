@@ -400,7 +400,10 @@ static int launch_bwd(const void* qkv, const AttnLayout& L, const float* scores,
     const int Tp = (Tn + 15) & ~15, ldn = d + 8, ldt = Tp + 8;
     const size_t smem_tc = (size_t)(2 * Tp * ldn + 3 * d * ldt + 2 * Tp * ldt) * 2;
     if (smem_tc <= 227 * 1024) {
-      const int nthr = 32 * (Tp / 16 < 4 ? 4 : Tp / 16);
+      // one warp per 16-row strip and no fewer than `minw`: 204 registers per thread make a 4-warp CTA a 26.6 K-register
+      // tenant that cannot share an SM with two resident GEMM CTAs (2 x 30.7 K of 64 K)
+      static const int minw = getenv("MMVQA_ATTN_BWD_WARPS") ? atoi(getenv("MMVQA_ATTN_BWD_WARPS")) : 4;
+      const int nthr = 32 * (Tp / 16 < minw ? minw : Tp / 16);
 #define TC_BWD(TPV)                                                                                                     \
   do {                                                                                                                  \
     auto k = attn_tc_bwd_kernel<RF, TPV>;                                                                               \

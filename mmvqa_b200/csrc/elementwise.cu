@@ -94,6 +94,16 @@ static int bias_act_launch(const void* x, const float* bias, const void* dy, voi
 // block = 32 columns x 8 row lanes; grid.y splits the rows; partial sums land with one atomic per
 // (block, column) into the zero-filled output.
 // ---------------------------------------------------------------------------------
+// L2 prefetch hints: every thread walks 128-byte lines of the listed ranges (grid-stride over all ranges at once)
+__global__ void __launch_bounds__(256) l2_prefetch_kernel(const mmvqa_prefetch_list list) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+  for (int r = 0; r < list.n; ++r) {
+    const char* base = reinterpret_cast<const char*>(list.ptr[r]);
+    const int64_t lines = (list.bytes[r] + 127) >> 7;
+    for (int64_t i = tid; i < lines; i += nthr) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (i << 7)));
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, int64_t ldx, float* __restrict__ out,
                                                      int64_t rows, int cols, int64_t rows_per_block) {
@@ -863,6 +873,16 @@ int mmvqa_bias_act_bwd(const void* x, const float* bias, const void* dy, void* d
   if (dtype == MMVQA_F32) return bias_act_launch<float, true>(x, bias, dy, dx, rows, cols, act, as_stream(stream));
   if (dtype == MMVQA_BF16) return bias_act_launch<__nv_bfloat16, true>(x, bias, dy, dx, rows, cols, act, as_stream(stream));
   return set_err(MMVQA_ERR_ARG, "bias_act_bwd: bad dtype %d", dtype);
+}
+
+int mmvqa_l2_prefetch(const mmvqa_prefetch_list* list, int ctas, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(list && list->n >= 0 && list->n <= MMVQA_PREFETCH_MAX, "l2_prefetch: bad list");
+  if (list->n == 0) return MMVQA_OK;
+  for (int i = 0; i < list->n; ++i) MMVQA_REQUIRE(list->ptr[i] && list->bytes[i] >= 0, "l2_prefetch: bad range %d", i);
+  if (ctas <= 0) ctas = 16;
+  l2_prefetch_kernel<<<ctas, 256, 0, as_stream(stream)>>>(*list);
+  MMVQA_LAUNCHED("l2_prefetch");
+  return MMVQA_OK;
 }
 
 int mmvqa_colsum(const void* x, int64_t ldx, float* out, int64_t rows, int cols, int dtype, mmvqa_stream_t stream) {

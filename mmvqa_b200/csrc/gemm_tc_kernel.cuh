@@ -824,13 +824,25 @@ static int launch_tc(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t
     if (rc) return rc;
   }
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, STAGES, KPS>;
+  // EXPERIMENT (MMVQA_WGRAD_SOLO): weight-gradient GEMMs (both operands MN-major) ask for > half of the shared memory and
+  // carry no programmatic edge, so at most one of their CTAs lives on an SM and the main chain keeps half of its registers
+  static const int solo_env = getenv("MMVQA_WGRAD_SOLO") ? atoi(getenv("MMVQA_WGRAD_SOLO")) : 0;
+  const bool solo = solo_env != 0 && A_MN && B_MN;
+  constexpr int SOLO_SMEM = Cfg::SMEM > 116 * 1024 ? Cfg::SMEM : 116 * 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    MMVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+    MMVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (A_MN && B_MN) ? SOLO_SMEM : Cfg::SMEM));
     attr_set = true;
   }
   dim3 grid((a->N + BN - 1) / BN, (a->M + TC_BM - 1) / TC_BM, a->batch * a->split_k);
   MMVQA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm(bf16): grid too large");
+  if (solo) {
+    const size_t sm_bytes = (solo_env & 2) ? (size_t)Cfg::SMEM : (size_t)SOLO_SMEM;
+    MMVQA_CUDA(launch_plain(kern, grid, dim3(TC_THREADS), sm_bytes, st, tmA, tmB, ep,
+                            (a->batch > 1 && a->a_batch_rows > 0) ? 1 : 0, (a->batch > 1 && a->b_batch_rows > 0) ? 1 : 0, 0));
+    MMVQA_LAUNCHED("gemm_tc_bf16");
+    return MMVQA_OK;
+  }
   MMVQA_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), (size_t)Cfg::SMEM, st, tmA, tmB, ep,
                         (a->batch > 1 && a->a_batch_rows > 0) ? 1 : 0, (a->batch > 1 && a->b_batch_rows > 0) ? 1 : 0,
                         (a->b_static && pdl_enabled()) ? 1 : 0));

@@ -223,6 +223,43 @@ __global__ void __launch_bounds__(256) adam_kernel(const mmvqa_adam_desc* __rest
   for (int ch = blockIdx.x; ch < n_chunks; ch += gridDim.x) {
   const mmvqa_adam_desc d = table[ch];
   const bool g16 = (d.flags & 1) != 0;
+  if (d.row_live != nullptr) {
+    // row-gated chunk (embedding table): one warp per row, rows that never received gradient are skipped (identity update)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int nrows = (int)(d.n / d.row_len), r4 = (int)(d.row_len / 4);
+    for (int r = warp; r < nrows; r += nwarp) {
+      if (d.row_live[r] == 0) continue;
+      const int64_t base4 = (int64_t)r * r4;
+      for (int i = lane; i < r4; i += 32) {
+        const int64_t q = base4 + i;
+        float4 p = __ldcs(reinterpret_cast<const float4*>(d.p) + q), m = __ldcs(reinterpret_cast<const float4*>(d.m) + q);
+        float4 v = __ldcs(reinterpret_cast<const float4*>(d.v) + q);
+        float4 g;
+        if (g16) {
+          const uint2 raw = __ldcs(reinterpret_cast<const uint2*>(d.g) + q);
+          g.x = __uint_as_float(raw.x << 16); g.y = __uint_as_float(raw.x & 0xffff0000u);
+          g.z = __uint_as_float(raw.y << 16); g.w = __uint_as_float(raw.y & 0xffff0000u);
+        } else {
+          g = __ldcs(reinterpret_cast<const float4*>(d.g) + q);
+        }
+        adam_one(p.x, m.x, v.x, g.x, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
+        adam_one(p.y, m.y, v.y, g.y, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
+        adam_one(p.z, m.z, v.z, g.z, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
+        adam_one(p.w, m.w, v.w, g.w, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
+        __stcs(reinterpret_cast<float4*>(d.p) + q, p);
+        __stcs(reinterpret_cast<float4*>(d.m) + q, m);
+        __stcs(reinterpret_cast<float4*>(d.v) + q, v);
+        if (d.bf16_out) {
+          __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
+          uint2 o;
+          o.x = *reinterpret_cast<uint32_t*>(&lo);
+          o.y = *reinterpret_cast<uint32_t*>(&hi);
+          __stcs(reinterpret_cast<uint2*>(d.bf16_out) + q, o);
+        }
+      }
+    }
+    continue;
+  }
   const float* g32 = reinterpret_cast<const float*>(d.g);
   const __nv_bfloat16* gb = reinterpret_cast<const __nv_bfloat16*>(d.g);
   const bool vec = ((reinterpret_cast<uintptr_t>(d.p) | reinterpret_cast<uintptr_t>(d.m) | reinterpret_cast<uintptr_t>(d.v)) & 15) == 0 &&
@@ -272,11 +309,27 @@ __global__ void __launch_bounds__(256) adam_kernel(const mmvqa_adam_desc* __rest
   }
 }
 
+__global__ void __launch_bounds__(256) mark_rows_kernel(unsigned char* __restrict__ row_live, const int64_t* __restrict__ ids,
+                                                        int64_t n, int64_t rows) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t id = ids[i];
+  if (id >= 0 && id < rows) row_live[id] = 1;
+}
+
 }  // namespace mmvqa
 
 using namespace mmvqa;
 
 extern "C" {
+
+int mmvqa_mark_rows(unsigned char* row_live, const int64_t* ids, int64_t n, int64_t rows, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(row_live && (ids || n == 0) && n >= 0 && rows > 0, "mark_rows: bad args");
+  if (n == 0) return MMVQA_OK;
+  mark_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(row_live, ids, n, rows);
+  MMVQA_LAUNCHED("mark_rows");
+  return MMVQA_OK;
+}
 
 int mmvqa_asl_fwd_bwd(const void* logits, int64_t ld, const int64_t* target, float* loss_rows, float* dlogits,
                       float* targets_classes, int B, int C, float gamma_pos, float gamma_neg, float eps, int dtype,

@@ -38,6 +38,8 @@ import os as _os
 
 _SIDE = {}
 _OVERLAP = _os.environ.get("MMVQA_NO_OVERLAP") is None
+_L2_PREFETCH = _os.environ.get("MMVQA_L2_PREFETCH", "1") != "0" and _OVERLAP
+_L2_PREFETCH_CTAS = int(_os.environ.get("MMVQA_L2_PREFETCH_CTAS", "16"))
 
 
 class SideBranch:
@@ -750,12 +752,19 @@ class RealFormerEncoderFn(torch.autograd.Function):
             ctx.save_for_backward(*saved, *params)
             ctx.meta = (B, T, H, heads, d, n_layers, p1, p2, seed, dt, prev is not None)
             return o["xout"][n_layers - 1].view(B, T, H), o["scores"][n_layers - 1]
+        # L2 prefetch one layer ahead (side branch, hints only): 12 layers x 14 MB of bf16 weights do not stay in L2 from
+        # one step to the next, and every kernel of this chain is latency bound at M = B*T
+        pf = SideBranch(x.device, index=7) if (_L2_PREFETCH and dt == torch.bfloat16 and n_layers > 1) else None
         for l in range(n_layers):
             kqv_w, proj_w, g1, b1, w0, bb0, w2, bb2, g2, b2 = params[l * RF_PARAMS_PER_LAYER:(l + 1) * RF_PARAMS_PER_LAYER]
             wk = weight_cache.get((kqv_w,), dt)
             wp = weight_cache.get((proj_w,), dt)
             wf0 = weight_cache.get((w0,), dt)
             wf2 = weight_cache.get((w2,), dt)
+            if pf is not None and l + 1 < n_layers:
+                nx = params[(l + 1) * RF_PARAMS_PER_LAYER:(l + 2) * RF_PARAMS_PER_LAYER]
+                with pf.after_now():
+                    ops.l2_prefetch([weight_cache.get((nx[i],), dt) for i in (0, 1, 4, 6)], _L2_PREFETCH_CTAS)
             if fuse_kqv:
                 attn, scores, kqv = ops.rf_attn_fwd_fused(xin, wk, scores, maskf, B, T, heads, d)
             else:
@@ -787,6 +796,8 @@ class RealFormerEncoderFn(torch.autograd.Function):
                 x2, _, mean2, rstd2 = ops.add_layernorm_fwd(y2, None, g2.detach(), b2.detach(), 1e-5, want_sum=False)
             saved += [xin, kqv, scores, attn, y1, mean1, rstd1, x1, hpre, hact, y2, mean2, rstd2]
             xin = x2
+        if pf is not None:
+            pf.join()
         ctx.save_for_backward(*saved, *params)
         ctx.meta = (B, T, H, heads, d, n_layers, p1, p2, seed, dt, prev is not None)
         return xin.view(B, T, H), scores
@@ -829,6 +840,7 @@ class RealFormerEncoderFn(torch.autograd.Function):
         # not the default.
         attn_block = (dt == torch.bfloat16 and _os.environ.get("MMVQA_RF_ATTN_BWD", "0") == "1" and
                       ops.rf_attn_block_bwd_supported(B, T, H, heads))
+        pf = SideBranch(saved[0].device, index=7) if (_L2_PREFETCH and dt == torch.bfloat16 and n_layers > 1) else None
         for l in reversed(range(n_layers)):
             xin, kqv, scores, attn, y1, mean1, rstd1, x1, hpre, hact, y2, mean2, rstd2 = saved[l * nsave:(l + 1) * nsave]
             kqv_w, proj_w, g1, b1, w0, bb0, w2, bb2, g2, b2 = params[l * RF_PARAMS_PER_LAYER:(l + 1) * RF_PARAMS_PER_LAYER]
@@ -836,6 +848,13 @@ class RealFormerEncoderFn(torch.autograd.Function):
             wp = weight_cache.get((proj_w,), dt)
             wf0 = weight_cache.get((w0,), dt)
             wf2 = weight_cache.get((w2,), dt)
+            if pf is not None and l > 0:
+                # the layer below: its weights and the activations its forward pass saved ~1 ms ago
+                nx = params[(l - 1) * RF_PARAMS_PER_LAYER:l * RF_PARAMS_PER_LAYER]
+                sv = saved[(l - 1) * nsave:l * nsave]
+                with pf.after_now():
+                    ops.l2_prefetch([weight_cache.get((nx[i],), dt) for i in (6, 4, 1, 0)] +
+                                    [sv[i] for i in (10, 8, 9, 7, 4, 3, 1, 2, 0)], _L2_PREFETCH_CTAS)
             zl = zws[l * per_layer:(l + 1) * per_layer]
             dg2, db2, dg1, db1, dbb2 = zl[0:H], zl[H:2 * H], zl[2 * H:3 * H], zl[3 * H:4 * H], zl[4 * H:5 * H]
             dbb0 = zl[5 * H:5 * H + F4]
@@ -927,6 +946,8 @@ class RealFormerEncoderFn(torch.autograd.Function):
             dx = dxin
             ds = dprev
         branch.join()
+        if pf is not None:
+            pf.join()
         del keep
         dprev_out = ds if (has_prev and ctx.needs_input_grad[2]) else None
         return (dx.view(B, T, H), None, dprev_out, None, None, None, None, *grads)

@@ -130,6 +130,19 @@ def colsum(x: Tensor, rows: int, cols: int, ldx: Optional[int] = None) -> Tensor
     return out
 
 
+def l2_prefetch(tensors, ctas: int = 16) -> None:
+    """L2 prefetch hints for the storage of `tensors` (contiguous ranges) on the current stream; no result."""
+    ts = [t for t in tensors if t is not None and t.numel() > 0]
+    for i in range(0, len(ts), L.PREFETCH_MAX):
+        pl = L.PrefetchList()
+        chunk = ts[i:i + L.PREFETCH_MAX]
+        for j, t in enumerate(chunk):
+            pl.ptr[j] = _p(t)
+            pl.bytes[j] = t.numel() * t.element_size()
+        pl.n = len(chunk)
+        L.check(L.lib().mmvqa_l2_prefetch(C.byref(pl), ctas, _stream()), "l2_prefetch")
+
+
 def cast(src: Tensor, dst_dtype: torch.dtype, out: Optional[Tensor] = None) -> Tensor:
     _cont(src, "src")
     dst = torch.empty(src.shape, device=src.device, dtype=dst_dtype) if out is None else out
@@ -450,6 +463,14 @@ def adam_step(table: Tensor, n_chunks: int, lr: float, beta1: float, beta2: floa
               step: int, step_dev: Optional[Tensor], grad_scale: float = 1.0, max_ctas: int = 0) -> None:
     L.check(L.lib().mmvqa_adam_step(C.cast(table.data_ptr(), C.POINTER(L.AdamDesc)), n_chunks, lr, beta1, beta2, eps,
                                    weight_decay, step, _p(step_dev), grad_scale, max_ctas, _stream()), "adam_step")
+
+
+def mark_rows(row_live: Tensor, ids: Tensor) -> None:
+    """row_live[ids] = 1 (uint8 flags of the rows of an embedding table that receive gradient in this step)."""
+    ids = ids.reshape(-1)
+    if ids.dtype != torch.int64 or not ids.is_contiguous():
+        ids = ids.contiguous().long()
+    L.check(L.lib().mmvqa_mark_rows(_p(row_live), _p(ids), ids.numel(), row_live.numel(), _stream()), "mark_rows")
 
 
 def adam_step_dev(table: Tensor, n_chunks: int, hyper_dev: Tensor, beta1: float, beta2: float, eps: float,

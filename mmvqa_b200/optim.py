@@ -13,7 +13,8 @@ from . import ops
 from .functional import weight_cache
 
 CHUNK = 32768
-_DESC = np.dtype([("p", "<u8"), ("m", "<u8"), ("v", "<u8"), ("g", "<u8"), ("bf16_out", "<u8"), ("n", "<i8"), ("flags", "<i8")])
+_DESC = np.dtype([("p", "<u8"), ("m", "<u8"), ("v", "<u8"), ("g", "<u8"), ("bf16_out", "<u8"), ("n", "<i8"), ("flags", "<i8"),
+                  ("row_live", "<u8"), ("row_len", "<i8")])
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -31,6 +32,7 @@ class FusedAdam(torch.optim.Optimizer):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self.grad_scale = 1.0
         self._tables = {}
+        self._row_gate = {}        # id(param) -> {"live": uint8 [rows], "ids_fn": callable}  (register_row_sparse)
         self._keepalive = []       # pinned host tables referenced by memcpy nodes of captured graphs
         self._eager_tables = {}    # last eagerly built table per key (kept until it is rebuilt)
         self._refreshed = {}       # group index -> ids of parameters whose bf16 cache copy the kernel rewrites
@@ -153,10 +155,23 @@ class FusedAdam(torch.optim.Optimizer):
                 raise RuntimeError("FusedAdam needs contiguous float32 parameters and float32 / bfloat16 gradients")
             n = p.numel()
             gsz = g.element_size()
+            gate = self._row_gate.get(id(p))
+            if gate is not None and self.param_groups[self._group_of[id(p)]]["weight_decay"] == 0 and p.dim() == 2 and \
+                    p.shape[1] % 4 == 0:
+                # row-gated chunks (whole rows): rows whose gradient has been zero in every step are skipped
+                live, rl = gate["live"], p.shape[1]
+                rpc = max(1, CHUNK // rl)
+                for r0 in range(0, p.shape[0], rpc):
+                    nr = min(rpc, p.shape[0] - r0)
+                    off = r0 * rl
+                    rows.append((p.data_ptr() + 4 * off, st["exp_avg"].data_ptr() + 4 * off,
+                                 st["exp_avg_sq"].data_ptr() + 4 * off, g.data_ptr() + gsz * off,
+                                 (bptr + 2 * off) if bptr else 0, nr * rl, 1 if gsz == 2 else 0, live.data_ptr() + r0, rl))
+                continue
             for off in range(0, n, CHUNK):
                 cnt = min(CHUNK, n - off)
                 rows.append((p.data_ptr() + 4 * off, st["exp_avg"].data_ptr() + 4 * off, st["exp_avg_sq"].data_ptr() + 4 * off,
-                             g.data_ptr() + gsz * off, (bptr + 2 * off) if bptr else 0, cnt, 1 if gsz == 2 else 0))
+                             g.data_ptr() + gsz * off, (bptr + 2 * off) if bptr else 0, cnt, 1 if gsz == 2 else 0, 0, 0))
         host = torch.from_numpy(np.array(rows, dtype=_DESC).view(np.uint8).reshape(-1)).pin_memory()
         dev = torch.empty(host.numel(), dtype=torch.uint8, device=plist[0].device)
         dev.copy_(host, non_blocking=True)
@@ -180,8 +195,26 @@ class FusedAdam(torch.optim.Optimizer):
             self._step_dev += 1
             self._stepped = True
 
+    def register_row_sparse(self, param: torch.nn.Parameter, ids_fn) -> None:
+        """`param` is an embedding table [V, H] whose gradient is zero outside the rows ``ids_fn()`` returns at update time
+        (int64, any shape, duplicates allowed; a fixed device tensor when the step is graph-captured; under data
+        parallelism the ids of EVERY rank -- `LayerwiseReducer.gathered_ids`): BertEmbeddings.word_embeddings with the
+        batch's input_ids (models/mmbert.py:52-63).  The optimizer keeps one byte per row, set for every id it has
+        ever been shown; rows never shown have zero gradient and zero moments, so torch.optim.Adam would leave them
+        bit-identical -- the kernel skips them (weight_decay == 0 only; with weight decay every row moves and the gate
+        is ignored).  Loading a state dict marks every row live."""
+        if param.dim() != 2:
+            raise ValueError("register_row_sparse: a 2-D embedding table is expected")
+        self._row_gate[id(param)] = {"live": torch.zeros(param.shape[0], dtype=torch.uint8, device=param.device),
+                                     "ids_fn": ids_fn}
+        self._tables.clear()
+
     def _launch(self, gi, key, plist, grads, max_ctas: int = 0):
         group = self.param_groups[gi]
+        for p in plist:
+            gate = self._row_gate.get(id(p))
+            if gate is not None:
+                ops.mark_rows(gate["live"], gate["ids_fn"]())
         table, n = self._table(key, plist, grads)
         b1, b2 = group["betas"]
         ops.adam_step_dev(table, n, self._hyper_dev[gi], b1, b2, group["eps"], group["weight_decay"], self._step_dev,
@@ -312,6 +345,8 @@ class FusedAdam(torch.optim.Optimizer):
 
     def load_state_dict(self, sd):
         super().load_state_dict(sd)
+        for gate in self._row_gate.values():
+            gate["live"].fill_(1)      # loaded moments may be non-zero anywhere
         self._tables.clear()
         self._init_step_counter()      # in place: a captured graph keeps reading the same device counter
         self.refresh_hyper()

@@ -110,6 +110,7 @@ class LayerwiseReducer:
         self.multimem = bool(multimem) and is_dist() and dist.get_backend() == "nccl"
         self.multimem_ctas = multimem_ctas
         self._handles = {}
+        self._gathered = {}        # id(param) -> all ranks' ids of the last exchange
         self._row_sparse = {}      # id(param) -> callable returning the int64 row ids this rank touched in the step
         self._dense = {}           # id(param) -> persistent dense gradient buffer of a row-sparse parameter
 
@@ -121,6 +122,11 @@ class LayerwiseReducer:
         the ranks all-gather the touched rows (<= B*T rows of H values each) and their ids and scatter-add them into a
         local dense buffer: the result equals the dense all-reduce(SUM) and Adam reads it exactly as before."""
         self._row_sparse[id(param)] = ids_fn
+
+    def gathered_ids(self, param) -> torch.Tensor:
+        """ids of every rank from the last row exchange of `param` (what FusedAdam.register_row_sparse needs under
+        data parallelism: the rows that hold gradient after the exchange)."""
+        return self._gathered[id(param)]
 
     def _exchange_rows(self, param, grad):
         ids = self._row_sparse[id(param)]().reshape(-1)
@@ -146,6 +152,7 @@ class LayerwiseReducer:
                 dist.all_gather(list(all_ids.chunk(world, dim=0)), ids.contiguous())
         else:
             all_rows, all_ids = rows, ids
+        self._gathered[id(param)] = all_ids
         dense.zero_()
         dense.index_add_(0, all_ids, all_rows.float())
         return dense

@@ -360,12 +360,14 @@ def test_mhsa_attention(dt, B, T, heads, d):
 # fusion / pooling / losses
 # ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dt", DTS)
-def test_embed_ln_scatter(dt):
-    B, T, H, V, nvis = 3, 12, 72, 50, 5
+@pytest.mark.parametrize("shape", [(3, 12, 72, 50, 5), (16, 28, 768, 300, 5), (5, 9, 256, 40, 2)])
+def test_embed_ln_scatter(dt, shape):
+    # (H = 768 / 256 with bf16 take the vector backward kernel: register-accumulated token-type / gamma / beta sums)
+    B, T, H, V, nvis = shape
     ids = torch.randint(0, V, (B, T), generator=torch.Generator().manual_seed(70))
     ids[:, 1:6] = 0
     seg = torch.randint(0, 2, (B, T), generator=torch.Generator().manual_seed(71))
-    word, pos, typ = rnd(V, H, seed=72), rnd(20, H, seed=73), rnd(2, H, seed=74)
+    word, pos, typ = rnd(V, H, seed=72), rnd(T + 8, H, seed=73), rnd(2, H, seed=74)
     gamma, beta = 1 + 0.1 * rnd(H, seed=75), 0.1 * rnd(H, seed=76)
     vis = rnd(nvis, B, H, seed=77)
     dh = rnd(B, T, H, seed=78).to(dt).float()

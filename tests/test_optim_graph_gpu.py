@@ -48,6 +48,55 @@ def test_fused_adam_matches_torch(wd):
         torch.testing.assert_close(b, a, rtol=2e-5, atol=2e-6)
 
 
+def test_fused_adam_row_gate_is_exact():
+    """register_row_sparse: embedding rows that never received gradient are skipped by the kernel; torch.optim.Adam would
+    leave them bit-identical, so the whole table must equal the dense update BITWISE (same kernel arithmetic), and match
+    torch.optim.Adam to rounding -- also for rows that were touched once and then only decay."""
+    torch.manual_seed(5)
+    V, H = 5000, 768
+    ref = [torch.randn(V, H, device=DEV).requires_grad_(True), torch.randn(H, device=DEV).requires_grad_(True)]
+    dense = [p.detach().clone().requires_grad_(True) for p in ref]
+    gated = [p.detach().clone().requires_grad_(True) for p in ref]
+    o_ref = torch.optim.Adam(ref, lr=1e-2)
+    o_dense, o_gated = FusedAdam(dense, lr=1e-2), FusedAdam(gated, lr=1e-2)
+    cur = {}
+    o_gated.register_row_sparse(gated[0], lambda: cur["ids"])
+    before = gated[0].detach().clone()
+    seen = set()
+    for step in range(5):
+        ids = torch.randint(0, V, (4, 28), device=DEV)
+        ids[0, 0] = V - 1                                  # last row of the last (short) chunk
+        cur["ids"] = ids
+        seen |= set(ids.reshape(-1).tolist())
+        g = torch.zeros(V, H, device=DEV)
+        g.index_add_(0, ids.reshape(-1), torch.randn(ids.numel(), H, device=DEV))
+        gb = torch.randn(H, device=DEV)
+        for grp in (ref, dense, gated):
+            grp[0].grad, grp[1].grad = g.clone(), gb.clone()
+        o_ref.step()
+        o_dense.step()
+        o_gated.step()
+    assert torch.equal(gated[0], dense[0]) and torch.equal(gated[1], dense[1])
+    torch.testing.assert_close(gated[0], ref[0], rtol=2e-5, atol=2e-6)
+    untouched = torch.ones(V, dtype=torch.bool, device=DEV)
+    untouched[torch.tensor(sorted(seen), device=DEV)] = False
+    assert torch.equal(gated[0][untouched], before[untouched])
+    live = o_gated._row_gate[id(gated[0])]["live"]
+    assert int(live.sum()) == len(seen)
+    # weight decay moves every row: the gate must be ignored
+    wd = [p.detach().clone().requires_grad_(True) for p in ref]
+    o_wd_ref = torch.optim.Adam(ref, lr=1e-2, weight_decay=0.01)
+    o_wd = FusedAdam(wd, lr=1e-2, weight_decay=0.01)
+    for a, b in zip(ref, wd):
+        b.data.copy_(a.data)
+    o_wd.register_row_sparse(wd[0], lambda: cur["ids"])
+    for grp in (ref, wd):
+        grp[0].grad, grp[1].grad = g.clone(), gb.clone()
+    o_wd_ref.step()
+    o_wd.step()
+    torch.testing.assert_close(wd[0], ref[0], rtol=2e-5, atol=2e-6)
+
+
 def test_fused_adam_bf16_gradient_buckets():
     torch.manual_seed(1)
     ref = [torch.randn(1000, 64, device=DEV).requires_grad_(True), torch.randn(77, device=DEV).requires_grad_(True)]

@@ -33,10 +33,14 @@ def main():
                 m.p = 0.0
     params = [p for p in model.parameters() if p.requires_grad]
     opt = FusedAdam(params, lr=1e-5, overlap_backward=bool(a.overlap),
-                    early_groups=[list(model.transformer.bert_embedding.parameters())])
+                    early_groups=[list(model.transformer.bert_embedding.parameters()),
+                                  list(model.fc1.parameters()) + list(model.classifier.parameters())])
     crit = ASLSingleLabel()
+    step_ids = {}
+    opt.register_row_sparse(model.transformer.bert_embedding.word_embeddings.weight, lambda: step_ids["ids"])
 
     def loss_fn(f0, f1, f2, f3, f4, ids, seg, mask, target):
+        step_ids["ids"] = ids
         logits, _, _ = model.forward_features([f0, f1, f2, f3, f4], ids, seg, mask)
         return crit(logits, target)
     dev = [t.cuda() for t in (lambda b: (*b[0], *b[1:]))(bench.synth_batch(a.batch, 0))]
