@@ -155,6 +155,18 @@ typedef struct mmvqa_prefetch_list {
   int n;
 } mmvqa_prefetch_list;
 int mmvqa_l2_prefetch(const mmvqa_prefetch_list* list, int ctas, mmvqa_stream_t stream);
+/* Several fp32 / bf16 -> bf16 cast_pad problems in ONE launch (the five feature maps of the pyramid, models/image_encoding.py:
+ * 71-87: five launches of 4-13 us each headed the critical path of every step).  ld_dst % 4 == 0, dst 8-byte aligned. */
+#define MMVQA_CAST_MULTI_MAX 8
+typedef struct mmvqa_cast_list {
+  const void* src[MMVQA_CAST_MULTI_MAX];       /* fp32, or bf16 where src_bf16[i] != 0 (a pure re-pad of the rows) */
+  void* dst[MMVQA_CAST_MULTI_MAX];             /* bf16 */
+  int64_t ld_src[MMVQA_CAST_MULTI_MAX], ld_dst[MMVQA_CAST_MULTI_MAX], rows[MMVQA_CAST_MULTI_MAX];
+  int cols[MMVQA_CAST_MULTI_MAX];
+  int src_bf16[MMVQA_CAST_MULTI_MAX];
+  int n;
+} mmvqa_cast_list;
+int mmvqa_cast_pad_multi(const mmvqa_cast_list* list, mmvqa_stream_t stream);
 /* x *= *scalar (device scalar); used to apply the incoming loss gradient without a host sync */
 int mmvqa_scale_by_device_scalar(void* x, int dtype, const float* scalar, float host_factor, int64_t n,
                                  mmvqa_stream_t stream);
@@ -193,6 +205,22 @@ int mmvqa_layernorm_bwd_parts(const float* dy_parts, int nparts, int64_t part_st
                               const void* xsum, const float* gamma, const float* mean, const float* rstd, void* dx,
                               float* dgamma, float* dbeta, void* dx_drop, float* dxsum, float dropout_p,
                               uint64_t dropout_seed, int64_t rows, int cols, int dtype, mmvqa_stream_t stream);
+
+/* LayerNorm backward with the column sums DEFERRED (transformer.py:78,83 / realformer.py:49-50 backward at M = B*T rows):
+ * the 112 CTAs of the small-batch problem each flushing 3 x cols sums with atomics onto the same addresses was the
+ * slowest part of a kernel that sits twice on the critical path of every layer.  Here every CTA stores its sums to
+ * partials[cta][3][cols] (dgamma | dbeta | column sums of dx_drop) with plain stores and returns; the caller folds them
+ * with mmvqa_ln_partials_reduce on a side stream, next to the weight-gradient GEMMs nothing waits for.
+ * dy may be NULL when dy_parts is given (split-K slabs, as mmvqa_layernorm_bwd_parts).  partial_rows must equal
+ * mmvqa_layernorm_bwd_partial_rows(rows, cols, dtype) (0 = this shape cannot use the deferred form). */
+int mmvqa_layernorm_bwd_partial_rows(int64_t rows, int cols, int dtype);
+int mmvqa_layernorm_bwd_deferred(const void* dy, const float* dy_parts, int nparts, int64_t part_stride, const void* xsum,
+                                 const float* gamma, const float* mean, const float* rstd, void* dx, void* dx_drop,
+                                 float dropout_p, uint64_t dropout_seed, int64_t rows, int cols, int dtype, float* partials,
+                                 int partial_rows, mmvqa_stream_t stream);
+/* dgamma / dbeta / dxsum [cols] (any may be NULL) += sum over the partial rows (fp32 atomics, caller zero-fills) */
+int mmvqa_ln_partials_reduce(const float* partials, int partial_rows, int cols, float* dgamma, float* dbeta, float* dxsum,
+                             mmvqa_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Attention (short sequence: T <= 128, head dim <= 128; one CTA per (batch, head))
@@ -344,6 +372,20 @@ typedef struct mmvqa_rf_attn_block_bwd_args {
 } mmvqa_rf_attn_block_bwd_args;
 int mmvqa_rf_attn_block_bwd_supported(int B, int T, int hidden, int heads);
 int mmvqa_rf_attn_block_bwd(const mmvqa_rf_attn_block_bwd_args* args, mmvqa_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Visual-token projector, forward with the weight-gradient contraction inside (models/image_encoding.py:74-87, 103-113):
+ *   vis[b, m]      += mean_hw act(sum_c W[m, c] f[b, c, hw])
+ *   pgrad[b, m, c] += sum_hw act'(.)[b, m, hw] f[b, c, hw]        (fp32 [B, M, C], caller zero-fills both)
+ * W bf16 [M, C] (ldw), f bf16 [B * C, ldf] = the NCHW map read in place.  The backward pass is then
+ *   dW[m, c] = scale * sum_b dv[b, m] pgrad[b, m, c]   with scale = 1 / HW  (mmvqa_vistok_dw)
+ * and the [B, M, HW] act' map of the EPI_ACT_ROWSUM path (aux_out) is never written: use it when the feature maps need no
+ * gradient.  C <= 64, C % 8 == 0, HW >= 128 (mmvqa_vistok_pgrad_supported); the other levels keep mmvqa_gemm.
+ * ---------------------------------------------------------------------------------- */
+int mmvqa_vistok_pgrad_supported(int M, int HW, int C);
+int mmvqa_vistok_fwd_pgrad(const void* W, int64_t ldw, const void* f, int64_t ldf, float* vis, float* pgrad, int M, int HW,
+                           int C, int B, int act, mmvqa_stream_t stream);
+int mmvqa_vistok_dw(const float* pgrad, const float* dv, float scale, float* dW, int B, int M, int C, mmvqa_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Optimiser: multi-tensor Adam, torch.optim.Adam semantics

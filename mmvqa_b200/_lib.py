@@ -44,6 +44,15 @@ class PrefetchList(C.Structure):
     _fields_ = [("ptr", vp * PREFETCH_MAX), ("bytes", i64 * PREFETCH_MAX), ("n", i32)]
 
 
+CAST_MULTI_MAX = 8
+
+
+class CastList(C.Structure):
+    _fields_ = [("src", vp * CAST_MULTI_MAX), ("dst", vp * CAST_MULTI_MAX), ("ld_src", i64 * CAST_MULTI_MAX),
+                ("ld_dst", i64 * CAST_MULTI_MAX), ("rows", i64 * CAST_MULTI_MAX), ("cols", i32 * CAST_MULTI_MAX), ("src_bf16", i32 * CAST_MULTI_MAX),
+                ("n", i32)]
+
+
 class RfEncoderArgs(C.Structure):
     _fields_ = [
         ("B", i32), ("T", i32), ("hidden", i32), ("heads", i32), ("ff", i32), ("n_layers", i32),
@@ -87,6 +96,13 @@ SIGNATURES = {
     "mmvqa_bias_act_fwd": (i32, [vp, vp, vp, i64, i32, i32, i32, vp]),
     "mmvqa_bias_act_bwd": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, vp]),
     "mmvqa_colsum": (i32, [vp, i64, vp, i64, i32, i32, vp]),
+    "mmvqa_cast_pad_multi": (i32, [C.POINTER(CastList), vp]),
+    "mmvqa_layernorm_bwd_partial_rows": (i32, [i64, i32, i32]),
+    "mmvqa_layernorm_bwd_deferred": (i32, [vp, vp, i32, i64, vp, vp, vp, vp, vp, vp, f32, u64, i64, i32, i32, vp, i32, vp]),
+    "mmvqa_ln_partials_reduce": (i32, [vp, i32, i32, vp, vp, vp, vp]),
+    "mmvqa_vistok_pgrad_supported": (i32, [i32, i32, i32]),
+    "mmvqa_vistok_fwd_pgrad": (i32, [vp, i64, vp, i64, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "mmvqa_vistok_dw": (i32, [vp, vp, f32, vp, i32, i32, i32, vp]),
     "mmvqa_l2_prefetch": (i32, [C.POINTER(PrefetchList), i32, vp]),
     "mmvqa_cast": (i32, [vp, i32, vp, i32, i64, vp]),
     "mmvqa_cast_pad": (i32, [vp, i32, i64, vp, i32, i64, i64, i32, vp]),

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libmmvqa_sm100.so")
 SOURCES = ["elementwise.cu", "gemm.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc_bn32.cu", "gemm_tc_bn64.cu", "gemm_tc_bn128.cu",
-           "gemm_tc_bn256.cu", "vistok.cu", "attention.cu", "rf_encoder.cu", "rf_attn_block.cu", "comm.cu", "fusion.cu", "losses.cu", "similarity.cu"]
+           "gemm_tc_bn256.cu", "vistok.cu", "vistok_pg.cu", "attention.cu", "rf_encoder.cu", "rf_attn_block.cu", "comm.cu", "fusion.cu", "losses.cu", "similarity.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -166,6 +166,55 @@ __global__ void __launch_bounds__(256) cast_pad_kernel(const S* __restrict__ src
   }
 }
 
+// multi-problem fp32 -> bf16 cast_pad: a thread converts 4 consecutive destination elements (one 8-byte store); the
+// source is read with one 16-byte load when its rows allow it.  unit_end[i] = running total of 4-element units.
+struct CastMultiArgs {
+  mmvqa_cast_list l;
+  int64_t unit_end[MMVQA_CAST_MULTI_MAX];
+  int vec_src[MMVQA_CAST_MULTI_MAX];
+};
+__global__ void __launch_bounds__(256) cast_pad_multi_kernel(const __grid_constant__ CastMultiArgs a) {
+  const int64_t total = a.unit_end[a.l.n - 1];
+  for (int64_t u = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; u < total; u += (int64_t)gridDim.x * blockDim.x) {
+    int s = 0;
+    while (u >= a.unit_end[s]) ++s;
+    const int64_t v = u - (s ? a.unit_end[s - 1] : 0);
+    const int64_t upr = a.l.ld_dst[s] >> 2;          // units per destination row
+    const int64_t r = v / upr;
+    const int c = (int)(v - r * upr) << 2;
+    const int cols = a.l.cols[s];
+    if (a.l.src_bf16[s]) {      // bf16 rows re-padded to the TMA leading dimension: copy the bits
+      const unsigned short* bp = reinterpret_cast<const unsigned short*>(a.l.src[s]) + r * a.l.ld_src[s] + c;
+      uint2 o;
+      if (a.vec_src[s] && c + 3 < cols) {
+        o = *reinterpret_cast<const uint2*>(bp);
+      } else {
+        const uint32_t e0 = c < cols ? bp[0] : 0u, e1 = c + 1 < cols ? bp[1] : 0u, e2 = c + 2 < cols ? bp[2] : 0u,
+                       e3 = c + 3 < cols ? bp[3] : 0u;
+        o.x = e0 | (e1 << 16);
+        o.y = e2 | (e3 << 16);
+      }
+      *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.l.dst[s]) + r * a.l.ld_dst[s] + c) = o;
+      continue;
+    }
+    const float* sp = reinterpret_cast<const float*>(a.l.src[s]) + r * a.l.ld_src[s] + c;
+    float4 x;
+    if (a.vec_src[s] && c + 3 < cols) {
+      x = __ldcs(reinterpret_cast<const float4*>(sp));
+    } else {
+      x.x = c < cols ? sp[0] : 0.0f;
+      x.y = c + 1 < cols ? sp[1] : 0.0f;
+      x.z = c + 2 < cols ? sp[2] : 0.0f;
+      x.w = c + 3 < cols ? sp[3] : 0.0f;
+    }
+    __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+    uint2 o;
+    o.x = *reinterpret_cast<uint32_t*>(&lo);
+    o.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(a.l.dst[s]) + r * a.l.ld_dst[s] + c) = o;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) scale_kernel(T* __restrict__ x, const float* __restrict__ scalar, float host_factor,
                                                     int64_t n) {
@@ -511,6 +560,9 @@ struct LnBwdExtra {
   const float* dy_parts;
   int nparts;
   long long part_stride;
+  // optional (packed kernel only): every CTA stores its [3][cols] column sums (dgamma | dbeta | dxsum) to
+  // partials + blockIdx.x * 3 * cols with plain stores instead of atomics; mmvqa_ln_partials_reduce folds them later
+  float* partials;
 };
 
 // Packed backward (vector path): the two input rows stay in registers as raw 128-bit vectors and are re-expanded in
@@ -531,7 +583,7 @@ __global__ void __launch_bounds__(128) ln_bwd_packed(const T* __restrict__ dy, c
   pdl_wait();
   pdl_trigger();
   T* dxd = reinterpret_cast<T*>(ex.dx_drop);
-  const bool want_sum = ex.dxsum != nullptr;
+  const bool want_sum = ex.dxsum != nullptr || ex.partials != nullptr;
   const bool drop = ex.p > 0.0f;
   if (drop) ex.seed = seed_eff(ex.seed, ex.seed_ctr);
   const uint32_t thr = (uint32_t)(ex.p * 4294967296.0);
@@ -621,7 +673,7 @@ __global__ void __launch_bounds__(128) ln_bwd_packed(const T* __restrict__ dy, c
       }
     }
   }
-  if (dgamma == nullptr && dbeta == nullptr && !want_sum) return;
+  if (dgamma == nullptr && dbeta == nullptr && !want_sum && ex.partials == nullptr) return;
   float* slab = sm + (size_t)warp * 3 * cols;
 #pragma unroll
   for (int k = 0; k < KU; ++k) {
@@ -640,14 +692,37 @@ __global__ void __launch_bounds__(128) ln_bwd_packed(const T* __restrict__ dy, c
   for (int i = threadIdx.x; i < 3 * nv; i += blockDim.x) {
     const int which = i / nv, c4 = (i - which * nv) * 4;
     float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : ex.dxsum);
-    if (dst == nullptr) continue;
+    if (dst == nullptr && ex.partials == nullptr) continue;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int w = 0; w < nwarp; ++w) {
       const float4 t = *reinterpret_cast<const float4*>(sm + (size_t)w * 3 * cols + which * cols + c4);
       acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
     }
-    atomicAdd(reinterpret_cast<float4*>(dst + c4), acc);
+    if (ex.partials) *reinterpret_cast<float4*>(ex.partials + ((size_t)blockIdx.x * 3 + which) * cols + c4) = acc;
+    else atomicAdd(reinterpret_cast<float4*>(dst + c4), acc);
   }
+}
+
+// out[which][c] += sum_p partials[p][which][c]: the deferred half of ln_bwd_packed (partials mode), off the critical path.
+// grid (ceil(3 * cols / 4 / 128), PSPLIT): a thread owns one float4 column group and a slice of the partial rows.
+__global__ void __launch_bounds__(128) ln_partials_reduce_kernel(const float* __restrict__ partials, int nparts, int cols,
+                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                 float* __restrict__ dxsum) {
+  const int nv = cols / 4;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * nv) return;
+  const int which = i / nv, c4 = (i - which * nv) * 4;
+  float* dst = which == 0 ? dgamma : (which == 1 ? dbeta : dxsum);
+  if (dst == nullptr) return;
+  const int per = (nparts + gridDim.y - 1) / gridDim.y;
+  const int p0 = blockIdx.y * per, p1 = min(nparts, p0 + per);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int p = p0; p < p1; ++p) {
+    const float4 t = *reinterpret_cast<const float4*>(partials + ((size_t)p * 3 + which) * cols + c4);
+    acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+  }
+  if (p1 > p0) atomicAdd(reinterpret_cast<float4*>(dst + c4), acc);
 }
 
 // backward.  Each warp walks rows (grid-stride); lanes own fixed columns, so dgamma/dbeta (and the column
@@ -961,6 +1036,31 @@ int mmvqa_cast_pad(const void* src, int src_dtype, int64_t ld_src, void* dst, in
   return MMVQA_OK;
 }
 
+int mmvqa_cast_pad_multi(const mmvqa_cast_list* list, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(list && list->n >= 0 && list->n <= MMVQA_CAST_MULTI_MAX, "cast_pad_multi: bad list");
+  if (list->n == 0) return MMVQA_OK;
+  CastMultiArgs a;
+  a.l = *list;
+  int64_t run = 0;
+  for (int i = 0; i < list->n; ++i) {
+    MMVQA_REQUIRE(list->src[i] && list->dst[i], "cast_pad_multi: null pointer in problem %d", i);
+    MMVQA_REQUIRE(list->rows[i] >= 0 && list->cols[i] > 0 && list->ld_src[i] >= list->cols[i] && list->ld_dst[i] >= list->cols[i],
+                  "cast_pad_multi: bad shape in problem %d", i);
+    MMVQA_REQUIRE(list->ld_dst[i] % 4 == 0 && (reinterpret_cast<uintptr_t>(list->dst[i]) & 7) == 0,
+                  "cast_pad_multi: problem %d needs ld_dst %% 4 == 0 and an 8-byte aligned destination", i);
+    run += list->rows[i] * (list->ld_dst[i] / 4);
+    a.unit_end[i] = run;
+    a.vec_src[i] = (list->ld_src[i] % 4 == 0 &&
+                    (reinterpret_cast<uintptr_t>(list->src[i]) & (list->src_bf16[i] ? 7 : 15)) == 0) ? 1 : 0;
+  }
+  for (int i = list->n; i < MMVQA_CAST_MULTI_MAX; ++i) { a.unit_end[i] = run; a.vec_src[i] = 0; }
+  if (run == 0) return MMVQA_OK;
+  const int64_t maxg = (int64_t)num_sms() * 8, want = (run + 255) / 256;
+  cast_pad_multi_kernel<<<(int)(want < maxg ? want : maxg), 256, 0, as_stream(stream)>>>(a);
+  MMVQA_LAUNCHED("cast_pad_multi");
+  return MMVQA_OK;
+}
+
 int mmvqa_scale_by_device_scalar(void* x, int dtype, const float* scalar, float host_factor, int64_t n,
                                  mmvqa_stream_t stream) {
   MMVQA_REQUIRE(n >= 0 && (n == 0 || x), "scale: null pointer");
@@ -1028,10 +1128,21 @@ int mmvqa_add_layernorm_fwd(const void* x, const void* res, const float* gamma, 
   return MMVQA_OK;
 }
 
+// CTAs of the packed backward kernel for this problem (= rows of the partials workspace), 0 if it does not apply
+static int ln_bwd_packed_grid(int64_t rows, int cols, int dtype) {
+  const int vn = dtype == MMVQA_F32 ? 4 : 8;
+  if (rows <= 0 || cols <= 0 || cols > 32 * LN_CACHE || cols % vn != 0) return 0;
+  const int nw = 4;
+  if (sizeof(float) * 3 * (size_t)cols * nw > 48 * 1024) return 0;
+  int64_t want2 = (rows + nw - 1) / nw, cap2 = (int64_t)num_sms() * 12;
+  return (int)(want2 < cap2 ? want2 : cap2);
+}
+
 static int layernorm_bwd_impl(const void* dy, const float* dy_parts, int nparts, int64_t part_stride, const void* xsum,
                               const float* gamma, const float* mean, const float* rstd, const void* dx_extra, void* dx,
                               float* dgamma, float* dbeta, void* dx_drop, float* dxsum, float dropout_p,
-                              uint64_t dropout_seed, int64_t rows, int cols, int dtype, mmvqa_stream_t stream) {
+                              uint64_t dropout_seed, int64_t rows, int cols, int dtype, mmvqa_stream_t stream,
+                              float* partials = nullptr, int partial_rows = 0) {
   MMVQA_REQUIRE((dy || dy_parts) && xsum && gamma && mean && rstd && dx, "layernorm_bwd: null pointer");
   MMVQA_REQUIRE(cols > 0 && rows >= 0, "layernorm_bwd: bad shape");
   MMVQA_REQUIRE(dtype == MMVQA_F32 || dtype == MMVQA_BF16, "layernorm_bwd: bad dtype %d", dtype);
@@ -1051,6 +1162,12 @@ static int layernorm_bwd_impl(const void* dy, const float* dy_parts, int nparts,
   LnBwdExtra ex;
   ex.dx_drop = dx_drop; ex.dxsum = dxsum; ex.p = dx_drop ? dropout_p : 0.0f; ex.seed = dropout_seed; ex.seed_ctr = g_seed_ctr;
   ex.dy_parts = dy_parts; ex.nparts = nparts; ex.part_stride = part_stride;
+  ex.partials = partials;
+  if (partials) {
+    MMVQA_REQUIRE(vec && aligned16(gamma) && aligned16(partials) && partial_rows == ln_bwd_packed_grid(rows, cols, dtype) &&
+                  partial_rows > 0, "layernorm_bwd: the partials mode needs the packed kernel (aligned, cols %% %d == 0) and "
+                  "a workspace of mmvqa_layernorm_bwd_partial_rows() rows", vn);
+  }
   // packed kernel: 4-warp CTAs (one row per warp) when the problem is small, 8-warp CTAs with a row loop otherwise
   if (vec && aligned16(gamma)) {
     const int vnn = dtype == MMVQA_F32 ? 4 : 8;
@@ -1108,6 +1225,31 @@ int mmvqa_layernorm_bwd_parts(const float* dy_parts, int nparts, int64_t part_st
   MMVQA_REQUIRE(dy_parts != nullptr && nparts >= 1 && part_stride >= rows * cols, "layernorm_bwd_parts: bad partials");
   return layernorm_bwd_impl(dy_res, dy_parts, nparts, part_stride, xsum, gamma, mean, rstd, nullptr, dx, dgamma, dbeta,
                             dx_drop, dxsum, dropout_p, dropout_seed, rows, cols, dtype, stream);
+}
+
+int mmvqa_layernorm_bwd_partial_rows(int64_t rows, int cols, int dtype) { return ln_bwd_packed_grid(rows, cols, dtype); }
+
+int mmvqa_layernorm_bwd_deferred(const void* dy, const float* dy_parts, int nparts, int64_t part_stride, const void* xsum,
+                                 const float* gamma, const float* mean, const float* rstd, void* dx, void* dx_drop,
+                                 float dropout_p, uint64_t dropout_seed, int64_t rows, int cols, int dtype, float* partials,
+                                 int partial_rows, mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(partials != nullptr, "layernorm_bwd_deferred: null workspace");
+  MMVQA_REQUIRE(dy_parts == nullptr || (nparts >= 1 && part_stride >= rows * cols), "layernorm_bwd_deferred: bad partial tiles");
+  return layernorm_bwd_impl(dy, dy_parts, nparts, part_stride, xsum, gamma, mean, rstd, nullptr, dx, nullptr, nullptr, dx_drop,
+                            nullptr, dropout_p, dropout_seed, rows, cols, dtype, stream, partials, partial_rows);
+}
+
+int mmvqa_ln_partials_reduce(const float* partials, int partial_rows, int cols, float* dgamma, float* dbeta, float* dxsum,
+                             mmvqa_stream_t stream) {
+  MMVQA_REQUIRE(partials && partial_rows > 0 && cols > 0 && cols % 4 == 0, "ln_partials_reduce: bad args");
+  MMVQA_REQUIRE(aligned16(partials) && (!dgamma || aligned16(dgamma)) && (!dbeta || aligned16(dbeta)) && (!dxsum || aligned16(dxsum)),
+                "ln_partials_reduce: 16-byte aligned buffers needed");
+  const int nv = 3 * cols / 4;
+  const int psplit = partial_rows >= 32 ? 4 : 1;
+  ln_partials_reduce_kernel<<<dim3((nv + 127) / 128, psplit), 128, 0, as_stream(stream)>>>(partials, partial_rows, cols, dgamma,
+                                                                                           dbeta, dxsum);
+  MMVQA_LAUNCHED("ln_partials_reduce");
+  return MMVQA_OK;
 }
 
 int mmvqa_add_layernorm_fwd_parts(const float* parts, int nparts, int64_t part_stride, const void* res,

@@ -39,6 +39,8 @@ import os as _os
 _SIDE = {}
 _OVERLAP = _os.environ.get("MMVQA_NO_OVERLAP") is None
 _L2_PREFETCH = _os.environ.get("MMVQA_L2_PREFETCH", "1") != "0" and _OVERLAP
+_LN_DEFER = _os.environ.get("MMVQA_LN_DEFER", "1") != "0"
+_VISTOK_PG = _os.environ.get("MMVQA_VISTOK_PG", "1") != "0"
 _L2_PREFETCH_CTAS = int(_os.environ.get("MMVQA_L2_PREFETCH_CTAS", "16"))
 
 
@@ -497,7 +499,20 @@ class VisTokAllFn(torch.autograd.Function):
 
         # operand casts of every level first, on the main stream: a cast issued next to another level's projector kernel
         # waits for SM slots (67 us instead of 13 for the 112 x 112 level) and it heads the critical path
-        casted = [_pad_ld(f.detach().reshape(B * f.shape[1], f.shape[2] * f.shape[3]), dtype) for f in feats]
+        # (fp32 maps -> bf16: ONE launch for all levels instead of five)
+        flat = [f.detach().reshape(B * f.shape[1], f.shape[2] * f.shape[3]) for f in feats]
+        if dtype == torch.bfloat16 and all(t.dtype in (torch.float32, torch.bfloat16) for t in flat):
+            # levels that are already bf16 with 16-byte rows are the TMA operand as they are; the rest share one launch
+            inplace = [t.dtype == torch.bfloat16 and t.is_contiguous() and t.shape[1] % 8 == 0 and t.data_ptr() % 16 == 0
+                       for t in flat]
+            todo = [n for n in range(nlev) if not inplace[n]]
+            lds = [_round_up(t.shape[1], 8) for t in flat]
+            done = ops.cast_pad_multi([flat[n].contiguous() for n in todo], [lds[n] for n in todo]) if todo else []
+            casted = [(flat[n], lds[n]) for n in range(nlev)]
+            for n, t in zip(todo, done):
+                casted[n] = (t, lds[n])
+        else:
+            casted = [_pad_ld(t, dtype) for t in flat]
 
         def run(n):
             f, cw = feats[n], convs[n]
@@ -505,12 +520,20 @@ class VisTokAllFn(torch.autograd.Function):
             HW = Hh * Ww
             w = weight_cache.get((cw,), dtype)
             fb, ld = casted[n]
-            need_bwd = ctx.needs_input_grad[3 + n] or ctx.needs_input_grad[3 + nlev + n]
-            actp = torch.empty(B, hidden, ld, device=dev, dtype=dtype) if need_bwd else None
+            need_df, need_dw = ctx.needs_input_grad[3 + n], ctx.needs_input_grad[3 + nlev + n]
+            if _VISTOK_PG and dtype == torch.bfloat16 and need_dw and not need_df and ops.vistok_pgrad_supported(hidden, HW, Cc):
+                # only the weight gradient is needed: the pixel contraction of act' with the map is finished inside the
+                # forward kernel (P [B, hidden, C]); the [B, hidden, HW] act' map is never written
+                pg = ops.vistok_fwd_pgrad(w.reshape(hidden, Cc), fb, ld, vis[n], B, hidden, HW, Cc, act)
+                saved[3 * n:3 * n + 3] = [None, cw, pg]
+                metas[n] = (Cc, Hh, Ww, ld, f.dtype, True)
+                keep.append((fb, pg))
+                return
+            actp = torch.empty(B, hidden, ld, device=dev, dtype=dtype) if (need_df or need_dw) else None
             ops.gemm(hidden, HW, Cc, w, Cc, False, fb, ld, True, None, 0, epilogue=EPI_ACT_ROWSUM, act=act, rowsum_out=vis[n],
                      scale=1.0 / HW, batch=B, a_batch_rows=0, b_batch_rows=Cc, aux_out=actp, ld_aux_out=ld)
             saved[3 * n:3 * n + 3] = [fb, cw, actp]
-            metas[n] = (Cc, Hh, Ww, ld, f.dtype)
+            metas[n] = (Cc, Hh, Ww, ld, f.dtype, False)
             keep.append((fb, actp))
         # fork BEFORE the big level is enqueued: the side branch only depends on what precedes this node.  (Issuing the
         # big level first was measured slower: the small levels then queue behind it and finish 45 us later.)
@@ -535,9 +558,12 @@ class VisTokAllFn(torch.autograd.Function):
 
         def run(n):
             fb, cw, actp = saved[3 * n:3 * n + 3]
-            Cc, Hh, Ww, ld, fdt = metas[n]
+            Cc, Hh, Ww, ld, fdt, is_pg = metas[n]
             HW = Hh * Ww
             dv = dvs[n]
+            if is_pg:           # actp holds P = sum_hw act' f: the weight gradient is a [hidden, C] contraction over the batch
+                dws[n] = ops.vistok_dw(actp, dv, 1.0 / HW).view(cw.shape)
+                return
             if ctx.needs_input_grad[3 + nlev + n]:
                 dw = torch.zeros(hidden, Cc, device=dev, dtype=torch.float32)
                 tiles = ((hidden + 127) // 128) * B
@@ -859,13 +885,23 @@ class RealFormerEncoderFn(torch.autograd.Function):
             dg2, db2, dg1, db1, dbb2 = zl[0:H], zl[H:2 * H], zl[2 * H:3 * H], zl[3 * H:4 * H], zl[4 * H:5 * H]
             dbb0 = zl[5 * H:5 * H + F4]
             # LN2 backward also emits dropout(dy2) for the FF branch and its column sums (= d ff.2.bias)
-            if p2 > 0.0:
+            # (column sums deferred: the kernel on the critical path stores per-CTA partials, the side branch folds them)
+            dfr = ops.layernorm_bwd_deferred(dx, None, y2, g2.detach(), mean2, rstd2, want_drop=p2 > 0.0, dropout_p=p2,
+                                             dropout_seed=seed + 2 * l + 1) if _LN_DEFER else None
+            if dfr is not None:
+                dy2, dff, lnp2 = dfr
+                if dff is None:
+                    dff = dy2
+            elif p2 > 0.0:
                 dy2, dff = ops.layernorm_bwd(dx, y2, g2.detach(), mean2, rstd2, None, dg2, db2, want_drop=True, dxsum=dbb2,
                                              dropout_p=p2, dropout_seed=seed + 2 * l + 1)
             else:
                 dy2 = ops.layernorm_bwd(dx, y2, g2.detach(), mean2, rstd2, None, dg2, db2, dxsum=dbb2)
                 dff = dy2
             with branch.after_now():
+                if dfr is not None:
+                    ops.ln_partials_reduce(lnp2, dg2, db2, dbb2)
+                    keep.append(lnp2)
                 dw2 = gemm_wgrad(dff, H, M, H, hact, F4, F4)
             # dgrad through FF2 with act'(h_pre) in the epilogue; its column sums are d ff.0.bias
             dhpre = gemm_dgrad(dff, H, M, H, wf2, F4, epilogue=EPI_DACT, act=ACT_SERF, aux_in=hpre, colsum_out=dbb0)
@@ -903,7 +939,16 @@ class RealFormerEncoderFn(torch.autograd.Function):
                 if parts is None:
                     parts = torch.empty(ns, M, H, device=dx.device, dtype=torch.float32)
                 ops.gemm(M, H, F4, dhpre, F4, False, wf0, H, True, parts, H, split_k=ns, c_split_stride=M * H, b_static=True)
-                if p1 > 0.0:
+                dfr1 = ops.layernorm_bwd_deferred(dy2, parts, y1, g1.detach(), mean1, rstd1, want_drop=p1 > 0.0, dropout_p=p1,
+                                                  dropout_seed=seed + 2 * l) if _LN_DEFER else None
+                if dfr1 is not None:
+                    dy1, dpr, lnp1 = dfr1
+                    if dpr is None:
+                        dpr = dy1
+                    with branch.after_now():
+                        ops.ln_partials_reduce(lnp1, dg1, db1, None)
+                    keep.append(lnp1)
+                elif p1 > 0.0:
                     dy1, dpr = ops.layernorm_bwd_parts(parts, dy2, y1, g1.detach(), mean1, rstd1, dg1, db1, want_drop=True,
                                                        dropout_p=p1, dropout_seed=seed + 2 * l)
                 else:
@@ -911,7 +956,16 @@ class RealFormerEncoderFn(torch.autograd.Function):
                     dpr = dy1
             else:
                 dx1 = gemm_dgrad(dhpre, F4, M, F4, wf0, H, epilogue=EPI_RESIDUAL, aux_in=dy2)
-                if p1 > 0.0:
+                dfr1 = ops.layernorm_bwd_deferred(dx1, None, y1, g1.detach(), mean1, rstd1, want_drop=p1 > 0.0, dropout_p=p1,
+                                                  dropout_seed=seed + 2 * l) if _LN_DEFER else None
+                if dfr1 is not None:
+                    dy1, dpr, lnp1 = dfr1
+                    if dpr is None:
+                        dpr = dy1
+                    with branch.after_now():
+                        ops.ln_partials_reduce(lnp1, dg1, db1, None)
+                    keep.append(lnp1)
+                elif p1 > 0.0:
                     dy1, dpr = ops.layernorm_bwd(dx1, y1, g1.detach(), mean1, rstd1, None, dg1, db1, want_drop=True,
                                                  dropout_p=p1, dropout_seed=seed + 2 * l)
                 else:

@@ -130,6 +130,30 @@ def colsum(x: Tensor, rows: int, cols: int, ldx: Optional[int] = None) -> Tensor
     return out
 
 
+def vistok_pgrad_supported(M: int, HW: int, C: int) -> bool:
+    return bool(L.lib().mmvqa_vistok_pgrad_supported(M, HW, C))
+
+
+def vistok_fwd_pgrad(w: Tensor, f2d: Tensor, ldf: int, vis: Tensor, B: int, M: int, HW: int, C: int, act: int) -> Tensor:
+    """vis [B, M] += mean_hw act(W f);  returns P [B, M, C] fp32 = sum_hw act'(W f) f  (see include/mmvqa.h)."""
+    if w.dtype != torch.bfloat16 or f2d.dtype != torch.bfloat16:
+        raise L.MMVQAError("vistok_fwd_pgrad: bf16 operands only")
+    _cont(w, "w")
+    pg = torch.zeros(B, M, C, device=w.device, dtype=torch.float32)
+    L.check(L.lib().mmvqa_vistok_fwd_pgrad(_p(w), C, _p(f2d), ldf, _p(vis), _p(pg), M, HW, C, B, act, _stream()),
+            "vistok_fwd_pgrad")
+    return pg
+
+
+def vistok_dw(pgrad: Tensor, dv: Tensor, scale: float) -> Tensor:
+    """dW [M, C] = scale * sum_b dv[b, m] P[b, m, c]"""
+    B, M, C = pgrad.shape
+    _cont(dv, "dv")
+    dw = torch.empty(M, C, device=pgrad.device, dtype=torch.float32)
+    L.check(L.lib().mmvqa_vistok_dw(_p(pgrad), _p(dv), scale, _p(dw), B, M, C, _stream()), "vistok_dw")
+    return dw
+
+
 def l2_prefetch(tensors, ctas: int = 16) -> None:
     """L2 prefetch hints for the storage of `tensors` (contiguous ranges) on the current stream; no result."""
     ts = [t for t in tensors if t is not None and t.numel() > 0]
@@ -155,6 +179,25 @@ def cast_pad(src: Tensor, rows: int, cols: int, ld_src: int, dst_dtype: torch.dt
     L.check(L.lib().mmvqa_cast_pad(_p(src), dtype_code(src), ld_src, _p(dst), dtype_code(dst), ld_dst, rows, cols, _stream()),
             "cast_pad")
     return dst
+
+
+def cast_pad_multi(srcs, ld_dsts) -> list:
+    """fp32 / bf16 [rows, cols] contiguous matrices -> bf16 [rows, ld_dst] (columns cols..ld_dst zero) in ONE launch."""
+    outs = []
+    for i in range(0, len(srcs), L.CAST_MULTI_MAX):
+        cl = L.CastList()
+        chunk = srcs[i:i + L.CAST_MULTI_MAX]
+        for j, (t, ld) in enumerate(zip(chunk, ld_dsts[i:i + L.CAST_MULTI_MAX])):
+            if t.dtype not in (torch.float32, torch.bfloat16) or t.dim() != 2 or not t.is_contiguous():
+                raise L.MMVQAError("cast_pad_multi: contiguous 2-D float32 / bfloat16 sources only")
+            rows, cols = t.shape
+            dst = torch.empty(rows, ld, device=t.device, dtype=torch.bfloat16)
+            cl.src[j], cl.dst[j], cl.ld_src[j], cl.ld_dst[j], cl.rows[j], cl.cols[j] = _p(t), _p(dst), cols, ld, rows, cols
+            cl.src_bf16[j] = 1 if t.dtype == torch.bfloat16 else 0
+            outs.append(dst)
+        cl.n = len(chunk)
+        L.check(L.lib().mmvqa_cast_pad_multi(C.byref(cl), _stream()), "cast_pad_multi")
+    return outs
 
 
 def scale_(x: Tensor, scalar: Optional[Tensor], host_factor: float = 1.0) -> Tensor:
@@ -231,6 +274,39 @@ def layernorm_bwd_parts(dy_parts: Tensor, dy_res: Optional[Tensor], xsum: Tensor
                                              _p(rstd), _p(dx), _p(dgamma), _p(dbeta), _p(dxd), _p(dxsum), dropout_p,
                                              dropout_seed, rows, cols, dtype_code(xsum), _stream()), "layernorm_bwd_parts")
     return (dx, dxd) if want_drop else dx
+
+
+def layernorm_bwd_deferred(dy: Optional[Tensor], dy_parts: Optional[Tensor], xsum: Tensor, gamma: Tensor, mean: Tensor,
+                           rstd: Tensor, *, want_drop: bool = False, dropout_p: float = 0.0, dropout_seed: int = 0):
+    """LayerNorm backward whose gamma / beta / bias column sums are left as per-CTA partials.  Returns
+    (dx, dx_drop or None, partials [n, 3, cols]) or None when this shape has no deferred form (use layernorm_bwd).
+    The incoming gradient is dy (+ sum of the fp32 slabs dy_parts [nparts, rows, cols])."""
+    cols = xsum.shape[-1]
+    rows = xsum.numel() // cols
+    n = L.lib().mmvqa_layernorm_bwd_partial_rows(rows, cols, dtype_code(xsum))
+    if n <= 0:
+        return None
+    _cont(xsum, "xsum")
+    nparts, stride = 0, 0
+    if dy_parts is not None:
+        _cont(dy_parts, "dy_parts")
+        nparts, stride = dy_parts.shape[0], rows * cols
+    if dy is not None:
+        _cont(dy, "dy")
+    dx = torch.empty_like(xsum)
+    dxd = torch.empty_like(xsum) if want_drop else None
+    partials = torch.empty(n, 3, cols, device=xsum.device, dtype=torch.float32)
+    L.check(L.lib().mmvqa_layernorm_bwd_deferred(_p(dy), _p(dy_parts), nparts, stride, _p(xsum), _p(gamma), _p(mean), _p(rstd),
+                                                _p(dx), _p(dxd), dropout_p, dropout_seed, rows, cols, dtype_code(xsum),
+                                                _p(partials), n, _stream()), "layernorm_bwd_deferred")
+    return dx, dxd, partials
+
+
+def ln_partials_reduce(partials: Tensor, dgamma: Optional[Tensor], dbeta: Optional[Tensor], dxsum: Optional[Tensor]) -> None:
+    """dgamma / dbeta / dxsum += column sums held in `partials` (layernorm_bwd_deferred)."""
+    n, _, cols = partials.shape
+    L.check(L.lib().mmvqa_ln_partials_reduce(_p(partials), n, cols, _p(dgamma), _p(dbeta), _p(dxsum), _stream()),
+            "ln_partials_reduce")
 
 
 # ------------------------------------------------------------------------------- attention

@@ -69,6 +69,98 @@ def test_serf_known_answers_fp32():
     assert torch.isfinite(ops.bias_act_fwd(torch.tensor([-100.0], device=DEV), None, ACT_SERF)).all()
 
 
+@pytest.mark.parametrize("act", ["serf", "relu"])
+def test_projector_weight_gradient_inside_the_forward_kernel(act):
+    """vistok_fwd_pgrad (P = sum_hw act' f finished on chip, dW = sum_b dv P / HW) == the act'-saving path (same bf16
+    rounding of act', fp32 accumulation in another order) and close to the oracle (image_encoding.py:100-115 + autograd),
+    incl. a ragged last pixel tile (36 x 36 = 20 x 64 + 16) and two 128-row output tiles."""
+    import mmvqa_b200
+    from mmvqa_b200 import functional as Fn
+    mmvqa_b200.set_compute_dtype("bf16")
+    try:
+        B, hidden = 3, 256
+        shapes = [(24, 40), (48, 36), (24, 16), (80, 12), (512, 3)]     # the last two keep the act'-saving path
+        feats = [rnd(B, c, s, s, seed=400 + i).abs().bfloat16().float().to(DEV) for i, (c, s) in enumerate(shapes)]
+        ws = [(rnd(hidden, c, 1, 1, seed=410 + i) * c ** -0.5).to(DEV).requires_grad_(True) for i, (c, _) in enumerate(shapes)]
+        go = rnd(len(shapes), B, hidden, seed=420).to(DEV)
+        res = {}
+        for flag in (False, True):
+            Fn._VISTOK_PG = flag
+            for w in ws:
+                w.grad = None
+            n0 = mmvqa_b200.launch_count()
+            v = Fn.vistok_project_all(feats, ws, ACTS[act])
+            v.backward(go)
+            res[flag] = (v.detach().clone(), [w.grad.detach().clone() for w in ws], mmvqa_b200.launch_count() - n0)
+        (v0, g0, _), (v1, g1, _) = res[False], res[True]
+        close(v1, v0, 1e-5, 1e-6, msg="tokens")
+        for n, (a, b) in enumerate(zip(g1, g0)):
+            close(a, b, 1e-4, 2e-5 * float(b.abs().max()), msg="dW level %d vs the act'-saving path" % n)
+        for n, (f, w) in enumerate(zip(feats, ws)):
+            wl = w.detach().reshape(hidden, -1).bfloat16().float().cpu().requires_grad_(True)
+            Y = torch.einsum("mc,bcn->bmn", wl, f.flatten(2).cpu())
+            vr = O.activation(act, Y).mean(-1)
+            (gr,) = torch.autograd.grad(vr, wl, go[n].cpu())
+            close(v1[n], vr.detach(), 1e-2, 2e-3, msg="level %d tokens vs oracle" % n)
+            close(g1[n].reshape(hidden, -1), gr, 2e-2, 2e-2 * float(gr.abs().max()), msg="level %d dW vs oracle" % n)
+    finally:
+        Fn._VISTOK_PG = True
+        mmvqa_b200.set_compute_dtype("bf16")
+
+
+@pytest.mark.parametrize("dt", DTS)
+@pytest.mark.parametrize("with_parts", [False, True])
+def test_layernorm_bwd_deferred_matches_atomics(dt, with_parts):
+    """per-CTA partial column sums + ln_partials_reduce == the atomics flush of layernorm_bwd (same dx bit for bit)."""
+    rows, cols = 448, 768
+    x = rnd(rows, cols, seed=300).to(dt).to(DEV)
+    dy = rnd(rows, cols, seed=301).to(dt).to(DEV)
+    g, b_ = (1 + 0.1 * rnd(cols, seed=302)).to(DEV), (0.1 * rnd(cols, seed=303)).to(DEV)
+    _, _, mean, rstd = ops.add_layernorm_fwd(x, None, g, b_, 1e-5, False)
+    parts = rnd(3, rows, cols, seed=304).to(DEV) if with_parts else None
+    for p in (0.0, 0.1):
+        dg0, db0, ds0 = (torch.zeros(cols, device=DEV) for _ in range(3))
+        if with_parts:
+            ref = ops.layernorm_bwd_parts(parts, dy, x, g, mean, rstd, dg0, db0, want_drop=p > 0, dxsum=ds0, dropout_p=p,
+                                          dropout_seed=11)
+        else:
+            ref = ops.layernorm_bwd(dy, x, g, mean, rstd, None, dg0, db0, want_drop=p > 0, dxsum=ds0, dropout_p=p,
+                                    dropout_seed=11)
+        out = ops.layernorm_bwd_deferred(dy, parts, x, g, mean, rstd, want_drop=p > 0, dropout_p=p, dropout_seed=11)
+        assert out is not None
+        dx, dxd, partials = out
+        dg1, db1, ds1 = (torch.zeros(cols, device=DEV) for _ in range(3))
+        ops.ln_partials_reduce(partials, dg1, db1, ds1)
+        if p > 0:
+            assert torch.equal(dx, ref[0]) and torch.equal(dxd, ref[1])
+        else:
+            assert torch.equal(dx, ref) and dxd is None
+        for a, b in ((dg1, dg0), (db1, db0), (ds1, ds0)):
+            close(a, b, 1e-4, 1e-3)
+    assert ops.layernorm_bwd_deferred(dy[:, :70].contiguous(), None, x[:, :70].contiguous(), g[:70], mean, rstd) is None
+
+
+def test_cast_pad_multi_and_l2_prefetch():
+    """one launch for the five pyramid levels (aligned, padded and odd leading dimensions) == per-tensor casts; the L2
+    prefetch hint touches nothing."""
+    shapes = [(16 * 24, 12544), (16 * 48, 3136), (16 * 176, 196), (16 * 512, 49), (3, 5), (7, 8), (2, 1), (4, 20), (9, 33)]
+    srcs = [rnd(r, c, seed=200 + i).to(DEV) for i, (r, c) in enumerate(shapes)]
+    srcs[2], srcs[3], srcs[8] = srcs[2].bfloat16(), srcs[3].bfloat16(), srcs[8].bfloat16()    # bf16 sources: pure re-pad
+    lds = [(c + 7) // 8 * 8 for _, c in shapes]
+    outs = ops.cast_pad_multi(srcs, lds)
+    assert len(outs) == len(shapes)
+    for (r, c), ld, x, y in zip(shapes, lds, srcs, outs):
+        assert y.shape == (r, ld) and y.dtype == torch.bfloat16
+        assert torch.equal(y[:, :c], x.to(torch.bfloat16)), (r, c)
+        assert float(y[:, c:].float().abs().sum()) == 0.0
+    before = [x.clone() for x in srcs[:3]]
+    ops.l2_prefetch(srcs[:3] + [None], 4)
+    ops.l2_prefetch(srcs + outs)            # more ranges than one list holds
+    torch.cuda.synchronize()
+    for a, b in zip(before, srcs[:3]):
+        assert torch.equal(a, b)
+
+
 @pytest.mark.parametrize("dt", DTS)
 def test_colsum_cast_dropout(dt):
     x = rnd(333, 70, seed=4).to(dt)
@@ -540,7 +632,12 @@ def test_projector_takes_bf16_feature_maps_in_place():
         close(v16, v32, 1e-5, 1e-6, msg="tokens from bf16 maps vs fp32 maps")
         for g32, g16 in zip(*grads):
             close(g16, g32, 1e-5, 1e-6 * float(g32.abs().max()), msg="dW")     # split-K atomics: order only
-        assert l16 < l32, "bf16 maps should skip the cast launches (%d vs %d)" % (l16, l32)
+        # fp32 maps: one multi-tensor cast launch; bf16 maps: the levels with 16-byte rows are used in place and only the
+        # two odd ones (36 and 9 pixels) are re-padded, in one launch -- never more launches than the fp32 hand-off
+        assert l16 <= l32, "bf16 maps must not need more launches than fp32 maps (%d vs %d)" % (l16, l32)
+        n0 = mmvqa_b200.launch_count()
+        Fn.vistok_project_all([f.bfloat16() for f in feats32[:3]], ws[:3], ACTS["serf"])      # 1600 / 400 / 144 pixels
+        assert mmvqa_b200.launch_count() - n0 == 3, "aligned bf16 maps are the TMA operand as they are: no cast launch"
         for n, (f, w) in enumerate(zip(feats32, ws)):
             Y = torch.einsum("mc,bcn->bmn", w.detach().reshape(hidden, -1).bfloat16().float().cpu(), f.flatten(2).cpu())
             close(v16[n], O.activation("serf", Y).mean(-1), 1e-2, 2e-3, msg="level %d vs oracle" % n)
