@@ -390,7 +390,7 @@ int mmvqa_vistok_dw(const float* pgrad, const float* dv, float scale, float* dW,
 /* ------------------------------------------------------------------------------------
  * Optimiser: multi-tensor Adam, torch.optim.Adam semantics
  * (vqamed2019/train.py:160, no amsgrad, L2 weight decay).  `table` is a DEVICE array of n_chunks
- * descriptors, each a contiguous chunk (<= 32768 elements is a good size) of one parameter
+ * descriptors, each a contiguous chunk (8192 elements is a good size) of one parameter
  * tensor; one CTA per chunk.  If bf16_out != NULL the updated parameter is also written as
  * bf16 (refreshes the tensor-core weight cache in the same pass).
  * ---------------------------------------------------------------------------------- */
@@ -411,14 +411,18 @@ int mmvqa_mark_rows(unsigned char* row_live, const int64_t* ids, int64_t n, int6
  * max_ctas > 0 caps the grid (the CTAs stride over the table): an update that runs underneath the backward pass
  * then takes a bounded share of the HBM bandwidth. */
 int mmvqa_adam_step(const mmvqa_adam_desc* table, int n_chunks, float lr, float beta1, float beta2, float eps,
-                    float weight_decay, int step, const int* step_dev, float grad_scale, int max_ctas,
+                    float weight_decay, int step, const int* step_dev, float grad_scale, int max_ctas, int background,
                     mmvqa_stream_t stream);
 /* Same update with the two values a training loop changes between steps read from DEVICE memory:
  * hyper_dev[0] = lr (ReduceLROnPlateau, vqamed2019/train.py:161,233; pretrain/roco_train.py:91,162),
  * hyper_dev[1] = grad_scale.  A captured graph of this launch follows scheduler.step() as long as the caller refreshes
- * the two floats before the replay. */
+ * the two floats before the replay.
+ * background != 0 (both entry points): the update runs underneath other work (a layer's update under the rest of the
+ * backward pass) -- one 16-byte group in flight per thread and array, so it streams gently; 0: on the critical path,
+ * two groups in flight (pair it with ~8192-element chunks). */
 int mmvqa_adam_step_dev(const mmvqa_adam_desc* table, int n_chunks, const float* hyper_dev, float beta1, float beta2,
-                        float eps, float weight_decay, const int* step_dev, int max_ctas, mmvqa_stream_t stream);
+                        float eps, float weight_decay, const int* step_dev, int max_ctas, int background,
+                        mmvqa_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * Data-parallel gradient exchange (collective 1; the reference has no distributed code -- this is

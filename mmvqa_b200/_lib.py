@@ -136,10 +136,10 @@ SIGNATURES = {
     "mmvqa_ce_chunk_stats": (i32, [vp, i64, vp, i64, i32, i32, vp, vp, vp, i32, vp]),
     "mmvqa_ce_chunk_grad": (i32, [vp, i64, vp, i64, i32, i32, vp, vp, vp, vp, i64, i32, vp]),
     "mmvqa_jaccard_mask": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, vp]),
-    "mmvqa_adam_step": (i32, [C.POINTER(AdamDesc), i32, f32, f32, f32, f32, f32, i32, vp, f32, i32, vp]),
+    "mmvqa_adam_step": (i32, [C.POINTER(AdamDesc), i32, f32, f32, f32, f32, f32, i32, vp, f32, i32, i32, vp]),
     "mmvqa_multimem_allreduce": (i32, [vp, vp, i32, i32, i64, i32, i32, vp]),
     "mmvqa_mark_rows": (i32, [vp, vp, i64, i64, vp]),
-    "mmvqa_adam_step_dev": (i32, [C.POINTER(AdamDesc), i32, vp, f32, f32, f32, f32, vp, i32, vp]),
+    "mmvqa_adam_step_dev": (i32, [C.POINTER(AdamDesc), i32, vp, f32, f32, f32, f32, vp, i32, i32, vp]),
 }
 
 _LIB = None

@@ -192,16 +192,22 @@ __global__ void __launch_bounds__(256) supcon_rows_kernel(const float* __restric
 // multi-tensor Adam
 // ---------------------------------------------------------------------------------
 // one block per table entry (a chunk of one parameter tensor, built once on the host)
+// (explicitly rounded operations: the dense and the row-gated loop must produce the same bits whatever the compiler's
+// FMA contraction choices in either context)
 __device__ __forceinline__ void adam_one(float& p, float& m, float& v, float g, float beta1, float beta2, float eps,
                                          float wd, float step, float bc2_sqrt, float grad_scale) {
-  g *= grad_scale;
-  if (wd != 0.0f) g = fmaf(wd, p, g);
-  m = beta1 * m + (1.0f - beta1) * g;
-  v = beta2 * v + (1.0f - beta2) * g * g;
-  p -= step * m / (sqrtf(v) / bc2_sqrt + eps);
+  g = __fmul_rn(g, grad_scale);
+  if (wd != 0.0f) g = __fmaf_rn(wd, p, g);
+  m = __fmaf_rn(beta1, m, __fmul_rn(1.0f - beta1, g));
+  v = __fmaf_rn(beta2, v, __fmul_rn(__fmul_rn(1.0f - beta2, g), g));
+  p = __fsub_rn(p, __fdiv_rn(__fmul_rn(step, m), __fadd_rn(__fdiv_rn(__fsqrt_rn(v), bc2_sqrt), eps)));
 }
 
-__global__ void __launch_bounds__(256) adam_kernel(const mmvqa_adam_desc* __restrict__ table, float lr, float beta1,
+// U = independent 16-byte groups per thread and iteration.  U = 1 ("background"): a gentle stream of few bytes in flight per
+// CTA for the per-layer updates that run underneath the latency-bound backward pass (the U = 2 loop finishes each update
+// sooner but slowed the whole step by ~0.1 ms).  U = 2: updates on the critical path (the tail of the step, plain step()).
+template <int U>
+__global__ void __launch_bounds__(256, 3) adam_kernel(const mmvqa_adam_desc* __restrict__ table, float lr, float beta1,
                                                    float beta2, float eps, float wd, float bc1, float bc2_sqrt,
                                                    float grad_scale, const int* __restrict__ step_dev, int n_chunks,
                                                    const float* __restrict__ hyper_dev) {
@@ -227,34 +233,39 @@ __global__ void __launch_bounds__(256) adam_kernel(const mmvqa_adam_desc* __rest
     // row-gated chunk (embedding table): one warp per row, rows that never received gradient are skipped (identity update)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const int nrows = (int)(d.n / d.row_len), r4 = (int)(d.row_len / 4);
-    for (int r = warp; r < nrows; r += nwarp) {
-      if (d.row_live[r] == 0) continue;
-      const int64_t base4 = (int64_t)r * r4;
-      for (int i = lane; i < r4; i += 32) {
-        const int64_t q = base4 + i;
-        float4 p = __ldcs(reinterpret_cast<const float4*>(d.p) + q), m = __ldcs(reinterpret_cast<const float4*>(d.m) + q);
-        float4 v = __ldcs(reinterpret_cast<const float4*>(d.v) + q);
-        float4 g;
-        if (g16) {
-          const uint2 raw = __ldcs(reinterpret_cast<const uint2*>(d.g) + q);
-          g.x = __uint_as_float(raw.x << 16); g.y = __uint_as_float(raw.x & 0xffff0000u);
-          g.z = __uint_as_float(raw.y << 16); g.w = __uint_as_float(raw.y & 0xffff0000u);
-        } else {
-          g = __ldcs(reinterpret_cast<const float4*>(d.g) + q);
-        }
-        adam_one(p.x, m.x, v.x, g.x, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
-        adam_one(p.y, m.y, v.y, g.y, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
-        adam_one(p.z, m.z, v.z, g.z, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
-        adam_one(p.w, m.w, v.w, g.w, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
-        __stcs(reinterpret_cast<float4*>(d.p) + q, p);
-        __stcs(reinterpret_cast<float4*>(d.m) + q, m);
-        __stcs(reinterpret_cast<float4*>(d.v) + q, v);
-        if (d.bf16_out) {
-          __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
-          uint2 o;
-          o.x = *reinterpret_cast<uint32_t*>(&lo);
-          o.y = *reinterpret_cast<uint32_t*>(&hi);
-          __stcs(reinterpret_cast<uint2*>(d.bf16_out) + q, o);
+    for (int rb = warp * 32; rb < nrows; rb += nwarp * 32) {
+      // 32 row flags per coalesced load; the warp then walks the live rows of this group
+      unsigned live = __ballot_sync(0xffffffffu, (rb + lane < nrows) && d.row_live[rb + lane] != 0);
+      while (live) {
+        const int r = rb + __ffs(live) - 1;
+        live &= live - 1;
+        const int64_t base4 = (int64_t)r * r4;
+        for (int i = lane; i < r4; i += 32) {
+          const int64_t q = base4 + i;
+          float4 p = __ldcs(reinterpret_cast<const float4*>(d.p) + q), m = __ldcs(reinterpret_cast<const float4*>(d.m) + q);
+          float4 v = __ldcs(reinterpret_cast<const float4*>(d.v) + q);
+          float4 g;
+          if (g16) {
+            const uint2 raw = __ldcs(reinterpret_cast<const uint2*>(d.g) + q);
+            g.x = __uint_as_float(raw.x << 16); g.y = __uint_as_float(raw.x & 0xffff0000u);
+            g.z = __uint_as_float(raw.y << 16); g.w = __uint_as_float(raw.y & 0xffff0000u);
+          } else {
+            g = __ldcs(reinterpret_cast<const float4*>(d.g) + q);
+          }
+          adam_one(p.x, m.x, v.x, g.x, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
+          adam_one(p.y, m.y, v.y, g.y, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
+          adam_one(p.z, m.z, v.z, g.z, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
+          adam_one(p.w, m.w, v.w, g.w, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
+          __stcs(reinterpret_cast<float4*>(d.p) + q, p);
+          __stcs(reinterpret_cast<float4*>(d.m) + q, m);
+          __stcs(reinterpret_cast<float4*>(d.v) + q, v);
+          if (d.bf16_out) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
+            uint2 o;
+            o.x = *reinterpret_cast<uint32_t*>(&lo);
+            o.y = *reinterpret_cast<uint32_t*>(&hi);
+            __stcs(reinterpret_cast<uint2*>(d.bf16_out) + q, o);
+          }
         }
       }
     }
@@ -268,32 +279,48 @@ __global__ void __launch_bounds__(256) adam_kernel(const mmvqa_adam_desc* __rest
   int64_t done = 0;
   if (vec) {
     const int64_t n4 = d.n / 4;
-    for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
-      // evict-first (streaming) accesses: 28 bytes per parameter pass through exactly once; keeping them out of the
-      // L2 working set matters when the update runs underneath the backward pass, whose saved activations live there
-      float4 p = __ldcs(reinterpret_cast<const float4*>(d.p) + i), m = __ldcs(reinterpret_cast<const float4*>(d.m) + i);
-      float4 v = __ldcs(reinterpret_cast<const float4*>(d.v) + i);
-      float4 g;
-      if (g16) {
-        const uint2 raw = __ldcs(reinterpret_cast<const uint2*>(gb) + i);
-        g.x = __uint_as_float(raw.x << 16); g.y = __uint_as_float(raw.x & 0xffff0000u);
-        g.z = __uint_as_float(raw.y << 16); g.w = __uint_as_float(raw.y & 0xffff0000u);
-      } else {
-        g = __ldcs(reinterpret_cast<const float4*>(g32) + i);
+    // U independent 16-byte groups per thread and iteration: all loads are issued before the first use, so a CTA
+    // pays ~one memory latency per 2048 elements (at <= 80 registers: its CTAs stay small tenants of an SM) (a one-group loop made every chunk a chain of 32 dependent HBM round
+    // trips: ~35 us per launch however small, which is what the updates at the tail of the step cost)
+    for (int64_t i0 = threadIdx.x; i0 < n4; i0 += (int64_t)blockDim.x * U) {
+      float4 p[U], m[U], v[U], g[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + (int64_t)u * blockDim.x;
+        if (i < n4) {
+          // evict-first (streaming) accesses: 28 bytes per parameter pass through exactly once; keeping them out of the
+          // L2 working set matters when the update runs underneath the backward pass, whose saved activations live there
+          p[u] = __ldcs(reinterpret_cast<const float4*>(d.p) + i);
+          m[u] = __ldcs(reinterpret_cast<const float4*>(d.m) + i);
+          v[u] = __ldcs(reinterpret_cast<const float4*>(d.v) + i);
+          if (g16) {
+            const uint2 raw = __ldcs(reinterpret_cast<const uint2*>(gb) + i);
+            g[u].x = __uint_as_float(raw.x << 16); g[u].y = __uint_as_float(raw.x & 0xffff0000u);
+            g[u].z = __uint_as_float(raw.y << 16); g[u].w = __uint_as_float(raw.y & 0xffff0000u);
+          } else {
+            g[u] = __ldcs(reinterpret_cast<const float4*>(g32) + i);
+          }
+        }
       }
-      adam_one(p.x, m.x, v.x, g.x, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
-      adam_one(p.y, m.y, v.y, g.y, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
-      adam_one(p.z, m.z, v.z, g.z, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
-      adam_one(p.w, m.w, v.w, g.w, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
-      __stcs(reinterpret_cast<float4*>(d.p) + i, p);
-      __stcs(reinterpret_cast<float4*>(d.m) + i, m);
-      __stcs(reinterpret_cast<float4*>(d.v) + i, v);
-      if (d.bf16_out) {
-        __nv_bfloat162 lo = __floats2bfloat162_rn(p.x, p.y), hi = __floats2bfloat162_rn(p.z, p.w);
-        uint2 o;
-        o.x = *reinterpret_cast<uint32_t*>(&lo);
-        o.y = *reinterpret_cast<uint32_t*>(&hi);
-        __stcs(reinterpret_cast<uint2*>(d.bf16_out) + i, o);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t i = i0 + (int64_t)u * blockDim.x;
+        if (i < n4) {
+          adam_one(p[u].x, m[u].x, v[u].x, g[u].x, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
+          adam_one(p[u].y, m[u].y, v[u].y, g[u].y, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
+          adam_one(p[u].z, m[u].z, v[u].z, g[u].z, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
+          adam_one(p[u].w, m[u].w, v[u].w, g[u].w, beta1, beta2, eps, wd, step, bc2_sqrt, grad_scale);
+          __stcs(reinterpret_cast<float4*>(d.p) + i, p[u]);
+          __stcs(reinterpret_cast<float4*>(d.m) + i, m[u]);
+          __stcs(reinterpret_cast<float4*>(d.v) + i, v[u]);
+          if (d.bf16_out) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(p[u].x, p[u].y), hi = __floats2bfloat162_rn(p[u].z, p[u].w);
+            uint2 o;
+            o.x = *reinterpret_cast<uint32_t*>(&lo);
+            o.y = *reinterpret_cast<uint32_t*>(&hi);
+            __stcs(reinterpret_cast<uint2*>(d.bf16_out) + i, o);
+          }
+        }
       }
     }
     done = n4 * 4;
@@ -401,7 +428,7 @@ int mmvqa_supcon_rows(const float* logits, const float* mask, float* loss_rows, 
 }
 
 int mmvqa_adam_step(const mmvqa_adam_desc* table, int n_chunks, float lr, float beta1, float beta2, float eps,
-                    float weight_decay, int step, const int* step_dev, float grad_scale, int max_ctas,
+                    float weight_decay, int step, const int* step_dev, float grad_scale, int max_ctas, int background,
                     mmvqa_stream_t stream) {
   MMVQA_REQUIRE(table && n_chunks >= 0 && (step >= 1 || step_dev), "adam: bad args");
   if (step < 1) step = 1;
@@ -409,19 +436,28 @@ int mmvqa_adam_step(const mmvqa_adam_desc* table, int n_chunks, float lr, float 
   const float bc1 = 1.0f - powf(beta1, (float)step);
   const float bc2 = 1.0f - powf(beta2, (float)step);
   const int grid = (max_ctas > 0 && max_ctas < n_chunks) ? max_ctas : n_chunks;
-  MMVQA_CUDA(launch_pdl(adam_kernel, dim3(grid), dim3(256), 0, as_stream(stream), table, lr, beta1, beta2, eps, weight_decay, bc1,
-                        sqrtf(bc2), grad_scale, step_dev, n_chunks, (const float*)nullptr));
+  if (background)
+    MMVQA_CUDA(launch_pdl(adam_kernel<1>, dim3(grid), dim3(256), 0, as_stream(stream), table, lr, beta1, beta2, eps, weight_decay,
+                          bc1, sqrtf(bc2), grad_scale, step_dev, n_chunks, (const float*)nullptr));
+  else
+    MMVQA_CUDA(launch_pdl(adam_kernel<2>, dim3(grid), dim3(256), 0, as_stream(stream), table, lr, beta1, beta2, eps, weight_decay,
+                          bc1, sqrtf(bc2), grad_scale, step_dev, n_chunks, (const float*)nullptr));
   MMVQA_LAUNCHED("adam_step");
   return MMVQA_OK;
 }
 
 int mmvqa_adam_step_dev(const mmvqa_adam_desc* table, int n_chunks, const float* hyper_dev, float beta1, float beta2,
-                        float eps, float weight_decay, const int* step_dev, int max_ctas, mmvqa_stream_t stream) {
+                        float eps, float weight_decay, const int* step_dev, int max_ctas, int background,
+                        mmvqa_stream_t stream) {
   MMVQA_REQUIRE(table && n_chunks >= 0 && hyper_dev && step_dev, "adam_dev: bad args");
   if (n_chunks == 0) return MMVQA_OK;
   const int grid = (max_ctas > 0 && max_ctas < n_chunks) ? max_ctas : n_chunks;
-  MMVQA_CUDA(launch_pdl(adam_kernel, dim3(grid), dim3(256), 0, as_stream(stream), table, 0.0f, beta1, beta2, eps, weight_decay,
-                        1.0f, 1.0f, 1.0f, step_dev, n_chunks, hyper_dev));
+  if (background)
+    MMVQA_CUDA(launch_pdl(adam_kernel<1>, dim3(grid), dim3(256), 0, as_stream(stream), table, 0.0f, beta1, beta2, eps, weight_decay,
+                          1.0f, 1.0f, 1.0f, step_dev, n_chunks, hyper_dev));
+  else
+    MMVQA_CUDA(launch_pdl(adam_kernel<2>, dim3(grid), dim3(256), 0, as_stream(stream), table, 0.0f, beta1, beta2, eps, weight_decay,
+                          1.0f, 1.0f, 1.0f, step_dev, n_chunks, hyper_dev));
   MMVQA_LAUNCHED("adam_step");
   return MMVQA_OK;
 }

@@ -41,6 +41,9 @@ _OVERLAP = _os.environ.get("MMVQA_NO_OVERLAP") is None
 _L2_PREFETCH = _os.environ.get("MMVQA_L2_PREFETCH", "1") != "0" and _OVERLAP
 _LN_DEFER = _os.environ.get("MMVQA_LN_DEFER", "1") != "0"
 _VISTOK_PG = _os.environ.get("MMVQA_VISTOK_PG", "1") != "0"
+TRAIN_STEP_CAPTURE = False      # set by graph.GraphedTrainStep while it captures forward + backward
+_EMBED_PREZERO = _os.environ.get("MMVQA_EMBED_PREZERO", "1") != "0"
+_WGRAD_LATE = _os.environ.get("MMVQA_WGRAD_LATE", "0") == "1"   # measured neutral (2.455 vs 2.457 ms/step; hot path 2.194 vs 2.158): opt-in
 _L2_PREFETCH_CTAS = int(_os.environ.get("MMVQA_L2_PREFETCH_CTAS", "16"))
 
 
@@ -610,6 +613,16 @@ class EmbedFuseFn(torch.autograd.Function):
                                                  beta.detach(), visc, out_dtype, eps, p, seed)
         ctx.save_for_backward(ids, seg, word, pos, typ, gamma, mean, rstd)
         ctx.meta = (0 if vis is None else vis.shape[0], p, seed, padding_idx)
+        # the dense word-table gradient (94 MB for bert-base) must be zero-filled before the backward kernel scatters into
+        # it: 20 us at the very end of the step's critical path.  Fill it now, on a side branch under the encoder.
+        ctx.prezero = None
+        # (inside a stream capture only when the capture is known to contain the backward pass -- graph.GraphedTrainStep
+        # sets TRAIN_STEP_CAPTURE -- because the branch is joined there: a forward-only capture must not end with it open)
+        if _EMBED_PREZERO and ctx.needs_input_grad[2] and word.numel() >= (1 << 20) and _OVERLAP and \
+                (TRAIN_STEP_CAPTURE or not torch.cuda.is_current_stream_capturing()):
+            br = SideBranch(word.device, index=8)
+            with br.after_now():
+                ctx.prezero = (torch.zeros_like(word, dtype=torch.float32), br)
         return h
 
     @staticmethod
@@ -619,7 +632,14 @@ class EmbedFuseFn(torch.autograd.Function):
         B, T = ids.shape
         H = word.shape[1]
         need = ctx.needs_input_grad
-        dword = torch.zeros_like(word, dtype=torch.float32) if need[2] else None
+        dword = None
+        if need[2]:
+            if ctx.prezero is not None:
+                dword, br = ctx.prezero
+                ctx.prezero = None          # a second backward through this node gets a fresh buffer
+                br.join()
+            else:
+                dword = torch.zeros_like(word, dtype=torch.float32)
         dpos = torch.zeros_like(pos, dtype=torch.float32) if need[3] else None
         dtyp = torch.zeros_like(typ, dtype=torch.float32) if need[4] else None
         dgamma = torch.zeros_like(gamma, dtype=torch.float32) if need[5] else None
@@ -898,15 +918,21 @@ class RealFormerEncoderFn(torch.autograd.Function):
             else:
                 dy2 = ops.layernorm_bwd(dx, y2, g2.detach(), mean2, rstd2, None, dg2, db2, dxsum=dbb2)
                 dff = dy2
-            with branch.after_now():
-                if dfr is not None:
-                    ops.ln_partials_reduce(lnp2, dg2, db2, dbb2)
-                    keep.append(lnp2)
-                dw2 = gemm_wgrad(dff, H, M, H, hact, F4, F4)
+            # Opt-in (MMVQA_WGRAD_LATE=1): the two FF weight-gradient GEMMs enqueued AFTER the FF1 dgrad, so that they share
+            # the chip with the LayerNorm / attention kernels instead of the FF dgrad GEMMs (FF2 dgrad takes 30 us inside
+            # the step against 13 alone).  Measured neutral: the layer is bound by the sum of its serialized kernel
+            # latencies, not by which kernels overlap.
+            if not _WGRAD_LATE:
+                with branch.after_now():
+                    if dfr is not None:
+                        ops.ln_partials_reduce(lnp2, dg2, db2, dbb2)
+                        keep.append(lnp2)
+                    dw2 = gemm_wgrad(dff, H, M, H, hact, F4, F4)
             # dgrad through FF2 with act'(h_pre) in the epilogue; its column sums are d ff.0.bias
             dhpre = gemm_dgrad(dff, H, M, H, wf2, F4, epilogue=EPI_DACT, act=ACT_SERF, aux_in=hpre, colsum_out=dbb0)
-            with branch.after_now():
-                dw0 = gemm_wgrad(dhpre, F4, M, F4, x1, H, H)
+            if not _WGRAD_LATE:
+                with branch.after_now():
+                    dw0 = gemm_wgrad(dhpre, F4, M, F4, x1, H, H)
             ns = split_k_slabs(M, H, F4, dx.device, dt)
             if attn_block:
                 # LN1 backward + proj dgrad + attention backward + kqv dgrad in ONE cluster launch (csrc/rf_attn_block.cu):
@@ -915,6 +941,13 @@ class RealFormerEncoderFn(torch.autograd.Function):
                     parts = torch.empty(max(ns, 1), M, H, device=dx.device, dtype=torch.float32)
                 ops.gemm(M, H, F4, dhpre, F4, False, wf0, H, True, parts, H, split_k=max(ns, 1), c_split_stride=M * H,
                          b_static=True)
+                if _WGRAD_LATE:
+                    with branch.after_now():
+                        if dfr is not None:
+                            ops.ln_partials_reduce(lnp2, dg2, db2, dbb2)
+                            keep.append(lnp2)
+                        dw2 = gemm_wgrad(dff, H, M, H, hact, F4, F4)
+                        dw0 = gemm_wgrad(dhpre, F4, M, F4, x1, H, H)
                 want_dprev = (l > 0) or (has_prev and ctx.needs_input_grad[2])
                 dpr, dkqv, dprev, dxin = ops.rf_attn_block_bwd(parts, dy2, y1, mean1, rstd1, g1.detach(), wp, wk, kqv, scores, ds,
                                                                want_dprev, dg1, db1, B, T, heads, p1, seed + 2 * l)
@@ -939,6 +972,13 @@ class RealFormerEncoderFn(torch.autograd.Function):
                 if parts is None:
                     parts = torch.empty(ns, M, H, device=dx.device, dtype=torch.float32)
                 ops.gemm(M, H, F4, dhpre, F4, False, wf0, H, True, parts, H, split_k=ns, c_split_stride=M * H, b_static=True)
+                if _WGRAD_LATE:
+                    with branch.after_now():
+                        if dfr is not None:
+                            ops.ln_partials_reduce(lnp2, dg2, db2, dbb2)
+                            keep.append(lnp2)
+                        dw2 = gemm_wgrad(dff, H, M, H, hact, F4, F4)
+                        dw0 = gemm_wgrad(dhpre, F4, M, F4, x1, H, H)
                 dfr1 = ops.layernorm_bwd_deferred(dy2, parts, y1, g1.detach(), mean1, rstd1, want_drop=p1 > 0.0, dropout_p=p1,
                                                   dropout_seed=seed + 2 * l) if _LN_DEFER else None
                 if dfr1 is not None:
@@ -956,6 +996,13 @@ class RealFormerEncoderFn(torch.autograd.Function):
                     dpr = dy1
             else:
                 dx1 = gemm_dgrad(dhpre, F4, M, F4, wf0, H, epilogue=EPI_RESIDUAL, aux_in=dy2)
+                if _WGRAD_LATE:
+                    with branch.after_now():
+                        if dfr is not None:
+                            ops.ln_partials_reduce(lnp2, dg2, db2, dbb2)
+                            keep.append(lnp2)
+                        dw2 = gemm_wgrad(dff, H, M, H, hact, F4, F4)
+                        dw0 = gemm_wgrad(dhpre, F4, M, F4, x1, H, H)
                 dfr1 = ops.layernorm_bwd_deferred(dx1, None, y1, g1.detach(), mean1, rstd1, want_drop=p1 > 0.0, dropout_p=p1,
                                                   dropout_seed=seed + 2 * l) if _LN_DEFER else None
                 if dfr1 is not None:

@@ -86,6 +86,17 @@ class GraphedTrainStep:
         # main_priority < 0: the step is captured on a high-priority stream, so the kernels of the main chain win the
         # SM slots over the work forked onto default-priority streams (weight-gradient branch, optimizer stream)
         cap_stream = torch.cuda.Stream(priority=main_priority) if main_priority != 0 else None
+        from . import functional as _Fn
+        _Fn.TRAIN_STEP_CAPTURE = True
+        try:
+            self._capture_graphs(cap_stream, capture_error_mode)
+        finally:
+            _Fn.TRAIN_STEP_CAPTURE = False
+        self.launches_per_step = _lib.launch_count() - n0
+        if self.casts_in_graph:
+            invalidate_weight_cache()
+
+    def _capture_graphs(self, cap_stream, capture_error_mode):
         if self.eager_between is None:
             # capture_error_mode="thread_local": needed when collectives are captured (the NCCL watchdog thread
             # polls events of earlier eager collectives while this thread captures)
@@ -99,9 +110,6 @@ class GraphedTrainStep:
             self.graph_opt = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph_opt, pool=self.graph.pool()):
                 self._opt()
-        self.launches_per_step = _lib.launch_count() - n0
-        if self.casts_in_graph:
-            invalidate_weight_cache()
 
     def _fwd_bwd(self, zero: bool = True):
         if zero:

@@ -536,9 +536,11 @@ def supcon_rows(raw: Tensor, mask: Optional[Tensor], bsz: int, row_offset: int, 
 
 
 def adam_step(table: Tensor, n_chunks: int, lr: float, beta1: float, beta2: float, eps: float, weight_decay: float,
-              step: int, step_dev: Optional[Tensor], grad_scale: float = 1.0, max_ctas: int = 0) -> None:
+              step: int, step_dev: Optional[Tensor], grad_scale: float = 1.0, max_ctas: int = 0,
+              background: bool = False) -> None:
     L.check(L.lib().mmvqa_adam_step(C.cast(table.data_ptr(), C.POINTER(L.AdamDesc)), n_chunks, lr, beta1, beta2, eps,
-                                   weight_decay, step, _p(step_dev), grad_scale, max_ctas, _stream()), "adam_step")
+                                   weight_decay, step, _p(step_dev), grad_scale, max_ctas, 1 if background else 0, _stream()),
+            "adam_step")
 
 
 def mark_rows(row_live: Tensor, ids: Tensor) -> None:
@@ -550,10 +552,11 @@ def mark_rows(row_live: Tensor, ids: Tensor) -> None:
 
 
 def adam_step_dev(table: Tensor, n_chunks: int, hyper_dev: Tensor, beta1: float, beta2: float, eps: float,
-                  weight_decay: float, step_dev: Tensor, max_ctas: int = 0) -> None:
+                  weight_decay: float, step_dev: Tensor, max_ctas: int = 0, background: bool = False) -> None:
     """Adam with lr = hyper_dev[0], grad_scale = hyper_dev[1] read on the device (graph replay follows lr schedulers)."""
     L.check(L.lib().mmvqa_adam_step_dev(C.cast(table.data_ptr(), C.POINTER(L.AdamDesc)), n_chunks, _p(hyper_dev), beta1, beta2,
-                                       eps, weight_decay, _p(step_dev), max_ctas, _stream()), "adam_step_dev")
+                                       eps, weight_decay, _p(step_dev), max_ctas, 1 if background else 0, _stream()),
+            "adam_step_dev")
 
 
 def multimem_allreduce(multicast_ptr: int, signal_pads_dev: int, rank: int, world: int, nbytes: int, dtype: torch.dtype,

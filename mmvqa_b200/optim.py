@@ -12,7 +12,9 @@ from . import functional as Fn
 from . import ops
 from .functional import weight_cache
 
-CHUNK = 32768
+CHUNK = 8192             # elements per table entry of an update on the critical path (two 16-byte groups in flight)
+CHUNK_BACKGROUND = 32768  # ... of an update that runs underneath the backward pass (one group in flight, long gentle CTAs)
+GATED_ROWS = 256         # rows per entry of a row-gated embedding table (a warp scans 32 row flags per load)
 _DESC = np.dtype([("p", "<u8"), ("m", "<u8"), ("v", "<u8"), ("g", "<u8"), ("bf16_out", "<u8"), ("n", "<i8"), ("flags", "<i8"),
                   ("row_live", "<u8"), ("row_len", "<i8")])
 
@@ -46,7 +48,7 @@ class FusedAdam(torch.optim.Optimizer):
         # on the stream that update runs on; packs / all-reduces and returns the tensors Adam should read
         # (mmvqa_b200.parallel.LayerwiseReducer).  With overlap_backward each layer's exchange overlaps the backward.
         self.reduce_fn = reduce_fn
-        # grid cap of the updates that run underneath the backward pass (0 = one CTA per 32768-element chunk)
+        # grid cap of the updates that run underneath the backward pass (0 = one CTA per CHUNK elements)
         self.early_ctas = int(os.environ.get("MMVQA_ADAM_EARLY_CTAS", "0"))
         self._stepped = False      # device step counter already advanced in this iteration
         self._early_ids = set()    # parameters already updated in this iteration
@@ -136,8 +138,8 @@ class FusedAdam(torch.optim.Optimizer):
         if self._step_dev is None:
             self._init_step_counter()
 
-    def _table(self, gi, plist, grads):
-        key = (weight_cache.generation, tuple((p.data_ptr(), g.data_ptr()) for p, g in zip(plist, grads)))
+    def _table(self, gi, plist, grads, chunk: int = CHUNK):
+        key = (weight_cache.generation, chunk, tuple((p.data_ptr(), g.data_ptr()) for p, g in zip(plist, grads)))
         ent = self._tables.get(gi)
         if ent is not None and ent[0] == key:
             return ent[1], ent[2]
@@ -160,7 +162,7 @@ class FusedAdam(torch.optim.Optimizer):
                     p.shape[1] % 4 == 0:
                 # row-gated chunks (whole rows): rows whose gradient has been zero in every step are skipped
                 live, rl = gate["live"], p.shape[1]
-                rpc = max(1, CHUNK // rl)
+                rpc = GATED_ROWS
                 for r0 in range(0, p.shape[0], rpc):
                     nr = min(rpc, p.shape[0] - r0)
                     off = r0 * rl
@@ -168,8 +170,8 @@ class FusedAdam(torch.optim.Optimizer):
                                  st["exp_avg_sq"].data_ptr() + 4 * off, g.data_ptr() + gsz * off,
                                  (bptr + 2 * off) if bptr else 0, nr * rl, 1 if gsz == 2 else 0, live.data_ptr() + r0, rl))
                 continue
-            for off in range(0, n, CHUNK):
-                cnt = min(CHUNK, n - off)
+            for off in range(0, n, chunk):
+                cnt = min(chunk, n - off)
                 rows.append((p.data_ptr() + 4 * off, st["exp_avg"].data_ptr() + 4 * off, st["exp_avg_sq"].data_ptr() + 4 * off,
                              g.data_ptr() + gsz * off, (bptr + 2 * off) if bptr else 0, cnt, 1 if gsz == 2 else 0, 0, 0))
         host = torch.from_numpy(np.array(rows, dtype=_DESC).view(np.uint8).reshape(-1)).pin_memory()
@@ -209,16 +211,16 @@ class FusedAdam(torch.optim.Optimizer):
                                      "ids_fn": ids_fn}
         self._tables.clear()
 
-    def _launch(self, gi, key, plist, grads, max_ctas: int = 0):
+    def _launch(self, gi, key, plist, grads, max_ctas: int = 0, background: bool = False):
         group = self.param_groups[gi]
         for p in plist:
             gate = self._row_gate.get(id(p))
             if gate is not None:
                 ops.mark_rows(gate["live"], gate["ids_fn"]())
-        table, n = self._table(key, plist, grads)
+        table, n = self._table(key, plist, grads, CHUNK_BACKGROUND if background else CHUNK)
         b1, b2 = group["betas"]
         ops.adam_step_dev(table, n, self._hyper_dev[gi], b1, b2, group["eps"], group["weight_decay"], self._step_dev,
-                          max_ctas)
+                          max_ctas, background)
 
     @torch.no_grad()
     def _sink(self, params, grads, side_stream, from_hook: bool = False) -> bool:
@@ -236,7 +238,7 @@ class FusedAdam(torch.optim.Optimizer):
                 p.grad = g          # visible to hooks / loggers exactly as after a normal backward
             self._early_ids.add(id(p))
         if from_hook or self.sink_group == 1:
-            self._flush_early(gi, list(params), gs, side_stream)
+            self._flush_early(gi, list(params), gs, side_stream, background=not from_hook)
         else:
             self._pending.append((gi, list(params), gs))
             if len(self._pending) >= self.sink_group:
@@ -252,7 +254,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._pending = []
         self._flush_early(gi, params, grads, side_stream)
 
-    def _flush_early(self, gi, params, gs, side_stream) -> None:
+    def _flush_early(self, gi, params, gs, side_stream, background: bool = True) -> None:
         """exchange (reduce_fn, communication stream) + update (optimizer stream) of `params`, ordered after everything
         enqueued so far on the current stream and on `side_stream`."""
         dev = params[0].device
@@ -277,7 +279,10 @@ class FusedAdam(torch.optim.Optimizer):
             ev3.record(self._comm_stream)
             self._opt_stream.wait_event(ev3)
         with torch.cuda.stream(self._opt_stream):
-            self._launch(gi, ("early", id(params[0]), len(params)), list(params), gr, self.early_ctas)
+            # layers handed in by the backward node run underneath the rest of the backward pass (background); hook groups
+            # (embeddings at the tail of the step, the heads) are small and on or near the critical path
+            self._launch(gi, ("early", id(params[0]), len(params)), list(params), gr, self.early_ctas if background else 0,
+                         background)
         self._early_keep.append(gs)
 
     @torch.no_grad()

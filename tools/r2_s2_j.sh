@@ -1,0 +1,8 @@
+cd $GRAFT_REPO_ROOT
+timeout 900 python -m pytest tests/test_optim_graph_gpu.py tests/test_kernels_gpu.py -q -m gpu -x > gpurun_out/j_pytest.log 2>&1; echo "pytest rc=$?"; tail -4 gpurun_out/j_pytest.log
+Q="--steps 40 --warmup 5 --quick --pad-steps 20"
+run() { n=$1; shift; timeout 200 python bench.py $Q "$@" > gpurun_out/j_$n.json 2>gpurun_out/j_$n.err; echo "$n rc=$? $(tail -n1 gpurun_out/j_$n.json | cut -c1-100)"; }
+run base
+run base2
+run hot --hot-only
+timeout 300 python tools/timeline.py --out gpurun_out/timeline_j.csv > gpurun_out/timeline_j.txt 2>&1; echo "timeline rc=$?"
