@@ -59,6 +59,7 @@ extern "C" int mmvqa_gemm(const mmvqa_gemm_args* a, mmvqa_stream_t stream) {
   ep.trace = reinterpret_cast<unsigned long long*>(a->trace);
   static const int no_stage_env = getenv("MMVQA_TC_NO_STAGE") != nullptr ? atoi(getenv("MMVQA_TC_NO_STAGE")) : 0;
   ep.no_stage = no_stage_env;
+  ep.serf_tab = 0;               // decided by the tcgen05 launcher
   if (a->dtype == MMVQA_F32) return gemm_simt_f32(&v, ep, as_stream(stream));
   int sm = mmvqa_device_sm();
   if (sm < 0) return sm;

@@ -18,6 +18,7 @@ struct EpiParams {
   float dropout_p; unsigned long long dropout_seed; const unsigned long long* seed_ctr;
   unsigned long long* trace;
   int no_stage;                                // 1: direct per-row stores in the tcgen05 epilogue (A/B tuning: MMVQA_TC_NO_STAGE)
+  int serf_tab;                                // 1: the launch carries TC_SERF_TAB_BYTES of shared memory for the SERF table
 };
 
 // one output element; AUX = storage type of aux_in / aux_out.  `first_split` gates bias so that

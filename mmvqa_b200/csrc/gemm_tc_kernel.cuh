@@ -126,6 +126,12 @@ __device__ __forceinline__ unsigned long long gtime() {
 // KPS = 64-wide k-blocks per ring stage.  Measured (tools/ubench/stream_bench*.cu, the phase tracer): a ring stage costs
 // a CTA ~0.3-0.4 us whatever its size up to 64 KB and whatever the ring depth, so small-K problems take FEWER, FATTER
 // stages: one TMA box per operand brings KPS k-blocks (4-D tensor map, tc_make_map_chunked).
+// SERF in the FF1 / FF2-dgrad epilogues (realformer.py:22-26 and its backward) from the shared-memory Hermite table of
+// common.cuh instead of 3-4 MUFU per element: two replicas (8 KB) fit next to a 96 KB ring at two CTAs per SM.  The
+// table is filled in the prologue, i.e. under the previous kernel's tail (programmatic dependent launch).
+constexpr int TC_SERF_REP = 2;
+constexpr int TC_SERF_TAB_BYTES = SERF_TAB_N * TC_SERF_REP * 16;
+
 template <int BN, int STAGES_, int KPS_ = 1>
 struct TcCfg {
   static constexpr int STAGES = STAGES_;
@@ -452,7 +458,7 @@ __device__ __forceinline__ void tc_epilogue(const EpiParams& p, uint32_t tmem_ro
 template <int EPI, int ACT, int BN>
 __device__ __forceinline__ void tc_epilogue_fast(const EpiParams& p, uint32_t tmem_row, int m, int n0, int bz, bool first,
                                                  int c_begin, int64_t c_split_off, uint32_t tmem_full_bar, uint8_t* stg,
-                                                 uint8_t* stg_aux) {
+                                                 uint8_t* stg_aux, uint32_t tab = 0) {
   constexpr int NCH = BN / 2 / 16;
   constexpr bool AUXIN = (EPI == MMVQA_EPI_RESIDUAL || EPI == MMVQA_EPI_DACT);
   const int lane = threadIdx.x & 31;
@@ -516,8 +522,13 @@ __device__ __forceinline__ void tc_epilogue_fast(const EpiParams& p, uint32_t tm
     }
     if (EPI == MMVQA_EPI_ACT) {
       if (stg_aux != nullptr) stg_put16(stg_aux, lane, (ci & 3) * 2, v, true);
+      if (ACT == MMVQA_ACT_SERF && tab != 0) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) v[j] = act_fast<ACT>(v[j]);
+        for (int j = 0; j < 16; ++j) v[j] = serf_tab<TC_SERF_REP>(tab, v[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = act_fast<ACT>(v[j]);
+      }
     } else if (AUXIN) {
       const uint32_t w[8] = {q_lo.x, q_lo.y, q_lo.z, q_lo.w, q_hi.x, q_hi.y, q_hi.z, q_hi.w};
       if (EPI == MMVQA_EPI_RESIDUAL) {
@@ -530,6 +541,12 @@ __device__ __forceinline__ void tc_epilogue_fast(const EpiParams& p, uint32_t tm
         for (int j = 0; j < 8; ++j) {
           v[2 * j] += __uint_as_float(w[j] << 16);
           v[2 * j + 1] += __uint_as_float(w[j] & 0xffff0000u);
+        }
+      } else if (ACT == MMVQA_ACT_SERF && tab != 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[2 * j] *= dserf_tab<TC_SERF_REP>(tab, __uint_as_float(w[j] << 16));
+          v[2 * j + 1] *= dserf_tab<TC_SERF_REP>(tab, __uint_as_float(w[j] & 0xffff0000u));
         }
       } else {
 #pragma unroll
@@ -562,9 +579,10 @@ __device__ __forceinline__ void tc_epilogue_fast(const EpiParams& p, uint32_t tm
 
 template <int EPI, int BN>
 __device__ __forceinline__ void tc_epilogue_fast_act(const EpiParams& p, uint32_t tmem_row, int m, int n0, int bz, bool first,
-                                                     int c_begin, uint32_t tmem_full_bar, uint8_t* stg, uint8_t* stg_aux) {
+                                                     int c_begin, uint32_t tmem_full_bar, uint8_t* stg, uint8_t* stg_aux,
+                                                     uint32_t tab = 0) {
   switch (p.act) {
-    case MMVQA_ACT_SERF: tc_epilogue_fast<EPI, MMVQA_ACT_SERF, BN>(p, tmem_row, m, n0, bz, first, c_begin, 0, tmem_full_bar, stg, stg_aux); break;
+    case MMVQA_ACT_SERF: tc_epilogue_fast<EPI, MMVQA_ACT_SERF, BN>(p, tmem_row, m, n0, bz, first, c_begin, 0, tmem_full_bar, stg, stg_aux, tab); break;
     case MMVQA_ACT_GELU: tc_epilogue_fast<EPI, MMVQA_ACT_GELU, BN>(p, tmem_row, m, n0, bz, first, c_begin, 0, tmem_full_bar, stg, stg_aux); break;
     case MMVQA_ACT_RELU: tc_epilogue_fast<EPI, MMVQA_ACT_RELU, BN>(p, tmem_row, m, n0, bz, first, c_begin, 0, tmem_full_bar, stg, stg_aux); break;
     default: tc_epilogue_fast<EPI, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, c_begin, 0, tmem_full_bar, stg, stg_aux); break;
@@ -612,6 +630,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
   const int nst = (nkb + KPS - 1) / KPS;          // ring stages of this CTA (KPS k-blocks each)
   if (threadIdx.x == 0) TC_TRACE(0);
 
+  // SERF table behind the barrier block (only when the launcher reserved the bytes: p.serf_tab)
+  float4* serf_tab_ptr = reinterpret_cast<float4*>(smem_gen + Cfg::STAGES * Cfg::STAGE_BYTES + 256);
+  if (p.serf_tab) serf_table_fill<TC_SERF_REP>(serf_tab_ptr, threadIdx.x, TC_THREADS);
   if (warp == 0) {
     tmem_alloc(tmem_ptr_addr, Cfg::TMEM_COLS);
   } else if (warp == 1 && lane == 0) {
@@ -769,11 +790,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gemm_tc_kernel(const __grid_con
       case MMVQA_EPI_DACT: fast_ok = fast_ok && aux_in_al; break;
       default: fast_ok = false;
     }
+    const uint32_t serf_h = p.serf_tab ? serf_tab_handle<TC_SERF_REP>(serf_tab_ptr) : 0u;
     if (fast_ok) {
       switch (p.epilogue) {
-        case MMVQA_EPI_ACT: tc_epilogue_fast_act<MMVQA_EPI_ACT, BN>(p, tmem_row, m, n0, bz, first, c_begin, tmem_full_bar, stg, stg_aux); break;
+        case MMVQA_EPI_ACT: tc_epilogue_fast_act<MMVQA_EPI_ACT, BN>(p, tmem_row, m, n0, bz, first, c_begin, tmem_full_bar, stg, stg_aux, serf_h); break;
         case MMVQA_EPI_RESIDUAL: tc_epilogue_fast<MMVQA_EPI_RESIDUAL, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, c_begin, c_split_off, tmem_full_bar, stg, nullptr); break;
-        case MMVQA_EPI_DACT: tc_epilogue_fast_act<MMVQA_EPI_DACT, BN>(p, tmem_row, m, n0, bz, first, c_begin, tmem_full_bar, stg, nullptr); break;
+        case MMVQA_EPI_DACT: tc_epilogue_fast_act<MMVQA_EPI_DACT, BN>(p, tmem_row, m, n0, bz, first, c_begin, tmem_full_bar, stg, nullptr, serf_h); break;
         default: tc_epilogue_fast<MMVQA_EPI_STORE, MMVQA_ACT_NONE, BN>(p, tmem_row, m, n0, bz, first, c_begin, c_split_off, tmem_full_bar, stg, nullptr); break;
       }
     } else
@@ -829,11 +851,21 @@ static int launch_tc(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t
   static const int solo_env = getenv("MMVQA_WGRAD_SOLO") ? atoi(getenv("MMVQA_WGRAD_SOLO")) : 0;
   const bool solo = solo_env != 0 && A_MN && B_MN;
   constexpr int SOLO_SMEM = Cfg::SMEM > 116 * 1024 ? Cfg::SMEM : 116 * 1024;
+  constexpr int TAB_SMEM = Cfg::SMEM + TC_SERF_TAB_BYTES;
+  static_assert(TAB_SMEM <= 227 * 1024, "ring + SERF table exceed the shared memory of an SM");
   static bool attr_set = false;
   if (!attr_set) {
-    MMVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (A_MN && B_MN) ? SOLO_SMEM : Cfg::SMEM));
+    MMVQA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (A_MN && B_MN) ? (SOLO_SMEM > TAB_SMEM ? SOLO_SMEM : TAB_SMEM) : TAB_SMEM));
     attr_set = true;
   }
+  // SERF / SERF' epilogues of the encoder's feed-forward GEMMs read the activation from a shared-memory table
+  // (opt-in, MMVQA_TC_SERF_TAB=1: measured at the flagship shape it is no faster than the MUFU formulas -- FF1 + SERF
+  // 11.5 vs 11.0 us warm, FF2 dgrad 10.95 vs 11.2 us -- the epilogue's cost is its stores and instruction count, not MUFU)
+  static const bool no_tab = getenv("MMVQA_TC_SERF_TAB") == nullptr;
+  EpiParams epl = ep;
+  epl.serf_tab = (!no_tab && a->act == MMVQA_ACT_SERF && (a->epilogue == MMVQA_EPI_ACT || a->epilogue == MMVQA_EPI_DACT)) ? 1 : 0;
+  const size_t smem_bytes = epl.serf_tab ? (size_t)TAB_SMEM : (size_t)Cfg::SMEM;
   dim3 grid((a->N + BN - 1) / BN, (a->M + TC_BM - 1) / TC_BM, a->batch * a->split_k);
   MMVQA_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm(bf16): grid too large");
   if (solo) {
@@ -843,7 +875,7 @@ static int launch_tc(const mmvqa_gemm_args* a, const EpiParams& ep, cudaStream_t
     MMVQA_LAUNCHED("gemm_tc_bf16");
     return MMVQA_OK;
   }
-  MMVQA_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), (size_t)Cfg::SMEM, st, tmA, tmB, ep,
+  MMVQA_CUDA(launch_pdl(kern, grid, dim3(TC_THREADS), smem_bytes, st, tmA, tmB, epl,
                         (a->batch > 1 && a->a_batch_rows > 0) ? 1 : 0, (a->batch > 1 && a->b_batch_rows > 0) ? 1 : 0,
                         (a->b_static && pdl_enabled()) ? 1 : 0));
   MMVQA_LAUNCHED("gemm_tc_bf16");

@@ -45,14 +45,24 @@ __device__ __forceinline__ void vp_epilogue_tile(uint32_t tmem_row, uint8_t* dbu
     float v[16];
     const int nvalid = row_ok ? max(0, min(16, nvalid_tile - c)) : 0;
     float part = 0.0f;
+    if (nvalid == 16) {     // interior chunk: no masks
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      float a, d;
-      const float x = j < nvalid ? __uint_as_float(r[j]) : 0.0f;
-      if (ACT == MMVQA_ACT_SERF) serf_both_tab<VP_REP>(tab, x, a, d);
-      else act_both_fast<ACT>(x, a, d);
-      part += j < nvalid ? a : 0.0f;
-      v[j] = j < nvalid ? d : 0.0f;     // pixels past the map / rows past M contribute nothing to P
+      for (int j = 0; j < 16; ++j) {
+        float a;
+        if (ACT == MMVQA_ACT_SERF) serf_both_tab<VP_REP>(tab, __uint_as_float(r[j]), a, v[j]);
+        else act_both_fast<ACT>(__uint_as_float(r[j]), a, v[j]);
+        part += a;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float a, d;
+        const float x = j < nvalid ? __uint_as_float(r[j]) : 0.0f;
+        if (ACT == MMVQA_ACT_SERF) serf_both_tab<VP_REP>(tab, x, a, d);
+        else act_both_fast<ACT>(x, a, d);
+        part += j < nvalid ? a : 0.0f;
+        v[j] = j < nvalid ? d : 0.0f;     // pixels past the map / rows past M contribute nothing to P
+      }
     }
     rowsum += part;
     // K-major SWIZZLE_128B: row r at (r / 8) * 1024 + (r % 8) * 128, its 16-byte chunk j at position j ^ (r % 8)

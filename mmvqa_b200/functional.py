@@ -540,12 +540,15 @@ class VisTokAllFn(torch.autograd.Function):
             keep.append((fb, actp))
         # fork BEFORE the big level is enqueued: the side branch only depends on what precedes this node.  (Issuing the
         # big level first was measured slower: the small levels then queue behind it and finish 45 us later.)
-        if nlev > 1:
-            with branch.after_now():
-                for n in order[1:]:
-                    run(n)
+        # (one branch per level, as in the backward pass: the small levels are latency-bound launches that would otherwise
+        # queue behind each other on one stream and end after the big level)
+        branches = [branch] + [SideBranch(dev, index=1 + i, priority=-1) for i in range(1, max(nlev - 1, 0))]
+        for br, n in zip(branches, order[1:]):
+            with br.after_now():
+                run(n)
         run(order[0])
-        branch.join()
+        for br in branches:
+            br.join()
         ctx.save_for_backward(*saved)
         ctx.meta = (act, dtype, nlev, B, hidden, metas, order)
         return vis

@@ -82,6 +82,16 @@ def _worker(rank, world, port, q):
     dense_sum = g_emb.clone()
     dist.all_reduce(dense_sum)
     q.put({"rank3": rank, "sparse": out2[0].clone(), "dense": dense_sum, "other": out2[1].clone()})
+    # a second step with other ids: the accumulator clears the rows of the previous exchange only (not the whole table)
+    ids2 = torch.tensor([[2, 2, 9, 7], [3, 18, 18, 9]][rank])
+    contrib2 = torch.randn(4, 4, generator=torch.Generator().manual_seed(60 + rank))
+    g_emb2 = torch.zeros(20, 4).index_add_(0, ids2, contrib2)
+    ids.copy_(ids2)                                                       # the registered ids tensor is a fixed buffer
+    out3 = red2([emb, other], [g_emb2, g_other])
+    dense_sum2 = g_emb2.clone()
+    dist.all_reduce(dense_sum2)
+    q.put({"rank3b": rank, "sparse": out3[0].clone(), "dense": dense_sum2,
+           "gathered": sorted(red2.gathered_ids(emb).tolist())})
     # local-anchor rows: the same gather with a reduce-scatter backward; each rank evaluates only the
     # loss rows of its own samples' anchors (here with plain torch ops restating loss.py:72-96 per anchor row)
     from mmvqa_b200.parallel import _GatherFeaturesRS
@@ -108,7 +118,7 @@ def test_dp_world2_gloo():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = [q.get(timeout=120) for _ in range(7)]
+    got = [q.get(timeout=120) for _ in range(9)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -141,6 +151,9 @@ def test_dp_world2_gloo():
         if "rank3" in x:
             torch.testing.assert_close(x["sparse"], x["dense"])
             torch.testing.assert_close(x["other"], torch.full((3,), 3.0))
+        if "rank3b" in x:
+            torch.testing.assert_close(x["sparse"], x["dense"])
+            assert x["gathered"] == sorted([2, 2, 9, 7, 3, 18, 18, 9])
     # local-anchor partition: mean over ranks of the per-rank losses == the global loss, and the reduce-scatter hands
     # every rank the same world x gradient of its slice as the redundant formulation above
     sh = {x["rank2"]: x for x in got if "rank2" in x}
