@@ -572,21 +572,26 @@ def main_gpu(a):
     # (2) Adam: 16 B read (p, m, v, g) + 12 B written (p, m, v) per parameter (+2 B bf16 operand copy where cached)
     # (timed alone over ALL parameters; inside the step the per-layer updates run underneath the backward pass)
     plist_all = [p for p in params if p.grad is not None]
-    table, nchunks = opt._table("roofline", plist_all, [p.grad for p in plist_all])
+    opt._row_gate = {}             # the roofline run updates EVERY row: 28 B for each of the 91 M parameters
+    opt._tables.clear()
+    from mmvqa_b200.optim import CHUNK_BACKGROUND
+    table, nchunks = opt._table("roofline", plist_all, [p.grad for p in plist_all], CHUNK_BACKGROUND)   # the bulk mode the step uses
     nparams_adam = sum(p.numel() for p in plist_all)
     grp = opt.param_groups[0]
     ms_adam = time_kernel(lambda: ops.adam_step(table, nchunks, grp["lr"], grp["betas"][0], grp["betas"][1], grp["eps"],
-                                                grp["weight_decay"], 0, opt._step_dev, opt.grad_scale), iters=10)
+                                                grp["weight_decay"], 0, opt._step_dev, opt.grad_scale, 0, True), iters=10)
     adam_gbs = nparams_adam * 28 / (ms_adam * 1e-3) / 1e9
     # DRAM bytes per launch of the same kernel family from the committed ncu launch list (profiles/, not measured here)
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     roof = {"kernel": "gemm_tc_kernel (tcgen05/TMEM/TMA bf16 GEMM family: %d launches per step, %.0f%% of the step time)"
                       % (gemm_n, 100.0 * gemm_ms / ms_step),
             "bound": "tensor", "achieved": gemm_tflops, "peak": tf_burst, "unit": "TFLOP/s", "frac": gemm_tflops / tf_burst,
-            "traffic": traffic, "traffic_source": "profiles/r01_launches_summary.txt (ncu dram__bytes_read+write per launch, family average)",
+            "traffic": traffic, "traffic_source": "profiles/%s (ncu dram__bytes_read+write per launch, family average)" % os.path.basename(tpath).replace("gemm_traffic.json", "launches_summary.txt"),
             "peak_source": which + " (MEASURED_PEAKS.json bf16_tflops, burst: kernels timed alone)",
             "flops_per_launch": g_flops / max(gemm_n, 1), "ms_per_launch": gemm_ms / max(gemm_n, 1),
             "how": "every mmvqa_gemm problem of one forward+backward at the bench shape (%d distinct), each replayed alone "

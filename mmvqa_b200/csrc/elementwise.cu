@@ -418,7 +418,9 @@ __global__ void __launch_bounds__(256) add_ln_fwd_packed(const T* __restrict__ x
 // slabs, the dropout of the branch, the residual add and the normalisation are ONE pass, so a K = 3072 GEMM at
 // M = 448 can spread over every SM without an atomic or a second sweep.  s = dropout(sum_i parts[i]) + res is
 // rounded to T and stored (sum_out) -- it is what the backward pass normalises again.
-template <typename T>
+// NP > 0: the slab count is a compile-time constant, so every slab load of a row is issued before the first use (the
+// run-time loop made a row a chain of nparts x 3 dependent L2 round trips: 10 us for a kernel that moves 5 MB).
+template <typename T, int NP>
 __global__ void __launch_bounds__(256) add_ln_fwd_parts(const float* __restrict__ parts, int nparts, int64_t part_stride,
                                                         const T* __restrict__ res, const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, T* __restrict__ y,
@@ -448,12 +450,29 @@ __global__ void __launch_bounds__(256) add_ln_fwd_parts(const float* __restrict_
       float acc[N];
 #pragma unroll
       for (int j = 0; j < N; ++j) acc[j] = 0.0f;
-      for (int i = 0; i < nparts; ++i) {
-        const float* pr = parts + (int64_t)i * part_stride + row * cols + c;
+      if (NP > 0) {
+        float4 t[NP > 0 ? NP : 1][N / 4];
 #pragma unroll
-        for (int j = 0; j < N; j += 4) {
-          const float4 t = *reinterpret_cast<const float4*>(pr + j);
-          acc[j] += t.x; acc[j + 1] += t.y; acc[j + 2] += t.z; acc[j + 3] += t.w;
+        for (int i = 0; i < NP; ++i) {
+          const float* pr = parts + (int64_t)i * part_stride + row * cols + c;
+#pragma unroll
+          for (int j = 0; j < N / 4; ++j) t[i][j] = __ldg(reinterpret_cast<const float4*>(pr) + j);
+        }
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {      // same summation order as the run-time loop
+#pragma unroll
+          for (int j = 0; j < N / 4; ++j) {
+            acc[4 * j] += t[i][j].x; acc[4 * j + 1] += t[i][j].y; acc[4 * j + 2] += t[i][j].z; acc[4 * j + 3] += t[i][j].w;
+          }
+        }
+      } else {
+        for (int i = 0; i < nparts; ++i) {
+          const float* pr = parts + (int64_t)i * part_stride + row * cols + c;
+#pragma unroll
+          for (int j = 0; j < N; j += 4) {
+            const float4 t = *reinterpret_cast<const float4*>(pr + j);
+            acc[j] += t.x; acc[j + 1] += t.y; acc[j + 2] += t.z; acc[j + 3] += t.w;
+          }
         }
       }
       Vec16<T> b;
@@ -568,7 +587,7 @@ struct LnBwdExtra {
 // Packed backward (vector path): the two input rows stay in registers as raw 128-bit vectors and are re-expanded in
 // the second pass instead of keeping 2 x 32 floats; KU = number of 32-lane vector slots actually used by `cols`
 // (3 for a 768-wide bf16 row), so the gamma / beta / bias-gradient accumulators are 3 x KU x N registers.
-template <typename T, int KU>
+template <typename T, int KU, int NP = 0>
 __global__ void __launch_bounds__(128) ln_bwd_packed(const T* __restrict__ dy, const T* __restrict__ xsum,
                                                      const float* __restrict__ gamma, const float* __restrict__ mean,
                                                      const float* __restrict__ rstd, const T* __restrict__ dx_extra,
@@ -614,12 +633,29 @@ __global__ void __launch_bounds__(128) ln_bwd_packed(const T* __restrict__ dy, c
           float acc[N];
 #pragma unroll
           for (int j = 0; j < N; ++j) acc[j] = 0.0f;
-          for (int i = 0; i < ex.nparts; ++i) {
-            const float* pr = ex.dy_parts + (int64_t)i * ex.part_stride + row * cols + c;
+          if (NP > 0) {      // compile-time slab count: all slab loads of the row in flight at once
+            float4 t[NP > 0 ? NP : 1][N / 4];
 #pragma unroll
-            for (int j = 0; j < N; j += 4) {
-              const float4 t = *reinterpret_cast<const float4*>(pr + j);
-              acc[j] += t.x; acc[j + 1] += t.y; acc[j + 2] += t.z; acc[j + 3] += t.w;
+            for (int i = 0; i < NP; ++i) {
+              const float* pr = ex.dy_parts + (int64_t)i * ex.part_stride + row * cols + c;
+#pragma unroll
+              for (int j = 0; j < N / 4; ++j) t[i][j] = __ldg(reinterpret_cast<const float4*>(pr) + j);
+            }
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+#pragma unroll
+              for (int j = 0; j < N / 4; ++j) {
+                acc[4 * j] += t[i][j].x; acc[4 * j + 1] += t[i][j].y; acc[4 * j + 2] += t[i][j].z; acc[4 * j + 3] += t[i][j].w;
+              }
+            }
+          } else {
+            for (int i = 0; i < ex.nparts; ++i) {
+              const float* pr = ex.dy_parts + (int64_t)i * ex.part_stride + row * cols + c;
+#pragma unroll
+              for (int j = 0; j < N; j += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(pr + j);
+                acc[j] += t.x; acc[j + 1] += t.y; acc[j + 2] += t.z; acc[j + 3] += t.w;
+              }
             }
           }
           if (dy) {
@@ -1183,7 +1219,10 @@ static int layernorm_bwd_impl(const void* dy, const float* dy_parts, int nparts,
     if (launched) {
       if (dtype == MMVQA_BF16) {
         using B = __nv_bfloat16;
-        if (ku <= 1) LN_BWDP(B, 1); else if (ku == 2) LN_BWDP(B, 2); else if (ku == 3) LN_BWDP(B, 3); else LN_BWDP(B, 4);
+        // (three slabs = the K = 3072 dgrad at M = 448 on 148 SMs: compile-time slab count for the 768-wide row)
+        if (ku == 3 && dy_parts != nullptr && nparts == 3)
+          MMVQA_CUDA(launch_pdl(ln_bwd_packed<B, 3, 3>, dim3(grid2), dim3(nthr), smem2, st, (const B*)dy, (const B*)xsum, gamma, mean, rstd, (const B*)dx_extra, (B*)dx, dgamma, dbeta, ex, rows, cols));
+        else if (ku <= 1) LN_BWDP(B, 1); else if (ku == 2) LN_BWDP(B, 2); else if (ku == 3) LN_BWDP(B, 3); else LN_BWDP(B, 4);
       } else {
         if (ku <= 2) LN_BWDP(float, 2); else if (ku <= 4) LN_BWDP(float, 4); else if (ku <= 6) LN_BWDP(float, 6); else LN_BWDP(float, 8);
       }
@@ -1268,14 +1307,14 @@ int mmvqa_add_layernorm_fwd_parts(const float* parts, int nparts, int64_t part_s
                 "add_layernorm_fwd_parts: needs cols %% %d == 0, cols <= %d and 16-byte aligned buffers", vn, 32 * LN_CACHE);
   cudaStream_t st = as_stream(stream);
   const dim3 grid((unsigned)((rows + 7) / 8));
-  if (dtype == MMVQA_F32)
-    MMVQA_CUDA(launch_pdl(add_ln_fwd_parts<float>, grid, dim3(256), 0, st, parts, nparts, part_stride, (const float*)res, gamma,
-                          beta, (float*)y, (float*)sum_out, mean, rstd, rows, cols, eps, dropout_p,
-                          (unsigned long long)dropout_seed, g_seed_ctr));
-  else
-    MMVQA_CUDA(launch_pdl(add_ln_fwd_parts<__nv_bfloat16>, grid, dim3(256), 0, st, parts, nparts, part_stride,
-                          (const __nv_bfloat16*)res, gamma, beta, (__nv_bfloat16*)y, (__nv_bfloat16*)sum_out, mean, rstd, rows,
-                          cols, eps, dropout_p, (unsigned long long)dropout_seed, g_seed_ctr));
+#define LN_PARTS(T, NP) MMVQA_CUDA(launch_pdl(add_ln_fwd_parts<T, NP>, grid, dim3(256), 0, st, parts, nparts, part_stride, (const T*)res, gamma, beta, (T*)y, (T*)sum_out, mean, rstd, rows, cols, eps, dropout_p, (unsigned long long)dropout_seed, g_seed_ctr))
+  if (dtype == MMVQA_F32) {
+    if (nparts == 2) LN_PARTS(float, 2); else if (nparts == 3) LN_PARTS(float, 3); else if (nparts == 4) LN_PARTS(float, 4); else LN_PARTS(float, 0);
+  } else {
+    using B = __nv_bfloat16;
+    if (nparts == 2) LN_PARTS(B, 2); else if (nparts == 3) LN_PARTS(B, 3); else if (nparts == 4) LN_PARTS(B, 4); else LN_PARTS(B, 0);
+  }
+#undef LN_PARTS
   MMVQA_LAUNCHED("add_layernorm_fwd_parts");
   return MMVQA_OK;
 }

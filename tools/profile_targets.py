@@ -44,4 +44,12 @@ for _ in range(3):
     ops.gemm(M, F4, H, xa, H, False, wa, H, False, ya, F4, bias=ba, epilogue=EPI_ACT, act=ACT_SERF, aux_out=pa, ld_aux_out=F4)
     ops.gemm(M, H, F4, xb, F4, False, wb, F4, False, yb, H, bias=bb, epilogue=EPI_RESIDUAL, aux_in=rb, ld_aux_in=H)
 torch.cuda.synchronize()
+# round 2: projector forward with the weight-gradient contraction inside (112 x 112 level), multi-tensor cast
+Wp = r(H, 24)
+fmaps = [torch.randn(B * c, s * s, device="cuda").abs() for c, s in ((24, 112), (48, 56), (80, 28), (176, 14), (512, 7))]
+for _ in range(3):
+    vv = torch.zeros(B, H, device="cuda")
+    ops.vistok_fwd_pgrad(Wp, f0, 12544, vv, B, H, 12544, 24, ACT_SERF)
+    ops.cast_pad_multi(fmaps, [(t.shape[1] + 7) // 8 * 8 for t in fmaps])
+torch.cuda.synchronize()
 print("done")

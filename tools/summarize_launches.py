@@ -35,9 +35,9 @@ def main(path, out_json=None):
     for name, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print("%10.1f %5.1f%% %6d %9.2f %12.3f %12.3f  %s" % (a[1], 100 * a[1] / tot, a[0], a[1] / a[0], a[2] / a[0] / 1e6,
                                                             a[3] / a[0] / 1e6, name))
-    fam = [a for n, a in agg.items() if "gemm_tc_kernel" in n or "vistok_kernel" in n]
+    fam = [a for n, a in agg.items() if "gemm_tc_kernel" in n or "vistok_kernel" in n or "vistok_pg_kernel" in n]
     n = sum(a[0] for a in fam)
-    info = {"family": "gemm_tc_kernel + vistok_kernel", "launches": n, "share_of_kernel_time": sum(a[1] for a in fam) / tot,
+    info = {"family": "gemm_tc_kernel + vistok_kernel + vistok_pg_kernel", "launches": n, "share_of_kernel_time": sum(a[1] for a in fam) / tot,
             "avg_us_per_launch": sum(a[1] for a in fam) / max(n, 1),
             "dram_bytes_per_launch": (sum(a[2] for a in fam) + sum(a[3] for a in fam)) / max(n, 1),
             "source": path}
