@@ -643,7 +643,8 @@ if __name__ == "__main__":
     ap.add_argument("--nccl-channels", type=int, default=0, help="cap NCCL channels (CTAs) per collective; 0 = NCCL default")
     ap.add_argument("--main-priority", type=int, default=-1, help="CUDA priority of the captured main stream (< 0 = above the side / optimizer streams)")
     ap.add_argument("--nccl-high-priority", type=int, default=0)
-    ap.add_argument("--sink-group", type=int, default=4, help="data parallel: encoder layers per all-reduce + Adam launch")
+    ap.add_argument("--sink-group", type=lambda v: [int(x) for x in v.split(",")], default=[4],
+                    help="data parallel: encoder layers per all-reduce + Adam launch; a comma list is a schedule (last entry repeats)")
     ap.add_argument("--sink-group-1gpu", type=int, default=1, help="single GPU: encoder layers per Adam launch")
     ap.add_argument("--dp-mode", default="overlapped", choices=["overlapped", "twograph"])
     ap.add_argument("--multimem", type=int, default=-1, help="data parallel: in-switch all-reduce kernel of the library (symmetric memory) instead of NCCL; -1 = from 4 GPUs on")

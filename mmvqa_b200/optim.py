@@ -60,7 +60,15 @@ class FusedAdam(torch.optim.Optimizer):
         self._hook_groups = []
         # sink_group: how many consecutive gradient-sink calls (layers) share one exchange + one update launch.  With a
         # reduce_fn, fewer and larger all-reduces use the links better and occupy the SMs for less time in total.
-        self.sink_group = max(1, int(sink_group))
+        # A sequence is a schedule: the i-th exchange takes sink_group[i] layers (the last entry repeats), e.g. (4, 4, 2, 1, 1)
+        # -- large exchanges while many layers of backward remain to hide them, single layers at the end of the backward
+        # pass, where the last exchange + update is exposed.
+        if isinstance(sink_group, (list, tuple)):
+            self._sink_schedule = [max(1, int(x)) for x in sink_group] or [1]
+        else:
+            self._sink_schedule = [max(1, int(sink_group))]
+        self.sink_group = self._sink_schedule[0]
+        self._sink_round = 0
         self._pending = []         # [(params, grads)] handed in by the sink, not launched yet
         if overlap_backward:
             Fn.set_grad_sink(self._sink)
@@ -243,11 +251,12 @@ class FusedAdam(torch.optim.Optimizer):
             if not from_hook:
                 p.grad = g          # visible to hooks / loggers exactly as after a normal backward
             self._early_ids.add(id(p))
-        if from_hook or self.sink_group == 1:
+        if from_hook or self._sink_schedule == [1]:
             self._flush_early(gi, list(params), gs, side_stream, background=not from_hook)
         else:
             self._pending.append((gi, list(params), gs))
-            if len(self._pending) >= self.sink_group:
+            if len(self._pending) >= self._sink_schedule[min(self._sink_round, len(self._sink_schedule) - 1)]:
+                self._sink_round += 1
                 self._flush_pending(side_stream)
         return True
 
@@ -322,6 +331,7 @@ class FusedAdam(torch.optim.Optimizer):
             self._early_keep = []
         for st in self._hook_groups:
             st["n"] = 0
+        self._sink_round = 0
         self._stepped = False
         ids = set()
         for r in self._refreshed.values():
