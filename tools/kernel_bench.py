@@ -70,8 +70,21 @@ def gemm_case(name, Mx, N, K, at=False, bt=False, cdt=bf, **kw):
            lambda: ops.gemm(Mx, N, K, A, Mx if at else K, at, Bm, N if bt else K, bt, C, N, **kw), flops=2.0 * Mx * N * K)
 
 
+ATTN_ONLY = os.environ.get("KB_ATTN_ONLY") is not None
 print(f"B={B} T={T} M={M}  env BN={os.environ.get('MMVQA_TC_BN')} STAGES={os.environ.get('MMVQA_TC_STAGES')}")
 bias_h, bias_f = torch.randn(H, device="cuda"), torch.randn(F4, device="cuda")
+if ATTN_ONLY:      # KB_ATTN_ONLY=1 python tools/kernel_bench.py 16 75: the attention rows at another sequence length
+    kqv = r(M * heads, 3 * d)
+    mask = torch.ones(B, T, device="cuda")
+    prev = torch.randn(B, heads, T, T, device="cuda")
+    xin, wk = r(M, H), r(3 * d, d)
+    report(f"rf_attn_fwd T={T}", lambda: ops.rf_attn_fwd(kqv, prev, mask, B, T, heads, d), flops=4.0 * B * heads * T * T * d)
+    report(f"rf_attn_fwd_fused (kqv inside) T={T}", lambda: ops.rf_attn_fwd_fused(xin, wk, prev, mask, B, T, heads, d),
+           flops=4.0 * B * heads * T * T * d + 2.0 * M * heads * 3 * d * d)
+    out, sc = ops.rf_attn_fwd(kqv, prev, mask, B, T, heads, d)
+    do = r(M, H)
+    report(f"rf_attn_bwd T={T}", lambda: ops.rf_attn_bwd(kqv, sc, do, prev, True, B, T, heads, d), flops=8.0 * B * heads * T * T * d)
+    sys.exit(0)
 gemm_case("kqv fwd", M * heads, 3 * d, d)
 gemm_case("proj fwd +residual", M, H, H, epilogue=EPI_RESIDUAL, aux_in=r(M, H), ld_aux_in=H)
 pre = torch.empty(M, F4, device="cuda", dtype=bf)
