@@ -380,7 +380,7 @@ int mmvqa_rf_attn_block_bwd(const mmvqa_rf_attn_block_bwd_args* args, mmvqa_stre
  * W bf16 [M, C] (ldw), f bf16 [B * C, ldf] = the NCHW map read in place.  The backward pass is then
  *   dW[m, c] = scale * sum_b dv[b, m] pgrad[b, m, c]   with scale = 1 / HW  (mmvqa_vistok_dw)
  * and the [B, M, HW] act' map of the EPI_ACT_ROWSUM path (aux_out) is never written: use it when the feature maps need no
- * gradient.  C <= 64, C % 8 == 0, HW >= 128 (mmvqa_vistok_pgrad_supported); the other levels keep mmvqa_gemm.
+ * gradient.  C <= 128, C % 8 == 0, HW >= 128 (mmvqa_vistok_pgrad_supported); the other levels keep mmvqa_gemm.
  * ---------------------------------------------------------------------------------- */
 int mmvqa_vistok_pgrad_supported(int M, int HW, int C);
 int mmvqa_vistok_fwd_pgrad(const void* W, int64_t ldw, const void* f, int64_t ldf, float* vis, float* pgrad, int M, int HW,

@@ -25,13 +25,21 @@ constexpr int VP_BN = 64;          // pixels per tile
 constexpr int VP_THREADS = 320;    // TMA warp + MMA warp + 8 epilogue warps
 constexpr int VP_STAGES = 3;
 constexpr int VP_REP = 8;          // SERF table replicas
-constexpr int VP_A_BYTES = 16384;  // W tile [128 x 64] bf16
-constexpr int VP_B_STAGE = 8192;   // f tile [64 channels x 64 pixels] bf16
 constexpr int VP_D_BYTES = 16384;  // act' tile [128 x 64 pixels] bf16
 constexpr int VP_TAB_BYTES = SERF_TAB_N * VP_REP * 16;
-constexpr int VP_SMEM = VP_A_BYTES + VP_STAGES * VP_B_STAGE + 2 * VP_D_BYTES + 1024 + 256 + VP_TAB_BYTES;
-static_assert(2 * (VP_SMEM + 1024) <= 233472, "two projector CTAs must fit on one SM");
-constexpr int VP_TMEM_COLS = 256;  // acc0 [0,64) | acc1 [64,128) | P [128,192)
+constexpr int VP_TMEM_COLS = 256;  // acc0 [0,64) | acc1 [64,128) | P [128, 128 + 64 KB)
+
+// KB = 64-channel blocks of the map (C <= 64 KB).  KB = 1: two CTAs per SM; KB = 2 (the 80-channel level): one.
+template <int KB>
+struct VpCfg {
+  static constexpr int A_BYTES = KB * 16384;   // W tile [128 x 64 KB] bf16
+  static constexpr int B_STAGE = KB * 8192;    // f tile [64 KB channels x 64 pixels] bf16
+  static constexpr int N2 = 64 * KB;           // columns of P
+  static constexpr int SMEM = A_BYTES + VP_STAGES * B_STAGE + 2 * VP_D_BYTES + 1024 + 256 + VP_TAB_BYTES;
+  static constexpr int CTAS_PER_SM = (2 * (SMEM + 1024) <= 233472) ? 2 : 1;
+  static_assert(SMEM + 1024 <= 233472, "projector CTA exceeds the shared memory of an SM");
+  static_assert(128 + N2 <= VP_TMEM_COLS, "TMEM: two z accumulators + P");
+};
 
 template <int ACT>
 __device__ __forceinline__ void vp_epilogue_tile(uint32_t tmem_row, uint8_t* dbuf, int row_local, int nvalid_tile, bool row_ok,
@@ -75,15 +83,17 @@ __device__ __forceinline__ void vp_epilogue_tile(uint32_t tmem_row, uint8_t* dbu
   }
 }
 
+template <int KB>
 __global__ void __launch_bounds__(VP_THREADS) vistok_pg_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                const __grid_constant__ CUtensorMap tmB, float* __restrict__ vis,
                                                                float* __restrict__ pgrad, int M, int N, int C, int act,
                                                                float scale, int n_tiles) {
+  using Cfg = VpCfg<KB>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t a_base = smem_base;
-  const uint32_t b_base = a_base + VP_A_BYTES;
-  const uint32_t d_base = b_base + VP_STAGES * VP_B_STAGE;
+  const uint32_t b_base = a_base + Cfg::A_BYTES;
+  const uint32_t d_base = b_base + VP_STAGES * Cfg::B_STAGE;
   const uint32_t bar = d_base + 2 * VP_D_BYTES;
   // barriers: a_full | b_full[S] | b_empty[S] | acc_full[2] | acc_empty[2] | d_full[2] | d_empty[2] | p_full | tmem ptr
   const uint32_t a_full = bar, b_full = bar + 8, b_empty = b_full + 8 * VP_STAGES, acc_full = b_empty + 8 * VP_STAGES,
@@ -128,13 +138,16 @@ __global__ void __launch_bounds__(VP_THREADS) vistok_pg_kernel(const __grid_cons
     if (lane == 0) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
-      mbar_expect_tx(a_full, VP_A_BYTES);
-      tma_load_3d(a_base, &tmA, a_full, 0, m0, 0);
+      mbar_expect_tx(a_full, Cfg::A_BYTES);
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) tma_load_3d(a_base + kb * 16384, &tmA, a_full, kb * TC_BK, m0, 0);
       for (int t = 0; t < my_tiles; ++t) {
         const int s = t % VP_STAGES;
         mbar_wait(b_empty + 8 * s, ((uint32_t)(t / VP_STAGES) & 1u) ^ 1u);
-        mbar_expect_tx(b_full + 8 * s, VP_B_STAGE);
-        tma_load_3d(b_base + s * VP_B_STAGE, &tmB, b_full + 8 * s, (split + t * nsplit) * VP_BN, 0, bz);
+        mbar_expect_tx(b_full + 8 * s, Cfg::B_STAGE);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)     // channels 64 kb .. 64 kb + 63 of the 64-pixel tile (rows past C are zero-filled)
+          tma_load_3d(b_base + s * Cfg::B_STAGE + kb * 8192, &tmB, b_full + 8 * s, (split + t * nsplit) * VP_BN, kb * TC_BK, bz);
       }
     }
   } else if (warp == 1) {
@@ -142,7 +155,7 @@ __global__ void __launch_bounds__(VP_THREADS) vistok_pg_kernel(const __grid_cons
       // GEMM 1: A = W K-major, B = f MN-major (pixels contiguous);  GEMM 2: A = act' K-major, B = f K-major (K = pixels)
       const uint32_t idesc1 = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (1u << 16) | ((uint32_t)(VP_BN >> 3) << 17) |
                               ((uint32_t)(TC_BM >> 4) << 24);
-      const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(64 >> 3) << 17) |
+      const uint32_t idesc2 = (1u << 4) | (1u << 7) | (1u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(Cfg::N2 >> 3) << 17) |
                               ((uint32_t)(TC_BM >> 4) << 24);
       auto gemm2 = [&](int u) {
         const int bu = u & 1, su = u % VP_STAGES;
@@ -151,7 +164,8 @@ __global__ void __launch_bounds__(VP_THREADS) vistok_pg_kernel(const __grid_cons
 #pragma unroll
         for (int j = 0; j < VP_BN / TC_UK; ++j) {
           const uint64_t ad = make_sdesc(d_base + bu * VP_D_BYTES + j * 32, 16, 1024);
-          const uint64_t bd = make_sdesc(b_base + su * VP_B_STAGE + j * 32, 16, 1024);
+          // K-major B with N = 64 KB channel rows: the KB boxes of a stage are consecutive 8-row groups (SBO = 1024)
+          const uint64_t bd = make_sdesc(b_base + su * Cfg::B_STAGE + j * 32, 16, 1024);
           umma_bf16(tmem_acc + 128u, ad, bd, idesc2, (u > 0 || j > 0) ? 1u : 0u);
         }
         umma_commit(b_empty + 8 * su);        // the pixel tile is free once BOTH contractions have read it
@@ -163,12 +177,15 @@ __global__ void __launch_bounds__(VP_THREADS) vistok_pg_kernel(const __grid_cons
         mbar_wait(acc_empty + 8 * buf, (((uint32_t)t >> 1) & 1u) ^ 1u);   // epilogue has drained this accumulator
         mbar_wait(b_full + 8 * s, (uint32_t)(t / VP_STAGES) & 1u);
         tc_fence_after();
-        const uint32_t sb = b_base + s * VP_B_STAGE;
+        const uint32_t sb = b_base + s * Cfg::B_STAGE;
 #pragma unroll
-        for (int j = 0; j < TC_BK / TC_UK; ++j) {
-          const uint64_t ad = make_sdesc(a_base + j * 32, 16, 1024);
-          const uint64_t bd = make_sdesc(sb + j * 2048, 8192, 1024);
-          umma_bf16(tmem_acc + (uint32_t)(buf * VP_BN), ad, bd, idesc1, j > 0 ? 1u : 0u);
+        for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+          for (int j = 0; j < TC_BK / TC_UK; ++j) {
+            const uint64_t ad = make_sdesc(a_base + kb * 16384 + j * 32, 16, 1024);
+            const uint64_t bd = make_sdesc(sb + kb * 8192 + j * 2048, 8192, 1024);
+            umma_bf16(tmem_acc + (uint32_t)(buf * VP_BN), ad, bd, idesc1, (kb > 0 || j > 0) ? 1u : 0u);
+          }
         }
         umma_commit(acc_full + 8 * buf);
         if (t >= 1) gemm2(t - 1);
@@ -217,7 +234,7 @@ __global__ void __launch_bounds__(VP_THREADS) vistok_pg_kernel(const __grid_cons
       const uint32_t prow = tmem_acc + ((uint32_t)(g * 32) << 16) + 128u;
       float* dst = pgrad + ((int64_t)bz * M + m) * C;
 #pragma unroll 1
-      for (int c = half * 32; c < half * 32 + 32; c += 16) {
+      for (int c = half * (Cfg::N2 / 2); c < (half + 1) * (Cfg::N2 / 2); c += 16) {
         if (c >= C) break;                       // warp-uniform
         uint32_t r[16];
         __syncwarp();
@@ -266,13 +283,13 @@ using namespace mmvqa;
 extern "C" {
 
 int mmvqa_vistok_pgrad_supported(int M, int HW, int C) {
-  return (M > 0 && C > 0 && C <= 64 && C % 8 == 0 && HW >= 2 * VP_BN) ? 1 : 0;
+  return (M > 0 && C > 0 && C <= 128 && C % 8 == 0 && HW >= 2 * VP_BN) ? 1 : 0;
 }
 
 int mmvqa_vistok_fwd_pgrad(const void* W, int64_t ldw, const void* f, int64_t ldf, float* vis, float* pgrad, int M, int HW,
                            int C, int B, int act, mmvqa_stream_t stream) {
   MMVQA_REQUIRE(W && f && vis && pgrad && B > 0, "vistok_fwd_pgrad: null pointer / empty batch");
-  MMVQA_REQUIRE(mmvqa_vistok_pgrad_supported(M, HW, C), "vistok_fwd_pgrad: needs C <= 64, C %% 8 == 0 and HW >= %d (M=%d HW=%d C=%d)",
+  MMVQA_REQUIRE(mmvqa_vistok_pgrad_supported(M, HW, C), "vistok_fwd_pgrad: needs C <= 128, C %% 8 == 0 and HW >= %d (M=%d HW=%d C=%d)",
                 2 * VP_BN, M, HW, C);
   MMVQA_REQUIRE(act >= MMVQA_ACT_NONE && act <= MMVQA_ACT_RELU, "vistok_fwd_pgrad: bad act %d", act);
   MMVQA_REQUIRE(ldw >= C && ldf >= HW, "vistok_fwd_pgrad: bad leading dimensions");
@@ -285,21 +302,32 @@ int mmvqa_vistok_fwd_pgrad(const void* W, int64_t ldw, const void* f, int64_t ld
   if (rc) return rc;
   rc = tc_make_map(&tmB, f, HW, C, ldf, B, C, 64, 64, "f");
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    MMVQA_CUDA(cudaFuncSetAttribute(vistok_pg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, VP_SMEM));
-    attr_set = true;
-  }
   const int n_tiles = (HW + VP_BN - 1) / VP_BN;
   const int mt = (M + TC_BM - 1) / TC_BM;
-  // two CTAs per SM (TMEM: 2 x 256 columns), ONE wave, at least 2 pixel tiles per CTA
-  int nsplit = (2 * num_sms()) / (mt * B);
+  const int kbn = C <= 64 ? 1 : 2;
+  // ONE wave (two CTAs per SM for C <= 64, one above), at least 2 pixel tiles per CTA
+  int nsplit = ((kbn == 1 ? VpCfg<1>::CTAS_PER_SM : VpCfg<2>::CTAS_PER_SM) * num_sms()) / (mt * B);
   if (nsplit > (n_tiles + 1) / 2) nsplit = (n_tiles + 1) / 2;
   if (nsplit < 1) nsplit = 1;
   dim3 grid(nsplit, mt, B);
   MMVQA_REQUIRE(grid.z <= 65535 && grid.y <= 65535, "vistok_fwd_pgrad: grid too large");
-  MMVQA_CUDA(launch_pdl(vistok_pg_kernel, grid, dim3(VP_THREADS), (size_t)VP_SMEM, as_stream(stream), tmA, tmB, vis, pgrad, M, HW, C,
-                        act, 1.0f / (float)HW, n_tiles));
+  if (kbn == 1) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      MMVQA_CUDA(cudaFuncSetAttribute(vistok_pg_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, VpCfg<1>::SMEM));
+      attr_set = true;
+    }
+    MMVQA_CUDA(launch_pdl(vistok_pg_kernel<1>, grid, dim3(VP_THREADS), (size_t)VpCfg<1>::SMEM, as_stream(stream), tmA, tmB, vis, pgrad,
+                          M, HW, C, act, 1.0f / (float)HW, n_tiles));
+  } else {
+    static bool attr_set = false;
+    if (!attr_set) {
+      MMVQA_CUDA(cudaFuncSetAttribute(vistok_pg_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, VpCfg<2>::SMEM));
+      attr_set = true;
+    }
+    MMVQA_CUDA(launch_pdl(vistok_pg_kernel<2>, grid, dim3(VP_THREADS), (size_t)VpCfg<2>::SMEM, as_stream(stream), tmA, tmB, vis, pgrad,
+                          M, HW, C, act, 1.0f / (float)HW, n_tiles));
+  }
   MMVQA_LAUNCHED("vistok_pg_kernel");
   return MMVQA_OK;
 }

@@ -88,9 +88,9 @@ _GRAD_SINK = None
 
 
 def set_grad_sink(fn) -> None:
-    """``fn(params, grads, side_stream) -> bool`` is called from inside multi-layer backward nodes with the
+    """``fn(params, grads, side_stream, tail) -> bool`` is called from inside multi-layer backward nodes with the
     parameters of ONE layer and their final fp32 gradients; work producing them is enqueued on the current stream
-    and on `side_stream`.  Returning True means the sink took the gradients (it may set ``p.grad`` itself): the node
+    and on `side_stream`; `tail` is True for the last layer of the node (no backward work is left to overlap with).  Returning True means the sink took the gradients (it may set ``p.grad`` itself): the node
     then returns None for them.  ``None`` removes the sink."""
     global _GRAD_SINK
     _GRAD_SINK = fn
@@ -963,7 +963,7 @@ class RealFormerEncoderFn(torch.autograd.Function):
                       dg2, db2]
                 pl = params[base:base + RF_PARAMS_PER_LAYER]
                 if sink is not None and all(ctx.needs_input_grad[7 + base + i] for i in range(RF_PARAMS_PER_LAYER)) and \
-                        sink(pl, gl, branch.side):
+                        sink(pl, gl, branch.side, l == 0):
                     keep.append(gl)
                 else:
                     grads[base:base + RF_PARAMS_PER_LAYER] = gl
@@ -1043,7 +1043,7 @@ class RealFormerEncoderFn(torch.autograd.Function):
                   dg2, db2]
             pl = params[base:base + RF_PARAMS_PER_LAYER]
             if sink is not None and all(ctx.needs_input_grad[7 + base + i] for i in range(RF_PARAMS_PER_LAYER)) and \
-                    sink(pl, gl, branch.side):
+                    sink(pl, gl, branch.side, l == 0):
                 keep.append(gl)
             else:
                 grads[base:base + RF_PARAMS_PER_LAYER] = gl

@@ -55,6 +55,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._early_ids = set()    # parameters already updated in this iteration
         self._early_keep = []      # gradients read by the optimizer stream (kept alive until step() joins it)
         self._opt_stream = None
+        self._hook_stream = None
         self._group_of = {id(p): gi for gi, g in enumerate(self.param_groups) for p in g["params"]}
         self._comm_stream = None
         self._hook_groups = []
@@ -220,7 +221,7 @@ class FusedAdam(torch.optim.Optimizer):
                                      "ids_fn": ids_fn}
         self._tables.clear()
 
-    def _launch(self, gi, key, plist, grads, max_ctas: int = 0, background: bool = False):
+    def _launch(self, gi, key, plist, grads, max_ctas: int = 0, background: bool = False, fast: bool = False):
         group = self.param_groups[gi]
         for p in plist:
             gate = self._row_gate.get(id(p))
@@ -230,14 +231,16 @@ class FusedAdam(torch.optim.Optimizer):
         # long one-group CTAs (0.95 of the HBM peak over 91 M parameters; the two-group loop with 8192-element chunks reaches
         # 0.74); the two-group loop is for the SMALL updates on the critical path, where per-CTA latency is the cost
         # (row-gated tables do not count: only their live rows are touched)
-        gentle = background or sum(p.numel() for p in plist if id(p) not in self._row_gate) >= SMALL_UPDATE
+        # `fast`: a bulk update with nothing left to hide under (the last encoder layer of the backward pass): the gentle
+        # loop has a latency floor of ~32 dependent round trips per CTA (68 us for one layer inside the step)
+        gentle = (background or sum(p.numel() for p in plist if id(p) not in self._row_gate) >= SMALL_UPDATE) and not fast
         table, n = self._table(key, plist, grads, CHUNK_BACKGROUND if gentle else CHUNK)
         b1, b2 = group["betas"]
         ops.adam_step_dev(table, n, self._hyper_dev[gi], b1, b2, group["eps"], group["weight_decay"], self._step_dev,
                           max_ctas, gentle)
 
     @torch.no_grad()
-    def _sink(self, params, grads, side_stream, from_hook: bool = False) -> bool:
+    def _sink(self, params, grads, side_stream, tail: bool = False, from_hook: bool = False) -> bool:
         """functional.set_grad_sink target (and the early_groups hook): update one set of parameters now, on the
         optimizer stream; with reduce_fn the exchange runs on a communication stream ahead of it, so the all-reduce
         of the next set overlaps this set's update."""
@@ -252,7 +255,7 @@ class FusedAdam(torch.optim.Optimizer):
                 p.grad = g          # visible to hooks / loggers exactly as after a normal backward
             self._early_ids.add(id(p))
         if from_hook or self._sink_schedule == [1]:
-            self._flush_early(gi, list(params), gs, side_stream, background=not from_hook)
+            self._flush_early(gi, list(params), gs, side_stream, background=not from_hook, fast=tail and self.reduce_fn is None)
         else:
             self._pending.append((gi, list(params), gs))
             if len(self._pending) >= self._sink_schedule[min(self._sink_round, len(self._sink_schedule) - 1)]:
@@ -269,7 +272,7 @@ class FusedAdam(torch.optim.Optimizer):
         self._pending = []
         self._flush_early(gi, params, grads, side_stream)
 
-    def _flush_early(self, gi, params, gs, side_stream, background: bool = True) -> None:
+    def _flush_early(self, gi, params, gs, side_stream, background: bool = True, fast: bool = False) -> None:
         """exchange (reduce_fn, communication stream) + update (optimizer stream) of `params`, ordered after everything
         enqueued so far on the current stream and on `side_stream`."""
         dev = params[0].device
@@ -277,8 +280,12 @@ class FusedAdam(torch.optim.Optimizer):
         if self._opt_stream is None:
             self._opt_stream = torch.cuda.Stream(dev)
             self._comm_stream = torch.cuda.Stream(dev)
+            self._hook_stream = torch.cuda.Stream(dev)
         self._advance(dev)          # on the main stream: ordered before every update of this iteration
-        first = self._comm_stream if self.reduce_fn is not None else self._opt_stream
+        # hook groups (embeddings at the tail of the step, heads) update on their own stream: queued behind the long
+        # background update of the last encoder layer they would end ~50 us after the gradients are there
+        upd = self._opt_stream if background else self._hook_stream
+        first = self._comm_stream if self.reduce_fn is not None else upd
         ev = torch.cuda.Event()
         ev.record(main)
         first.wait_event(ev)
@@ -292,12 +299,12 @@ class FusedAdam(torch.optim.Optimizer):
                 gr = self.reduce_fn(list(params), gs)
             ev3 = torch.cuda.Event()
             ev3.record(self._comm_stream)
-            self._opt_stream.wait_event(ev3)
-        with torch.cuda.stream(self._opt_stream):
+            upd.wait_event(ev3)
+        with torch.cuda.stream(upd):
             # layers handed in by the backward node run underneath the rest of the backward pass (background); hook groups
             # (embeddings at the tail of the step, the heads) are small and on or near the critical path
             self._launch(gi, ("early", id(params[0]), len(params)), list(params), gr, self.early_ctas if background else 0,
-                         background)
+                         background, fast)
         self._early_keep.append(gs)
 
     @torch.no_grad()
@@ -324,9 +331,10 @@ class FusedAdam(torch.optim.Optimizer):
             self._launch(gi, gi, plist, g)
         if self._early_ids:         # join the optimizer stream; its gradient buffers may be released after this point
             dev = self._opt_stream.device
-            ev = torch.cuda.Event()
-            ev.record(self._opt_stream)
-            torch.cuda.current_stream(dev).wait_event(ev)
+            for st_ in (self._opt_stream, self._hook_stream):
+                ev = torch.cuda.Event()
+                ev.record(st_)
+                torch.cuda.current_stream(dev).wait_event(ev)
             self._early_ids = set()
             self._early_keep = []
         for st in self._hook_groups:

@@ -95,7 +95,10 @@ def test_projector_weight_gradient_inside_the_forward_kernel(act):
         (v0, g0, _), (v1, g1, _) = res[False], res[True]
         close(v1, v0, 1e-5, 1e-6, msg="tokens")
         for n, (a, b) in enumerate(zip(g1, g0)):
-            close(a, b, 1e-4, 2e-5 * float(b.abs().max()), msg="dW level %d vs the act'-saving path" % n)
+            # (levels 0-2: both paths read SERF' from the same table -> order of summation only; level 3 (144 pixels) takes the
+            # MUFU formulas on the act'-saving path, so a few act' values round to the neighbouring bf16)
+            close(a, b, 1e-3 if n == 3 else 1e-4, (2e-4 if n == 3 else 2e-5) * float(b.abs().max()),
+                  msg="dW level %d vs the act'-saving path" % n)
         for n, (f, w) in enumerate(zip(feats, ws)):
             wl = w.detach().reshape(hidden, -1).bfloat16().float().cpu().requires_grad_(True)
             Y = torch.einsum("mc,bcn->bmn", wl, f.flatten(2).cpu())

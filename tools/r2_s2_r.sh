@@ -1,0 +1,6 @@
+cd $GRAFT_REPO_ROOT
+timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_optim_graph_gpu.py tests/test_parity_golden_gpu.py tests/test_fullsize_gpu.py tests/test_rf_encoder_gpu.py -q -m gpu -x > gpurun_out/r_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r_pytest.log
+Q="--steps 40 --warmup 5 --quick --pad-steps 20"
+run() { n=$1; shift; timeout 200 python bench.py $Q "$@" > gpurun_out/r_$n.json 2>gpurun_out/r_$n.err; echo "$n rc=$? $(tail -n1 gpurun_out/r_$n.json | cut -c1-100)"; }
+run base
+timeout 300 python tools/timeline.py --out gpurun_out/timeline_r.csv > gpurun_out/timeline_r.txt 2>&1; echo "timeline rc=$?"
