@@ -280,7 +280,7 @@ class FusedAdam(torch.optim.Optimizer):
         if self._opt_stream is None:
             self._opt_stream = torch.cuda.Stream(dev)
             self._comm_stream = torch.cuda.Stream(dev)
-            self._hook_stream = torch.cuda.Stream(dev)
+            self._hook_stream = torch.cuda.Stream(dev, priority=-1)   # small updates: ahead of the bulk update's CTAs
         self._advance(dev)          # on the main stream: ordered before every update of this iteration
         # hook groups (embeddings at the tail of the step, heads) update on their own stream: queued behind the long
         # background update of the last encoder layer they would end ~50 us after the gradients are there
