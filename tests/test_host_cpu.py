@@ -219,3 +219,48 @@ def test_resnet_single_pass_taps_equal_the_five_prefix_runs():
     # deep -> shallow token order, the channel counts of models_dict scale with the architecture (resnet18: /4)
     assert [t.shape[1] for t in taps] == [512, 256, 128, 64, 64]
     assert [t.shape[-1] for t in taps] == [2, 4, 8, 16, 32]
+
+
+def test_struct_layouts_of_round2_entry_points_match_the_header():
+    """ctypes mirrors of the by-value / by-pointer structs added in round 2 (descriptor of the multi-tensor Adam with the
+    row gate, prefetch and multi-cast lists) have the header's field order, and the numpy descriptor the optimizer uploads
+    has the same size as the C struct."""
+    import ctypes as C
+    import numpy as np
+    from mmvqa_b200 import optim
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "mmvqa.h")).read()
+    body = re.search(r"typedef struct mmvqa_adam_desc \{(.*?)\} mmvqa_adam_desc;", hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = re.findall(r"(\w+)\s*(?:;|,)", body)
+    assert names == [f[0] for f in _lib.AdamDesc._fields_]
+    assert C.sizeof(_lib.AdamDesc) == optim._DESC.itemsize == 72
+    assert list(optim._DESC.names) == [f[0] for f in _lib.AdamDesc._fields_]
+    assert int(re.search(r"#define MMVQA_PREFETCH_MAX (\d+)", hdr).group(1)) == _lib.PREFETCH_MAX
+    assert int(re.search(r"#define MMVQA_CAST_MULTI_MAX (\d+)", hdr).group(1)) == _lib.CAST_MULTI_MAX
+    assert [f[0] for f in _lib.PrefetchList._fields_] == ["ptr", "bytes", "n"]
+    assert [f[0] for f in _lib.CastList._fields_] == ["src", "dst", "ld_src", "ld_dst", "rows", "cols", "src_bf16", "n"]
+    assert int(re.search(r"#define MMVQA_ABI_VERSION (\d+)", hdr).group(1)) == _lib.ABI_VERSION
+
+
+def test_sink_group_schedule_and_update_modes():
+    """FusedAdam host logic (no kernels): a sink-group schedule (4, 2, 1) flushes after 4, then 2, then single layers and
+    restarts at step(); hook groups bypass it; the update mode follows the size of the launch and the tail flag."""
+    from mmvqa_b200 import optim
+    ps = [nn.Parameter(torch.zeros(4, 4)) for _ in range(9)]
+    opt = optim.FusedAdam(ps, lr=1e-3, sink_group=(4, 2, 1))
+    flushed = []
+    opt._flush_early = lambda gi, params, gs, side, background=True, fast=False: flushed.append((len(params), background, fast))
+    for i, p in enumerate(ps[:8]):
+        assert opt._sink([p], [torch.zeros(4, 4)], None, i == 7)
+    assert [n for n, _, _ in flushed] == [4, 2, 1, 1]
+    assert all(b for _, b, _ in flushed)                      # pending layers are bulk (background) updates
+    assert opt._sink([ps[8]], [torch.zeros(4, 4)], None, from_hook=True)
+    assert flushed[-1] == (1, False, False)                   # hook groups: critical-path mode, own stream
+    opt._early_ids.clear()
+    opt._sink_round = 0
+    one = optim.FusedAdam([nn.Parameter(torch.zeros(2))], lr=1e-3)
+    calls = []
+    one._flush_early = lambda gi, params, gs, side, background=True, fast=False: calls.append((background, fast))
+    one._sink(one.param_groups[0]["params"], [torch.zeros(2)], None, True)
+    assert calls == [(True, True)]                            # last layer of the backward pass: fast bulk update
+    assert optim.CHUNK < optim.CHUNK_BACKGROUND and optim.GATED_ROWS <= 1024
